@@ -1,0 +1,137 @@
+/*
+ * s3d.h -- C ABI of libs3d_b200.so, the B200 (sm_100a) hot path for the
+ * Stereo2Voxel / Stereo2Point inference pipeline.
+ *
+ * Boundary contract:
+ *   - plain C: raw DEVICE pointers, integer shapes, a cudaStream_t passed as void*;
+ *     no torch types, no allocation, no synchronisation, no global state except the
+ *     last-error slot; every entry point enqueues on the caller's stream and returns
+ *     0 on success or a negative S3D_ERR_* code (never throws across the ABI);
+ *   - all memory (inputs, outputs, workspaces) is owned by the caller (PyTorch);
+ *   - there is NO CPU fallback: on a box without a CUDA device every compute entry
+ *     point returns S3D_ERR_CUDA.
+ *
+ * What each entry point replaces in the reference.  The reference's model code is on
+ * the upstream Stereo2Voxel / Stereo2Point branches (/root/reference/README.md:5,56,62)
+ * and is NOT on disk, so the only citable reference interfaces are
+ *   - extensions/chamfer_dist (README.md:62-65)  -> s3d_chamfer_forward
+ *   - runner.py --test --weights (README.md:91)  -> the nn.Module forwards in
+ *     stereo_3d_reconstruction_b200/, which call the s3d_* entry points below where
+ *     upstream calls torch.nn.functional conv2d / conv3d / conv_transpose3d / softmax
+ *     (torch>=1.4.0, requirements.txt:8).
+ *
+ * Tensor layout: activations are channels-last, 5-D [N, D, H, W, C] (2-D maps have D=1),
+ * dense, C padded to a multiple of 16 (bf16) / 8 (fp32).
+ */
+#ifndef S3D_H_
+#define S3D_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define S3D_OK                0
+#define S3D_ERR_INVALID      -1   /* bad argument / unsupported shape            */
+#define S3D_ERR_CUDA         -2   /* CUDA runtime / driver error (s3d_last_error) */
+#define S3D_ERR_UNSUPPORTED  -3   /* device is not sm_100                         */
+
+#define S3D_DTYPE_F32   0
+#define S3D_DTYPE_BF16  1
+
+#define S3D_ACT_NONE     0
+#define S3D_ACT_RELU     1
+#define S3D_ACT_LEAKY    2   /* slope = act_param                       */
+#define S3D_ACT_SIGMOID  3
+#define S3D_ACT_TANH     4   /* act_param * tanh(x)                     */
+
+#define S3D_MAX_TAPS 64
+
+/* One convolution-like layer as an implicit GEMM:
+ *   out[n, z*omz+ooz, y*omy+ooy, x*omx+oox, co] =
+ *     act( bias[co] + sum_{t<ntaps} sum_{ci<Cin}
+ *            in[n, z*sz+dz[t], y*sy+dy[t], x*sx+dx[t], ci] * w[cls*ntaps+t, co, ci]  (+ residual) )
+ * for (z,y,x) in the logical output grid oD x oH x oW; out-of-range input samples read 0.
+ * Ordinary convs use n_classes=1, om*=1, oo*=0 and d*[t] = k - pad.  A stride-2
+ * ConvTranspose3d(k4,p1) is n_classes=8 sub-pixel classes of 8 taps each; class bits
+ * (cz,cy,cx) select oo* = (cz,cy,cx) with om*=2, and use tap rows cls*ntaps .. +ntaps. */
+typedef struct S3dConvParams {
+  int32_t N, iD, iH, iW, Cin;       /* input  [N,iD,iH,iW,Cin]                          */
+  int32_t oD, oH, oW, Cout;         /* logical output grid per class, padded Cout (GEMM N) */
+  int32_t sz, sy, sx;               /* input stride per output step (1 or 2)            */
+  int32_t ntaps, n_classes;         /* taps per class; 1 or 8 classes                   */
+  int8_t  dz[S3D_MAX_TAPS], dy[S3D_MAX_TAPS], dx[S3D_MAX_TAPS]; /* [n_classes*ntaps]   */
+  int64_t osN, osD, osH, osW;       /* output element strides (channel stride is 1)     */
+  int32_t omz, omy, omx;            /* output coordinate multiplier                     */
+  int32_t cout_store;               /* channels actually written (<= Cout)              */
+  int32_t in_dtype, out_dtype;      /* S3D_DTYPE_*; weights have in_dtype               */
+  int32_t act;  float act_param;
+  int32_t tw, th, td, tn;           /* M-tile box, powers of two, tw*th*td*tn == 128    */
+  int32_t bn;                       /* GEMM N tile: multiple of 16, <= 256, divides Cout */
+} S3dConvParams;
+
+const char* s3d_version(void);
+/* Human-readable text of the last error seen on this thread ("" if none). */
+const char* s3d_last_error(void);
+/* 0 if device `dev` is usable (compute capability 10.x), else a negative code. */
+int s3d_device_check(int dev);
+
+/* --- convolution engines ------------------------------------------------------------ */
+/* tcgen05/TMEM/TMA implicit GEMM (bf16 -> kind::f16, fp32 -> kind::tf32), fp32 accumulate.
+ * bias: fp32[Cout] or NULL; residual: NULL or a tensor addressed exactly like `out`. */
+int s3d_conv_igemm(const S3dConvParams* p, const void* in, const void* w, const float* bias,
+                   const void* residual, void* out, void* stream);
+/* Same contract, plain fp32 SIMT FMA loop (exact-fp32 validation mode; in/out dtype free). */
+int s3d_conv_direct(const S3dConvParams* p, const void* in, const void* w, const float* bias,
+                    const void* residual, void* out, void* stream);
+
+/* --- input staging ------------------------------------------------------------------ */
+/* NCHW fp32 image [B,3,H,W] (+ optional fp32 disparity plane [B,H,W], scaled by disp_scale
+ * into channel 3) -> channels-last [B,1,H,W,Cpad], zero padded channels. */
+int s3d_pack_image(const float* img, const float* disp, float disp_scale, void* out,
+                   int B, int H, int W, int Cpad, int out_dtype, void* stream);
+
+/* --- cost volume / disparity (rows V, S) ---------------------------------------------- */
+/* feat: [2B,1,h,w,C] (left maps first, then right).  vol: [2B,D,h,w,2C]; entries [0,B) are
+ * left-referenced (target sampled at x-d), [B,2B) right-referenced (target at x+d). */
+int s3d_cost_volume_concat(const void* feat, void* vol, int B, int h, int w, int C, int D,
+                           int dtype, void* stream);
+/* cost: fp32 [N,D,h,w] -> disp fp32 [N,h,w] = sum_d d*softmax_d(sign*cost).  sign=-1: soft-argmin. */
+int s3d_soft_argmin(const float* cost, float* disp, int N, int D, int h, int w, float sign,
+                    void* stream);
+/* Fused correlation + soft-argmax; the [2B,D,h,w] cost is never materialised.
+ * disp: fp32 [2B,h,w]; cost_out may be NULL (debug: fp32 [2B,D,h,w]). */
+int s3d_corr_soft_argmin(const void* feat, float* disp, float* cost_out, int B, int h, int w,
+                         int C, int D, int dtype, void* stream);
+/* disp_q fp32 [N,h,w] (1/4-res units) -> fp32 [N,H,W] = bilinear(scale*disp_q), align_corners=False. */
+int s3d_upsample_disp(const float* disp_q, float* disp, int N, int h, int w, int H, int W,
+                      float scale, void* stream);
+
+/* --- decoder glue (rows X, D, F, M) ---------------------------------------------------- */
+/* adaptive average pool [N,1,H,W,C] -> [N,1,L,L,C], then the NCHW .view(N,C*L*L/8,2,2,2)
+ * re-indexing of the oracle, written channels-last as [N,2,2,2,C*L*L/8]. */
+int s3d_latent_to_vox(const void* x, void* out, int N, int H, int W, int C, int L, int dtype,
+                      void* stream);
+/* Generic adaptive average pool, channels-last [N,1,H,W,C] -> [N,1,L,L,C]. */
+int s3d_avg_pool(const void* x, void* out, int N, int H, int W, int C, int L, int dtype,
+                 void* stream);
+/* Context-aware fusion epilogue + IoU.  score, vol: [V*B, 32^3] planes with element strides
+ * score_stride / vol_stride (view-major); fused[b,v] = clamp(sum_v softmax_v(score)*vol, 0, 1).
+ * gt (uint8 [B,32^3]) and iou (int64 [B,T,2] = intersection, union) may be NULL. */
+int s3d_fuse_views(const void* score, int64_t score_stride, const void* vol, int64_t vol_stride,
+                   int dtype, float* fused, int B, int V, int nvox, const uint8_t* gt,
+                   const float* thresholds, int T, long long* iou, void* stream);
+
+/* --- Chamfer distance (row C; replaces extensions/chamfer_dist, README.md:62-65) ------- */
+/* xyz1 fp32 [B,N,3], xyz2 fp32 [B,M,3] -> dist1 fp32 [B,N], idx1 int32 [B,N] (nearest in
+ * xyz2), dist2 fp32 [B,M], idx2 int32 [B,M] (nearest in xyz1).  Squared L2, computed as
+ * ((x1-x2)^2 + (y1-y2)^2) + (z1-z2)^2 with round-to-nearest mul/add and no FMA contraction;
+ * ties resolve to the lowest index. */
+int s3d_chamfer_forward(const float* xyz1, const float* xyz2, float* dist1, int32_t* idx1,
+                        float* dist2, int32_t* idx2, int B, int N, int M, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* S3D_H_ */

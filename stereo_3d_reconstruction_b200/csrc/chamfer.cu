@@ -1,0 +1,104 @@
+// Row C: Chamfer nearest-neighbour search (forward), replacing the reference's
+// extensions/chamfer_dist CUDA extension (/root/reference/README.md:62-65; its source is on the
+// upstream Stereo2Point branch and not on disk).
+//
+// For every query point: min over the other set of ((dx*dx + dy*dy) + dz*dz), with explicit
+// round-to-nearest mul/add (no FMA contraction) so the distances -- and therefore the argmin --
+// are bit-identical to the C oracle (oracle/chamfer_ref.c).  Ties go to the lowest index.
+//
+// Tiled shared-memory min-reduction: the "other" set streams through shared memory in tiles of
+// kTile points (float4, broadcast reads); every thread keeps kQ query points and their running
+// (best distance, best index) in registers; S lanes of a warp split each tile between them and
+// finish with a warp-shuffle lexicographic (distance, index) argmin.  Bound by the fp32 ALU issue
+// rate (about 11 instructions per point pair), not by HBM: B*(N+M)*20 bytes move in total.
+#include "common.cuh"
+
+namespace s3d {
+namespace {
+
+constexpr int kQ = 4;        // queries per thread
+constexpr int kTile = 1024;  // reference points per shared-memory tile
+constexpr int kThreads = 256;
+
+__global__ void __launch_bounds__(kThreads)
+chamfer_nn_kernel(const float* __restrict__ q_xyz, const float* __restrict__ r_xyz, float* __restrict__ dist,
+                  int32_t* __restrict__ idx, int nq, int nr, int S, int blocks_per_batch) {
+  __shared__ float4 tile[kTile];
+  const int b = blockIdx.x / blocks_per_batch;
+  const int blk = blockIdx.x % blocks_per_batch;
+  const int s = threadIdx.x % S;                       // slice of the tile this lane scans
+  const int group = threadIdx.x / S;                   // query group within the block
+  const int groups = kThreads / S;
+  const int q0 = (blk * groups + group) * kQ;          // first query of this thread
+  const float* qb = q_xyz + (int64_t)b * nq * 3;
+  const float* rb = r_xyz + (int64_t)b * nr * 3;
+
+  float qx[kQ], qy[kQ], qz[kQ], best[kQ];
+  int bi[kQ];
+#pragma unroll
+  for (int k = 0; k < kQ; ++k) {
+    const int qi = min(q0 + k, nq - 1);
+    qx[k] = qb[qi * 3 + 0];  qy[k] = qb[qi * 3 + 1];  qz[k] = qb[qi * 3 + 2];
+    best[k] = INFINITY;  bi[k] = 0x7fffffff;
+  }
+
+  for (int j0 = 0; j0 < nr; j0 += kTile) {
+    const int cnt = min(kTile, nr - j0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < cnt; i += kThreads) {
+      const float* p = rb + (int64_t)(j0 + i) * 3;
+      tile[i] = make_float4(p[0], p[1], p[2], 0.f);
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int j = s; j < cnt; j += S) {
+      const float4 r = tile[j];
+#pragma unroll
+      for (int k = 0; k < kQ; ++k) {
+        const float dx = __fsub_rn(qx[k], r.x), dy = __fsub_rn(qy[k], r.y), dz = __fsub_rn(qz[k], r.z);
+        const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+        if (d < best[k]) { best[k] = d; bi[k] = j0 + j; }
+      }
+    }
+  }
+  // lexicographic (distance, index) argmin across the S lanes of the group
+#pragma unroll
+  for (int k = 0; k < kQ; ++k) {
+    for (int o = S >> 1; o > 0; o >>= 1) {
+      const float od = __shfl_xor_sync(0xffffffffu, best[k], o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi[k], o);
+      if (od < best[k] || (od == best[k] && oi < bi[k])) { best[k] = od; bi[k] = oi; }
+    }
+    if (s == 0 && q0 + k < nq) {
+      dist[(int64_t)b * nq + q0 + k] = best[k];
+      idx[(int64_t)b * nq + q0 + k] = bi[k];
+    }
+  }
+}
+
+int launch_dir(const float* q, const float* r, float* dist, int32_t* idx, int B, int nq, int nr, cudaStream_t st) {
+  // lanes per query group: enough threads to fill the chip (~2 waves of 2048 threads / SM)
+  const int64_t want = (int64_t)num_sms() * 2048 * 2;
+  int S = 1;
+  while (S < 32 && (int64_t)B * ceil_div(nq, kQ) * S < want && S * 2 <= nr) S <<= 1;
+  const int groups = kThreads / S;
+  const int blocks_per_batch = ceil_div(nq, groups * kQ);
+  chamfer_nn_kernel<<<B * blocks_per_batch, kThreads, 0, st>>>(q, r, dist, idx, nq, nr, S, blocks_per_batch);
+  S3D_LAUNCH_CHECK();
+  return S3D_OK;
+}
+
+}  // namespace
+}  // namespace s3d
+
+extern "C" int s3d_chamfer_forward(const float* xyz1, const float* xyz2, float* dist1, int32_t* idx1, float* dist2,
+                                   int32_t* idx2, int B, int N, int M, void* stream) {
+  using namespace s3d;
+  if (!xyz1 || !xyz2 || !dist1 || !idx1 || !dist2 || !idx2) { set_error("chamfer: null argument"); return S3D_ERR_INVALID; }
+  S3D_CHECK_ARG(B >= 0 && N > 0 && M > 0, "chamfer: empty point set (N=%d, M=%d)", N, M);
+  if (B == 0) return S3D_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc = launch_dir(xyz1, xyz2, dist1, idx1, B, N, M, st);
+  if (rc != S3D_OK) return rc;
+  return launch_dir(xyz2, xyz1, dist2, idx2, B, M, N, st);
+}

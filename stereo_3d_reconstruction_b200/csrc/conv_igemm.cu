@@ -1,0 +1,403 @@
+// Implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05 + TMEM), operands staged by TMA.
+//
+// One kernel covers Conv2d / Conv3d (stride 1 or 2), the 8 sub-pixel classes of a stride-2
+// ConvTranspose3d(k4,p1), and Linear layers (a conv whose taps cover the whole input map).
+//
+//   GEMM view    M = output positions (N x oD x oH x oW), tiled 128 rows per CTA step as a
+//                (tn, td, th, tw) box;  N = Cout (tile bn <= 256);  K = taps x Cin.
+//   A operand    for tap t the 128 x KC activation slab is ONE 5-D TMA box of the channels-last
+//                input, shifted by the tap offset; out-of-image rows are zero-filled by the TMA
+//                unit, so padding costs nothing and no im2col buffer ever exists.  Stride-2
+//                layers use the tensor map's elementStrides.  Rows are KC*elem = 32/64/128 B wide,
+//                matching the 32B/64B/128B swizzle so the slab is a canonical K-major UMMA tile.
+//   B operand    pre-packed weights [class*taps][Cout][Cin], one 3-D TMA box per (tap, K chunk).
+//   accumulate   fp32 in TMEM, two accumulator buffers of 256 columns so the epilogue of tile i
+//                overlaps the MMAs of tile i+1.
+//   epilogue     4 warps, tcgen05.ld 32x32b: thread = one output row; bias (+BN folded on host),
+//                optional residual, activation, bf16/fp32 store with arbitrary output strides
+//                (sub-pixel interleave of transposed convs, channel slices of concat buffers).
+//
+// Warp roles (256 threads, 1 CTA / SM, persistent over tiles):
+//   warp 0: TMA producer   warp 1: MMA issuer (one elected lane)   warp 2: TMEM alloc/dealloc
+//   warps 4-7: epilogue (warp%4 selects the 32-lane TMEM quarter it may read)
+#include <cuda.h>
+#include <stdarg.h>
+#include <string.h>
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace s3d {
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kTileM = 128;
+constexpr int kMaxStages = 8;
+constexpr int kTmemCols = 512;
+constexpr int kAccStride = 256;   // TMEM columns per accumulator buffer
+
+struct KernelArgs {
+  S3dConvParams p;
+  const float* bias;
+  const void* residual;
+  void* out;
+  int kc;            // channels per K chunk
+  int row_bytes;     // kc * elem size: 32 / 64 / 128
+  int n_kchunks;     // Cin / kc
+  int stages;
+  int a_bytes, b_bytes, stage_bytes;
+  int tiles_x, tiles_y, tiles_z, tiles_n;   // M tiling
+  int n_ntiles;                             // Cout / bn
+  int total_tiles;                          // n_classes * M tiles * N tiles
+  int lw, lh, ld;                           // log2 of tw, th, td
+  uint32_t idesc;
+};
+
+struct SharedCtrl {
+  uint64_t full[kMaxStages];
+  uint64_t empty[kMaxStages];
+  uint64_t acc_full[2];
+  uint64_t acc_empty[2];
+  uint32_t tmem_base;
+};
+
+struct TileCoord {
+  int cls, n0, z0, y0, x0, nt;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const KernelArgs& a, int tile) {
+  TileCoord t;
+  t.nt = tile % a.n_ntiles;  tile /= a.n_ntiles;
+  const int tx = tile % a.tiles_x;  tile /= a.tiles_x;
+  const int ty = tile % a.tiles_y;  tile /= a.tiles_y;
+  const int tz = tile % a.tiles_z;  tile /= a.tiles_z;
+  const int tn = tile % a.tiles_n;  tile /= a.tiles_n;
+  t.cls = tile;
+  t.x0 = tx << a.lw;  t.y0 = ty << a.lh;  t.z0 = tz << a.ld;  t.n0 = tn * a.p.tn;
+  return t;
+}
+
+template <bool kTF32>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                  const __grid_constant__ KernelArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  // 1024 B alignment: required by the 128B swizzle atom (8 rows x 128 B).
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ SharedCtrl ctrl;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&map_a);
+    ptx::prefetch_tensormap(&map_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < a.stages; ++s) {
+      ptx::mbar_init(&ctrl.full[s], 1);
+      ptx::mbar_init(&ctrl.empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      ptx::mbar_init(&ctrl.acc_full[b], 1);
+      ptx::mbar_init(&ctrl.acc_empty[b], 128);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) ptx::tmem_alloc(&ctrl.tmem_base, kTmemCols);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = ctrl.tmem_base;
+
+  const int ksteps = a.p.ntaps * a.n_kchunks;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int stage = 0;  uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(a, tile);
+        const int xin = t.x0 * a.p.sx, yin = t.y0 * a.p.sy, zin = t.z0 * a.p.sz;
+        for (int tap = 0; tap < a.p.ntaps; ++tap) {
+          const int ti = t.cls * a.p.ntaps + tap;
+          const int cx = xin + a.p.dx[ti], cy = yin + a.p.dy[ti], cz = zin + a.p.dz[ti];
+          for (int kc = 0; kc < a.n_kchunks; ++kc) {
+            ptx::mbar_wait(&ctrl.empty[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * a.stage_bytes;
+            uint8_t* sb = sa + a.a_bytes;
+            ptx::mbar_arrive_expect_tx(&ctrl.full[stage], a.a_bytes + a.b_bytes);
+            ptx::tma_load_5d(sa, &map_a, &ctrl.full[stage], kc * a.kc, cx, cy, cz, t.n0);
+            ptx::tma_load_3d(sb, &map_b, &ctrl.full[stage], kc * a.kc, t.nt * a.p.bn, ti);
+            if (++stage == a.stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      int stage = 0;  uint32_t phase = 0;
+      int buf = 0;    uint32_t acc_phase = 0;
+      const int mma_per_stage = a.row_bytes / 32;   // each tcgen05.mma consumes 32 B of K per row
+      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+        ptx::mbar_wait(&ctrl.acc_empty[buf], acc_phase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * kAccStride;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          ptx::mbar_wait(&ctrl.full[stage], phase);
+          ptx::tc_fence_after();
+          const uint32_t sa = ptx::smem_u32(smem + stage * a.stage_bytes);
+          const uint64_t adesc = ptx::make_smem_desc(sa, a.row_bytes);
+          const uint64_t bdesc = ptx::make_smem_desc(sa + a.a_bytes, a.row_bytes);
+          for (int k = 0; k < mma_per_stage; ++k) {
+            const uint32_t acc = (ks | k) != 0;
+            // advance 32 B along K inside the swizzle atom: +2 in the (addr >> 4) field
+            if (kTF32) ptx::mma_tf32(d_tmem, adesc + 2 * k, bdesc + 2 * k, a.idesc, acc);
+            else       ptx::mma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, a.idesc, acc);
+          }
+          ptx::tc_commit(&ctrl.empty[stage]);          // frees the smem slot when the MMAs retire
+          if (++stage == a.stages) { stage = 0; phase ^= 1; }
+        }
+        ptx::tc_commit(&ctrl.acc_full[buf]);           // accumulator complete -> epilogue
+        if (++buf == 2) { buf = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ================= epilogue =================
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;            // row of the 128-row tile
+    const int dxr = r & (a.p.tw - 1);
+    const int dyr = (r >> a.lw) & (a.p.th - 1);
+    const int dzr = (r >> (a.lw + a.lh)) & (a.p.td - 1);
+    const int dnr = r >> (a.lw + a.lh + a.ld);
+    const bool out_bf16 = a.p.out_dtype == S3D_DTYPE_BF16;
+    int buf = 0;  uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(a, tile);
+      const int x = t.x0 + dxr, y = t.y0 + dyr, z = t.z0 + dzr, n = t.n0 + dnr;
+      const bool valid = x < a.p.oW && y < a.p.oH && z < a.p.oD && n < a.p.N;
+      const int ooz = (t.cls >> 2) & 1, ooy = (t.cls >> 1) & 1, oox = t.cls & 1;
+      const int64_t off = (int64_t)n * a.p.osN + (int64_t)(z * a.p.omz + ooz) * a.p.osD +
+                          (int64_t)(y * a.p.omy + ooy) * a.p.osH + (int64_t)(x * a.p.omx + oox) * a.p.osW;
+      ptx::mbar_wait(&ctrl.acc_full[buf], acc_phase);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + buf * kAccStride + (static_cast<uint32_t>(q * 32) << 16);
+      const int c_base = t.nt * a.p.bn;
+      for (int c0 = 0; c0 < a.p.bn; c0 += 16) {
+        uint32_t v[16];
+        ptx::tmem_ld16(taddr + c0, v);
+        ptx::tmem_ld_wait();
+        const int cg = c_base + c0;                    // first global channel of this group
+        if (valid && cg < a.p.cout_store) {
+          float f[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            f[i] = __uint_as_float(v[i]);
+            if (a.bias) f[i] += __ldg(a.bias + cg + i);
+          }
+          const bool full = cg + 16 <= a.p.cout_store;
+          if (out_bf16) {
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(a.out) + off + cg;
+            const __nv_bfloat16* rs = a.residual ? reinterpret_cast<const __nv_bfloat16*>(a.residual) + off + cg : nullptr;
+            const bool vec = full && ((reinterpret_cast<uintptr_t>(o) & 15) == 0) &&
+                             (!rs || (reinterpret_cast<uintptr_t>(rs) & 15) == 0);
+            if (vec) {
+              if (rs) {
+                uint4 r0 = __ldg(reinterpret_cast<const uint4*>(rs));
+                uint4 r1 = __ldg(reinterpret_cast<const uint4*>(rs) + 1);
+                const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&r0);
+                const __nv_bfloat162* h1 = reinterpret_cast<const __nv_bfloat162*>(&r1);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  float2 g0 = __bfloat1622float2(h0[i]), g1 = __bfloat1622float2(h1[i]);
+                  f[2 * i] += g0.x;  f[2 * i + 1] += g0.y;
+                  f[8 + 2 * i] += g1.x;  f[8 + 2 * i + 1] += g1.y;
+                }
+              }
+              uint4 w0, w1;
+              __nv_bfloat162* p0 = reinterpret_cast<__nv_bfloat162*>(&w0);
+              __nv_bfloat162* p1 = reinterpret_cast<__nv_bfloat162*>(&w1);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                p0[i] = __floats2bfloat162_rn(apply_act(f[2 * i], a.p.act, a.p.act_param),
+                                              apply_act(f[2 * i + 1], a.p.act, a.p.act_param));
+                p1[i] = __floats2bfloat162_rn(apply_act(f[8 + 2 * i], a.p.act, a.p.act_param),
+                                              apply_act(f[8 + 2 * i + 1], a.p.act, a.p.act_param));
+              }
+              reinterpret_cast<uint4*>(o)[0] = w0;
+              reinterpret_cast<uint4*>(o)[1] = w1;
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                if (cg + i < a.p.cout_store) {
+                  float s = f[i];
+                  if (rs) s += __bfloat162float(rs[i]);
+                  o[i] = __float2bfloat16_rn(apply_act(s, a.p.act, a.p.act_param));
+                }
+              }
+            }
+          } else {
+            float* o = reinterpret_cast<float*>(a.out) + off + cg;
+            const float* rs = a.residual ? reinterpret_cast<const float*>(a.residual) + off + cg : nullptr;
+            const bool vec = full && ((reinterpret_cast<uintptr_t>(o) & 15) == 0) &&
+                             (!rs || (reinterpret_cast<uintptr_t>(rs) & 15) == 0);
+            if (vec) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                float4 s = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+                if (rs) {
+                  float4 g = __ldg(reinterpret_cast<const float4*>(rs) + i);
+                  s.x += g.x; s.y += g.y; s.z += g.z; s.w += g.w;
+                }
+                s.x = apply_act(s.x, a.p.act, a.p.act_param);  s.y = apply_act(s.y, a.p.act, a.p.act_param);
+                s.z = apply_act(s.z, a.p.act, a.p.act_param);  s.w = apply_act(s.w, a.p.act, a.p.act_param);
+                reinterpret_cast<float4*>(o)[i] = s;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                if (cg + i < a.p.cout_store) {
+                  float s = f[i];
+                  if (rs) s += rs[i];
+                  o[i] = apply_act(s, a.p.act, a.p.act_param);
+                }
+              }
+            }
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&ctrl.acc_empty[buf]);
+      if (++buf == 2) { buf = 0; acc_phase ^= 1; }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ---- host side -------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
+bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+}  // namespace
+
+int conv_igemm_launch(const S3dConvParams* p, const void* in, const void* w, const float* bias,
+                      const void* residual, void* out, cudaStream_t stream) {
+  const bool tf32 = p->in_dtype == S3D_DTYPE_F32;
+  const int esz = tf32 ? 4 : 2;
+  S3D_CHECK_ARG(p->in_dtype == S3D_DTYPE_F32 || p->in_dtype == S3D_DTYPE_BF16, "igemm: bad in_dtype");
+  S3D_CHECK_ARG(p->out_dtype == S3D_DTYPE_F32 || p->out_dtype == S3D_DTYPE_BF16, "igemm: bad out_dtype");
+  S3D_CHECK_ARG(p->Cin > 0 && (p->Cin * esz) % 32 == 0, "igemm: Cin*elem must be a multiple of 32 B (Cin=%d)", p->Cin);
+  S3D_CHECK_ARG(p->bn >= 16 && p->bn <= 256 && p->bn % 16 == 0 && p->Cout % p->bn == 0,
+                "igemm: bn=%d must be a multiple of 16 <= 256 dividing Cout=%d", p->bn, p->Cout);
+  S3D_CHECK_ARG(is_pow2(p->tw) && is_pow2(p->th) && is_pow2(p->td) && is_pow2(p->tn) &&
+                p->tw * p->th * p->td * p->tn == kTileM, "igemm: tile box must be powers of two with product 128");
+  S3D_CHECK_ARG(p->ntaps >= 1 && (p->n_classes == 1 || p->n_classes == 8) &&
+                p->ntaps * p->n_classes <= S3D_MAX_TAPS, "igemm: bad tap table");
+  S3D_CHECK_ARG(p->sx >= 1 && p->sx <= 2 && p->sy >= 1 && p->sy <= 2 && p->sz >= 1 && p->sz <= 2, "igemm: stride");
+  S3D_CHECK_ARG(p->cout_store >= 1 && p->cout_store <= p->Cout, "igemm: cout_store");
+  S3D_CHECK_ARG((reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0,
+                "igemm: in / w must be 16 B aligned");
+
+  EncodeTiledFn encode = get_encode_fn();
+  if (!encode) { set_error("igemm: cuTensorMapEncodeTiled unavailable"); return S3D_ERR_CUDA; }
+
+  KernelArgs a;
+  memset(&a, 0, sizeof(a));
+  a.p = *p;  a.bias = bias;  a.residual = residual;  a.out = out;
+  const int cin_bytes = p->Cin * esz;
+  a.row_bytes = cin_bytes % 128 == 0 ? 128 : (cin_bytes % 64 == 0 ? 64 : 32);
+  a.kc = a.row_bytes / esz;
+  a.n_kchunks = p->Cin / a.kc;
+  a.a_bytes = kTileM * a.row_bytes;
+  a.b_bytes = ((p->bn * a.row_bytes + 1023) / 1024) * 1024;
+  a.stage_bytes = a.a_bytes + a.b_bytes;          // a_bytes is a multiple of 1024 (4096..16384)
+  const int smem_budget = 200 * 1024;
+  a.stages = smem_budget / a.stage_bytes;
+  if (a.stages > kMaxStages) a.stages = kMaxStages;
+  const int ksteps = p->ntaps * a.n_kchunks;
+  if (a.stages < 2) a.stages = 2;
+  a.tiles_x = ceil_div(p->oW, p->tw);  a.tiles_y = ceil_div(p->oH, p->th);
+  a.tiles_z = ceil_div(p->oD, p->td);  a.tiles_n = ceil_div(p->N, p->tn);
+  a.n_ntiles = p->Cout / p->bn;
+  const int64_t total = (int64_t)p->n_classes * a.tiles_x * a.tiles_y * a.tiles_z * a.tiles_n * a.n_ntiles;
+  S3D_CHECK_ARG(total > 0 && total < (1ll << 31), "igemm: tile count out of range");
+  a.total_tiles = (int)total;
+  a.lw = ilog2(p->tw);  a.lh = ilog2(p->th);  a.ld = ilog2(p->td);
+  a.idesc = ptx::make_instr_desc(tf32 ? 2 : 1, kTileM, p->bn);
+  (void)ksteps;
+
+  const CUtensorMapDataType dt = tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  const CUtensorMapSwizzle sw = a.row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                              : a.row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+  CUtensorMap map_a, map_b;
+  {
+    cuuint64_t dims[5] = {(cuuint64_t)p->Cin, (cuuint64_t)p->iW, (cuuint64_t)p->iH, (cuuint64_t)p->iD, (cuuint64_t)p->N};
+    cuuint64_t strides[4];
+    strides[0] = (cuuint64_t)p->Cin * esz;
+    strides[1] = strides[0] * p->iW;
+    strides[2] = strides[1] * p->iH;
+    strides[3] = strides[2] * p->iD;
+    cuuint32_t box[5] = {(cuuint32_t)a.kc, (cuuint32_t)(p->tw * p->sx), (cuuint32_t)(p->th * p->sy),
+                         (cuuint32_t)(p->td * p->sz), (cuuint32_t)p->tn};
+    cuuint32_t estr[5] = {1, (cuuint32_t)p->sx, (cuuint32_t)p->sy, (cuuint32_t)p->sz, 1};
+    S3D_CHECK_ARG(box[1] <= 256 && box[2] <= 256 && box[3] <= 256 && box[4] <= 256, "igemm: TMA box too large");
+    CUresult r = encode(&map_a, dt, 5, const_cast<void*>(in), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("igemm: cuTensorMapEncodeTiled(A) failed: %d", (int)r); return S3D_ERR_CUDA; }
+  }
+  {
+    const int rows = p->ntaps * p->n_classes;
+    cuuint64_t dims[3] = {(cuuint64_t)p->Cin, (cuuint64_t)p->Cout, (cuuint64_t)rows};
+    cuuint64_t strides[2] = {(cuuint64_t)p->Cin * esz, (cuuint64_t)p->Cin * esz * p->Cout};
+    cuuint32_t box[3] = {(cuuint32_t)a.kc, (cuuint32_t)p->bn, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = encode(&map_b, dt, 3, const_cast<void*>(w), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("igemm: cuTensorMapEncodeTiled(B) failed: %d", (int)r); return S3D_ERR_CUDA; }
+  }
+
+  const int smem_bytes = a.stages * a.stage_bytes + 1024;
+  auto kern = tf32 ? conv_igemm_kernel<true> : conv_igemm_kernel<false>;
+  static bool attr_set[2] = {false, false};
+  if (!attr_set[tf32]) {
+    S3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    attr_set[tf32] = true;
+  }
+  int grid = num_sms();
+  if (grid > a.total_tiles) grid = a.total_tiles;
+  kern<<<grid, kThreads, smem_bytes, stream>>>(map_a, map_b, a);
+  S3D_LAUNCH_CHECK();
+  return S3D_OK;
+}
+
+}  // namespace s3d
+
+extern "C" int s3d_conv_igemm(const S3dConvParams* p, const void* in, const void* w, const float* bias,
+                              const void* residual, void* out, void* stream) {
+  if (!p || !in || !w || !out) { s3d::set_error("s3d_conv_igemm: null argument"); return S3D_ERR_INVALID; }
+  return s3d::conv_igemm_launch(p, in, w, bias, residual, out, static_cast<cudaStream_t>(stream));
+}

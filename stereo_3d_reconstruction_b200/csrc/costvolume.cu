@@ -1,0 +1,279 @@
+// Rows V and S: disparity cost volume and soft-argmin regression.  All HBM-bound kernels.
+//
+//   cost_volume_concat   one CTA per (volume, image row): the reference row and the target row
+//                        are staged once in shared memory, then D planes of 2C channels are
+//                        streamed out with 16 B coalesced stores.  Bytes: read 2*C*w*e, write
+//                        D*2C*w*e per row -- write-bound.
+//   soft_argmin          lanes along x (coalesced planes), online softmax over d in registers.
+//   corr_soft_argmin     fused correlation + soft-argmax: the [D,h,w] cost never reaches HBM.
+//                        Rows staged (transposed, zero padded by D) in shared memory; each thread
+//                        owns a 4(x) x 8(d) register tile, the disparity axis is finished with
+//                        warp-shuffle (max, sum, weighted-sum) reductions.
+#include "common.cuh"
+
+namespace s3d {
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// concat volume
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+concat_volume_kernel(const uint4* __restrict__ feat, uint4* __restrict__ vol, int B, int h, int w,
+                     int vpp /* 16-B vectors per pixel of one feature map */, int D) {
+  extern __shared__ uint4 srow[];          // [2][w*vpp]: ref row, tgt row
+  const int n = blockIdx.x / h, y = blockIdx.x % h;
+  const bool left_ref = n < B;
+  const int tgt_n = left_ref ? n + B : n - B;
+  const int rowv = w * vpp;
+  const uint4* ref_g = feat + ((int64_t)n * h + y) * rowv;
+  const uint4* tgt_g = feat + ((int64_t)tgt_n * h + y) * rowv;
+  for (int i = threadIdx.x; i < rowv; i += blockDim.x) {
+    srow[i] = __ldg(ref_g + i);
+    srow[rowv + i] = __ldg(tgt_g + i);
+  }
+  __syncthreads();
+  const int outv = 2 * rowv;               // vectors per (d, row) output line
+  const uint4 zero = make_uint4(0, 0, 0, 0);
+  for (int d = 0; d < D; ++d) {
+    uint4* o = vol + (((int64_t)n * D + d) * h + y) * outv;
+    for (int i = threadIdx.x; i < outv; i += blockDim.x) {
+      const int x = i / (2 * vpp), j = i % (2 * vpp);
+      uint4 v;
+      if (j < vpp) {
+        v = srow[x * vpp + j];
+      } else {
+        const int xs = left_ref ? x - d : x + d;
+        v = (xs >= 0 && xs < w) ? srow[rowv + xs * vpp + (j - vpp)] : zero;
+      }
+      __stcs(o + i, v);                    // streaming store: the volume is consumed much later
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// standalone soft-argmin over a [N,D,h,w] fp32 cost
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+soft_argmin_kernel(const float* __restrict__ cost, float* __restrict__ disp, int64_t npix_total, int64_t plane,
+                   int D, float sign) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= npix_total) return;
+  const int64_t n = i / plane, pix = i % plane;
+  const float* c = cost + n * D * plane + pix;
+  float m = -INFINITY, s = 0.f, t = 0.f;
+  int d = 0;
+  for (; d + 4 <= D; d += 4) {
+    float v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = sign * __ldcs(c + (int64_t)(d + k) * plane);
+    const float mm = fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3]));
+    if (mm > m) { const float sc = expf(m - mm); s *= sc; t *= sc; m = mm; }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { const float e = expf(v[k] - m); s += e; t += e * (float)(d + k); }
+  }
+  for (; d < D; ++d) {
+    const float v = sign * __ldcs(c + (int64_t)d * plane);
+    if (v > m) { const float sc = expf(m - v); s *= sc; t *= sc; m = v; }
+    const float e = expf(v - m);  s += e;  t += e * (float)d;
+  }
+  disp[i] = t / s;
+}
+
+// ------------------------------------------------------------------------------------------
+// fused correlation + soft-argmax
+// ------------------------------------------------------------------------------------------
+constexpr int kXG = 4;   // x per thread
+constexpr int kDG = 8;   // d per thread
+
+template <typename T, bool kLeftRef>
+__device__ __forceinline__ void corr_row(const T* __restrict__ ref_g, const T* __restrict__ tgt_g,
+                                         float* __restrict__ disp_row, float* __restrict__ cost_row,
+                                         int64_t cost_plane, int w, int C, int D, float* smem) {
+  const int WP = ((w + 3) & ~3);
+  const int rs = WP + 4;                       // ref row stride (floats); +4 spreads banks
+  const int ts = WP + D + 12 + 4;              // tgt row stride: zero pad D + window slack
+  float* refT = smem;                          // [C][rs]
+  float* tgtT = smem + C * rs;                 // [C][ts]
+  // zero fill (padding must read as 0), then transposed fill
+  for (int i = threadIdx.x; i < C * ts; i += blockDim.x) tgtT[i] = 0.f;
+  for (int i = threadIdx.x; i < C * rs; i += blockDim.x) refT[i] = 0.f;
+  __syncthreads();
+  const int shift = kLeftRef ? D : 0;
+  for (int i = threadIdx.x; i < w * C; i += blockDim.x) {
+    const int x = i / C, c = i % C;
+    refT[c * rs + x] = to_f32(ref_g[i]);
+    tgtT[c * ts + x + shift] = to_f32(tgt_g[i]);
+  }
+  __syncthreads();
+
+  const int ndg = D / kDG;                     // lanes sharing one x-group (power of two <= 16)
+  const int nxg = WP / kXG;
+  const int groups_per_pass = blockDim.x / ndg;
+  const int dgi = threadIdx.x % ndg;
+  const int d0 = dgi * kDG;
+  const float inv_c = 1.f / (float)C;
+  for (int xg0 = 0; xg0 < nxg; xg0 += groups_per_pass) {
+    const int xg = xg0 + threadIdx.x / ndg;
+    const bool active = xg < nxg;
+    const int x0 = (active ? xg : 0) * kXG;
+    const int base = kLeftRef ? (x0 - d0 - 8 + D) : (x0 + d0);
+    float acc[kXG][kDG];
+#pragma unroll
+    for (int i = 0; i < kXG; ++i)
+#pragma unroll
+      for (int j = 0; j < kDG; ++j) acc[i][j] = 0.f;
+    for (int c = 0; c < C; ++c) {
+      const float4 r4 = *reinterpret_cast<const float4*>(refT + c * rs + x0);
+      const float4* tp = reinterpret_cast<const float4*>(tgtT + c * ts + base);
+      const float4 t0 = tp[0], t1 = tp[1], t2 = tp[2];
+      const float r[4] = {r4.x, r4.y, r4.z, r4.w};
+      const float t[12] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w, t2.x, t2.y, t2.z, t2.w};
+#pragma unroll
+      for (int i = 0; i < kXG; ++i)
+#pragma unroll
+        for (int j = 0; j < kDG; ++j) acc[i][j] = fmaf(r[i], t[kLeftRef ? (8 + i - j) : (i + j)], acc[i][j]);
+    }
+    float res[kXG];
+#pragma unroll
+    for (int i = 0; i < kXG; ++i) {
+      float m = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < kDG; ++j) { acc[i][j] *= inv_c; m = fmaxf(m, acc[i][j]); }
+      for (int o = ndg >> 1; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      float s = 0.f, tt = 0.f;
+#pragma unroll
+      for (int j = 0; j < kDG; ++j) { const float e = __expf(acc[i][j] - m); s += e; tt += e * (float)(d0 + j); }
+      for (int o = ndg >> 1; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        tt += __shfl_xor_sync(0xffffffffu, tt, o);
+      }
+      res[i] = tt / s;
+    }
+    if (active) {
+      if (dgi == 0) {
+#pragma unroll
+        for (int i = 0; i < kXG; ++i) if (x0 + i < w) disp_row[x0 + i] = res[i];
+      }
+      if (cost_row) {
+#pragma unroll
+        for (int i = 0; i < kXG; ++i)
+#pragma unroll
+          for (int j = 0; j < kDG; ++j)
+            if (x0 + i < w) cost_row[(int64_t)(d0 + j) * cost_plane + x0 + i] = acc[i][j];
+      }
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+corr_soft_argmin_kernel(const T* __restrict__ feat, float* __restrict__ disp, float* __restrict__ cost_out,
+                        int B, int h, int w, int C, int D) {
+  extern __shared__ float smem_f[];
+  const int n = blockIdx.x / h, y = blockIdx.x % h;
+  const bool left_ref = n < B;
+  const int tgt_n = left_ref ? n + B : n - B;
+  const T* ref_g = feat + ((int64_t)n * h + y) * w * C;
+  const T* tgt_g = feat + ((int64_t)tgt_n * h + y) * w * C;
+  float* disp_row = disp + ((int64_t)n * h + y) * w;
+  const int64_t plane = (int64_t)h * w;
+  float* cost_row = cost_out ? cost_out + (int64_t)n * D * plane + (int64_t)y * w : nullptr;
+  if (left_ref) corr_row<T, true>(ref_g, tgt_g, disp_row, cost_row, plane, w, C, D, smem_f);
+  else          corr_row<T, false>(ref_g, tgt_g, disp_row, cost_row, plane, w, C, D, smem_f);
+}
+
+// ------------------------------------------------------------------------------------------
+// bilinear upsample (align_corners = False), PyTorch index / weight convention
+// ------------------------------------------------------------------------------------------
+__global__ void upsample_disp_kernel(const float* __restrict__ q, float* __restrict__ out, int N, int h, int w,
+                                     int H, int W, float scale) {
+  const int64_t total = (int64_t)N * H * W;
+  const float ry = (float)h / (float)H, rx = (float)w / (float)W;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int X = (int)(i % W), Y = (int)((i / W) % H);
+    const int64_t n = i / ((int64_t)W * H);
+    float sy = ((float)Y + 0.5f) * ry - 0.5f;  if (sy < 0.f) sy = 0.f;
+    float sx = ((float)X + 0.5f) * rx - 0.5f;  if (sx < 0.f) sx = 0.f;
+    const int y0 = (int)sy, x0 = (int)sx;
+    const int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < w - 1 ? 1 : 0);
+    const float ly = sy - (float)y0, lx = sx - (float)x0;
+    const float hy = 1.f - ly, hx = 1.f - lx;
+    const float* p = q + n * h * w;
+    const float v = hy * (hx * p[y0 * w + x0] + lx * p[y0 * w + x1]) + ly * (hx * p[y1 * w + x0] + lx * p[y1 * w + x1]);
+    out[i] = v * scale;
+  }
+}
+
+}  // namespace
+}  // namespace s3d
+
+using namespace s3d;
+
+extern "C" int s3d_cost_volume_concat(const void* feat, void* vol, int B, int h, int w, int C, int D, int dtype,
+                                      void* stream) {
+  if (!feat || !vol) { set_error("cost_volume_concat: null argument"); return S3D_ERR_INVALID; }
+  S3D_CHECK_ARG(dtype == S3D_DTYPE_F32 || dtype == S3D_DTYPE_BF16, "cost_volume_concat: bad dtype");
+  const int esz = dtype == S3D_DTYPE_F32 ? 4 : 2;
+  S3D_CHECK_ARG(B > 0 && h > 0 && w > 0 && D > 0 && C > 0 && (C * esz) % 16 == 0,
+                "cost_volume_concat: C*elem must be a multiple of 16 B");
+  const int vpp = C * esz / 16;
+  const size_t smem = (size_t)2 * w * vpp * sizeof(uint4);
+  S3D_CHECK_ARG(smem <= 200 * 1024, "cost_volume_concat: row too large for shared memory");
+  static bool attr = false;
+  if (!attr) { S3D_CUDA(cudaFuncSetAttribute(concat_volume_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
+  concat_volume_kernel<<<2 * B * h, 256, smem, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(feat), static_cast<uint4*>(vol), B, h, w, vpp, D);
+  S3D_LAUNCH_CHECK();
+  return S3D_OK;
+}
+
+extern "C" int s3d_soft_argmin(const float* cost, float* disp, int N, int D, int h, int w, float sign, void* stream) {
+  if (!cost || !disp) { set_error("soft_argmin: null argument"); return S3D_ERR_INVALID; }
+  S3D_CHECK_ARG(N > 0 && D > 0 && h > 0 && w > 0, "soft_argmin: bad shape");
+  const int64_t plane = (int64_t)h * w, total = plane * N;
+  soft_argmin_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      cost, disp, total, plane, D, sign);
+  S3D_LAUNCH_CHECK();
+  return S3D_OK;
+}
+
+extern "C" int s3d_corr_soft_argmin(const void* feat, float* disp, float* cost_out, int B, int h, int w, int C, int D,
+                                    int dtype, void* stream) {
+  if (!feat || !disp) { set_error("corr_soft_argmin: null argument"); return S3D_ERR_INVALID; }
+  S3D_CHECK_ARG(dtype == S3D_DTYPE_F32 || dtype == S3D_DTYPE_BF16, "corr_soft_argmin: bad dtype");
+  S3D_CHECK_ARG(D >= 8 && D <= 128 && (D & (D - 1)) == 0, "corr_soft_argmin: D must be a power of two in [8,128]");
+  S3D_CHECK_ARG(B > 0 && h > 0 && w > 0 && C > 0, "corr_soft_argmin: bad shape");
+  const int WP = (w + 3) & ~3;
+  const size_t smem = (size_t)C * ((WP + 4) + (WP + D + 16)) * sizeof(float);
+  S3D_CHECK_ARG(smem <= 200 * 1024, "corr_soft_argmin: row too large for shared memory");
+  const int ndg = D / kDG;
+  int threads = (WP / kXG) * ndg;
+  threads = ((threads + 31) / 32) * 32;
+  if (threads > 256) threads = 256;
+  if (threads < 32) threads = 32;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  static bool attr[2] = {false, false};
+  if (dtype == S3D_DTYPE_BF16) {
+    if (!attr[0]) { S3D_CUDA(cudaFuncSetAttribute(corr_soft_argmin_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr[0] = true; }
+    corr_soft_argmin_kernel<__nv_bfloat16><<<2 * B * h, threads, smem, st>>>(
+        static_cast<const __nv_bfloat16*>(feat), disp, cost_out, B, h, w, C, D);
+  } else {
+    if (!attr[1]) { S3D_CUDA(cudaFuncSetAttribute(corr_soft_argmin_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr[1] = true; }
+    corr_soft_argmin_kernel<float><<<2 * B * h, threads, smem, st>>>(
+        static_cast<const float*>(feat), disp, cost_out, B, h, w, C, D);
+  }
+  S3D_LAUNCH_CHECK();
+  return S3D_OK;
+}
+
+extern "C" int s3d_upsample_disp(const float* disp_q, float* disp, int N, int h, int w, int H, int W, float scale,
+                                 void* stream) {
+  if (!disp_q || !disp) { set_error("upsample_disp: null argument"); return S3D_ERR_INVALID; }
+  S3D_CHECK_ARG(N > 0 && h > 0 && w > 0 && H > 0 && W > 0, "upsample_disp: bad shape");
+  const int64_t total = (int64_t)N * H * W;
+  int64_t blocks = ceil_div64(total, 256);
+  if (blocks > (int64_t)num_sms() * 16) blocks = (int64_t)num_sms() * 16;
+  upsample_disp_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(disp_q, disp, N, h, w, H, W, scale);
+  S3D_LAUNCH_CHECK();
+  return S3D_OK;
+}

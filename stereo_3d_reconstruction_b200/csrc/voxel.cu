@@ -1,0 +1,200 @@
+// Glue kernels around the conv engine: input staging, latent re-indexing, pooling, and the
+// context-aware fusion epilogue fused with the IoU statistics (rows X, F, M).  All bandwidth-bound
+// elementwise / small-reduction kernels.
+#include <stdarg.h>
+#include "common.cuh"
+
+namespace s3d {
+
+// ---- error slot / device info (library-wide) -------------------------------------------------
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  }
+  return n;
+}
+
+namespace {
+
+template <typename T>
+__global__ void pack_image_kernel(const float* __restrict__ img, const float* __restrict__ disp, float disp_scale,
+                                  T* __restrict__ out, int B, int H, int W, int Cpad) {
+  const int64_t plane = (int64_t)H * W, total = plane * B;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / plane, pix = i % plane;
+    T* o = out + i * Cpad;
+    const float* ip = img + b * 3 * plane + pix;
+    o[0] = from_f32<T>(ip[0]);
+    o[1] = from_f32<T>(ip[plane]);
+    o[2] = from_f32<T>(ip[2 * plane]);
+    o[3] = from_f32<T>(disp ? disp[i] * disp_scale : 0.f);
+    for (int c = 4; c < Cpad; ++c) o[c] = from_f32<T>(0.f);
+  }
+}
+
+__device__ __forceinline__ void pool_bin(int i, int in, int out, int& s, int& e) {
+  s = (i * in) / out;
+  e = ((i + 1) * in + out - 1) / out;
+}
+
+// [N,H,W,C] -> pooled [N,L,L,C]; if to_vox, written as [N,2,2,2,C*L*L/8] with the NCHW .view order.
+template <typename T>
+__global__ void pool_kernel(const T* __restrict__ x, T* __restrict__ out, int N, int H, int W, int C, int L, int to_vox) {
+  const int64_t total = (int64_t)N * L * L * C;
+  const int K = C * L * L / 8;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i;
+    const int c = (int)(r % C);  r /= C;
+    const int px = (int)(r % L);  r /= L;
+    const int py = (int)(r % L);  r /= L;
+    const int n = (int)r;
+    int ys, ye, xs, xe;
+    pool_bin(py, H, L, ys, ye);
+    pool_bin(px, W, L, xs, xe);
+    float acc = 0.f;
+    for (int yy = ys; yy < ye; ++yy)
+      for (int xx = xs; xx < xe; ++xx) acc += to_f32(x[(((int64_t)n * H + yy) * W + xx) * C + c]);
+    acc /= (float)((ye - ys) * (xe - xs));
+    if (to_vox) {
+      const int f = (c * L + py) * L + px;
+      const int k = f >> 3, cell = f & 7;           // cell = z*4 + y*2 + x of the 2x2x2 grid
+      out[((int64_t)n * 8 + cell) * K + k] = from_f32<T>(acc);
+    } else {
+      out[i] = from_f32<T>(acc);
+    }
+  }
+}
+
+constexpr int kMaxThresh = 8;
+struct Thresh { float t[kMaxThresh]; };
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+fuse_views_kernel(const T* __restrict__ score, int64_t sstride, const T* __restrict__ vol, int64_t vstride,
+                  float* __restrict__ fused, int B, int V, int nvox, const uint8_t* __restrict__ gt, Thresh th, int nT,
+                  unsigned long long* __restrict__ iou) {
+  const int b = blockIdx.y;
+  unsigned inter[kMaxThresh], uni[kMaxThresh];
+#pragma unroll
+  for (int t = 0; t < kMaxThresh; ++t) { inter[t] = 0; uni[t] = 0; }
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nvox; i += gridDim.x * blockDim.x) {
+    float m = -INFINITY;
+    for (int v = 0; v < V; ++v) m = fmaxf(m, to_f32(score[(((int64_t)v * B + b) * nvox + i) * sstride]));
+    float s = 0.f, acc = 0.f;
+    for (int v = 0; v < V; ++v) {
+      const int64_t e = ((int64_t)v * B + b) * nvox + i;
+      const float w = expf(to_f32(score[e * sstride]) - m);
+      s += w;
+      acc += w * to_f32(vol[e * vstride]);
+    }
+    float f = acc / s;
+    f = fminf(fmaxf(f, 0.f), 1.f);
+    fused[(int64_t)b * nvox + i] = f;
+    if (gt) {
+      const bool g = gt[(int64_t)b * nvox + i] != 0;
+#pragma unroll
+      for (int t = 0; t < kMaxThresh; ++t)
+        if (t < nT) { const bool p = f >= th.t[t]; inter[t] += (p && g); uni[t] += (p || g); }
+    }
+  }
+  if (gt && iou) {
+#pragma unroll
+    for (int t = 0; t < kMaxThresh; ++t) {
+      if (t >= nT) break;
+      unsigned a = inter[t], u = uni[t];
+      for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); u += __shfl_xor_sync(0xffffffffu, u, o); }
+      if ((threadIdx.x & 31) == 0) {
+        if (a) atomicAdd(iou + ((int64_t)b * nT + t) * 2 + 0, (unsigned long long)a);
+        if (u) atomicAdd(iou + ((int64_t)b * nT + t) * 2 + 1, (unsigned long long)u);
+      }
+    }
+  }
+}
+
+int grid_for(int64_t total, int threads) {
+  int64_t blocks = ceil_div64(total, threads);
+  const int64_t cap = (int64_t)num_sms() * 16;
+  return (int)(blocks > cap ? cap : (blocks < 1 ? 1 : blocks));
+}
+
+}  // namespace
+}  // namespace s3d
+
+using namespace s3d;
+
+extern "C" const char* s3d_version(void) { return "s3d_b200 0.1 (sm_100a)"; }
+extern "C" const char* s3d_last_error(void) { return g_err; }
+
+extern "C" int s3d_device_check(int dev) {
+  cudaDeviceProp prop;
+  cudaError_t e = cudaGetDeviceProperties(&prop, dev);
+  if (e != cudaSuccess) { set_error("s3d_device_check: %s", cudaGetErrorString(e)); cudaGetLastError(); return S3D_ERR_CUDA; }
+  if (prop.major != 10) { set_error("s3d_device_check: device %d is sm_%d%d, need sm_100", dev, prop.major, prop.minor); return S3D_ERR_UNSUPPORTED; }
+  return S3D_OK;
+}
+
+extern "C" int s3d_pack_image(const float* img, const float* disp, float disp_scale, void* out, int B, int H, int W,
+                              int Cpad, int out_dtype, void* stream) {
+  if (!img || !out) { set_error("pack_image: null argument"); return S3D_ERR_INVALID; }
+  S3D_CHECK_ARG(B > 0 && H > 0 && W > 0 && Cpad >= 4, "pack_image: bad shape");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t total = (int64_t)B * H * W;
+  if (out_dtype == S3D_DTYPE_BF16)
+    pack_image_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, st>>>(img, disp, disp_scale, static_cast<__nv_bfloat16*>(out), B, H, W, Cpad);
+  else if (out_dtype == S3D_DTYPE_F32)
+    pack_image_kernel<float><<<grid_for(total, 256), 256, 0, st>>>(img, disp, disp_scale, static_cast<float*>(out), B, H, W, Cpad);
+  else { set_error("pack_image: bad dtype"); return S3D_ERR_INVALID; }
+  S3D_LAUNCH_CHECK();
+  return S3D_OK;
+}
+
+static int pool_launch(const void* x, void* out, int N, int H, int W, int C, int L, int dtype, int to_vox, void* stream) {
+  if (!x || !out) { set_error("pool: null argument"); return S3D_ERR_INVALID; }
+  S3D_CHECK_ARG(N > 0 && H > 0 && W > 0 && C > 0 && L > 0, "pool: bad shape");
+  S3D_CHECK_ARG(!to_vox || (C * L * L) % 8 == 0, "latent_to_vox: C*L*L must be a multiple of 8");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t total = (int64_t)N * L * L * C;
+  if (dtype == S3D_DTYPE_BF16)
+    pool_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(out), N, H, W, C, L, to_vox);
+  else if (dtype == S3D_DTYPE_F32)
+    pool_kernel<float><<<grid_for(total, 256), 256, 0, st>>>(static_cast<const float*>(x), static_cast<float*>(out), N, H, W, C, L, to_vox);
+  else { set_error("pool: bad dtype"); return S3D_ERR_INVALID; }
+  S3D_LAUNCH_CHECK();
+  return S3D_OK;
+}
+
+extern "C" int s3d_latent_to_vox(const void* x, void* out, int N, int H, int W, int C, int L, int dtype, void* stream) {
+  return pool_launch(x, out, N, H, W, C, L, dtype, 1, stream);
+}
+extern "C" int s3d_avg_pool(const void* x, void* out, int N, int H, int W, int C, int L, int dtype, void* stream) {
+  return pool_launch(x, out, N, H, W, C, L, dtype, 0, stream);
+}
+
+extern "C" int s3d_fuse_views(const void* score, int64_t score_stride, const void* vol, int64_t vol_stride, int dtype,
+                              float* fused, int B, int V, int nvox, const uint8_t* gt, const float* thresholds, int T,
+                              long long* iou, void* stream) {
+  if (!score || !vol || !fused) { set_error("fuse_views: null argument"); return S3D_ERR_INVALID; }
+  S3D_CHECK_ARG(B > 0 && V > 0 && nvox > 0 && T >= 0 && T <= kMaxThresh, "fuse_views: bad shape (T<=8)");
+  S3D_CHECK_ARG(!gt || (thresholds && iou), "fuse_views: gt needs thresholds and iou");
+  Thresh th;
+  for (int t = 0; t < kMaxThresh; ++t) th.t[t] = (gt && t < T) ? thresholds[t] : 2.f;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  dim3 grid(ceil_div(nvox, 256 * 4), B);
+  if (dtype == S3D_DTYPE_BF16)
+    fuse_views_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(score), score_stride, static_cast<const __nv_bfloat16*>(vol), vol_stride, fused, B, V, nvox, gt, th, T, reinterpret_cast<unsigned long long*>(iou));
+  else if (dtype == S3D_DTYPE_F32)
+    fuse_views_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(score), score_stride, static_cast<const float*>(vol), vol_stride, fused, B, V, nvox, gt, th, T, reinterpret_cast<unsigned long long*>(iou));
+  else { set_error("fuse_views: bad dtype"); return S3D_ERR_INVALID; }
+  S3D_LAUNCH_CHECK();
+  return S3D_OK;
+}

@@ -1,0 +1,226 @@
+# -*- coding: utf-8 -*-
+"""Host-side layer packing for the implicit-GEMM conv engine (s3d_conv_igemm / s3d_conv_direct).
+
+At weight-load time every conv-like layer is folded and packed ONCE:
+  * eval-mode BatchNorm is folded into the weights (scale) and a fp32 bias (shift);
+  * weights are re-laid out as [class*taps][Cout_pad][Cin_pad] (K-major rows, what the TMA box of
+    the B operand reads) in the compute dtype;
+  * the tap table (input offset per tap) is built: ordinary convs, the 8 sub-pixel classes of a
+    stride-2 ConvTranspose3d(k4,p1), 1x1x1 transposed convs, and Linear layers seen as a conv whose
+    taps cover the whole input map.
+The forward then has zero layout work: one C-ABI call per layer.
+"""
+import ctypes
+import itertools
+
+import torch
+
+from . import lib as _lib
+
+PAD = 16   # channel padding granule (bf16: 32 B rows = one UMMA K step)
+
+
+def pad_to(c, m=PAD):
+    return (c + m - 1) // m * m
+
+
+def torch_dtype(code):
+    return torch.bfloat16 if code == _lib.DTYPE_BF16 else torch.float32
+
+
+def _fold_bn(w_out_first, bias, bn):
+    """w_out_first: weight with the output channel as dim 0.  Returns folded (w, bias) in fp32."""
+    w = w_out_first.detach().float()
+    cout = w.shape[0]
+    b = bias.detach().float() if bias is not None else torch.zeros(cout, device=w.device)
+    if bn is not None:
+        scale = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
+        shift = bn.bias.detach().float() - bn.running_mean.detach().float() * scale
+        w = w * scale.view(-1, *([1] * (w.dim() - 1)))
+        b = b * scale + shift
+    return w, b
+
+
+def _choose_tile(N, oD, oH, oW, sx, sy, sz):
+    """(tw, th, td, tn): powers of two, product 128, minimising padded work; ties -> wide tw."""
+    best = None
+    for lw, lh, ld in itertools.product(range(8), repeat=3):
+        ln = 7 - lw - lh - ld
+        if ln < 0:
+            continue
+        tw, th, td, tn = 1 << lw, 1 << lh, 1 << ld, 1 << ln
+        if tw * sx > 256 or th * sy > 256 or td * sz > 256:
+            continue
+        waste = (-(-oW // tw) * tw) * (-(-oH // th) * th) * (-(-oD // td) * td) * (-(-N // tn) * tn)
+        key = (waste, -lw, -lh, -ld)
+        if best is None or key < best[0]:
+            best = (key, (tw, th, td, tn))
+    return best[1]
+
+
+def _choose_bn(cout_pad):
+    if cout_pad <= 256:
+        return cout_pad
+    for bn in range(256, 15, -16):
+        if cout_pad % bn == 0:
+            return bn
+    raise ValueError('no N tile for Cout=%d' % cout_pad)
+
+
+class PackedConv:
+    """One folded + packed conv-like layer.  `taps`: list (per class) of lists of (dz,dy,dx)."""
+
+    def __init__(self, w_rows, bias, taps, stride, out_mult, cin, cout, act, act_param, dtype_code, device,
+                 ksize=(1, 1, 1), pad=(0, 0, 0)):
+        # w_rows: fp32 [n_classes*ntaps, cout, cin]
+        self.n_classes = len(taps)
+        self.ntaps = len(taps[0])
+        assert self.n_classes * self.ntaps <= _lib.S3D_MAX_TAPS
+        self.cin, self.cout = cin, cout
+        self.cin_pad, self.cout_pad = pad_to(cin), pad_to(cout)
+        self.stride = stride              # (sz, sy, sx)
+        self.out_mult = out_mult          # (omz, omy, omx)
+        self.act, self.act_param = act, float(act_param)
+        self.dtype_code = dtype_code
+        wp = torch.zeros(self.n_classes * self.ntaps, self.cout_pad, self.cin_pad, dtype=torch.float32)
+        wp[:, :cout, :cin] = w_rows.cpu()
+        self.weight = wp.to(torch_dtype(dtype_code)).to(device).contiguous()
+        bp = torch.zeros(self.cout_pad, dtype=torch.float32)
+        bp[:cout] = bias.cpu()
+        self.bias = bp.to(device)
+        self.taps = taps
+        self.ksize, self.pad = tuple(ksize), tuple(pad)
+        self.bn = _choose_bn(self.cout_pad)
+        self._cache = {}
+
+    # ---- constructors ------------------------------------------------------------------
+    @classmethod
+    def from_conv(cls, conv, bn, act, dtype_code, device, act_param=0.0):
+        """nn.Conv2d / nn.Conv3d, odd kernel, symmetric padding, stride 1 or 2."""
+        w, b = _fold_bn(conv.weight, conv.bias, bn)
+        if w.dim() == 4:
+            w = w.unsqueeze(2)
+            ks, st, pd = (1,) + tuple(conv.kernel_size), (1,) + tuple(conv.stride), (0,) + tuple(conv.padding)
+        else:
+            ks, st, pd = tuple(conv.kernel_size), tuple(conv.stride), tuple(conv.padding)
+        cout, cin = w.shape[0], w.shape[1]
+        taps, rows = [], []
+        for kz, ky, kx in itertools.product(range(ks[0]), range(ks[1]), range(ks[2])):
+            taps.append((kz - pd[0], ky - pd[1], kx - pd[2]))
+            rows.append(w[:, :, kz, ky, kx])
+        return cls(torch.stack(rows), b, [taps], st, (1, 1, 1), cin, cout, act, act_param, dtype_code, device,
+                   ksize=ks, pad=pd)
+
+    @classmethod
+    def from_deconv_k4s2p1(cls, deconv, bn, act, dtype_code, device, act_param=0.0):
+        """nn.ConvTranspose3d(k=4, s=2, p=1): out o = 2i - 1 + k.  Output parity a uses, per dim,
+        a=0: (input offset 0, k=1), (-1, k=3);  a=1: (+1, k=0), (0, k=2)."""
+        assert tuple(deconv.kernel_size) == (4, 4, 4) and tuple(deconv.stride) == (2, 2, 2) and \
+            tuple(deconv.padding) == (1, 1, 1) and tuple(deconv.output_padding) == (0, 0, 0)
+        w, b = _fold_bn(deconv.weight.transpose(0, 1), deconv.bias, bn)   # -> [Cout, Cin, 4,4,4]
+        cout, cin = w.shape[0], w.shape[1]
+        per_dim = {0: [(0, 1), (-1, 3)], 1: [(1, 0), (0, 2)]}
+        taps, rows = [], []
+        for cz, cy, cx in itertools.product(range(2), repeat=3):      # class index = cz*4 + cy*2 + cx
+            ct = []
+            for (oz, kz), (oy, ky), (ox, kx) in itertools.product(per_dim[cz], per_dim[cy], per_dim[cx]):
+                ct.append((oz, oy, ox))
+                rows.append(w[:, :, kz, ky, kx])
+            taps.append(ct)
+        return cls(torch.stack(rows), b, taps, (1, 1, 1), (2, 2, 2), cin, cout, act, act_param, dtype_code, device)
+
+    @classmethod
+    def from_pointwise(cls, w_out_in, bias, bn, act, dtype_code, device, act_param=0.0):
+        """1x1(x1) conv / transposed conv given as a [Cout, Cin] matrix."""
+        w, b = _fold_bn(w_out_in, bias, bn)
+        return cls(w.unsqueeze(0), b, [[(0, 0, 0)]], (1, 1, 1), (1, 1, 1), w.shape[1], w.shape[0], act, act_param,
+                   dtype_code, device)
+
+    @classmethod
+    def from_linear_over_map(cls, linear, C, h, w_, act, dtype_code, device, act_param=0.0):
+        """nn.Linear over a flattened NCHW map [C,h,w] == conv with h*w taps, no padding, 1x1 output."""
+        w, b = _fold_bn(linear.weight, linear.bias, None)
+        w = w.view(w.shape[0], C, h, w_)
+        taps, rows = [], []
+        for y, x in itertools.product(range(h), range(w_)):
+            taps.append((0, y, x))
+            rows.append(w[:, :, y, x])
+        return cls(torch.stack(rows), b, [taps], (1, 1, 1), (1, 1, 1), C, w.shape[0], act, act_param, dtype_code,
+                   device, ksize=(1, h, w_), pad=(0, 0, 0))
+
+    # ---- launch ------------------------------------------------------------------------
+    def out_grid(self, iD, iH, iW):
+        """Logical output grid per class for an input of the given size."""
+        if self.n_classes == 8:
+            return iD, iH, iW
+        return tuple((i + 2 * p - k) // s + 1 for i, k, p, s in zip((iD, iH, iW), self.ksize, self.pad, self.stride))
+
+    def params(self, N, iD, iH, iW, out_strides, out_dtype_code, cout_store=None):
+        key = (N, iD, iH, iW, tuple(out_strides), out_dtype_code, cout_store)
+        p = self._cache.get(key)
+        if p is not None:
+            return p
+        oD, oH, oW = self.out_grid(iD, iH, iW)
+        p = _lib.S3dConvParams()
+        p.N, p.iD, p.iH, p.iW, p.Cin = N, iD, iH, iW, self.cin_pad
+        p.oD, p.oH, p.oW, p.Cout = oD, oH, oW, self.cout_pad
+        p.sz, p.sy, p.sx = self.stride
+        p.ntaps, p.n_classes = self.ntaps, self.n_classes
+        i = 0
+        for ct in self.taps:
+            for (dz, dy, dx) in ct:
+                p.dz[i], p.dy[i], p.dx[i] = dz, dy, dx
+                i += 1
+        p.osN, p.osD, p.osH, p.osW = out_strides
+        p.omz, p.omy, p.omx = self.out_mult
+        p.cout_store = self.cout_pad if cout_store is None else cout_store
+        p.in_dtype, p.out_dtype = self.dtype_code, out_dtype_code
+        p.act, p.act_param = self.act, self.act_param
+        p.tw, p.th, p.td, p.tn = _choose_tile(N, oD, oH, oW, self.stride[2], self.stride[1], self.stride[0])
+        p.bn = self.bn
+        self._cache[key] = p
+        return p
+
+    def __call__(self, x, out=None, residual=None, out_dtype=None, cout_store=None, out_view=None, engine='igemm'):
+        """x: channels-last [N,D,H,W,Cin_pad] contiguous CUDA tensor.
+
+        out: destination tensor (allocated if None) -- `out_view` optionally gives
+        (data_ptr_offset_elems, (osN, osD, osH, osW)) to write into a channel slice of a wider buffer."""
+        assert x.is_cuda and x.is_contiguous() and x.dim() == 5 and x.shape[-1] == self.cin_pad, \
+            (tuple(x.shape), self.cin_pad)
+        assert x.dtype == torch_dtype(self.dtype_code)
+        N, iD, iH, iW, _ = x.shape
+        oD, oH, oW = self.out_grid(iD, iH, iW)
+        m = self.out_mult
+        odt = x.dtype if out_dtype is None else out_dtype
+        if out is None:
+            out = torch.empty((N, oD * m[0], oH * m[1], oW * m[2], self.cout_pad), dtype=odt, device=x.device)
+        code = _lib.DTYPE_BF16 if out.dtype == torch.bfloat16 else _lib.DTYPE_F32
+        if out_view is None:
+            assert out.is_contiguous() and out.dim() == 5
+            C = out.shape[-1]
+            strides = (out.shape[1] * out.shape[2] * out.shape[3] * C, out.shape[2] * out.shape[3] * C,
+                       out.shape[3] * C, C)
+            off = 0
+            if cout_store is None:
+                cout_store = min(self.cout_pad, C)
+        else:
+            off, strides = out_view
+        p = self.params(N, iD, iH, iW, strides, code, cout_store)
+        L = _lib.load()
+        fn = L.s3d_conv_igemm if engine == 'igemm' else L.s3d_conv_direct
+        esz = out.element_size()
+        rptr = None
+        if residual is not None:
+            assert residual.dtype == out.dtype and residual.shape == out.shape and residual.is_contiguous()
+            rptr = residual.data_ptr() + off * esz
+        rc = fn(ctypes.byref(p), x.data_ptr(), self.weight.data_ptr(), self.bias.data_ptr(), rptr,
+                out.data_ptr() + off * esz, torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, 's3d_conv_%s' % engine)
+        _lib.count_launch()
+        return out
+
+    def flops(self, N, iD, iH, iW):
+        """Algorithmic (unpadded) FLOPs: 2 * outputs * Cout * Cin * taps-that-hit."""
+        oD, oH, oW = self.out_grid(iD, iH, iW)
+        return 2.0 * N * oD * oH * oW * self.n_classes * self.cout * self.cin * self.ntaps

@@ -1,0 +1,363 @@
+# -*- coding: utf-8 -*-
+"""Stereo2Voxel / Stereo2Point inference modules on the B200 kernels.
+
+Drop-in boundary: `nn.Module`s with `forward(left, right)` and a `state_dict`
+whose keys and shapes are exactly those of the stock-PyTorch restatement of the north_star
+(oracle/models.py), so a checkpoint round-trips with `load_state_dict`.  The reference's own module
+code lives on branches that are not on disk (/root/reference/README.md:5,56,62); the only attested
+contract is `runner.py --test --weights=...` (README.md:91) and `cfg.SECTION.KEY` (README.md:68-78).
+
+The torch.nn layers below are PARAMETER CONTAINERS only -- their forward is never called.  `pack()`
+folds BatchNorm and re-lays every weight for the tcgen05 implicit-GEMM engine once; `forward()` is a
+sequence of C-ABI calls (include/s3d.h) on the current CUDA stream, with no torch math on the path.
+"""
+import torch
+import torch.nn as nn
+
+from . import lib as _lib
+from . import ops
+from .layers import PackedConv, pad_to, torch_dtype
+
+A = _lib  # activation / dtype codes
+
+
+def _conv_bn2d(cin, cout, k, s, p):
+    return nn.Sequential(nn.Conv2d(cin, cout, k, s, p, bias=False), nn.BatchNorm2d(cout))
+
+
+def _conv_bn3d(cin, cout):
+    return nn.Sequential(nn.Conv3d(cin, cout, 3, 1, 1, bias=False), nn.BatchNorm3d(cout))
+
+
+class _FeatureEncoder(nn.Module):
+    def __init__(self, cfg):
+        super().__init__()
+        c1, c2 = cfg.NETWORK.ENC_CHANNELS
+        cf = cfg.NETWORK.FEAT_CHANNELS
+        self.conv0 = _conv_bn2d(3, c1, 3, 2, 1)
+        self.conv1 = _conv_bn2d(c1, c1, 3, 1, 1)
+        self.conv2 = _conv_bn2d(c1, c2, 3, 2, 1)
+        self.conv3 = _conv_bn2d(c2, c2, 3, 1, 1)
+        self.conv4 = _conv_bn2d(c2, c2, 3, 1, 1)
+        self.conv5 = nn.Conv2d(c2, cf, 3, 1, 1, bias=True)
+
+
+class _CostAggregation(nn.Module):
+    def __init__(self, cfg):
+        super().__init__()
+        cin, a = 2 * cfg.NETWORK.FEAT_CHANNELS, cfg.NETWORK.AGG_CHANNELS
+        self.dres0a = _conv_bn3d(cin, a)
+        self.dres0b = _conv_bn3d(a, a)
+        self.dres1a = _conv_bn3d(a, a)
+        self.dres1b = _conv_bn3d(a, a)
+        self.cls_a = _conv_bn3d(a, a)
+        self.cls_b = nn.Conv3d(a, 1, 3, 1, 1, bias=False)
+
+
+class _DispNet(nn.Module):
+    def __init__(self, cfg):
+        super().__init__()
+        self.encoder = _FeatureEncoder(cfg)
+        if cfg.NETWORK.COST_VOLUME == 'concat':
+            self.aggregation = _CostAggregation(cfg)
+
+
+class _RGBDEncoder(nn.Module):
+    def __init__(self, cfg):
+        super().__init__()
+        ch = [4] + list(cfg.NETWORK.REC_CHANNELS)
+        self.layers = nn.ModuleList([_conv_bn2d(ch[i], ch[i + 1], 3, 2, 1) for i in range(len(ch) - 1)])
+
+
+class _VoxelDecoder(nn.Module):
+    def __init__(self, cfg):
+        super().__init__()
+        ch = list(cfg.NETWORK.DEC_CHANNELS)
+        self.layers = nn.ModuleList([
+            nn.Sequential(nn.ConvTranspose3d(ch[i], ch[i + 1], 4, 2, 1, bias=False), nn.BatchNorm3d(ch[i + 1]))
+            for i in range(len(ch) - 1)])
+        self.out = nn.ConvTranspose3d(ch[-1], 1, 1, bias=False)
+
+
+class _Merger(nn.Module):
+    def __init__(self, cfg):
+        super().__init__()
+        ch = list(cfg.NETWORK.MERGER_CHANNELS)
+        self.layers = nn.ModuleList([_conv_bn3d(ch[i], ch[i + 1]) for i in range(len(ch) - 1)])
+
+
+class _PointDecoder(nn.Module):
+    def __init__(self, cfg):
+        super().__init__()
+        c, L = cfg.NETWORK.REC_CHANNELS[-1], cfg.NETWORK.LATENT_HW
+        self.conv = _conv_bn2d(2 * c, 2 * c, 3, 2, 1)
+        self.fc1 = nn.Linear(2 * c * (L // 2) * (L // 2), cfg.NETWORK.POINT_FC)
+        self.fc2 = nn.Linear(cfg.NETWORK.POINT_FC, cfg.CONST.N_POINTS * 3)
+
+
+def init_synthetic_weights(model, seed=0):
+    """Seeded He-normal weights + randomised eval-mode BN statistics (pretrained weights are not
+    available offline, BASELINE.json north_star).  Same recipe as the oracle's initialiser."""
+    g = torch.Generator().manual_seed(seed + 12345)
+    gains = {'decoder.out': 3.0, 'merger.layers.4.0': 4.0, 'point_decoder.fc2': 2.0}
+    with torch.no_grad():
+        for name, m in model.named_modules():
+            if isinstance(m, (nn.Conv2d, nn.Conv3d, nn.Linear, nn.ConvTranspose3d)):
+                w = m.weight
+                if isinstance(m, nn.ConvTranspose3d):
+                    taps = 1
+                    for k, s in zip(m.kernel_size, m.stride):
+                        taps *= max(k // s, 1)
+                    fan_in = w.shape[0] * taps
+                else:
+                    fan_in = w[0].numel()
+                std = (2.0 / fan_in) ** 0.5 * gains.get(name, 1.0)
+                w.copy_((torch.randn(w.shape, generator=g) * std).to(w.device))
+                if m.bias is not None:
+                    m.bias.copy_((torch.randn(m.bias.shape, generator=g) * 0.1).to(w.device))
+            elif isinstance(m, (nn.BatchNorm2d, nn.BatchNorm3d)):
+                n, dev = m.num_features, m.weight.device
+                m.running_mean.copy_((torch.randn(n, generator=g) * 0.1).to(dev))
+                m.running_var.copy_((torch.rand(n, generator=g) + 0.5).to(dev))
+                m.weight.copy_((torch.rand(n, generator=g) * 0.4 + 0.8).to(dev))
+                m.bias.copy_((torch.randn(n, generator=g) * 0.1).to(dev))
+    return model.eval()
+
+
+class _StereoBase(nn.Module):
+    """Shared disparity stage (rows E, V, A, S) and RGB-D encoder (row X)."""
+
+    def __init__(self, cfg):
+        super().__init__()
+        self.cfg = cfg
+        self.dispnet = _DispNet(cfg)
+        self.rgbd_encoder = _RGBDEncoder(cfg)
+        self._packed = None
+        self._ws = {}
+
+    # ---- packing ---------------------------------------------------------------------------
+    @property
+    def precision(self):
+        return self.cfg.NETWORK.PRECISION
+
+    def _dtype_code(self):
+        return A.DTYPE_BF16 if self.precision == 'bf16' else A.DTYPE_F32
+
+    def _engine(self):
+        return 'direct' if self.precision == 'fp32' else 'igemm'
+
+    def pack(self):
+        """Fold BN + re-lay weights for the conv engine.  Call after load_state_dict / .cuda()."""
+        dev = next(self.parameters()).device
+        if dev.type != 'cuda':
+            raise _lib.S3dError('Stereo2Voxel/Stereo2Point run on CUDA only (no CPU fallback); call .cuda() first')
+        _lib.load()
+        dc = self._dtype_code()
+        P = {}
+        e = self.dispnet.encoder
+        for i in range(5):
+            seq = getattr(e, 'conv%d' % i)
+            P['enc%d' % i] = PackedConv.from_conv(seq[0], seq[1], A.ACT_NONE if i == 4 else A.ACT_RELU, dc, dev)
+        P['enc5'] = PackedConv.from_conv(e.conv5, None, A.ACT_NONE, dc, dev)
+        if self.cfg.NETWORK.COST_VOLUME == 'concat':
+            ag = self.dispnet.aggregation
+            for n in ('dres0a', 'dres0b', 'dres1a', 'dres1b', 'cls_a'):
+                seq = getattr(ag, n)
+                P[n] = PackedConv.from_conv(seq[0], seq[1], A.ACT_NONE if n == 'dres1b' else A.ACT_RELU, dc, dev)
+            P['cls_b'] = PackedConv.from_conv(ag.cls_b, None, A.ACT_NONE, dc, dev)
+        for i, seq in enumerate(self.rgbd_encoder.layers):
+            P['rec%d' % i] = PackedConv.from_conv(seq[0], seq[1], A.ACT_RELU, dc, dev)
+        self._pack_head(P, dc, dev)
+        self._packed = P
+        self._ws = {}
+        return self
+
+    def _pack_head(self, P, dc, dev):
+        raise NotImplementedError
+
+    def _buf(self, name, shape, dtype, zero=False):
+        key = (name, tuple(shape), dtype)
+        t = self._ws.get(key)
+        if t is None:
+            dev = next(self.parameters()).device
+            t = (torch.zeros if zero else torch.empty)(shape, dtype=dtype, device=dev)
+            self._ws[key] = t
+        return t
+
+    def _conv(self, name, x, **kw):
+        return self._packed[name](x, engine=self._engine(), **kw)
+
+    # ---- stages ----------------------------------------------------------------------------
+    def _disparity(self, left, right):
+        """-> disp fp32 [2B,H,W] (left-referenced first), in input pixels."""
+        cfg = self.cfg
+        B, _, H, W = left.shape
+        D = cfg.NETWORK.MAX_DISP
+        dt = torch_dtype(self._dtype_code())
+        x = self._buf('img', (2 * B, 1, H, W, 16), dt)
+        ops.pack_image(left, out=x[:B])
+        ops.pack_image(right, out=x[B:])
+        x = self._conv('enc0', x, out=self._bufo('e0', 'enc0', x))
+        x = self._conv('enc1', x, out=self._bufo('e1', 'enc1', x))
+        x = self._conv('enc2', x, out=self._bufo('e2', 'enc2', x))
+        y = self._conv('enc3', x, out=self._bufo('e3', 'enc3', x))
+        x = self._conv('enc4', y, residual=x, out=self._bufo('e4', 'enc4', y))
+        feat = self._conv('enc5', x, out=self._bufo('e5', 'enc5', x))
+        h, w = feat.shape[2], feat.shape[3]
+        disp_q = self._buf('disp_q', (2 * B, h, w), torch.float32)
+        if cfg.NETWORK.COST_VOLUME == 'concat':
+            C = cfg.NETWORK.FEAT_CHANNELS
+            assert feat.shape[-1] == C, 'FEAT_CHANNELS must be a multiple of 16'
+            vol = ops.cost_volume_concat(feat, B, D, out=self._buf('vol', (2 * B, D, h, w, 2 * C), dt))
+            a = self._conv('dres0a', vol, out=self._bufo('a0', 'dres0a', vol))
+            a = self._conv('dres0b', a, out=self._bufo('a1', 'dres0b', a))
+            y = self._conv('dres1a', a, out=self._bufo('a2', 'dres1a', a))
+            a = self._conv('dres1b', y, residual=a, out=self._bufo('a3', 'dres1b', y))
+            c = self._conv('cls_a', a, out=self._bufo('a0', 'cls_a', a))
+            cost = self._buf('cost', (2 * B, D, h, w), torch.float32)
+            self._conv('cls_b', c, out=cost, out_view=(0, (D * h * w, h * w, w, 1)), cout_store=1)
+            ops.soft_argmin(cost, -1.0, out=disp_q)
+        else:
+            ops.corr_soft_argmin(feat, B, D, out=disp_q)
+        disp = ops.upsample_disp(disp_q, H, W, 4.0, out=self._buf('disp', (2 * B, H, W), torch.float32))
+        return disp, disp_q
+
+    def _bufo(self, name, layer, x):
+        """Output buffer of `layer` for input x (channels-last, padded channels)."""
+        pc = self._packed[layer]
+        N, iD, iH, iW, _ = x.shape
+        oD, oH, oW = pc.out_grid(iD, iH, iW)
+        m = pc.out_mult
+        return self._buf(name, (N, oD * m[0], oH * m[1], oW * m[2], pc.cout_pad), x.dtype)
+
+    def _latent(self, left, right, disp):
+        """RGB-D encoder on both views -> [2B,1,h',w',C_last] (before pooling)."""
+        B, _, H, W = left.shape
+        dt = torch_dtype(self._dtype_code())
+        scale = 1.0 / (4.0 * self.cfg.NETWORK.MAX_DISP)
+        x = self._buf('rgbd', (2 * B, 1, H, W, 16), dt)
+        ops.pack_image(left, disp[:B], scale, out=x[:B])
+        ops.pack_image(right, disp[B:], scale, out=x[B:])
+        for i in range(len(self.rgbd_encoder.layers)):
+            x = self._conv('rec%d' % i, x, out=self._bufo('r%d' % i, 'rec%d' % i, x))
+        return x
+
+    def _check_inputs(self, left, right):
+        if self._packed is None:
+            self.pack()
+        if not (left.is_cuda and right.is_cuda):
+            raise _lib.S3dError('inputs must be CUDA tensors (no CPU fallback)')
+        if left.shape != right.shape or left.dim() != 4 or left.shape[1] != 3:
+            raise ValueError('expected left/right of shape [B,3,H,W], got %s / %s' % (tuple(left.shape), tuple(right.shape)))
+        return left.contiguous().float(), right.contiguous().float()
+
+
+class Stereo2Voxel(_StereoBase):
+    """forward(left, right[, gt]) -> (disp_left [B,1,H,W], disp_right [B,1,H,W], voxels [B,32,32,32]
+    [, iou_counts int64 [B,T,2]]).  Outputs are views of the module's workspace: clone to keep them."""
+
+    def __init__(self, cfg):
+        super().__init__(cfg)
+        self.decoder = _VoxelDecoder(cfg)
+        self.merger = _Merger(cfg)
+        assert cfg.NETWORK.MERGER_CHANNELS[0] == cfg.NETWORK.DEC_CHANNELS[-1] + 1
+
+    def _pack_head(self, P, dc, dev):
+        for i, seq in enumerate(self.decoder.layers):
+            P['dec%d' % i] = PackedConv.from_deconv_k4s2p1(seq[0], seq[1], A.ACT_RELU, dc, dev)
+        w = self.decoder.out.weight            # [Cin, 1, 1,1,1]
+        P['dec_out'] = PackedConv.from_pointwise(w.view(w.shape[0], 1).t(), None, None, A.ACT_SIGMOID, dc, dev)
+        for i, seq in enumerate(self.merger.layers):
+            P['mrg%d' % i] = PackedConv.from_conv(seq[0], seq[1], A.ACT_LEAKY, dc, dev,
+                                                  act_param=self.cfg.NETWORK.LEAKY_VALUE)
+
+    def forward(self, left, right, gt=None):
+        left, right = self._check_inputs(left, right)
+        mb = int(self.cfg.CONST.get('MICRO_BATCH', 0) or 0)
+        B = left.shape[0]
+        if mb and B > mb:
+            outs = []
+            for s in range(0, B, mb):
+                o = self._forward_chunk(left[s:s + mb], right[s:s + mb], None if gt is None else gt[s:s + mb])
+                outs.append(tuple(t.clone() for t in o))
+            return tuple(torch.cat(ts, 0) for ts in zip(*outs))
+        return self._forward_chunk(left, right, gt)
+
+    def _forward_chunk(self, left, right, gt):
+        cfg = self.cfg
+        B, _, H, W = left.shape
+        nv = cfg.CONST.N_VOX
+        disp, _ = self._disparity(left, right)
+        x = self._latent(left, right, disp)
+        L = cfg.NETWORK.LATENT_HW
+        k0 = cfg.NETWORK.DEC_CHANNELS[0]
+        assert x.shape[-1] * L * L == k0 * 8, 'REC_CHANNELS[-1]*LATENT_HW^2 must equal DEC_CHANNELS[0]*8'
+        x = ops.latent_to_vox(x, L, out=self._buf('lat', (2 * B, 2, 2, 2, pad_to(k0)), x.dtype, zero=True))
+        nl = len(self.decoder.layers)
+        for i in range(nl):
+            x = self._conv('dec%d' % i, x, out=self._bufo('d%d' % i, 'dec%d' % i, x))
+        m_in = x                                                   # [2B,32,32,32,16]: ch 0-7 raw, 8.. zero
+        cm = m_in.shape[-1]
+        craw = cfg.NETWORK.DEC_CHANNELS[-1]
+        assert m_in.shape[1] == nv and cm > craw
+        # coarse volume = sigmoid(1x1x1 transposed conv), written into channel `craw` of the same
+        # buffer (the conv's weights are zero for input channels >= craw, so the in-place write of
+        # channel `craw` cannot feed back).
+        self._conv('dec_out', m_in, out=m_in, out_view=(craw, (nv ** 3 * cm, nv * nv * cm, nv * cm, cm)), cout_store=1)
+        s = m_in
+        for i in range(len(self.merger.layers)):
+            s = self._conv('mrg%d' % i, s, out=self._bufo('m%d' % (i % 2), 'mrg%d' % i, s))
+        fused = self._buf('fused', (B, nv ** 3), torch.float32)
+        iou = None
+        gt8 = None
+        if gt is not None:
+            th = list(cfg.TEST.VOXEL_THRESH)
+            iou = self._buf('iou', (B, len(th), 2), torch.int64)
+            iou.zero_()
+            gt8 = gt.reshape(B, -1).to(torch.uint8).contiguous()
+        ops.fuse_views(s, 0, s.shape[-1], m_in, craw, cm, B, 2, nv ** 3, gt=gt8,
+                       thresholds=list(cfg.TEST.VOXEL_THRESH) if gt is not None else None, iou=iou, out=fused)
+        out = (disp[:B].unsqueeze(1), disp[B:].unsqueeze(1), fused.view(B, nv, nv, nv))
+        return out + (iou,) if gt is not None else out
+
+
+class Stereo2Point(_StereoBase):
+    """forward(left, right) -> (disp_left, disp_right, points [B,N_POINTS,3])."""
+
+    def __init__(self, cfg):
+        super().__init__(cfg)
+        self.point_decoder = _PointDecoder(cfg)
+
+    def _pack_head(self, P, dc, dev):
+        pd = self.point_decoder
+        c, L = self.cfg.NETWORK.REC_CHANNELS[-1], self.cfg.NETWORK.LATENT_HW
+        P['pt_conv'] = PackedConv.from_conv(pd.conv[0], pd.conv[1], A.ACT_RELU, dc, dev)
+        P['pt_fc1'] = PackedConv.from_linear_over_map(pd.fc1, 2 * c, L // 2, L // 2, A.ACT_RELU, dc, dev)
+        P['pt_fc2'] = PackedConv.from_pointwise(pd.fc2.weight, pd.fc2.bias, None, A.ACT_TANH, dc, dev, act_param=0.5)
+
+    def forward(self, left, right):
+        left, right = self._check_inputs(left, right)
+        cfg = self.cfg
+        B = left.shape[0]
+        disp, _ = self._disparity(left, right)
+        x = self._latent(left, right, disp)
+        L = cfg.NETWORK.LATENT_HW
+        if x.shape[2] != L or x.shape[3] != L:
+            x = ops.avg_pool(x, L, out=self._buf('pool', (2 * B, 1, L, L, x.shape[-1]), x.dtype))
+        c = x.shape[-1]
+        cat = self._buf('latcat', (B, 1, L, L, 2 * c), x.dtype)
+        cat[..., :c].copy_(x[:B])          # channel concat of the two views' latents (tiny copy)
+        cat[..., c:].copy_(x[B:])
+        y = self._conv('pt_conv', cat, out=self._bufo('p0', 'pt_conv', cat))
+        y = self._conv('pt_fc1', y, out=self._bufo('p1', 'pt_fc1', y))
+        npts = cfg.CONST.N_POINTS
+        pts = self._buf('pts', (B, 1, 1, 1, pad_to(npts * 3)), torch.float32)
+        self._conv('pt_fc2', y, out=pts)
+        return disp[:B].unsqueeze(1), disp[B:].unsqueeze(1), pts.view(B, -1)[:, :npts * 3].reshape(B, npts, 3)
+
+
+def build_model(name, cfg, seed=None):
+    m = {'Stereo2Voxel': Stereo2Voxel, 'Stereo2Point': Stereo2Point}[name](cfg)
+    if seed is not None:
+        init_synthetic_weights(m, seed)
+    return m.eval()

@@ -1,0 +1,166 @@
+# -*- coding: utf-8 -*-
+"""Python wrappers over the non-conv C-ABI entry points (include/s3d.h).  Every wrapper validates
+device / dtype / contiguity, allocates outputs with torch, passes raw pointers and the current
+CUDA stream, and raises on a non-zero return code.  None of them computes anything in Python."""
+import ctypes
+
+import torch
+
+from . import lib as _lib
+
+
+def _code(t):
+    if t.dtype == torch.bfloat16:
+        return _lib.DTYPE_BF16
+    if t.dtype == torch.float32:
+        return _lib.DTYPE_F32
+    raise TypeError('unsupported dtype %s' % t.dtype)
+
+
+def _chk(*ts):
+    for t in ts:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise _lib.S3dError('s3d ops need CUDA tensors (there is no CPU fallback)')
+        if not t.is_contiguous():
+            raise ValueError('tensor must be contiguous')
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def pack_image(img, disp=None, disp_scale=1.0, cpad=16, dtype=torch.bfloat16, out=None):
+    """img fp32 NCHW [B,3,H,W] (+ disp fp32 [B,H,W]) -> channels-last [B,1,H,W,cpad]."""
+    _chk(img, disp, out)
+    B, C, H, W = img.shape
+    assert C == 3 and img.dtype == torch.float32
+    if out is None:
+        out = torch.empty((B, 1, H, W, cpad), dtype=dtype, device=img.device)
+    rc = _lib.load().s3d_pack_image(img.data_ptr(), disp.data_ptr() if disp is not None else None, float(disp_scale),
+                                    out.data_ptr(), B, H, W, cpad, _code(out), _stream())
+    _lib.check(rc, 's3d_pack_image')
+    _lib.count_launch()
+    return out
+
+
+def cost_volume_concat(feat, B, D, C=None, out=None):
+    """feat [2B,1,h,w,C] -> vol [2B,D,h,w,2C]."""
+    _chk(feat, out)
+    n2, one, h, w, Cf = feat.shape
+    C = Cf if C is None else C
+    assert n2 == 2 * B and one == 1 and C == Cf
+    if out is None:
+        out = torch.empty((2 * B, D, h, w, 2 * C), dtype=feat.dtype, device=feat.device)
+    rc = _lib.load().s3d_cost_volume_concat(feat.data_ptr(), out.data_ptr(), B, h, w, C, D, _code(feat), _stream())
+    _lib.check(rc, 's3d_cost_volume_concat')
+    _lib.count_launch()
+    return out
+
+
+def soft_argmin(cost, sign=-1.0, out=None):
+    """cost fp32 [N,D,h,w] -> disp fp32 [N,h,w] = sum_d d * softmax_d(sign*cost)."""
+    _chk(cost, out)
+    assert cost.dtype == torch.float32
+    N, D, h, w = cost.shape
+    if out is None:
+        out = torch.empty((N, h, w), dtype=torch.float32, device=cost.device)
+    rc = _lib.load().s3d_soft_argmin(cost.data_ptr(), out.data_ptr(), N, D, h, w, float(sign), _stream())
+    _lib.check(rc, 's3d_soft_argmin')
+    _lib.count_launch()
+    return out
+
+
+def corr_soft_argmin(feat, B, D, out=None, want_cost=False):
+    """feat [2B,1,h,w,C] -> disp fp32 [2B,h,w] (fused correlation + soft-argmax)."""
+    _chk(feat, out)
+    n2, one, h, w, C = feat.shape
+    assert n2 == 2 * B and one == 1
+    if out is None:
+        out = torch.empty((2 * B, h, w), dtype=torch.float32, device=feat.device)
+    cost = torch.empty((2 * B, D, h, w), dtype=torch.float32, device=feat.device) if want_cost else None
+    rc = _lib.load().s3d_corr_soft_argmin(feat.data_ptr(), out.data_ptr(), cost.data_ptr() if want_cost else None,
+                                          B, h, w, C, D, _code(feat), _stream())
+    _lib.check(rc, 's3d_corr_soft_argmin')
+    _lib.count_launch()
+    return (out, cost) if want_cost else out
+
+
+def upsample_disp(disp_q, H, W, scale, out=None):
+    _chk(disp_q, out)
+    assert disp_q.dtype == torch.float32
+    N, h, w = disp_q.shape
+    if out is None:
+        out = torch.empty((N, H, W), dtype=torch.float32, device=disp_q.device)
+    rc = _lib.load().s3d_upsample_disp(disp_q.data_ptr(), out.data_ptr(), N, h, w, H, W, float(scale), _stream())
+    _lib.check(rc, 's3d_upsample_disp')
+    _lib.count_launch()
+    return out
+
+
+def latent_to_vox(x, L, out=None):
+    """[N,1,H,W,C] -> pooled to LxL -> [N,2,2,2,C*L*L/8] (oracle's NCHW .view order)."""
+    _chk(x, out)
+    N, one, H, W, C = x.shape
+    if out is None:
+        out = torch.empty((N, 2, 2, 2, C * L * L // 8), dtype=x.dtype, device=x.device)
+    rc = _lib.load().s3d_latent_to_vox(x.data_ptr(), out.data_ptr(), N, H, W, C, L, _code(x), _stream())
+    _lib.check(rc, 's3d_latent_to_vox')
+    _lib.count_launch()
+    return out
+
+
+def avg_pool(x, L, out=None):
+    _chk(x, out)
+    N, one, H, W, C = x.shape
+    if out is None:
+        out = torch.empty((N, 1, L, L, C), dtype=x.dtype, device=x.device)
+    rc = _lib.load().s3d_avg_pool(x.data_ptr(), out.data_ptr(), N, H, W, C, L, _code(x), _stream())
+    _lib.check(rc, 's3d_avg_pool')
+    _lib.count_launch()
+    return out
+
+
+def fuse_views(score, score_off, score_stride, vol, vol_off, vol_stride, B, V, nvox, gt=None, thresholds=None,
+               iou=None, out=None):
+    """Context-aware fusion epilogue (+ IoU counts).  score/vol: tensors holding [V*B, nvox] planes
+    at element offset *_off with element stride *_stride between voxels."""
+    _chk(score, vol, gt, iou, out)
+    assert score.dtype == vol.dtype
+    if out is None:
+        out = torch.empty((B, nvox), dtype=torch.float32, device=score.device)
+    T = 0
+    th = None
+    if gt is not None:
+        assert gt.dtype == torch.uint8 and iou is not None and iou.dtype == torch.int64
+        T = len(thresholds)
+        th = (ctypes.c_float * T)(*[float(t) for t in thresholds])
+    esz = score.element_size()
+    rc = _lib.load().s3d_fuse_views(score.data_ptr() + score_off * esz, score_stride,
+                                    vol.data_ptr() + vol_off * esz, vol_stride, _code(score), out.data_ptr(), B, V,
+                                    nvox, gt.data_ptr() if gt is not None else None, th, T,
+                                    iou.data_ptr() if iou is not None else None, _stream())
+    _lib.check(rc, 's3d_fuse_views')
+    _lib.count_launch()
+    return out
+
+
+def chamfer_forward(xyz1, xyz2):
+    """xyz1 [B,N,3], xyz2 [B,M,3] fp32 -> dist1 [B,N], dist2 [B,M], idx1 [B,N], idx2 [B,M] (int32)."""
+    _chk(xyz1, xyz2)
+    assert xyz1.dtype == torch.float32 and xyz2.dtype == torch.float32
+    B, N, three = xyz1.shape
+    B2, M, three2 = xyz2.shape
+    if three != 3 or three2 != 3 or B != B2:
+        raise ValueError('chamfer: expected [B,N,3] and [B,M,3]')
+    dev = xyz1.device
+    dist1 = torch.empty((B, N), dtype=torch.float32, device=dev)
+    dist2 = torch.empty((B, M), dtype=torch.float32, device=dev)
+    idx1 = torch.empty((B, N), dtype=torch.int32, device=dev)
+    idx2 = torch.empty((B, M), dtype=torch.int32, device=dev)
+    rc = _lib.load().s3d_chamfer_forward(xyz1.data_ptr(), xyz2.data_ptr(), dist1.data_ptr(), idx1.data_ptr(),
+                                         dist2.data_ptr(), idx2.data_ptr(), B, N, M, _stream())
+    _lib.check(rc, 's3d_chamfer_forward')
+    _lib.count_launch(2)
+    return dist1, dist2, idx1, idx2

@@ -1,0 +1,90 @@
+"""tcgen05 implicit-GEMM conv engine vs the torch fp32 reference of the same op (GPU)."""
+import pytest
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from stereo_3d_reconstruction_b200 import lib
+from stereo_3d_reconstruction_b200.layers import PackedConv
+from tests.emulate import to_cl, pad_c
+
+pytestmark = pytest.mark.gpu
+
+# tolerances relative to the output's max magnitude: bf16 inputs are rounded once (2^-9 each),
+# products accumulate in fp32; TF32 keeps 10 mantissa bits.
+TOL = {'bf16': 2e-2, 'tf32': 3e-3}
+
+
+def _check(pc, x_nc, ref_nc, prec, cout, **kw):
+    dt = torch.bfloat16 if prec == 'bf16' else torch.float32
+    x = pad_c(to_cl(x_nc), pc.cin_pad).to(dt).cuda()
+    got = pc(x, engine='igemm', **kw).float().cpu()
+    ref = to_cl(ref_nc)
+    assert got.shape[:4] == ref.shape[:4]
+    err = (got[..., :cout] - ref).abs().max().item()
+    assert err <= TOL[prec] * (ref.abs().max().item() + 1e-6), (err, ref.abs().max().item())
+    if got.shape[-1] > cout and pc.act != lib.ACT_SIGMOID:
+        assert got[..., cout:].abs().max().item() == 0.0
+
+
+def _code(prec):
+    return lib.DTYPE_BF16 if prec == 'bf16' else lib.DTYPE_F32
+
+
+@pytest.mark.parametrize('prec', ['bf16', 'tf32'])
+@pytest.mark.parametrize('cin,cout,H,W,stride', [(3, 32, 32, 32, 2), (32, 64, 35, 35, 1), (64, 64, 16, 16, 1),
+                                                 (16, 32, 37, 41, 2), (128, 256, 9, 9, 2), (256, 320, 8, 8, 1)])
+def test_conv2d(prec, cin, cout, H, W, stride):
+    torch.manual_seed(0)
+    conv = nn.Conv2d(cin, cout, 3, stride, 1)
+    x = torch.randn(3, cin, H, W)
+    pc = PackedConv.from_conv(conv, None, lib.ACT_RELU, _code(prec), 'cuda')
+    _check(pc, x, F.relu(conv(x)), prec, cout)
+
+
+@pytest.mark.parametrize('prec', ['bf16', 'tf32'])
+@pytest.mark.parametrize('cin,cout,D,H,W', [(64, 64, 8, 16, 16), (32, 32, 5, 9, 11), (9, 16, 8, 8, 8), (64, 1, 4, 8, 8)])
+def test_conv3d(prec, cin, cout, D, H, W):
+    torch.manual_seed(1)
+    conv = nn.Conv3d(cin, cout, 3, 1, 1, bias=False)
+    x = torch.randn(2, cin, D, H, W)
+    pc = PackedConv.from_conv(conv, None, lib.ACT_LEAKY, _code(prec), 'cuda', act_param=0.2)
+    _check(pc, x, F.leaky_relu(conv(x), 0.2), prec, cout)
+
+
+@pytest.mark.parametrize('prec', ['bf16', 'tf32'])
+@pytest.mark.parametrize('cin,cout,S,N', [(64, 32, 2, 5), (32, 8, 8, 2), (128, 64, 4, 3)])
+def test_deconv(prec, cin, cout, S, N):
+    torch.manual_seed(2)
+    dc = nn.ConvTranspose3d(cin, cout, 4, 2, 1, bias=False)
+    x = torch.randn(N, cin, S, S, S)
+    pc = PackedConv.from_deconv_k4s2p1(dc, None, lib.ACT_RELU, _code(prec), 'cuda')
+    _check(pc, x, F.relu(dc(x)), prec, cout)
+
+
+@pytest.mark.parametrize('prec', ['bf16', 'tf32'])
+def test_residual_and_linear(prec):
+    torch.manual_seed(3)
+    conv = nn.Conv2d(32, 32, 3, 1, 1)
+    x = torch.randn(2, 32, 12, 12)
+    dt = torch.bfloat16 if prec == 'bf16' else torch.float32
+    res = torch.randn(2, 32, 12, 12).to(dt).float()
+    pc = PackedConv.from_conv(conv, None, lib.ACT_NONE, _code(prec), 'cuda')
+    _check(pc, x, conv(x) + res, prec, 32, residual=to_cl(res).to(dt).cuda())
+    fc = nn.Linear(32 * 4 * 4, 100)
+    xf = torch.randn(7, 32, 4, 4)
+    pc = PackedConv.from_linear_over_map(fc, 32, 4, 4, lib.ACT_TANH, _code(prec), 'cuda', act_param=0.5)
+    ref = (0.5 * torch.tanh(fc(xf.flatten(1)))).view(7, 100, 1, 1)
+    _check(pc, xf, ref, prec, 100)
+
+
+def test_igemm_rejects_bad_shapes():
+    conv = nn.Conv2d(16, 16, 3, 1, 1)
+    pc = PackedConv.from_conv(conv, None, lib.ACT_NONE, lib.DTYPE_BF16, 'cuda')
+    x = torch.zeros(1, 1, 8, 8, 16, dtype=torch.bfloat16).cuda()
+    p = pc.params(1, 1, 8, 8, (8 * 8 * 16, 8 * 8 * 16, 8 * 16, 16), lib.DTYPE_BF16, 16)
+    import copy, ctypes
+    q = copy.copy(p); q.tw = 3
+    out = torch.zeros(1, 1, 8, 8, 16, dtype=torch.bfloat16).cuda()
+    rc = lib.load().s3d_conv_igemm(ctypes.byref(q), x.data_ptr(), pc.weight.data_ptr(), None, None, out.data_ptr(), None)
+    assert rc == -1 and b'tile' in lib.load().s3d_last_error()

@@ -1,0 +1,81 @@
+"""End-to-end parity: product modules (CUDA) vs the oracle (CPU fp32) on identical weights/inputs."""
+import pytest
+import torch
+
+from oracle import models as O
+from stereo_3d_reconstruction_b200 import models as M
+from stereo_3d_reconstruction_b200.utils import synthetic
+from tests.common import small_cfg
+
+pytestmark = pytest.mark.gpu
+
+# relative-to-range tolerances on (disparity, occupancy).  'fp32' is the exact SIMT engine,
+# 'tf32' the fp32-storage tensor-core mode (north_star: 1e-3 relative), bf16 states a wider one.
+TOLS = {'fp32': (1e-4, 1e-4), 'tf32': (3e-3, 3e-3), 'bf16': (3e-2, 3e-2)}
+
+
+def _pair(cfg, B):
+    return synthetic.stereo_pair(B, cfg.CONST.IMG_H, cfg.CONST.IMG_W, 4 * cfg.NETWORK.MAX_DISP // 2, seed=0)[:2]
+
+
+@pytest.mark.parametrize('prec', ['fp32', 'tf32', 'bf16'])
+@pytest.mark.parametrize('cv', ['concat', 'corr'])
+def test_stereo2voxel_matches_oracle(prec, cv):
+    cfg = small_cfg(NETWORK__PRECISION=prec, NETWORK__COST_VOLUME=cv)
+    oracle = O.make_model('Stereo2Voxel', cfg, seed=0)
+    model = M.build_model('Stereo2Voxel', cfg)
+    model.load_state_dict(oracle.state_dict())           # identical keys and shapes
+    model.cuda().pack()
+    left, right = _pair(cfg, 3)
+    gt = synthetic.gt_volume(3)
+    with torch.no_grad():
+        rdl, rdr, rvox = oracle(left, right)
+        dl, dr, vox, iou = model(left.cuda(), right.cuda(), gt.cuda())
+    td, tv = TOLS[prec]
+    dmax = rdl.abs().max().item()
+    assert (dl.cpu() - rdl).abs().max().item() <= td * dmax
+    assert (dr.cpu() - rdr).abs().max().item() <= td * dmax
+    assert (vox.cpu() - rvox).abs().max().item() <= tv
+    # thresholded voxels identical apart from boundary flips (|v - t| within tolerance)
+    for t in cfg.TEST.VOXEL_THRESH:
+        flips = ((vox.cpu() >= t) != (rvox >= t))
+        assert ((rvox - t).abs()[flips] <= tv).all()
+    # IoU counts are exact for the voxels the kernel produced
+    assert torch.equal(iou.cpu(), O.iou_counts(vox.cpu(), gt, cfg.TEST.VOXEL_THRESH))
+
+
+@pytest.mark.parametrize('prec', ['fp32', 'bf16'])
+def test_stereo2point_matches_oracle(prec):
+    cfg = small_cfg(NETWORK__PRECISION=prec)
+    oracle = O.make_model('Stereo2Point', cfg, seed=0)
+    model = M.build_model('Stereo2Point', cfg)
+    model.load_state_dict(oracle.state_dict())
+    model.cuda().pack()
+    left, right = _pair(cfg, 2)
+    with torch.no_grad():
+        _, _, rp = oracle(left, right)
+        _, _, p = model(left.cuda(), right.cuda())
+    assert p.shape == rp.shape
+    assert (p.cpu() - rp).abs().max().item() <= (1e-4 if prec == 'fp32' else 3e-2)
+
+
+def test_odd_input_size_fp32():
+    cfg = small_cfg(NETWORK__PRECISION='fp32', CONST__IMG_H=70, CONST__IMG_W=50)
+    oracle = O.make_model('Stereo2Voxel', cfg, seed=1)
+    model = M.build_model('Stereo2Voxel', cfg)
+    model.load_state_dict(oracle.state_dict())
+    model.cuda().pack()
+    left, right = _pair(cfg, 2)
+    with torch.no_grad():
+        rdl, _, rvox = oracle(left, right)
+        dl, _, vox = model(left.cuda(), right.cuda())
+    assert (dl.cpu() - rdl).abs().max().item() <= 1e-4 * rdl.abs().max().item()
+    assert (vox.cpu() - rvox).abs().max().item() <= 1e-4
+
+
+def test_cpu_inputs_fail_loudly():
+    from stereo_3d_reconstruction_b200 import lib
+    cfg = small_cfg()
+    model = M.build_model('Stereo2Voxel', cfg, seed=0).cuda().pack()
+    with pytest.raises(lib.S3dError):
+        model(torch.zeros(1, 3, 64, 64), torch.zeros(1, 3, 64, 64))

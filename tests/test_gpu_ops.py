@@ -1,0 +1,139 @@
+"""Parity of the bandwidth-bound kernels and the SIMT conv against the oracle (GPU)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from oracle import models as O
+from oracle import chamfer as OC
+from stereo_3d_reconstruction_b200 import lib, ops
+from stereo_3d_reconstruction_b200.layers import PackedConv
+from stereo_3d_reconstruction_b200.utils import synthetic
+from tests.emulate import to_cl, pad_c
+
+pytestmark = pytest.mark.gpu
+
+
+def cl_feat(f):            # [N,C,h,w] -> [N,1,h,w,C]
+    return to_cl(f)
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('B,C,h,w,D', [(2, 32, 16, 16, 8), (1, 16, 9, 21, 32), (3, 64, 5, 40, 16)])
+def test_cost_volume_concat(dtype, B, C, h, w, D):
+    g = torch.Generator().manual_seed(0)
+    f = torch.randn(2 * B, C, h, w, generator=g).to(dtype).float()
+    ref = torch.cat([O.build_concat_volume(f[:B], f[B:], D, -1), O.build_concat_volume(f[B:], f[:B], D, +1)], 0)
+    got = ops.cost_volume_concat(cl_feat(f).to(dtype).cuda(), B, D)
+    assert torch.equal(got.float().cpu(), ref.permute(0, 2, 3, 4, 1).contiguous())      # pure data movement: exact
+
+
+@pytest.mark.parametrize('N,D,h,w', [(2, 8, 16, 16), (3, 32, 7, 13), (1, 128, 4, 33), (2, 5, 3, 3)])
+def test_soft_argmin(N, D, h, w):
+    g = torch.Generator().manual_seed(1)
+    cost = torch.randn(N, D, h, w, generator=g) * 3
+    ref = O.soft_argmin(cost)
+    got = ops.soft_argmin(cost.cuda(), -1.0).cpu()
+    torch.testing.assert_close(got, ref, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize('dtype,tol', [(torch.float32, 1e-3), (torch.bfloat16, 1e-3)])
+@pytest.mark.parametrize('B,C,h,w,D', [(2, 32, 8, 64, 32), (1, 16, 5, 21, 8), (1, 64, 3, 35, 64), (1, 32, 2, 40, 128)])
+def test_corr_soft_argmin(dtype, tol, B, C, h, w, D):
+    g = torch.Generator().manual_seed(2)
+    f = torch.randn(2 * B, C, h, w, generator=g).to(dtype).float()     # same rounded inputs for both sides
+    cost_ref = torch.cat([O.build_corr_volume(f[:B], f[B:], D, -1), O.build_corr_volume(f[B:], f[:B], D, +1)], 0)
+    ref = O.soft_argmax(cost_ref)
+    got, cost = ops.corr_soft_argmin(cl_feat(f).to(dtype).cuda(), B, D, want_cost=True)
+    torch.testing.assert_close(cost.cpu(), cost_ref, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(got.cpu(), ref, rtol=tol, atol=tol)
+
+
+@pytest.mark.parametrize('N,h,w,H,W', [(2, 16, 16, 64, 64), (1, 35, 35, 137, 137), (3, 8, 12, 32, 48)])
+def test_upsample_disp(N, h, w, H, W):
+    g = torch.Generator().manual_seed(3)
+    q = torch.rand(N, h, w, generator=g) * 8
+    ref = F.interpolate(q.unsqueeze(1) * 4.0, size=(H, W), mode='bilinear', align_corners=False).squeeze(1)
+    got = ops.upsample_disp(q.cuda(), H, W, 4.0).cpu()
+    torch.testing.assert_close(got, ref, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize('B,N,M,dup', [(2, 300, 1000, True), (1, 1, 1, False), (3, 17, 5, True), (2, 2048, 4096, True),
+                                       (1, 1025, 1023, False)])
+def test_chamfer_bit_exact(B, N, M, dup):
+    a, b = synthetic.point_clouds(B, N, M, seed=5, duplicates=dup)
+    rd1, rd2, ri1, ri2 = OC.chamfer_c(a.numpy(), b.numpy())
+    d1, d2, i1, i2 = ops.chamfer_forward(a.cuda(), b.cuda())
+    assert np.array_equal(i1.cpu().numpy(), ri1) and np.array_equal(i2.cpu().numpy(), ri2)          # bit-exact indices
+    assert np.array_equal(d1.cpu().numpy(), rd1) and np.array_equal(d2.cpu().numpy(), rd2)          # bit-exact distances
+
+
+def test_chamfer_rejects_empty():
+    with pytest.raises(lib.S3dError):
+        ops.chamfer_forward(torch.zeros(1, 0, 3).cuda(), torch.zeros(1, 4, 3).cuda())
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_fuse_views_and_iou(dtype):
+    g = torch.Generator().manual_seed(4)
+    B, V, nv = 3, 2, 32 ** 3
+    score = torch.randn(V * B, nv, 16, generator=g).to(dtype)
+    vol = torch.rand(V * B, nv, 16, generator=g).to(dtype)
+    gt = synthetic.gt_volume(B, seed=7)
+    th = [0.2, 0.3, 0.4, 0.5]
+    s = score[..., 0].float().view(V, B, nv)
+    v = vol[..., 8].float().view(V, B, nv)
+    ref = torch.clamp((F.softmax(s, 0) * v).sum(0), 0, 1)
+    iou = torch.zeros(B, 4, 2, dtype=torch.int64).cuda()
+    got = ops.fuse_views(score.cuda(), 0, 16, vol.cuda(), 8, 16, B, V, nv, gt=gt.view(B, -1).cuda(), thresholds=th,
+                         iou=iou).cpu()
+    torch.testing.assert_close(got, ref, rtol=1e-5, atol=1e-6)
+    # integer stats must be exact for the fused values the kernel itself produced
+    ref_iou = O.iou_counts(got.view(B, 32, 32, 32), gt, th)
+    assert torch.equal(iou.cpu(), ref_iou)
+
+
+def test_latent_to_vox_and_pool():
+    g = torch.Generator().manual_seed(6)
+    N, C, H, W, L = 3, 16, 5, 7, 2
+    x = torch.randn(N, C, H, W, generator=g)
+    pooled = F.adaptive_avg_pool2d(x, L)
+    ref_vox = pooled.reshape(N, C * L * L // 8, 2, 2, 2).permute(0, 2, 3, 4, 1).contiguous()
+    got = ops.latent_to_vox(to_cl(x).cuda(), L).cpu()
+    torch.testing.assert_close(got, ref_vox, rtol=1e-5, atol=1e-6)
+    got2 = ops.avg_pool(to_cl(x).cuda(), L).cpu()
+    torch.testing.assert_close(got2, to_cl(pooled), rtol=1e-5, atol=1e-6)
+
+
+def test_pack_image():
+    g = torch.Generator().manual_seed(8)
+    img = torch.rand(2, 3, 9, 11, generator=g)
+    disp = torch.rand(2, 9, 11, generator=g) * 30
+    got = ops.pack_image(img.cuda(), disp.cuda(), 0.25, dtype=torch.float32).cpu()
+    assert got.shape == (2, 1, 9, 11, 16)
+    torch.testing.assert_close(got[:, 0, :, :, :3], img.permute(0, 2, 3, 1))
+    torch.testing.assert_close(got[:, 0, :, :, 3], disp * 0.25)
+    assert got[..., 4:].abs().max() == 0
+
+
+# ---- SIMT conv (exact fp32 engine) vs torch.nn.functional --------------------------------------
+def _run(pc, x_nc, engine, dtype=torch.float32):
+    x = pad_c(to_cl(x_nc), pc.cin_pad).to(dtype).cuda()
+    return pc(x, engine=engine).float().cpu()
+
+
+def test_direct_conv_family_fp32():
+    torch.manual_seed(0)
+    conv = nn.Conv2d(3, 20, 3, 2, 1)
+    x = torch.randn(2, 3, 11, 13)
+    pc = PackedConv.from_conv(conv, None, lib.ACT_RELU, lib.DTYPE_F32, 'cuda')
+    torch.testing.assert_close(_run(pc, x, 'direct')[..., :20], to_cl(F.relu(conv(x))), rtol=1e-4, atol=1e-5)
+    conv3 = nn.Conv3d(5, 7, 3, 1, 1)
+    x3 = torch.randn(1, 5, 4, 6, 5)
+    pc = PackedConv.from_conv(conv3, None, lib.ACT_NONE, lib.DTYPE_F32, 'cuda')
+    torch.testing.assert_close(_run(pc, x3, 'direct')[..., :7], to_cl(conv3(x3)), rtol=1e-4, atol=1e-5)
+    dc = nn.ConvTranspose3d(6, 5, 4, 2, 1, bias=False)
+    xd = torch.randn(2, 6, 2, 3, 4)
+    pc = PackedConv.from_deconv_k4s2p1(dc, None, lib.ACT_NONE, lib.DTYPE_F32, 'cuda')
+    torch.testing.assert_close(_run(pc, xd, 'direct')[..., :5], to_cl(dc(xd)), rtol=1e-4, atol=1e-5)
