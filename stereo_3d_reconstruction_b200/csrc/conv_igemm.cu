@@ -45,7 +45,8 @@ struct KernelArgs {
   int row_bytes;     // kc * elem size: 32 / 64 / 128
   int n_kchunks;     // Cin / kc
   int stages;
-  int a_bytes, b_bytes, stage_bytes;
+  int a_bytes, b_bytes, stage_bytes;   // smem footprint (b_bytes rounded up to 1024)
+  int tx_bytes;                        // bytes the two TMA boxes actually deliver per stage
   int tiles_x, tiles_y, tiles_z, tiles_n;   // M tiling
   int n_ntiles;                             // Cout / bn
   int total_tiles;                          // n_classes * M tiles * N tiles
@@ -126,7 +127,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             ptx::mbar_wait(&ctrl.empty[stage], phase ^ 1);
             uint8_t* sa = smem + stage * a.stage_bytes;
             uint8_t* sb = sa + a.a_bytes;
-            ptx::mbar_arrive_expect_tx(&ctrl.full[stage], a.a_bytes + a.b_bytes);
+            ptx::mbar_arrive_expect_tx(&ctrl.full[stage], a.tx_bytes);
             ptx::tma_load_5d(sa, &map_a, &ctrl.full[stage], kc * a.kc, cx, cy, cz, t.n0);
             ptx::tma_load_3d(sb, &map_b, &ctrl.full[stage], kc * a.kc, t.nt * a.p.bn, ti);
             if (++stage == a.stages) { stage = 0; phase ^= 1; }
@@ -334,6 +335,7 @@ int conv_igemm_launch(const S3dConvParams* p, const void* in, const void* w, con
   a.n_kchunks = p->Cin / a.kc;
   a.a_bytes = kTileM * a.row_bytes;
   a.b_bytes = ((p->bn * a.row_bytes + 1023) / 1024) * 1024;
+  a.tx_bytes = a.a_bytes + p->bn * a.row_bytes;
   a.stage_bytes = a.a_bytes + a.b_bytes;          // a_bytes is a multiple of 1024 (4096..16384)
   const int smem_budget = 200 * 1024;
   a.stages = smem_budget / a.stage_bytes;
