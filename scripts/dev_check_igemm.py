@@ -32,7 +32,17 @@ CONFIGS = {
     'conv2d_s1_tf32':   ('conv2d', 'tf32', 2, 1, 16, 16, 32, 64, {'stride': 1}),
     'conv3d_tf32':      ('conv3d', 'tf32', 1, 4, 8, 8, 16, 32, {}),
     'conv3d_big_bf16':  ('conv3d', 'bf16', 4, 32, 64, 64, 64, 64, {'act': 'relu', 'time': True}),
+    'conv3d_big_nohalo': ('conv3d', 'bf16', 4, 32, 64, 64, 64, 64, {'act': 'relu', 'time': True, 'env': {'S3D_NO_HALO': '1'}}),
+    'conv3d_big_tf32':  ('conv3d', 'tf32', 4, 32, 64, 64, 32, 64, {'act': 'relu', 'time': True}),
+    'conv3d_x32_bf16':  ('conv3d', 'bf16', 32, 32, 64, 64, 64, 64, {'act': 'relu', 'time': True}),
+    'conv3d_bf16_bo1':  ('conv3d', 'bf16', 2, 8, 8, 8, 64, 64, {'env': {'S3D_HALO_BASE_OFFSET': '1'}}),
+    'conv2d_s1_bo1':    ('conv2d', 'bf16', 2, 1, 16, 16, 64, 64, {'stride': 1, 'env': {'S3D_HALO_BASE_OFFSET': '1'}}),
+    'conv3d_odd':       ('conv3d', 'bf16', 2, 5, 19, 13, 64, 48, {'act': 'relu'}),
+    'conv3d_odd_bo1':   ('conv3d', 'bf16', 2, 5, 19, 13, 64, 48, {'act': 'relu', 'env': {'S3D_HALO_BASE_OFFSET': '1'}}),
+    'conv2d_c128':      ('conv2d', 'bf16', 3, 1, 40, 24, 128, 256, {'stride': 1}),
+    'conv2d_big':       ('conv2d', 'bf16', 128, 1, 64, 64, 64, 64, {'stride': 1, 'act': 'relu', 'time': True}),
 }
+ONLY = os.environ.get('S3D_DEV_ONLY')
 
 
 def run_one(name):
@@ -117,10 +127,14 @@ def main():
     os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
     lines = []
     for name in CONFIGS:
+        if ONLY and not any(name.startswith(o) for o in ONLY.split(',')):
+            continue
         t = time.time()
+        env = dict(os.environ)
+        env.update(CONFIGS[name][8].get('env', {}))
         try:
             r = subprocess.run([sys.executable, os.path.abspath(__file__), name], capture_output=True, text=True,
-                               timeout=240)
+                               timeout=240, env=env)
             txt = r.stdout.strip() or ''
             if r.returncode != 0 and 'FAIL' not in txt:
                 txt += '\n   rc=%d stderr tail: %s' % (r.returncode, r.stderr.strip()[-1500:])

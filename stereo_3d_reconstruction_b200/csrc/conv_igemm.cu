@@ -23,8 +23,10 @@
 #include <cuda.h>
 #include <stdarg.h>
 #include <string.h>
+#include <stdlib.h>
 #include "common.cuh"
 #include "ptx.cuh"
+#include "epilogue.cuh"
 
 namespace s3d {
 
@@ -137,32 +139,37 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
-    if (lane == 0) {
-      int stage = 0;  uint32_t phase = 0;
-      int buf = 0;    uint32_t acc_phase = 0;
-      const int mma_per_stage = a.row_bytes / 32;   // each tcgen05.mma consumes 32 B of K per row
-      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
-        ptx::mbar_wait(&ctrl.acc_empty[buf], acc_phase ^ 1);
+    // Warp-uniform control flow (descriptors stay in uniform registers); only the tcgen05.mma /
+    // tcgen05.commit instructions sit under elect_one.
+    int stage = 0;  uint32_t phase = 0;
+    int buf = 0;    uint32_t acc_phase = 0;
+    const int mma_per_stage = a.row_bytes / 32;   // each tcgen05.mma consumes 32 B of K per row
+    const uint64_t desc_hi = ptx::make_smem_desc(0, a.row_bytes) & 0xFFFFFFFF00000000ull;
+    const uint32_t smem_u = ptx::smem_u32(smem);
+    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+      ptx::mbar_wait(&ctrl.acc_empty[buf], acc_phase ^ 1);
+      ptx::tc_fence_after();
+      const uint32_t d_tmem = tmem_base + buf * kAccStride;
+      for (int ks = 0; ks < ksteps; ++ks) {
+        ptx::mbar_wait(&ctrl.full[stage], phase);
         ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + buf * kAccStride;
-        for (int ks = 0; ks < ksteps; ++ks) {
-          ptx::mbar_wait(&ctrl.full[stage], phase);
-          ptx::tc_fence_after();
-          const uint32_t sa = ptx::smem_u32(smem + stage * a.stage_bytes);
-          const uint64_t adesc = ptx::make_smem_desc(sa, a.row_bytes);
-          const uint64_t bdesc = ptx::make_smem_desc(sa + a.a_bytes, a.row_bytes);
+        const uint32_t sa = smem_u + stage * a.stage_bytes;
+        const uint64_t adesc = desc_hi | ((sa >> 4) | (1u << 16));
+        const uint64_t bdesc = desc_hi | (((sa + a.a_bytes) >> 4) | (1u << 16));
+        if (ptx::elect_one()) {
           for (int k = 0; k < mma_per_stage; ++k) {
-            const uint32_t acc = (ks | k) != 0;
             // advance 32 B along K inside the swizzle atom: +2 in the (addr >> 4) field
-            if (kTF32) ptx::mma_tf32(d_tmem, adesc + 2 * k, bdesc + 2 * k, a.idesc, acc);
-            else       ptx::mma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, a.idesc, acc);
+            if (kTF32) ptx::mma_tf32(d_tmem, adesc + 2 * k, bdesc + 2 * k, a.idesc, (ks | k) != 0);
+            else       ptx::mma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, a.idesc, (ks | k) != 0);
           }
           ptx::tc_commit(&ctrl.empty[stage]);          // frees the smem slot when the MMAs retire
-          if (++stage == a.stages) { stage = 0; phase ^= 1; }
         }
-        ptx::tc_commit(&ctrl.acc_full[buf]);           // accumulator complete -> epilogue
-        if (++buf == 2) { buf = 0; acc_phase ^= 1; }
+        __syncwarp();
+        if (++stage == a.stages) { stage = 0; phase ^= 1; }
       }
+      if (ptx::elect_one()) ptx::tc_commit(&ctrl.acc_full[buf]);   // accumulator complete -> epilogue
+      __syncwarp();
+      if (++buf == 2) { buf = 0; acc_phase ^= 1; }
     }
   } else if (warp >= 4) {
     // ================= epilogue =================
@@ -172,7 +179,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const int dyr = (r >> a.lw) & (a.p.th - 1);
     const int dzr = (r >> (a.lw + a.lh)) & (a.p.td - 1);
     const int dnr = r >> (a.lw + a.lh + a.ld);
-    const bool out_bf16 = a.p.out_dtype == S3D_DTYPE_BF16;
+    const EpiParams epi = {a.bias, a.residual, a.out, a.p.cout_store, a.p.out_dtype == S3D_DTYPE_BF16, a.p.act,
+                           a.p.act_param};
     int buf = 0;  uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(a, tile);
@@ -189,84 +197,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         uint32_t v[16];
         ptx::tmem_ld16(taddr + c0, v);
         ptx::tmem_ld_wait();
-        const int cg = c_base + c0;                    // first global channel of this group
-        if (valid && cg < a.p.cout_store) {
-          float f[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            f[i] = __uint_as_float(v[i]);
-            if (a.bias) f[i] += __ldg(a.bias + cg + i);
-          }
-          const bool full = cg + 16 <= a.p.cout_store;
-          if (out_bf16) {
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(a.out) + off + cg;
-            const __nv_bfloat16* rs = a.residual ? reinterpret_cast<const __nv_bfloat16*>(a.residual) + off + cg : nullptr;
-            const bool vec = full && ((reinterpret_cast<uintptr_t>(o) & 15) == 0) &&
-                             (!rs || (reinterpret_cast<uintptr_t>(rs) & 15) == 0);
-            if (vec) {
-              if (rs) {
-                uint4 r0 = __ldg(reinterpret_cast<const uint4*>(rs));
-                uint4 r1 = __ldg(reinterpret_cast<const uint4*>(rs) + 1);
-                const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&r0);
-                const __nv_bfloat162* h1 = reinterpret_cast<const __nv_bfloat162*>(&r1);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  float2 g0 = __bfloat1622float2(h0[i]), g1 = __bfloat1622float2(h1[i]);
-                  f[2 * i] += g0.x;  f[2 * i + 1] += g0.y;
-                  f[8 + 2 * i] += g1.x;  f[8 + 2 * i + 1] += g1.y;
-                }
-              }
-              uint4 w0, w1;
-              __nv_bfloat162* p0 = reinterpret_cast<__nv_bfloat162*>(&w0);
-              __nv_bfloat162* p1 = reinterpret_cast<__nv_bfloat162*>(&w1);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                p0[i] = __floats2bfloat162_rn(apply_act(f[2 * i], a.p.act, a.p.act_param),
-                                              apply_act(f[2 * i + 1], a.p.act, a.p.act_param));
-                p1[i] = __floats2bfloat162_rn(apply_act(f[8 + 2 * i], a.p.act, a.p.act_param),
-                                              apply_act(f[8 + 2 * i + 1], a.p.act, a.p.act_param));
-              }
-              reinterpret_cast<uint4*>(o)[0] = w0;
-              reinterpret_cast<uint4*>(o)[1] = w1;
-            } else {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                if (cg + i < a.p.cout_store) {
-                  float s = f[i];
-                  if (rs) s += __bfloat162float(rs[i]);
-                  o[i] = __float2bfloat16_rn(apply_act(s, a.p.act, a.p.act_param));
-                }
-              }
-            }
-          } else {
-            float* o = reinterpret_cast<float*>(a.out) + off + cg;
-            const float* rs = a.residual ? reinterpret_cast<const float*>(a.residual) + off + cg : nullptr;
-            const bool vec = full && ((reinterpret_cast<uintptr_t>(o) & 15) == 0) &&
-                             (!rs || (reinterpret_cast<uintptr_t>(rs) & 15) == 0);
-            if (vec) {
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                float4 s = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
-                if (rs) {
-                  float4 g = __ldg(reinterpret_cast<const float4*>(rs) + i);
-                  s.x += g.x; s.y += g.y; s.z += g.z; s.w += g.w;
-                }
-                s.x = apply_act(s.x, a.p.act, a.p.act_param);  s.y = apply_act(s.y, a.p.act, a.p.act_param);
-                s.z = apply_act(s.z, a.p.act, a.p.act_param);  s.w = apply_act(s.w, a.p.act, a.p.act_param);
-                reinterpret_cast<float4*>(o)[i] = s;
-              }
-            } else {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                if (cg + i < a.p.cout_store) {
-                  float s = f[i];
-                  if (rs) s += rs[i];
-                  o[i] = apply_act(s, a.p.act, a.p.act_param);
-                }
-              }
-            }
-          }
-        }
+        if (valid) epilogue_store16(epi, off, c_base + c0, v);
       }
       ptx::tc_fence_before();
       ptx::mbar_arrive(&ctrl.acc_empty[buf]);
@@ -283,32 +214,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 }
 
 // ---- host side -------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
-                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
-                                  CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  }
-  return fn;
-}
-
 int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
 bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
 }  // namespace
 
-int conv_igemm_launch(const S3dConvParams* p, const void* in, const void* w, const float* bias,
-                      const void* residual, void* out, cudaStream_t stream) {
-  const bool tf32 = p->in_dtype == S3D_DTYPE_F32;
-  const int esz = tf32 ? 4 : 2;
+int conv_igemm_validate(const S3dConvParams* p, const void* in, const void* w) {
+  const int esz = p->in_dtype == S3D_DTYPE_F32 ? 4 : 2;
   S3D_CHECK_ARG(p->in_dtype == S3D_DTYPE_F32 || p->in_dtype == S3D_DTYPE_BF16, "igemm: bad in_dtype");
   S3D_CHECK_ARG(p->out_dtype == S3D_DTYPE_F32 || p->out_dtype == S3D_DTYPE_BF16, "igemm: bad out_dtype");
   S3D_CHECK_ARG(p->Cin > 0 && (p->Cin * esz) % 32 == 0, "igemm: Cin*elem must be a multiple of 32 B (Cin=%d)", p->Cin);
@@ -322,10 +234,15 @@ int conv_igemm_launch(const S3dConvParams* p, const void* in, const void* w, con
   S3D_CHECK_ARG(p->cout_store >= 1 && p->cout_store <= p->Cout, "igemm: cout_store");
   S3D_CHECK_ARG((reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0,
                 "igemm: in / w must be 16 B aligned");
+  return S3D_OK;
+}
 
-  EncodeTiledFn encode = get_encode_fn();
-  if (!encode) { set_error("igemm: cuTensorMapEncodeTiled unavailable"); return S3D_ERR_CUDA; }
-
+int conv_igemm_launch(const S3dConvParams* p, const void* in, const void* w, const float* bias,
+                      const void* residual, void* out, cudaStream_t stream) {
+  const int vrc = conv_igemm_validate(p, in, w);
+  if (vrc != S3D_OK) return vrc;
+  const bool tf32 = p->in_dtype == S3D_DTYPE_F32;
+  const int esz = tf32 ? 4 : 2;
   KernelArgs a;
   memset(&a, 0, sizeof(a));
   a.p = *p;  a.bias = bias;  a.residual = residual;  a.out = out;
@@ -352,34 +269,18 @@ int conv_igemm_launch(const S3dConvParams* p, const void* in, const void* w, con
   a.idesc = ptx::make_instr_desc(tf32 ? 2 : 1, kTileM, p->bn);
   (void)ksteps;
 
-  const CUtensorMapDataType dt = tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   const CUtensorMapSwizzle sw = a.row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                               : a.row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
   CUtensorMap map_a, map_b;
   {
-    cuuint64_t dims[5] = {(cuuint64_t)p->Cin, (cuuint64_t)p->iW, (cuuint64_t)p->iH, (cuuint64_t)p->iD, (cuuint64_t)p->N};
-    cuuint64_t strides[4];
-    strides[0] = (cuuint64_t)p->Cin * esz;
-    strides[1] = strides[0] * p->iW;
-    strides[2] = strides[1] * p->iH;
-    strides[3] = strides[2] * p->iD;
     cuuint32_t box[5] = {(cuuint32_t)a.kc, (cuuint32_t)(p->tw * p->sx), (cuuint32_t)(p->th * p->sy),
                          (cuuint32_t)(p->td * p->sz), (cuuint32_t)p->tn};
     cuuint32_t estr[5] = {1, (cuuint32_t)p->sx, (cuuint32_t)p->sy, (cuuint32_t)p->sz, 1};
     S3D_CHECK_ARG(box[1] <= 256 && box[2] <= 256 && box[3] <= 256 && box[4] <= 256, "igemm: TMA box too large");
-    CUresult r = encode(&map_a, dt, 5, const_cast<void*>(in), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { set_error("igemm: cuTensorMapEncodeTiled(A) failed: %d", (int)r); return S3D_ERR_CUDA; }
-  }
-  {
-    const int rows = p->ntaps * p->n_classes;
-    cuuint64_t dims[3] = {(cuuint64_t)p->Cin, (cuuint64_t)p->Cout, (cuuint64_t)rows};
-    cuuint64_t strides[2] = {(cuuint64_t)p->Cin * esz, (cuuint64_t)p->Cin * esz * p->Cout};
-    cuuint32_t box[3] = {(cuuint32_t)a.kc, (cuuint32_t)p->bn, 1};
-    cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = encode(&map_b, dt, 3, const_cast<void*>(w), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { set_error("igemm: cuTensorMapEncodeTiled(B) failed: %d", (int)r); return S3D_ERR_CUDA; }
+    int rc = encode_act_map(&map_a, in, esz, tf32, p->Cin, p->iW, p->iH, p->iD, p->N, box, estr, sw);
+    if (rc != S3D_OK) return rc;
+    rc = encode_weight_map(&map_b, w, esz, tf32, p->Cin, p->Cout, p->ntaps * p->n_classes, a.kc, p->bn, sw);
+    if (rc != S3D_OK) return rc;
   }
 
   const int smem_bytes = a.stages * a.stage_bytes + 1024;
@@ -398,8 +299,22 @@ int conv_igemm_launch(const S3dConvParams* p, const void* in, const void* w, con
 
 }  // namespace s3d
 
+namespace s3d {
+bool conv_halo_eligible(const S3dConvParams* p);
+int conv_halo_launch(const S3dConvParams* p, const void* in, const void* w, const float* bias, const void* residual,
+                     void* out, cudaStream_t stream);
+}
+
+// Dispatch: stride-1 3x3 / 3x3x3 layers with 128-byte rows go to the halo-reuse kernel (conv_halo.cu),
+// everything else to the generic per-tap kernel.  S3D_NO_HALO=1 forces the generic kernel (A/B testing).
 extern "C" int s3d_conv_igemm(const S3dConvParams* p, const void* in, const void* w, const float* bias,
                               const void* residual, void* out, void* stream) {
   if (!p || !in || !w || !out) { s3d::set_error("s3d_conv_igemm: null argument"); return S3D_ERR_INVALID; }
+  static const bool no_halo = getenv("S3D_NO_HALO") != nullptr;
+  if (!no_halo && s3d::conv_halo_eligible(p)) {
+    const int rc = s3d::conv_igemm_validate(p, in, w);
+    if (rc != S3D_OK) return rc;
+    return s3d::conv_halo_launch(p, in, w, bias, residual, out, static_cast<cudaStream_t>(stream));
+  }
   return s3d::conv_igemm_launch(p, in, w, bias, residual, out, static_cast<cudaStream_t>(stream));
 }
