@@ -1,0 +1,319 @@
+#!/usr/bin/env python3
+# -*- coding: utf-8 -*-
+"""Benchmark of the Stereo2Voxel forward hot path (BASELINE.json: "stereo pairs/sec Stereo2Voxel fwd").
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path, one rank per GPU
+    python bench.py --impl reference --gpus N --steps K ...  # CPU oracle (north_star restatement) on host cores
+
+A "step" is one Stereo2Voxel forward over one batch of synthetic stereo pairs (config.py default
+size, random-init weights): BASELINE configs[1] (batch 64 per GPU, bf16 unless --precision).  With
+N GPUs every rank runs its own batch of 64 (weak scaling: 64*N pairs per step = configs[2]'s 512 at
+N=8) and the per-shard IoU counts are summed with one NCCL all-reduce per step.
+
+Prints ONE JSON line (rank 0).  `value` = pairs/s with inputs resident in HBM; `e2e` = the same through
+the public nn.Module call with pinned HOST inputs (H2D inside the timed region, voxels + IoU read back).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument('--gpus', type=int, default=1)
+    p.add_argument('--steps', type=int, default=10)
+    p.add_argument('--warmup', type=int, default=3)
+    p.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    p.add_argument('--batch', type=int, default=None, help='pairs per GPU per step (default cfg.CONST.BATCH_SIZE = 64)')
+    p.add_argument('--precision', default='bf16', choices=['bf16', 'tf32', 'fp32'])
+    p.add_argument('--no-cpu-baseline', action='store_true')
+    return p.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return {'hbm_gbs': d['hbm_gbs'], 'bf16_tflops': d['bf16_tflops'], 'bf16_tflops_sustained': d['bf16_tflops_sustained'],
+                'source': 'measured'}
+    return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0, 'source': 'fallback'}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, index=0):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._index = index
+        self._t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self._index), '--query-gpu=' + q, '--format=csv,noheader,nounits'],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(',')
+                self.samples.append(float(out[0]))
+                self.max_mhz = float(out[1])
+                for n, v in zip(names, out[2:]):
+                    if v.strip().lower().startswith('active'):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(2)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {'sm_mhz': s[len(s) // 2] if s else None, 'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons),
+                'samples': len(s)}
+
+
+def cpu_oracle_run(cfg, sample_pairs, steps, warmup, threads):
+    """Times the oracle (stock torch.nn restatement of the north_star) on the host cores."""
+    import torch
+    from oracle import models as O
+    from stereo_3d_reconstruction_b200.utils import synthetic
+    torch.set_num_threads(threads)
+    m = O.make_model('Stereo2Voxel', cfg, seed=cfg.CONST.SEED)
+    left, right, _ = synthetic.stereo_pair(sample_pairs, cfg.CONST.IMG_H, cfg.CONST.IMG_W, 2 * cfg.NETWORK.MAX_DISP, seed=0)
+    with torch.no_grad():
+        for _ in range(warmup):
+            m(left, right)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            m(left, right)
+        dt = time.perf_counter() - t0
+    return sample_pairs * steps / dt, dt / steps
+
+
+def run_reference(args):
+    """--impl reference: the reference's own implementation of the path cannot be run (its source is
+    not on disk: /root/reference = README.md + requirements.txt), so this arm times the oracle port on
+    all host cores, on a bounded sample of the same workload."""
+    rank = int(os.environ.get('RANK', 0))
+    if rank != 0:
+        return
+    from config import cfg
+    cores = os.cpu_count() or 1
+    sample = 2
+    value, sec = cpu_oracle_run(cfg, sample, max(1, args.steps), max(1, min(args.warmup, 2)), cores)
+    B = args.batch or cfg.CONST.BATCH_SIZE
+    line = {
+        'impl': 'reference', 'metric': 'stereo pairs/sec Stereo2Voxel fwd', 'value': value, 'unit': 'pairs/s',
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': sec * 1e3,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'Stereo2Voxel forward, batch %d per GPU, %dx%d, D=%d (CPU arm: bounded sample of %d pairs per step)'
+                   % (B, cfg.CONST.IMG_H, cfg.CONST.IMG_W, cfg.NETWORK.MAX_DISP, sample)},
+        'cpu_baseline': {'value': value, 'unit': 'pairs/s', 'cores': cores, 'kind': 'port',
+                         'sample': '%d pairs per step, %d steps, fp32 torch.nn oracle (north_star restatement; reference source not on disk)'
+                                   % (sample, args.steps)},
+        'e2e': {'value': value, 'unit': 'pairs/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from config import cfg
+    from stereo_3d_reconstruction_b200 import lib, models
+    from stereo_3d_reconstruction_b200.utils import synthetic
+
+    rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    if not torch.cuda.is_available():
+        sys.exit('bench.py needs a CUDA device: the product path has no CPU fallback (use --impl reference for the CPU arm)')
+    torch.cuda.set_device(local)
+    lib.check(lib.load().s3d_device_check(local), 's3d_device_check')
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    dev = torch.device('cuda', local)
+
+    cfg.NETWORK.PRECISION = args.precision
+    B = args.batch or cfg.CONST.BATCH_SIZE
+    cfg.CONST.MICRO_BATCH = max(B, cfg.CONST.MICRO_BATCH)
+    H, W, D = cfg.CONST.IMG_H, cfg.CONST.IMG_W, cfg.NETWORK.MAX_DISP
+    model = models.build_model('Stereo2Voxel', cfg, seed=cfg.CONST.SEED).to(dev).pack()
+
+    # rotating input sets: 4 x (left,right) batches > 126 MB L2 (and each step streams >10 GB of activations)
+    n_sets = 4
+    host_sets, dev_sets = [], []
+    for i in range(n_sets):
+        l, r, _ = synthetic.stereo_pair(B, H, W, 2 * D, seed=1000 * rank + i)
+        g = synthetic.gt_volume(B, cfg.CONST.N_VOX, seed=5000 * rank + i)
+        host_sets.append((l.pin_memory(), r.pin_memory(), g.pin_memory()))
+        dev_sets.append((l.to(dev), r.to(dev), g.to(dev)))
+    T = len(cfg.TEST.VOXEL_THRESH)
+    stats = torch.zeros(2 * T + 1, dtype=torch.int64, device=dev)
+
+    def step_resident(i):
+        l, r, g = dev_sets[i % n_sets]
+        _, _, vox, iou = model(l, r, g)
+        stats[:T] = iou[:, :, 0].sum(0)
+        stats[T:2 * T] = iou[:, :, 1].sum(0)
+        stats[2 * T] = B
+        if world > 1:
+            dist.all_reduce(stats)
+        return vox
+
+    h_vox = torch.empty((B, cfg.CONST.N_VOX, cfg.CONST.N_VOX, cfg.CONST.N_VOX), dtype=torch.float32).pin_memory()
+    h_stats = torch.empty(2 * T + 1, dtype=torch.int64).pin_memory()
+    d_l = torch.empty((B, 3, H, W), dtype=torch.float32, device=dev)
+    d_r = torch.empty_like(d_l)
+    d_g = torch.empty((B, cfg.CONST.N_VOX, cfg.CONST.N_VOX, cfg.CONST.N_VOX), dtype=torch.uint8, device=dev)
+
+    def step_e2e(i):
+        hl, hr, hg = host_sets[i % n_sets]
+        d_l.copy_(hl, non_blocking=True); d_r.copy_(hr, non_blocking=True); d_g.copy_(hg, non_blocking=True)
+        _, _, vox, iou = model(d_l, d_r, d_g)
+        stats[:T] = iou[:, :, 0].sum(0)
+        stats[T:2 * T] = iou[:, :, 1].sum(0)
+        stats[2 * T] = B
+        if world > 1:
+            dist.all_reduce(stats)
+        h_vox.copy_(vox, non_blocking=True)
+        h_stats.copy_(stats, non_blocking=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for i in range(warmup):
+            fn(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(warmup + i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms
+
+    # ---- dominant-kernel timing hooks (CUDA events on the launching stream, inside the timed region) ----
+    dom_layers = ('dres0b', 'dres1a', 'dres1b', 'cls_a')          # four identical 64->64 3x3x3 layers
+    dom_events = []
+    orig_conv = model._conv
+
+    def hooked(name, x, **kw):
+        if name in dom_layers:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            out = orig_conv(name, x, **kw)
+            b.record()
+            dom_events.append((a, b))
+            return out
+        return orig_conv(name, x, **kw)
+
+    model._conv = hooked
+    n0 = lib.launches()
+    with ClockSampler(local) as clk:
+        ms = timed(step_resident, args.steps, args.warmup)
+    launches = (lib.launches() - n0) * args.steps // (args.steps + args.warmup)
+    dom_ms = [a.elapsed_time(b) for a, b in dom_events[len(dom_layers) * args.warmup:]]
+    model._conv = orig_conv
+    ms_e2e = timed(step_e2e, args.steps, min(args.warmup, 2) or 1)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pk = peaks()
+    value = B * world * args.steps / (ms / 1e3)
+    e2e = B * world * args.steps / (ms_e2e / 1e3)
+    pc = model._packed['dres0b']
+    h, w = -(-H // 4), -(-W // 4)
+    flops = pc.flops(2 * B, D, h, w)                  # algorithmic FLOPs of one launch (2B volumes)
+    dom = sum(dom_ms) / max(len(dom_ms), 1)
+    achieved = flops / (dom / 1e3) / 1e12
+    peak = pk['bf16_tflops_sustained']
+    total_flops = sum(model._packed[k].flops(*shape) for k, shape in model_flop_shapes(cfg, B).items())
+    line = {
+        'metric': 'stereo pairs/sec Stereo2Voxel fwd', 'value': value, 'unit': 'pairs/s', 'n_gpus': world,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': args.precision, 'data': 'synthetic',
+        'config': {'workload': 'Stereo2Voxel forward, batch %d per GPU (BASELINE configs[1]; x%d GPUs = configs[2] sharding), '
+                               '%dx%d input, D=%d planes at 1/4 res, random-init weights' % (B, world, H, W, D),
+                   'global_batch': B * world, 'cost_volume': cfg.NETWORK.COST_VOLUME,
+                   'l2': 'inputs rotate over %d batches (%d MB > 126 MB L2); each step streams >10 GB of activations'
+                         % (n_sets, n_sets * 2 * B * 3 * H * W * 4 // 2 ** 20)},
+        'e2e': {'value': e2e, 'unit': 'pairs/s', 'ms_per_step': ms_e2e / args.steps,
+                'h2d_bytes_per_step': 2 * B * 3 * H * W * 4 + B * cfg.CONST.N_VOX ** 3,
+                'd2h_bytes_per_step': B * cfg.CONST.N_VOX ** 3 * 4 + (2 * T + 1) * 8},
+        'gpu_launches': launches,
+        'clocks': clk.summary(),
+        'roofline': {'bound': 'tensor', 'kernel': 'conv_halo_kernel (3x3x3 64->64 cost aggregation, 4 of the 6 aggregation layers)',
+                     'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,
+                     'peak_source': '%s bf16_tflops_sustained (kernel timed inside a long step)' % pk['source'],
+                     'ms_per_launch': dom, 'flops_per_launch': flops, 'share_of_step': dom * len(dom_layers) / (ms / args.steps),
+                     'traffic': None},
+        'model_tflops_per_step': total_flops / 1e12,
+        'model_tflops_achieved': total_flops / (ms / args.steps / 1e3) / 1e12,
+    }
+    if not args.no_cpu_baseline and world == 1:
+        cores = os.cpu_count() or 1
+        v, sec = cpu_oracle_run(cfg, 1, 5, 1, cores)
+        line['cpu_baseline'] = {'value': v, 'unit': 'pairs/s', 'cores': cores, 'kind': 'port',
+                                'sample': 'batch 1 (BASELINE configs[0]), 5 forwards, fp32 torch.nn oracle on %d threads' % cores}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def model_flop_shapes(cfg, B):
+    """(N, D, H, W) input shape of every packed conv layer of the Stereo2Voxel forward at batch B."""
+    H, W, D = cfg.CONST.IMG_H, cfg.CONST.IMG_W, cfg.NETWORK.MAX_DISP
+    h2, w2, h4, w4 = -(-H // 2), -(-W // 2), -(-H // 4), -(-W // 4)
+    s = {'enc0': (2 * B, 1, H, W), 'enc1': (2 * B, 1, h2, w2), 'enc2': (2 * B, 1, h2, w2)}
+    for k in ('enc3', 'enc4', 'enc5'):
+        s[k] = (2 * B, 1, h4, w4)
+    if cfg.NETWORK.COST_VOLUME == 'concat':
+        for k in ('dres0a', 'dres0b', 'dres1a', 'dres1b', 'cls_a', 'cls_b'):
+            s[k] = (2 * B, D, h4, w4)
+    hh, ww = H, W
+    for i in range(len(cfg.NETWORK.REC_CHANNELS)):
+        s['rec%d' % i] = (2 * B, 1, hh, ww)
+        hh, ww = -(-hh // 2), -(-ww // 2)
+    v = 2
+    for i in range(len(cfg.NETWORK.DEC_CHANNELS) - 1):
+        s['dec%d' % i] = (2 * B, v, v, v)
+        v *= 2
+    s['dec_out'] = (2 * B, v, v, v)
+    for i in range(len(cfg.NETWORK.MERGER_CHANNELS) - 1):
+        s['mrg%d' % i] = (2 * B, v, v, v)
+    return s
+
+
+if __name__ == '__main__':
+    a = parse()
+    if a.impl == 'reference':
+        run_reference(a)
+    else:
+        run_ours(a)

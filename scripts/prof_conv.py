@@ -11,11 +11,13 @@ if name == 'agg':          # the dominant layer: 64->64 3x3x3 at D=32, 64x64, 12
     conv = nn.Conv3d(64, 64, 3, 1, 1, bias=False); shape = (128, 32, 64, 64, 64)
 elif name == 'agg32':
     conv = nn.Conv3d(64, 64, 3, 1, 1, bias=False); shape = (32, 32, 64, 64, 64)
+elif name == 'agg128':
+    conv = nn.Conv3d(64, 128, 3, 1, 1, bias=False); shape = (32, 32, 64, 64, 64)
 elif name == 'enc':
     conv = nn.Conv2d(64, 64, 3, 1, 1, bias=False); shape = (128, 1, 64, 64, 64)
 pc = PackedConv.from_conv(conv, None, lib.ACT_RELU, lib.DTYPE_BF16, 'cuda')
 x = torch.randn(*shape, device='cuda').to(torch.bfloat16)
-out = torch.empty_like(x)
+out = torch.empty(*shape[:4], pc.cout_pad, device='cuda', dtype=torch.bfloat16)
 for _ in range(2):
     pc(x, out=out)
 torch.cuda.synchronize()

@@ -54,6 +54,7 @@ struct HaloArgs {
   int b_stages, b_bytes, b_tx;
   int cols_x, cols_y, n_ntiles, total_cols;
   int base_offset_mode;
+  int debug;          // timing experiments only (S3D_HALO_DEBUG): 1 = no tap offsets, 2 = +SBO 1024, 3 = SBO 1024
   uint32_t idesc;
 };
 
@@ -179,7 +180,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     int waited = 0, col_base = 0;
     const uint32_t planes_u32 = ptx::smem_u32(smem);
     const uint32_t b_u32 = ptx::smem_u32(smem_b);
-    const uint64_t a_hi = make_desc_128(0, kHX * kRowBytes, 0) & 0xFFFFFFFF00000000ull;
+    const uint64_t a_hi = make_desc_128(0, a.debug >= 2 ? 1024 : kHX * kRowBytes, 0) & 0xFFFFFFFF00000000ull;
     const uint64_t b_hi = ptx::make_smem_desc(0, kRowBytes) & 0xFFFFFFFF00000000ull;
     constexpr uint32_t kMtStep = (16 * kHX * kRowBytes) >> 4;      // second M tile: 16 halo rows of y further
     for (int col = blockIdx.x; col < a.total_cols; col += gridDim.x) {
@@ -198,7 +199,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           const uint32_t slot_lo = ((planes_u32 + slot * a.slot_bytes) >> 4) | (1u << 16);
           for (int kyx = 0; kyx < 9; ++kyx) {
             const int ky = kyx / 3, kx = kyx - ky * 3;
-            const uint32_t tap_lo = slot_lo + (((ky * kHX + kx) * kRowBytes) >> 4);
+            const uint32_t tap_lo = slot_lo + ((a.debug == 1 || a.debug == 2) ? 0u : (((ky * kHX + kx) * kRowBytes) >> 4));
             for (int ch = 0; ch < a.nchunks; ++ch) {
               ptx::mbar_wait(&ctrl.b_full[bstage], bphase);
               ptx::tc_fence_after();
@@ -332,6 +333,8 @@ int conv_halo_launch(const S3dConvParams* p_in, const void* in, const void* w, c
   a.idesc = ptx::make_instr_desc(tf32 ? 2 : 1, 128, p.bn);
   const char* bo = getenv("S3D_HALO_BASE_OFFSET");
   a.base_offset_mode = bo ? atoi(bo) : 0;
+  const char* dbg = getenv("S3D_HALO_DEBUG");
+  a.debug = dbg ? atoi(dbg) : 0;
 
   CUtensorMap map_a, map_b;
   cuuint32_t box[5] = {(cuuint32_t)a.kc, kHX, kHY, 1, 1};
