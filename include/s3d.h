@@ -100,6 +100,12 @@ int s3d_cost_volume_concat(const void* feat, void* vol, int B, int h, int w, int
 /* cost: fp32 [N,D,h,w] -> disp fp32 [N,h,w] = sum_d d*softmax_d(sign*cost).  sign=-1: soft-argmin. */
 int s3d_soft_argmin(const float* cost, float* disp, int N, int D, int h, int w, float sign,
                     void* stream);
+/* Cout=1 3x3x3 classifier conv + soft-argmin from per-tap planes.  taps: fp32 [N,D,h,w,tap_stride] with
+ * taps[..., (kz*3+ky)*3+kx] = W[kz,ky,kx,:] . x[pixel,:] (a pointwise GEMM done by s3d_conv_igemm);
+ * cost[z,y,x] = sum_t taps[z+kz-1, y+ky-1, x+kx-1, t] (zero outside), disp = sum_z z*softmax_z(sign*cost).
+ * cost_out may be NULL (debug: fp32 [N,D,h,w]). */
+int s3d_tap_gather_soft_argmin(const float* taps, float* disp, float* cost_out, int N, int D, int h, int w,
+                               int tap_stride, float sign, void* stream);
 /* Fused correlation + soft-argmax; the [2B,D,h,w] cost is never materialised.
  * disp: fp32 [2B,h,w]; cost_out may be NULL (debug: fp32 [2B,D,h,w]). */
 int s3d_corr_soft_argmin(const void* feat, float* disp, float* cost_out, int B, int h, int w,

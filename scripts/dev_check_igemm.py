@@ -40,6 +40,8 @@ CONFIGS = {
     'conv3d_odd':       ('conv3d', 'bf16', 2, 5, 19, 13, 64, 48, {'act': 'relu'}),
     'conv3d_odd_bo1':   ('conv3d', 'bf16', 2, 5, 19, 13, 64, 48, {'act': 'relu', 'env': {'S3D_HALO_BASE_OFFSET': '1'}}),
     'conv2d_c128':      ('conv2d', 'bf16', 3, 1, 40, 24, 128, 256, {'stride': 1}),
+    'conv3d_c16':       ('conv3d', 'bf16', 2, 8, 8, 8, 16, 16, {'act': 'relu'}),
+    'conv3d_c32_odd':   ('conv3d', 'bf16', 1, 5, 37, 11, 32, 32, {}),
     'conv2d_big':       ('conv2d', 'bf16', 128, 1, 64, 64, 64, 64, {'stride': 1, 'act': 'relu', 'time': True}),
 }
 ONLY = os.environ.get('S3D_DEV_ONLY')

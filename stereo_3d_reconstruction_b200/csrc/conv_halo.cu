@@ -1,26 +1,32 @@
-// Halo-reuse implicit GEMM for stride-1 3x3 / 3x3x3 convolutions (the cost-aggregation stack and
-// the 1/4-resolution encoder layers: >95 % of the network's FLOPs).
+// Halo-reuse implicit GEMM for stride-1 3x3 / 3x3x3 convolutions (cost aggregation, the 1/4- and
+// 1/2-resolution encoder layers, the fusion scorer: > 95 % of the network's FLOPs).
 //
-// Why a second kernel.  In the generic engine (conv_igemm.cu) every tap re-fetches its shifted
-// 128 x 128 B activation slab through TMA, 27 slabs per output tile for a 3x3x3 conv: measured on
-// B200 that is ~8.5 TB/s of L2->SM traffic and the kernel sits on the L2 bandwidth ceiling
-// (373 TFLOP/s).  Here the activations are staged ONCE per input plane, with their halo, and all
-// 9 in-plane taps (x 3 planes) are issued straight out of that buffer by moving the UMMA
-// shared-memory descriptor: tap (ky,kx) is the same 128-byte-swizzled buffer read from a start
-// address ((16*mt + ky)*10 + kx) rows further on, with the 8-row groups 10 rows apart.
+// Two measurements on B200 shaped this kernel (profiles/r1_conv_notes.md):
+//  1. In the generic engine (conv_igemm.cu) every tap re-fetches its shifted activation slab through
+//     TMA -- 27 slabs per output tile for a 3x3x3 conv -- and the kernel sits on the L2->SM bandwidth
+//     ceiling (~11 TB/s, 480 TFLOP/s).  Here each input plane is staged ONCE, with its halo, and every
+//     in-plane tap is issued straight out of that buffer by moving the UMMA shared-memory descriptor:
+//     tap (ky,kx) is the same swizzled buffer read from a start address (ky*10 + kx) rows further on,
+//     with the 8-row groups 10 rows apart (the hardware applies the swizzle XOR to absolute smem
+//     address bits, so an unaligned start inside a 1024-byte aligned buffer is legal; measured).
+//  2. A tcgen05.mma in SS mode pays a fixed ~95 cycles to read its 128-row A operand whatever N is,
+//     while B rows stream at full shared-memory bandwidth.  With pixels on the M side and Cout = 64 on
+//     the N side that read is 3x the 32 math cycles.  So the operands are SWAPPED: the weights are the
+//     A operand (M = 64 or 128 output channels) and the pixels are the B operand with N = 256, which
+//     buys 128 math cycles per A read:  D[co, p] += sum_ci W_t[co, ci] * X[p + off_t, ci].
 //
-//   CTA work item  a "column": one image/volume n, a 32(y) x 8(x) output patch, marching over z.
-//   plane slot     input plane z' of the patch with halo: 34 x 10 rows x 128 B (one 5-D TMA box,
-//                  out-of-image rows zero-filled), in a ring of 4 slots: planes z-1,z,z+1 feed
-//                  output plane z while plane z+2 streams in.  Each plane is fetched once per
-//                  column: activation traffic drops 19x against the per-tap scheme.
-//   M tiles        the 32 x 8 patch is two 128-row tiles (16 y x 8 x each) with their own TMEM
-//                  accumulators, so every weight tile fetched from L2 feeds two MMA groups.
-//   weights        [27][Cout][Cin] streamed per tap through a small TMA ring (L2 resident).
-//   accumulators   2 buffers x 2 tiles x bn (<=128) fp32 columns of TMEM.
+//   CTA work item  a "column": one image/volume n, a 32(y) x 8(x) output patch (256 pixels = N),
+//                  marching over z.
+//   plane slot     input plane z' of the patch with halo, 34 x 10 rows of row_bytes (one 5-D TMA box,
+//                  out-of-image rows zero-filled), ring of up to 4 slots: planes z-1,z,z+1 feed output
+//                  plane z while z+2 streams in.  Every plane is fetched once per column.
+//   weights        [taps][Cout][Cin] streamed through a TMA ring of 128-byte-wide stages (1/2/4 taps
+//                  per stage for 128/64/32-byte rows), L2 resident.
+//   accumulators   fp32 in TMEM, [channel lanes x 256 pixel columns], two buffers (512 columns).
+//   epilogue       thread = output channel (TMEM lane); a warp stores 32 (16 for M=64) consecutive
+//                  channels of one pixel per instruction.
 //
-// Warp roles are those of conv_igemm.cu: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM
-// allocator, warps 4-7 epilogue.
+// Warp roles: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-7 epilogue.
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
@@ -33,12 +39,11 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kTX = 8, kHX = kTX + 2;          // output x per patch, + halo
-constexpr int kTY = 32, kHY = kTY + 2;         // output y per patch (two 16-row M tiles), + halo
-constexpr int kRowBytes = 128;
-constexpr int kChunkBytes = kHX * kHY * kRowBytes;                   // 43520 B per plane per K chunk
-constexpr int kChunkStride = (kChunkBytes + 1023) / 1024 * 1024;     // 44032: keeps 1024 B alignment
+constexpr int kTY = 32, kHY = kTY + 2;         // output y per patch, + halo
+constexpr int kPix = kTX * kTY;                // 256 = UMMA N
+constexpr int kPlaneRows = kHX * kHY;          // 340
 constexpr int kMaxRing = 4;
-constexpr int kMaxBStages = 6;
+constexpr int kMaxWStages = 6;
 constexpr int kTmemCols = 512;
 
 struct HaloArgs {
@@ -47,55 +52,52 @@ struct HaloArgs {
   const void* residual;
   void* out;
   int nz;             // taps along z: 1 (2-D conv) or 3
-  int nchunks;        // 128-byte K chunks per row (Cin*elem / 128)
-  int kc;             // channels per chunk
-  int slot_bytes;     // nchunks * kChunkStride
-  int ring;           // plane slots in the ring (nz + 1 .. 4)
-  int b_stages, b_bytes, b_tx;
-  int cols_x, cols_y, n_ntiles, total_cols;
-  int base_offset_mode;
-  int debug;          // timing experiments only (S3D_HALO_DEBUG): 1 = no tap offsets, 2 = +SBO 1024, 3 = SBO 1024
+  int row_bytes;      // bytes of one K chunk of a pixel row: 32 / 64 / 128
+  int kc;             // channels per K chunk
+  int nchunks;        // K chunks per row (Cin / kc)
+  int chunk_stride;   // bytes per plane per chunk, rounded to 1024
+  int slot_bytes;     // nchunks * chunk_stride
+  int ring;           // plane slots
+  int um;             // UMMA M: 64 or 128 (output channels per tile)
+  int tps;            // taps per weight stage (128 / row_bytes)
+  int w_stages, w_bytes, w_tx;
+  int cols_x, cols_y, n_mtiles, total_cols;
   uint32_t idesc;
+  int debug;          // S3D_HALO_DEBUG timing experiments: 1 = no tap offsets, 2 = +aligned groups (SBO 1024), 3 = SBO 1024 only
 };
 
 struct HaloCtrl {
   uint64_t plane_full[kMaxRing], plane_empty[kMaxRing];
-  uint64_t b_full[kMaxBStages], b_empty[kMaxBStages];
+  uint64_t w_full[kMaxWStages], w_empty[kMaxWStages];
   uint64_t acc_full[2], acc_empty[2];
   uint32_t tmem_base;
 };
 
-struct Col { int nt, n, y0, x0; };
+struct Col { int mt, n, y0, x0; };
 
 __device__ __forceinline__ Col decode_col(const HaloArgs& a, int c) {
   Col r;
-  r.nt = c % a.n_ntiles;  c /= a.n_ntiles;
+  r.mt = c % a.n_mtiles;  c /= a.n_mtiles;
   r.x0 = (c % a.cols_x) * kTX;  c /= a.cols_x;
   r.y0 = (c % a.cols_y) * kTY;  c /= a.cols_y;
   r.n = c;
   return r;
 }
 
-// K-major, 128B-swizzled operand whose 8-row groups are `sbo` bytes apart, starting at any
-// 16-byte aligned address inside a 1024-byte aligned buffer.
-__device__ __forceinline__ uint64_t make_desc_128(uint32_t addr, uint32_t sbo, int base_offset_mode) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((addr & 0x3FFFF) >> 4);
-  d |= static_cast<uint64_t>(1) << 16;
-  d |= static_cast<uint64_t>(sbo >> 4) << 32;
-  d |= static_cast<uint64_t>(1) << 46;
-  if (base_offset_mode) d |= static_cast<uint64_t>((addr >> 7) & 7) << 49;
-  d |= static_cast<uint64_t>(2) << 61;
-  return d;
+// High word of a K-major descriptor: SBO (bytes between 8-row groups), version 1, swizzle mode.
+__device__ __forceinline__ uint64_t desc_hi(uint32_t sbo, int row_bytes) {
+  const uint64_t layout = row_bytes == 128 ? 2ull : (row_bytes == 64 ? 4ull : 6ull);
+  return (static_cast<uint64_t>(sbo >> 4) << 32) | (1ull << 46) | (layout << 61);
 }
+__device__ __forceinline__ uint32_t desc_lo(uint32_t addr) { return ((addr & 0x3FFFF) >> 4) | (1u << 16); }
 
 template <bool kTF32>
 __global__ void __launch_bounds__(kThreads, 1)
-conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+conv_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                  const __grid_constant__ HaloArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* smem_b = smem + a.ring * a.slot_bytes;
+  uint8_t* smem_w = smem + a.ring * a.slot_bytes;
   const int ring = a.ring;
   __shared__ HaloCtrl ctrl;
 
@@ -106,14 +108,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   const int pad_z = (nz - 1) >> 1;
   const int nplanes = D + nz - 1;            // input planes per column (incl. the zero planes beyond the volume)
   const int ntaps = a.p.ntaps;
+  const int plane_tx = a.nchunks * kPlaneRows * a.row_bytes;
 
   if (warp == 0 && lane == 0) {
-    ptx::prefetch_tensormap(&map_a);
-    ptx::prefetch_tensormap(&map_b);
+    ptx::prefetch_tensormap(&map_x);
+    ptx::prefetch_tensormap(&map_w);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kMaxRing; ++s) { ptx::mbar_init(&ctrl.plane_full[s], 1); ptx::mbar_init(&ctrl.plane_empty[s], 1); }
-    for (int s = 0; s < kMaxBStages; ++s) { ptx::mbar_init(&ctrl.b_full[s], 1); ptx::mbar_init(&ctrl.b_empty[s], 1); }
+    for (int s = 0; s < kMaxWStages; ++s) { ptx::mbar_init(&ctrl.w_full[s], 1); ptx::mbar_init(&ctrl.w_empty[s], 1); }
     for (int b = 0; b < 2; ++b) { ptx::mbar_init(&ctrl.acc_full[b], 1); ptx::mbar_init(&ctrl.acc_empty[b], 128); }
     ptx::fence_barrier_init();
   }
@@ -135,9 +138,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         const uint32_t ph = ((issued / ring) & 1) ^ 1;
         if (blocking) ptx::mbar_wait(&ctrl.plane_empty[slot], ph);
         else if (!ptx::mbar_try_wait(&ctrl.plane_empty[slot], ph)) return false;
-        ptx::mbar_arrive_expect_tx(&ctrl.plane_full[slot], a.nchunks * kChunkBytes);
+        ptx::mbar_arrive_expect_tx(&ctrl.plane_full[slot], plane_tx);
         for (int ch = 0; ch < a.nchunks; ++ch)
-          ptx::tma_load_5d(smem + slot * a.slot_bytes + ch * kChunkStride, &map_a, &ctrl.plane_full[slot], ch * a.kc,
+          ptx::tma_load_5d(smem + slot * a.slot_bytes + ch * a.chunk_stride, &map_x, &ctrl.plane_full[slot], ch * a.kc,
                            pc.x0 - 1, pc.y0 - 1, pj - pad_z, pc.n);
         ++issued;
         if (++pj == nplanes) {
@@ -146,7 +149,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         }
         return true;
       };
-      int bstage = 0;  uint32_t bphase = 0;
+      int ws = 0;  uint32_t wphase = 0;
       int col_base = 0;
       for (int col = blockIdx.x; col < a.total_cols; col += gridDim.x) {
         const Col c = decode_col(a, col);
@@ -155,13 +158,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           while (issued < need) issue_plane(true);
           // planes of the next step (possibly of the next column): fetched opportunistically below
           const int need_next = (z + 1 < D) ? need + 1 : col_base + nplanes + nz;
-          for (int tap = 0; tap < ntaps; ++tap) {
+          for (int t0 = 0; t0 < ntaps; t0 += a.tps) {
             if (issued < need_next) issue_plane(false);
             for (int ch = 0; ch < a.nchunks; ++ch) {
-              ptx::mbar_wait(&ctrl.b_empty[bstage], bphase ^ 1);
-              ptx::mbar_arrive_expect_tx(&ctrl.b_full[bstage], a.b_tx);
-              ptx::tma_load_3d(smem_b + bstage * a.b_bytes, &map_b, &ctrl.b_full[bstage], ch * a.kc, c.nt * a.p.bn, tap);
-              if (++bstage == a.b_stages) { bstage = 0; bphase ^= 1; }
+              ptx::mbar_wait(&ctrl.w_empty[ws], wphase ^ 1);
+              ptx::mbar_arrive_expect_tx(&ctrl.w_full[ws], a.w_tx);
+              ptx::tma_load_3d(smem_w + ws * a.w_bytes, &map_w, &ctrl.w_full[ws], ch * a.kc, c.mt * a.um, t0);
+              if (++ws == a.w_stages) { ws = 0; wphase ^= 1; }
             }
           }
         }
@@ -170,19 +173,19 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
-    // The whole warp runs the (warp-uniform) control flow so every address / descriptor lives in
-    // uniform registers; only the tcgen05.mma / tcgen05.commit instructions sit under elect_one.
-    // Descriptors: the high word (SBO, version, swizzle) is constant, the low word is
-    // (addr >> 4) | LBO, so moving along K (+32 B), to the second M tile (+16 halo rows) or to
-    // another tap is a plain 32-bit add.
-    int bstage = 0;  uint32_t bphase = 0;
-    int buf = 0;     uint32_t acc_phase = 0;
+    // Warp-uniform control flow: every address / descriptor lives in uniform registers and only the
+    // tcgen05.mma / tcgen05.commit instructions sit under elect_one.  Descriptor high words are
+    // constant; the low word is (addr >> 4) | LBO, so K steps (+32 B) and tap shifts are 32-bit adds.
+    int ws = 0;  uint32_t wphase = 0;
+    int buf = 0; uint32_t acc_phase = 0;
     int waited = 0, col_base = 0;
     const uint32_t planes_u32 = ptx::smem_u32(smem);
-    const uint32_t b_u32 = ptx::smem_u32(smem_b);
-    const uint64_t a_hi = make_desc_128(0, a.debug >= 2 ? 1024 : kHX * kRowBytes, 0) & 0xFFFFFFFF00000000ull;
-    const uint64_t b_hi = ptx::make_smem_desc(0, kRowBytes) & 0xFFFFFFFF00000000ull;
-    constexpr uint32_t kMtStep = (16 * kHX * kRowBytes) >> 4;      // second M tile: 16 halo rows of y further
+    const uint32_t w_u32 = ptx::smem_u32(smem_w);
+    const int rb = a.row_bytes;
+    const uint64_t x_hi = desc_hi(a.debug >= 2 ? 8 * rb : kHX * rb, rb);   // pixel rows: 8-row groups one halo line (10 rows) apart
+    const uint64_t w_hi = desc_hi(8 * rb, rb);                // weights: dense rows
+    const int kper = rb >> 5;                                 // tcgen05.mma per tap per chunk (32 B of K each)
+    const uint32_t w_tap_step = (a.um * rb) >> 4;             // next tap inside a weight stage
     for (int col = blockIdx.x; col < a.total_cols; col += gridDim.x) {
       for (int z = 0; z < D; ++z) {
         ptx::mbar_wait(&ctrl.acc_empty[buf], acc_phase ^ 1);
@@ -192,38 +195,37 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           ++waited;
         }
         ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + buf * 256;
+        const uint32_t d_tmem = tmem_base + buf * kPix;
         uint32_t accum = 0;
-        int slot = (col_base + z) % ring;
-        for (int kz = 0; kz < nz; ++kz) {
-          const uint32_t slot_lo = ((planes_u32 + slot * a.slot_bytes) >> 4) | (1u << 16);
-          for (int kyx = 0; kyx < 9; ++kyx) {
-            const int ky = kyx / 3, kx = kyx - ky * 3;
-            const uint32_t tap_lo = slot_lo + ((a.debug == 1 || a.debug == 2) ? 0u : (((ky * kHX + kx) * kRowBytes) >> 4));
-            for (int ch = 0; ch < a.nchunks; ++ch) {
-              ptx::mbar_wait(&ctrl.b_full[bstage], bphase);
-              ptx::tc_fence_after();
-              const uint64_t adesc = a_hi | (tap_lo + ch * (kChunkStride >> 4));
-              const uint64_t bdesc = b_hi | (((b_u32 + bstage * a.b_bytes) >> 4) | (1u << 16));
-              if (ptx::elect_one()) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  if (kTF32) {
-                    ptx::mma_tf32(d_tmem, adesc + 2 * k, bdesc + 2 * k, a.idesc, accum | k);
-                    ptx::mma_tf32(d_tmem + 128, adesc + kMtStep + 2 * k, bdesc + 2 * k, a.idesc, accum | k);
-                  } else {
-                    ptx::mma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, a.idesc, accum | k);
-                    ptx::mma_bf16(d_tmem + 128, adesc + kMtStep + 2 * k, bdesc + 2 * k, a.idesc, accum | k);
+        const int slot0 = (col_base + z) % ring;
+        for (int t0 = 0; t0 < ntaps; t0 += a.tps) {
+          for (int ch = 0; ch < a.nchunks; ++ch) {
+            ptx::mbar_wait(&ctrl.w_full[ws], wphase);
+            ptx::tc_fence_after();
+            const uint32_t wlo = desc_lo(w_u32 + ws * a.w_bytes);
+            for (int tt = 0; tt < a.tps; ++tt) {
+              const int tap = t0 + tt;
+              if (tap < ntaps) {
+                const int kz = tap / 9, kyx = tap - kz * 9;
+                const int ky = kyx / 3, kx = kyx - ky * 3;
+                int slot = slot0 + kz;  if (slot >= ring) slot -= ring;
+                const uint32_t xlo = desc_lo(planes_u32 + slot * a.slot_bytes + ch * a.chunk_stride + ((a.debug == 1 || a.debug == 2) ? 0 : (ky * kHX + kx) * rb));
+                const uint64_t wdesc = w_hi | (wlo + tt * w_tap_step);
+                const uint64_t xdesc = x_hi | xlo;
+                if (ptx::elect_one()) {
+                  for (int k = 0; k < kper; ++k) {
+                    if (kTF32) ptx::mma_tf32(d_tmem, wdesc + 2 * k, xdesc + 2 * k, a.idesc, accum | k);
+                    else       ptx::mma_bf16(d_tmem, wdesc + 2 * k, xdesc + 2 * k, a.idesc, accum | k);
                   }
                 }
-                ptx::tc_commit(&ctrl.b_empty[bstage]);
+                __syncwarp();
+                accum = 1;
               }
-              __syncwarp();
-              accum = 1;
-              if (++bstage == a.b_stages) { bstage = 0; bphase ^= 1; }
             }
+            if (ptx::elect_one()) ptx::tc_commit(&ctrl.w_empty[ws]);
+            __syncwarp();
+            if (++ws == a.w_stages) { ws = 0; wphase ^= 1; }
           }
-          if (++slot == ring) slot = 0;
         }
         if (ptx::elect_one()) {
           ptx::tc_commit(&ctrl.acc_full[buf]);
@@ -239,28 +241,109 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
   } else if (warp >= 4) {
     // ================= epilogue =================
+    // TMEM lane = output channel.  M = 128: lane l of quarter q is channel 32q + l.  M = 64: the 64
+    // rows sit in lanes 0-15 of each quarter (row 16q + l), lanes 16-31 are unused.
     const int q = warp & 3;
-    const int r = q * 32 + lane;
-    const EpiParams epi = {a.bias, a.residual, a.out, a.p.cout_store, a.p.out_dtype == S3D_DTYPE_BF16, a.p.act,
-                           a.p.act_param};
+    const bool lane_has_row = a.um == 128 || lane < 16;
+    const int ch_local = a.um == 128 ? q * 32 + lane : q * 16 + lane;
+    const bool out_bf16 = a.p.out_dtype == S3D_DTYPE_BF16;
+    const bool simple_act = a.p.act == S3D_ACT_NONE || a.p.act == S3D_ACT_RELU || a.p.act == S3D_ACT_LEAKY;
+    // none / relu / leaky as one branch-free formula: max(v,0) + slope * min(v,0)
+    const float slope = a.p.act == S3D_ACT_NONE ? 1.f : (a.p.act == S3D_ACT_LEAKY ? a.p.act_param : 0.f);
+    const int osH = (int)a.p.osH, osW = (int)a.p.osW;          // patch-relative offsets fit 32 bits
+    int xw[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) xw[i] = i * osW;
     int buf = 0;  uint32_t acc_phase = 0;
     for (int col = blockIdx.x; col < a.total_cols; col += gridDim.x) {
       const Col c = decode_col(a, col);
-      const int x = c.x0 + (r & 7);
+      const int ch = c.mt * a.um + ch_local;
+      const bool ch_ok = lane_has_row && ch < a.p.cout_store;
+      const float bias = (ch_ok && a.bias) ? __ldg(a.bias + ch) : 0.f;
+      const int64_t col_off = (int64_t)c.n * a.p.osN + (int64_t)c.y0 * a.p.osH + (int64_t)c.x0 * a.p.osW + ch;
+      const int xlim = a.p.oW - c.x0;        // valid x_local < xlim
+      const int ylim = a.p.oH - c.y0;
+      const bool interior = xlim >= kTX && ylim >= kTY;
+      const bool warp_any = __any_sync(0xffffffffu, ch_ok);
       for (int z = 0; z < D; ++z) {
         ptx::mbar_wait(&ctrl.acc_full[buf], acc_phase);
         ptx::tc_fence_after();
+        const uint32_t taddr = tmem_base + buf * kPix + (static_cast<uint32_t>(q * 32) << 16);
+        const int64_t zoff = col_off + (int64_t)z * a.p.osD;
+        if (warp_any) {
+          if (interior && simple_act) {
+            // fast path (interior patches): no bounds checks, no per-pixel branches; the dtype /
+            // residual variants are warp-uniform branches around fully unrolled bodies.
+#pragma unroll 1
+            for (int j0 = 0; j0 < kPix; j0 += 16) {
+              uint32_t v[16];
+              ptx::tmem_ld16(taddr + j0, v);
+              ptx::tmem_ld_wait();
+              if (ch_ok) {
+                const int l0 = (j0 >> 3) * osH, l1 = l0 + osH;
+                float f[16];
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
-          const int y = c.y0 + mt * 16 + (r >> 3);
-          const bool valid = x < a.p.oW && y < a.p.oH;
-          const int64_t off = (int64_t)c.n * a.p.osN + (int64_t)z * a.p.osD + (int64_t)y * a.p.osH + (int64_t)x * a.p.osW;
-          const uint32_t taddr = tmem_base + buf * 256 + mt * 128 + (static_cast<uint32_t>(q * 32) << 16);
-          for (int c0 = 0; c0 < a.p.bn; c0 += 16) {
-            uint32_t v[16];
-            ptx::tmem_ld16(taddr + c0, v);
-            ptx::tmem_ld_wait();
-            if (valid) epilogue_store16(epi, off, c.nt * a.p.bn + c0, v);
+                for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) + bias;
+                if (out_bf16) {
+                  __nv_bfloat16* __restrict__ o = reinterpret_cast<__nv_bfloat16*>(a.out) + zoff;
+                  if (a.residual) {
+                    const __nv_bfloat16* __restrict__ rs = reinterpret_cast<const __nv_bfloat16*>(a.residual) + zoff;
+                    __nv_bfloat16 r[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) r[i] = rs[(i < 8 ? l0 : l1) + xw[i & 7]];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) f[i] += __bfloat162float(r[i]);
+                  }
+#pragma unroll
+                  for (int i = 0; i < 16; ++i)
+                    o[(i < 8 ? l0 : l1) + xw[i & 7]] = __float2bfloat16_rn(fmaxf(f[i], 0.f) + slope * fminf(f[i], 0.f));
+                } else {
+                  float* __restrict__ o = reinterpret_cast<float*>(a.out) + zoff;
+                  if (a.residual) {
+                    const float* __restrict__ rs = reinterpret_cast<const float*>(a.residual) + zoff;
+                    float r[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) r[i] = rs[(i < 8 ? l0 : l1) + xw[i & 7]];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) f[i] += r[i];
+                  }
+#pragma unroll
+                  for (int i = 0; i < 16; ++i)
+                    o[(i < 8 ? l0 : l1) + xw[i & 7]] = fmaxf(f[i], 0.f) + slope * fminf(f[i], 0.f);
+                }
+              }
+            }
+          } else {
+#pragma unroll 1
+            for (int j0 = 0; j0 < kPix; j0 += 16) {      // 16 pixel columns = two patch lines of 8
+              uint32_t v[16];
+              ptx::tmem_ld16(taddr + j0, v);
+              ptx::tmem_ld_wait();
+              if (ch_ok) {
+                float r[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {           // batch the residual loads (independent, in flight together)
+                  const int yl = (j0 >> 3) + (i >> 3), xl = i & 7;
+                  r[i] = 0.f;
+                  if (a.residual && yl < ylim && xl < xlim) {
+                    const int64_t off = zoff + yl * osH + xw[xl];
+                    r[i] = out_bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(a.residual)[off])
+                                    : reinterpret_cast<const float*>(a.residual)[off];
+                  }
+                }
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                  const int yl = (j0 >> 3) + (i >> 3), xl = i & 7;
+                  if (yl < ylim && xl < xlim) {
+                    const int64_t off = zoff + yl * osH + xw[xl];
+                    const float f = __uint_as_float(v[i]) + bias + r[i];
+                    const float g = simple_act ? fmaxf(f, 0.f) + slope * fminf(f, 0.f) : apply_act(f, a.p.act, a.p.act_param);
+                    if (out_bf16) reinterpret_cast<__nv_bfloat16*>(a.out)[off] = __float2bfloat16_rn(g);
+                    else          reinterpret_cast<float*>(a.out)[off] = g;
+                  }
+                }
+              }
+            }
           }
         }
         ptx::tc_fence_before();
@@ -281,70 +364,77 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 }  // namespace
 
 // Does this layer fit the halo kernel?  stride 1, 3x3 (D==1) or 3x3x3 taps with pad 1 in the canonical
-// (kz,ky,kx) order, rows of whole 128-byte chunks, Cout tile <= 128, identity output mapping.
+// (kz,ky,kx) order, identity output mapping, channel rows of 32 / 64 / 128-byte chunks that fit the ring.
 bool conv_halo_eligible(const S3dConvParams* p) {
   const int esz = p->in_dtype == S3D_DTYPE_F32 ? 4 : 2;
   if (p->n_classes != 1 || p->sx != 1 || p->sy != 1 || p->sz != 1) return false;
   if (p->omx != 1 || p->omy != 1 || p->omz != 1) return false;
   if (p->ntaps != 9 && p->ntaps != 27) return false;
-  if ((p->Cin * esz) % kRowBytes != 0) return false;
-  const int nchunks = p->Cin * esz / kRowBytes;
-  if (nchunks > (p->ntaps == 27 ? 1 : 2)) return false;
   if (p->oD != p->iD || p->oH != p->iH || p->oW != p->iW) return false;
   if (p->ntaps == 9 && p->iD != 1) return false;
   for (int t = 0; t < p->ntaps; ++t) {
     const int kz = p->ntaps == 27 ? t / 9 - 1 : 0, ky = (t % 9) / 3 - 1, kx = t % 3 - 1;
     if (p->dz[t] != kz || p->dy[t] != ky || p->dx[t] != kx) return false;
   }
-  int bn = p->bn;
-  if (bn > 128) { if (p->Cout % 128 != 0) return false; }
+  const int cin_bytes = p->Cin * esz;
+  if (cin_bytes % 32 != 0) return false;
+  const int rb = cin_bytes % 128 == 0 ? 128 : (cin_bytes % 64 == 0 ? 64 : 32);
+  const int nchunks = cin_bytes / rb;
+  const int slot = nchunks * ((kPlaneRows * rb + 1023) / 1024 * 1024);
+  const int nz = p->ntaps == 27 ? 3 : 1;
+  if ((nz + 1) * slot + 2 * 16384 > 225 * 1024) return false;          // plane ring + 2 weight stages must fit
+  if (p->Cout > 64 && p->Cout % 128 != 0) return false;                // M tiles of 128 channels, or one of 64
   return true;
 }
 
 int conv_halo_launch(const S3dConvParams* p_in, const void* in, const void* w, const float* bias, const void* residual,
                      void* out, cudaStream_t stream) {
-  S3dConvParams p = *p_in;
-  if (p.bn > 128) p.bn = 128;
+  const S3dConvParams& p = *p_in;
   const bool tf32 = p.in_dtype == S3D_DTYPE_F32;
   const int esz = tf32 ? 4 : 2;
-  S3D_CHECK_ARG(p.bn % 16 == 0 && p.Cout % p.bn == 0, "halo: bn");
   S3D_CHECK_ARG(p.cout_store >= 1 && p.cout_store <= p.Cout, "halo: cout_store");
   HaloArgs a;
   memset(&a, 0, sizeof(a));
   a.p = p;  a.bias = bias;  a.residual = residual;  a.out = out;
   a.nz = p.ntaps == 27 ? 3 : 1;
-  a.nchunks = p.Cin * esz / kRowBytes;
-  a.kc = kRowBytes / esz;
-  a.slot_bytes = a.nchunks * kChunkStride;
-  a.b_tx = p.bn * kRowBytes;
-  a.b_bytes = (a.b_tx + 1023) / 1024 * 1024;
+  const int cin_bytes = p.Cin * esz;
+  a.row_bytes = cin_bytes % 128 == 0 ? 128 : (cin_bytes % 64 == 0 ? 64 : 32);
+  a.kc = a.row_bytes / esz;
+  a.nchunks = cin_bytes / a.row_bytes;
+  a.chunk_stride = (kPlaneRows * a.row_bytes + 1023) / 1024 * 1024;
+  a.slot_bytes = a.nchunks * a.chunk_stride;
+  a.um = p.Cout > 64 ? 128 : 64;
+  a.n_mtiles = p.Cout > 64 ? p.Cout / 128 : 1;
+  a.tps = 128 / a.row_bytes;
+  // weight map [taps][Cout][Cin]: a stage is a (kc, um, tps) box; rows beyond Cout / taps beyond ntaps
+  // are zero-filled by the TMA unit (and still count towards the transaction bytes).
+  a.w_tx = a.tps * a.um * a.row_bytes;
+  a.w_bytes = (a.w_tx + 1023) / 1024 * 1024;
   const int budget_total = 225 * 1024;
-  a.ring = (budget_total - 2 * a.b_bytes) / a.slot_bytes;
+  a.ring = (budget_total - 2 * a.w_bytes) / a.slot_bytes;
   if (a.ring > kMaxRing) a.ring = kMaxRing;
   S3D_CHECK_ARG(a.ring >= a.nz + 1, "halo: not enough shared memory for the plane ring");
-  a.b_stages = (budget_total - a.ring * a.slot_bytes) / a.b_bytes;
-  if (a.b_stages > kMaxBStages) a.b_stages = kMaxBStages;
-  S3D_CHECK_ARG(a.b_stages >= 2, "halo: not enough shared memory for the weight ring");
+  a.w_stages = (budget_total - a.ring * a.slot_bytes) / a.w_bytes;
+  if (a.w_stages > kMaxWStages) a.w_stages = kMaxWStages;
+  S3D_CHECK_ARG(a.w_stages >= 2, "halo: not enough shared memory for the weight ring");
   a.cols_x = ceil_div(p.oW, kTX);  a.cols_y = ceil_div(p.oH, kTY);
-  a.n_ntiles = p.Cout / p.bn;
-  const int64_t total = (int64_t)p.N * a.cols_x * a.cols_y * a.n_ntiles;
+  const int64_t total = (int64_t)p.N * a.cols_x * a.cols_y * a.n_mtiles;
   S3D_CHECK_ARG(total > 0 && total < (1ll << 31), "halo: column count out of range");
   a.total_cols = (int)total;
-  a.idesc = ptx::make_instr_desc(tf32 ? 2 : 1, 128, p.bn);
-  const char* bo = getenv("S3D_HALO_BASE_OFFSET");
-  a.base_offset_mode = bo ? atoi(bo) : 0;
-  const char* dbg = getenv("S3D_HALO_DEBUG");
-  a.debug = dbg ? atoi(dbg) : 0;
+  a.idesc = ptx::make_instr_desc(tf32 ? 2 : 1, a.um, kPix);
+  { const char* dbg = getenv("S3D_HALO_DEBUG"); a.debug = dbg ? atoi(dbg) : 0; }
 
-  CUtensorMap map_a, map_b;
+  const CUtensorMapSwizzle sw = a.row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                              : a.row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+  CUtensorMap map_x, map_w;
   cuuint32_t box[5] = {(cuuint32_t)a.kc, kHX, kHY, 1, 1};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  int rc = encode_act_map(&map_a, in, esz, tf32, p.Cin, p.iW, p.iH, p.iD, p.N, box, estr, CU_TENSOR_MAP_SWIZZLE_128B);
+  int rc = encode_act_map(&map_x, in, esz, tf32, p.Cin, p.iW, p.iH, p.iD, p.N, box, estr, sw);
   if (rc != S3D_OK) return rc;
-  rc = encode_weight_map(&map_b, w, esz, tf32, p.Cin, p.Cout, p.ntaps, a.kc, p.bn, CU_TENSOR_MAP_SWIZZLE_128B);
+  rc = encode_weight_map(&map_w, w, esz, tf32, p.Cin, p.Cout, p.ntaps, a.kc, a.um, sw, a.tps);
   if (rc != S3D_OK) return rc;
 
-  const int smem_bytes = a.ring * a.slot_bytes + a.b_stages * a.b_bytes + 1024;
+  const int smem_bytes = a.ring * a.slot_bytes + a.w_stages * a.w_bytes + 1024;
   auto kern = tf32 ? conv_halo_kernel<true> : conv_halo_kernel<false>;
   static int attr_set[2] = {0, 0};
   if (attr_set[tf32] < smem_bytes) {
@@ -353,7 +443,7 @@ int conv_halo_launch(const S3dConvParams* p_in, const void* in, const void* w, c
   }
   int grid = num_sms();
   if (grid > a.total_cols) grid = a.total_cols;
-  kern<<<grid, kThreads, smem_bytes, stream>>>(map_a, map_b, a);
+  kern<<<grid, kThreads, smem_bytes, stream>>>(map_x, map_w, a);
   S3D_LAUNCH_CHECK();
   return S3D_OK;
 }

@@ -80,6 +80,56 @@ soft_argmin_kernel(const float* __restrict__ cost, float* __restrict__ disp, int
 }
 
 // ------------------------------------------------------------------------------------------
+// tap-plane gather + soft-argmin: the Cout = 1 classifier conv of the aggregation stack.
+// A 3x3x3 conv with ONE output channel wastes a 128-row tensor-core tile per tap, so it is computed
+// as a pointwise GEMM P[pix][t] = W_t . x[pix] (27 taps = 27 output "channels", one pass over the
+// activations, tensor cores) followed by this gather: cost[z,y,x] = sum_t P[z+kz-1, y+ky-1, x+kx-1][t],
+// fused with the soft-argmin over z so the cost volume itself never reaches HBM.
+// One thread per (n, y, x); marching over the input plane z' it keeps the three partial sums of the
+// output planes z'-1, z', z'+1 in registers and retires plane z'-1 into an online softmax.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+tap_gather_soft_argmin_kernel(const float* __restrict__ P, float* __restrict__ disp, float* __restrict__ cost_out,
+                              int N, int D, int h, int w, int ts, float sign) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y, n = blockIdx.z;
+  if (x >= w) return;
+  const int64_t plane = (int64_t)h * w;
+  const float* Pn = P + (int64_t)n * D * plane * ts;
+  float m = -INFINITY, s = 0.f, t = 0.f;
+  float c0 = 0.f, c1 = 0.f, c2 = 0.f;            // partial costs of output planes z'-1, z', z'+1
+  auto retire = [&](int z, float c) {
+    if (cost_out) cost_out[((int64_t)n * D + z) * plane + (int64_t)y * w + x] = c;
+    const float v = sign * c;
+    if (v > m) { const float sc = expf(m - v); s *= sc; t *= sc; m = v; }
+    const float e = expf(v - m);  s += e;  t += e * (float)z;
+  };
+  for (int zi = 0; zi < D; ++zi) {
+    const float* Pz = Pn + (int64_t)zi * plane * ts;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;          // contributions of input plane zi with kz = 2, 1, 0
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int yy = y + ky - 1;
+      if (yy < 0 || yy >= h) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int xx = x + kx - 1;
+        if (xx < 0 || xx >= w) continue;
+        const float* p = Pz + ((int64_t)yy * w + xx) * ts + ky * 3 + kx;
+        a0 += __ldg(p + 18);   // kz = 2: input plane zi feeds output plane zi - 1
+        a1 += __ldg(p + 9);    // kz = 1: output plane zi
+        a2 += __ldg(p);        // kz = 0: output plane zi + 1
+      }
+    }
+    c0 += a0;  c1 += a1;  c2 += a2;
+    if (zi >= 1) retire(zi - 1, c0);
+    c0 = c1;  c1 = c2;  c2 = 0.f;
+  }
+  retire(D - 1, c0);
+  disp[(int64_t)n * plane + (int64_t)y * w + x] = t / s;
+}
+
+// ------------------------------------------------------------------------------------------
 // fused correlation + soft-argmax
 // ------------------------------------------------------------------------------------------
 constexpr int kXG = 4;   // x per thread
@@ -274,6 +324,18 @@ extern "C" int s3d_upsample_disp(const float* disp_q, float* disp, int N, int h,
   int64_t blocks = ceil_div64(total, 256);
   if (blocks > (int64_t)num_sms() * 16) blocks = (int64_t)num_sms() * 16;
   upsample_disp_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(disp_q, disp, N, h, w, H, W, scale);
+  S3D_LAUNCH_CHECK();
+  return S3D_OK;
+}
+
+extern "C" int s3d_tap_gather_soft_argmin(const float* taps, float* disp, float* cost_out, int N, int D, int h, int w,
+                                          int tap_stride, float sign, void* stream) {
+  if (!taps || !disp) { set_error("tap_gather_soft_argmin: null argument"); return S3D_ERR_INVALID; }
+  S3D_CHECK_ARG(N > 0 && D > 0 && h > 0 && w > 0 && tap_stride >= 27 && h < 65536 && N < 65536,
+                "tap_gather_soft_argmin: bad shape");
+  dim3 grid(ceil_div(w, 128), h, N);
+  tap_gather_soft_argmin_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(taps, disp, cost_out, N, D, h, w,
+                                                                                      tap_stride, sign);
   S3D_LAUNCH_CHECK();
   return S3D_OK;
 }

@@ -131,14 +131,14 @@ inline int encode_act_map(CUtensorMap* m, const void* base, int esz, bool f32, i
   return S3D_OK;
 }
 
-// Packed weights [rows][Cout][Cin] as a 3-D map (Cin, Cout, rows), box (kc, bn, 1).
+// Packed weights [rows][Cout][Cin] as a 3-D map (Cin, Cout, rows), box (kc, bn, box_taps).
 inline int encode_weight_map(CUtensorMap* m, const void* base, int esz, bool f32, int Cin, int Cout, int rows, int kc,
-                             int bn, CUtensorMapSwizzle sw) {
+                             int bn, CUtensorMapSwizzle sw, int box_taps = 1) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return S3D_ERR_CUDA; }
   cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)Cout, (cuuint64_t)rows};
   cuuint64_t strides[2] = {(cuuint64_t)Cin * esz, (cuuint64_t)Cin * esz * Cout};
-  cuuint32_t box[3] = {(cuuint32_t)kc, (cuuint32_t)bn, 1};
+  cuuint32_t box[3] = {(cuuint32_t)kc, (cuuint32_t)bn, (cuuint32_t)box_taps};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
                    const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,

@@ -32,13 +32,26 @@ __global__ void pack_image_kernel(const float* __restrict__ img, const float* __
   const int64_t plane = (int64_t)H * W, total = plane * B;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t b = i / plane, pix = i % plane;
-    T* o = out + i * Cpad;
     const float* ip = img + b * 3 * plane + pix;
-    o[0] = from_f32<T>(ip[0]);
-    o[1] = from_f32<T>(ip[plane]);
-    o[2] = from_f32<T>(ip[2 * plane]);
-    o[3] = from_f32<T>(disp ? disp[i] * disp_scale : 0.f);
-    for (int c = 4; c < Cpad; ++c) o[c] = from_f32<T>(0.f);
+    const float c0 = ip[0], c1 = ip[plane], c2 = ip[2 * plane], c3 = disp ? disp[i] * disp_scale : 0.f;
+    T* o = out + i * Cpad;
+    if (sizeof(T) == 2 && (Cpad & 7) == 0) {
+      // 16-byte stores: channels 0-3 real, the rest zero
+      uint4 v0 = make_uint4(0, 0, 0, 0);
+      __nv_bfloat162 p01 = __floats2bfloat162_rn(c0, c1), p23 = __floats2bfloat162_rn(c2, c3);
+      v0.x = *reinterpret_cast<uint32_t*>(&p01);
+      v0.y = *reinterpret_cast<uint32_t*>(&p23);
+      uint4* o4 = reinterpret_cast<uint4*>(o);
+      o4[0] = v0;
+      for (int c = 1; c < Cpad / 8; ++c) o4[c] = make_uint4(0, 0, 0, 0);
+    } else if (sizeof(T) == 4 && (Cpad & 3) == 0) {
+      float4* o4 = reinterpret_cast<float4*>(o);
+      o4[0] = make_float4(c0, c1, c2, c3);
+      for (int c = 1; c < Cpad / 4; ++c) o4[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+      o[0] = from_f32<T>(c0);  o[1] = from_f32<T>(c1);  o[2] = from_f32<T>(c2);  o[3] = from_f32<T>(c3);
+      for (int c = 4; c < Cpad; ++c) o[c] = from_f32<T>(0.f);
+    }
   }
 }
 

@@ -164,7 +164,9 @@ class _StereoBase(nn.Module):
             for n in ('dres0a', 'dres0b', 'dres1a', 'dres1b', 'cls_a'):
                 seq = getattr(ag, n)
                 P[n] = PackedConv.from_conv(seq[0], seq[1], A.ACT_NONE if n == 'dres1b' else A.ACT_RELU, dc, dev)
-            P['cls_b'] = PackedConv.from_conv(ag.cls_b, None, A.ACT_NONE, dc, dev)
+            # Cout = 1: per-tap projections (pointwise GEMM, 27 "channels") + gather/soft-argmin kernel
+            wb = ag.cls_b.weight                                      # [1, A, 3, 3, 3]
+            P['cls_b'] = PackedConv.from_pointwise(wb[0].reshape(wb.shape[1], 27).t(), None, None, A.ACT_NONE, dc, dev)
         for i, seq in enumerate(self.rgbd_encoder.layers):
             P['rec%d' % i] = PackedConv.from_conv(seq[0], seq[1], A.ACT_RELU, dc, dev)
         self._pack_head(P, dc, dev)
@@ -214,9 +216,9 @@ class _StereoBase(nn.Module):
             y = self._conv('dres1a', a, out=self._bufo('a2', 'dres1a', a))
             a = self._conv('dres1b', y, residual=a, out=self._bufo('a3', 'dres1b', y))
             c = self._conv('cls_a', a, out=self._bufo('a0', 'cls_a', a))
-            cost = self._buf('cost', (2 * B, D, h, w), torch.float32)
-            self._conv('cls_b', c, out=cost, out_view=(0, (D * h * w, h * w, w, 1)), cout_store=1)
-            ops.soft_argmin(cost, -1.0, out=disp_q)
+            taps = self._conv('cls_b', c, out=self._buf('taps', (2 * B, D, h, w, self._packed['cls_b'].cout_pad),
+                                                        torch.float32))
+            ops.tap_gather_soft_argmin(taps, -1.0, out=disp_q)
         else:
             ops.corr_soft_argmin(feat, B, D, out=disp_q)
         disp = ops.upsample_disp(disp_q, H, W, 4.0, out=self._buf('disp', (2 * B, H, W), torch.float32))

@@ -72,6 +72,21 @@ def soft_argmin(cost, sign=-1.0, out=None):
     return out
 
 
+def tap_gather_soft_argmin(taps, sign=-1.0, out=None, want_cost=False):
+    """taps fp32 [N,D,h,w,S>=27] (per-tap projections) -> disp fp32 [N,h,w]; see include/s3d.h."""
+    _chk(taps, out)
+    assert taps.dtype == torch.float32 and taps.dim() == 5
+    N, D, h, w, S = taps.shape
+    if out is None:
+        out = torch.empty((N, h, w), dtype=torch.float32, device=taps.device)
+    cost = torch.empty((N, D, h, w), dtype=torch.float32, device=taps.device) if want_cost else None
+    rc = _lib.load().s3d_tap_gather_soft_argmin(taps.data_ptr(), out.data_ptr(), cost.data_ptr() if want_cost else None,
+                                                N, D, h, w, S, float(sign), _stream())
+    _lib.check(rc, 's3d_tap_gather_soft_argmin')
+    _lib.count_launch()
+    return (out, cost) if want_cost else out
+
+
 def corr_soft_argmin(feat, B, D, out=None, want_cost=False):
     """feat [2B,1,h,w,C] -> disp fp32 [2B,h,w] (fused correlation + soft-argmax)."""
     _chk(feat, out)

@@ -137,3 +137,18 @@ def test_direct_conv_family_fp32():
     xd = torch.randn(2, 6, 2, 3, 4)
     pc = PackedConv.from_deconv_k4s2p1(dc, None, lib.ACT_NONE, lib.DTYPE_F32, 'cuda')
     torch.testing.assert_close(_run(pc, xd, 'direct')[..., :5], to_cl(dc(xd)), rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize('N,C,D,h,w', [(2, 16, 8, 9, 13), (1, 64, 32, 16, 16), (1, 8, 1, 3, 3), (1, 8, 2, 1, 5)])
+def test_tap_gather_soft_argmin_equals_cout1_conv(N, C, D, h, w):
+    """cls_b path: pointwise per-tap projections + gather == Conv3d(C,1,3,1,1) -> soft-argmin."""
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(N, C, D, h, w, generator=g)
+    wt = torch.randn(1, C, 3, 3, 3, generator=g) * 0.3
+    cost_ref = F.conv3d(x, wt, padding=1).squeeze(1)
+    ref = O.soft_argmin(cost_ref)
+    taps = torch.einsum('ncdhw,tc->ndhwt', x, wt[0].reshape(C, 27).t())
+    taps = torch.cat([taps, torch.zeros(N, D, h, w, 5)], -1).contiguous()        # stride 32
+    got, cost = ops.tap_gather_soft_argmin(taps.cuda(), -1.0, want_cost=True)
+    torch.testing.assert_close(cost.cpu(), cost_ref, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(got.cpu(), ref, rtol=1e-4, atol=1e-4)
