@@ -59,6 +59,7 @@ struct HaloArgs {
   int slot_bytes;     // nchunks * chunk_stride
   int ring;           // plane slots
   int um;             // UMMA M: 64 or 128 (output channels per tile)
+  int zstack;         // 1: M = 128 = two output planes (z, z+1) x 64 channels stacked (3x3x3, Cout <= 64)
   int tps;            // taps per weight stage (128 / row_bytes)
   int w_stages, w_bytes, w_tx;
   int cols_x, cols_y, n_mtiles, total_cols;
@@ -106,7 +107,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
   const int D = a.p.oD;
   const int nz = a.nz;
   const int pad_z = (nz - 1) >> 1;
-  const int nplanes = D + nz - 1;            // input planes per column (incl. the zero planes beyond the volume)
+  // z-stacked mode: one step = output planes (2s, 2s+1); it reads the 4 input planes 2s-1 .. 2s+2.
+  const int zs = a.zstack ? 2 : 1;           // output planes per step
+  const int nsteps = (D + zs - 1) / zs;
+  const int win = a.zstack ? 4 : nz;         // input planes read by one step
+  const int nplanes = zs * (nsteps - 1) + win;   // input planes per column (incl. zero planes beyond the volume)
   const int ntaps = a.p.ntaps;
   const int plane_tx = a.nchunks * kPlaneRows * a.row_bytes;
 
@@ -153,18 +158,36 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       int col_base = 0;
       for (int col = blockIdx.x; col < a.total_cols; col += gridDim.x) {
         const Col c = decode_col(a, col);
-        for (int z = 0; z < D; ++z) {
-          const int need = col_base + z + nz;                  // planes this step reads (global count)
-          while (issued < need) issue_plane(true);
-          // planes of the next step (possibly of the next column): fetched opportunistically below
-          const int need_next = (z + 1 < D) ? need + 1 : col_base + nplanes + nz;
-          for (int t0 = 0; t0 < ntaps; t0 += a.tps) {
-            if (issued < need_next) issue_plane(false);
-            for (int ch = 0; ch < a.nchunks; ++ch) {
-              ptx::mbar_wait(&ctrl.w_empty[ws], wphase ^ 1);
-              ptx::mbar_arrive_expect_tx(&ctrl.w_full[ws], a.w_tx);
-              ptx::tma_load_3d(smem_w + ws * a.w_bytes, &map_w, &ctrl.w_full[ws], ch * a.kc, c.mt * a.um, t0);
-              if (++ws == a.w_stages) { ws = 0; wphase ^= 1; }
+        for (int st = 0; st < nsteps; ++st) {
+          const int need = col_base + st * zs + win;            // planes this step reads (global count)
+          // the first plane(s) must be there before the step starts; later ones are awaited lazily by the
+          // MMA warp, so fetch them without blocking the weight stream whenever their slot is free
+          const int need_first = a.zstack ? need - 2 : need;
+          while (issued < need_first) issue_plane(true);
+          const int need_next = (st + 1 < nsteps) ? need + zs : col_base + nplanes + win;
+          if (a.zstack) {
+            for (int sv = 0; sv < 4; ++sv) {                    // stacked variant: rows 0-63 use kz = sv, rows 64-127 kz = sv-1
+              if (sv == 2) while (issued < need) issue_plane(true);
+              for (int kyx = 0; kyx < 9; ++kyx) {
+                if (issued < need_next) issue_plane(false);
+                ptx::mbar_wait(&ctrl.w_empty[ws], wphase ^ 1);
+                ptx::mbar_arrive_expect_tx(&ctrl.w_full[ws], a.w_tx);
+                uint8_t* dst = smem_w + ws * a.w_bytes;
+                // a tap coordinate of `ntaps` is out of range: the TMA unit zero-fills that half
+                ptx::tma_load_3d(dst, &map_w, &ctrl.w_full[ws], 0, 0, sv <= 2 ? sv * 9 + kyx : ntaps);
+                ptx::tma_load_3d(dst + 64 * a.row_bytes, &map_w, &ctrl.w_full[ws], 0, 0, sv >= 1 ? (sv - 1) * 9 + kyx : ntaps);
+                if (++ws == a.w_stages) { ws = 0; wphase ^= 1; }
+              }
+            }
+          } else {
+            for (int t0 = 0; t0 < ntaps; t0 += a.tps) {
+              if (issued < need_next) issue_plane(false);
+              for (int ch = 0; ch < a.nchunks; ++ch) {
+                ptx::mbar_wait(&ctrl.w_empty[ws], wphase ^ 1);
+                ptx::mbar_arrive_expect_tx(&ctrl.w_full[ws], a.w_tx);
+                ptx::tma_load_3d(smem_w + ws * a.w_bytes, &map_w, &ctrl.w_full[ws], ch * a.kc, c.mt * a.um, t0);
+                if (++ws == a.w_stages) { ws = 0; wphase ^= 1; }
+              }
             }
           }
         }
@@ -186,66 +209,116 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     const uint64_t w_hi = desc_hi(8 * rb, rb);                // weights: dense rows
     const int kper = rb >> 5;                                 // tcgen05.mma per tap per chunk (32 B of K each)
     const uint32_t w_tap_step = (a.um * rb) >> 4;             // next tap inside a weight stage
-    for (int col = blockIdx.x; col < a.total_cols; col += gridDim.x) {
-      for (int z = 0; z < D; ++z) {
-        ptx::mbar_wait(&ctrl.acc_empty[buf], acc_phase ^ 1);
-        const int need = col_base + z + nz;
-        while (waited < need) {
-          ptx::mbar_wait(&ctrl.plane_full[waited % ring], (waited / ring) & 1);
-          ++waited;
-        }
-        ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + buf * kPix;
-        uint32_t accum = 0;
-        const int slot0 = (col_base + z) % ring;
-        for (int t0 = 0; t0 < ntaps; t0 += a.tps) {
-          for (int ch = 0; ch < a.nchunks; ++ch) {
-            ptx::mbar_wait(&ctrl.w_full[ws], wphase);
-            ptx::tc_fence_after();
-            const uint32_t wlo = desc_lo(w_u32 + ws * a.w_bytes);
-            for (int tt = 0; tt < a.tps; ++tt) {
-              const int tap = t0 + tt;
-              if (tap < ntaps) {
-                const int kz = tap / 9, kyx = tap - kz * 9;
-                const int ky = kyx / 3, kx = kyx - ky * 3;
-                int slot = slot0 + kz;  if (slot >= ring) slot -= ring;
-                const uint32_t xlo = desc_lo(planes_u32 + slot * a.slot_bytes + ch * a.chunk_stride + ((a.debug == 1 || a.debug == 2) ? 0 : (ky * kHX + kx) * rb));
-                const uint64_t wdesc = w_hi | (wlo + tt * w_tap_step);
-                const uint64_t xdesc = x_hi | xlo;
-                if (ptx::elect_one()) {
-                  for (int k = 0; k < kper; ++k) {
-                    if (kTF32) ptx::mma_tf32(d_tmem, wdesc + 2 * k, xdesc + 2 * k, a.idesc, accum | k);
-                    else       ptx::mma_bf16(d_tmem, wdesc + 2 * k, xdesc + 2 * k, a.idesc, accum | k);
-                  }
-                }
-                __syncwarp();
-                accum = 1;
-              }
+    if (a.zstack) {
+      for (int col = blockIdx.x; col < a.total_cols; col += gridDim.x) {
+        for (int st = 0; st < nsteps; ++st) {
+          ptx::mbar_wait(&ctrl.acc_empty[buf], acc_phase ^ 1);
+          const uint32_t d_tmem = tmem_base + buf * kPix;
+          const int j0 = col_base + st * 2;                    // global index of input plane 2*st - 1
+          uint32_t accum = 0;
+          for (int sv = 0; sv < 4; ++sv) {
+            while (waited < j0 + sv + 1) {
+              ptx::mbar_wait(&ctrl.plane_full[waited % ring], (waited / ring) & 1);
+              ++waited;
             }
-            if (ptx::elect_one()) ptx::tc_commit(&ctrl.w_empty[ws]);
+            ptx::tc_fence_after();
+            const int slot = (j0 + sv) % ring;
+            const uint32_t slot_lo = planes_u32 + slot * a.slot_bytes;
+            for (int kyx = 0; kyx < 9; ++kyx) {
+              const int ky = kyx / 3, kx = kyx - ky * 3;
+              ptx::mbar_wait(&ctrl.w_full[ws], wphase);
+              ptx::tc_fence_after();
+              const uint64_t wdesc = w_hi | desc_lo(w_u32 + ws * a.w_bytes);
+              const uint64_t xdesc = x_hi | desc_lo(slot_lo + (ky * kHX + kx) * rb);
+              if (ptx::elect_one()) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  if (kTF32) ptx::mma_tf32(d_tmem, wdesc + 2 * k, xdesc + 2 * k, a.idesc, accum | k);
+                  else       ptx::mma_bf16(d_tmem, wdesc + 2 * k, xdesc + 2 * k, a.idesc, accum | k);
+                }
+                ptx::tc_commit(&ctrl.w_empty[ws]);
+              }
+              __syncwarp();
+              accum = 1;
+              if (++ws == a.w_stages) { ws = 0; wphase ^= 1; }
+            }
+            // input planes 2st-1 and 2st are dead once their 9 taps are issued; the other two feed the
+            // next step too, except at the end of the column
+            if (ptx::elect_one()) {
+              if (sv < 2 || st == nsteps - 1) ptx::tc_commit(&ctrl.plane_empty[slot]);
+            }
             __syncwarp();
-            if (++ws == a.w_stages) { ws = 0; wphase ^= 1; }
           }
+          if (ptx::elect_one()) ptx::tc_commit(&ctrl.acc_full[buf]);
+          __syncwarp();
+          if (++buf == 2) { buf = 0; acc_phase ^= 1; }
         }
-        if (ptx::elect_one()) {
-          ptx::tc_commit(&ctrl.acc_full[buf]);
-          // the oldest plane is dead after this step; at the end of the column so are the rest
-          ptx::tc_commit(&ctrl.plane_empty[(col_base + z) % ring]);
-          if (z == D - 1)
-            for (int e = 1; e < nz; ++e) ptx::tc_commit(&ctrl.plane_empty[(col_base + z + e) % ring]);
-        }
-        __syncwarp();
-        if (++buf == 2) { buf = 0; acc_phase ^= 1; }
+        col_base += nplanes;
       }
-      col_base += nplanes;
+    } else {
+    for (int col = blockIdx.x; col < a.total_cols; col += gridDim.x) {
+        for (int z = 0; z < D; ++z) {
+          ptx::mbar_wait(&ctrl.acc_empty[buf], acc_phase ^ 1);
+          const int need = col_base + z + nz;
+          while (waited < need) {
+            ptx::mbar_wait(&ctrl.plane_full[waited % ring], (waited / ring) & 1);
+            ++waited;
+          }
+          ptx::tc_fence_after();
+          const uint32_t d_tmem = tmem_base + buf * kPix;
+          uint32_t accum = 0;
+          const int slot0 = (col_base + z) % ring;
+          for (int t0 = 0; t0 < ntaps; t0 += a.tps) {
+            for (int ch = 0; ch < a.nchunks; ++ch) {
+              ptx::mbar_wait(&ctrl.w_full[ws], wphase);
+              ptx::tc_fence_after();
+              const uint32_t wlo = desc_lo(w_u32 + ws * a.w_bytes);
+              for (int tt = 0; tt < a.tps; ++tt) {
+                const int tap = t0 + tt;
+                if (tap < ntaps) {
+                  const int kz = tap / 9, kyx = tap - kz * 9;
+                  const int ky = kyx / 3, kx = kyx - ky * 3;
+                  int slot = slot0 + kz;  if (slot >= ring) slot -= ring;
+                  const uint32_t xlo = desc_lo(planes_u32 + slot * a.slot_bytes + ch * a.chunk_stride + ((a.debug == 1 || a.debug == 2) ? 0 : (ky * kHX + kx) * rb));
+                  const uint64_t wdesc = w_hi | (wlo + tt * w_tap_step);
+                  const uint64_t xdesc = x_hi | xlo;
+                  if (ptx::elect_one()) {
+                    for (int k = 0; k < kper; ++k) {
+                      if (kTF32) ptx::mma_tf32(d_tmem, wdesc + 2 * k, xdesc + 2 * k, a.idesc, accum | k);
+                      else       ptx::mma_bf16(d_tmem, wdesc + 2 * k, xdesc + 2 * k, a.idesc, accum | k);
+                    }
+                  }
+                  __syncwarp();
+                  accum = 1;
+                }
+              }
+              if (ptx::elect_one()) ptx::tc_commit(&ctrl.w_empty[ws]);
+              __syncwarp();
+              if (++ws == a.w_stages) { ws = 0; wphase ^= 1; }
+            }
+          }
+          if (ptx::elect_one()) {
+            ptx::tc_commit(&ctrl.acc_full[buf]);
+            // the oldest plane is dead after this step; at the end of the column so are the rest
+            ptx::tc_commit(&ctrl.plane_empty[(col_base + z) % ring]);
+            if (z == D - 1)
+              for (int e = 1; e < nz; ++e) ptx::tc_commit(&ctrl.plane_empty[(col_base + z + e) % ring]);
+          }
+          __syncwarp();
+          if (++buf == 2) { buf = 0; acc_phase ^= 1; }
+        }
+        col_base += nplanes;
+      }
     }
   } else if (warp >= 4) {
     // ================= epilogue =================
     // TMEM lane = output channel.  M = 128: lane l of quarter q is channel 32q + l.  M = 64: the 64
     // rows sit in lanes 0-15 of each quarter (row 16q + l), lanes 16-31 are unused.
     const int q = warp & 3;
+    // z-stacked: lanes 0-63 are output plane 2s (channel = lane), lanes 64-127 plane 2s+1.
     const bool lane_has_row = a.um == 128 || lane < 16;
-    const int ch_local = a.um == 128 ? q * 32 + lane : q * 16 + lane;
+    const int ch_local = a.zstack ? (q & 1) * 32 + lane : (a.um == 128 ? q * 32 + lane : q * 16 + lane);
+    const int zsel = a.zstack ? (q >> 1) : 0;
     const bool out_bf16 = a.p.out_dtype == S3D_DTYPE_BF16;
     const bool simple_act = a.p.act == S3D_ACT_NONE || a.p.act == S3D_ACT_RELU || a.p.act == S3D_ACT_LEAKY;
     // none / relu / leaky as one branch-free formula: max(v,0) + slope * min(v,0)
@@ -265,12 +338,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       const int ylim = a.p.oH - c.y0;
       const bool interior = xlim >= kTX && ylim >= kTY;
       const bool warp_any = __any_sync(0xffffffffu, ch_ok);
-      for (int z = 0; z < D; ++z) {
+      for (int st = 0; st < nsteps; ++st) {
+        const int z = st * zs + zsel;
         ptx::mbar_wait(&ctrl.acc_full[buf], acc_phase);
         ptx::tc_fence_after();
         const uint32_t taddr = tmem_base + buf * kPix + (static_cast<uint32_t>(q * 32) << 16);
         const int64_t zoff = col_off + (int64_t)z * a.p.osD;
-        if (warp_any) {
+        if (warp_any && z < D) {
           if (interior && simple_act) {
             // fast path (interior patches): no bounds checks, no per-pixel branches; the dtype /
             // residual variants are warp-uniform branches around fully unrolled bodies.
@@ -403,7 +477,8 @@ int conv_halo_launch(const S3dConvParams* p_in, const void* in, const void* w, c
   a.nchunks = cin_bytes / a.row_bytes;
   a.chunk_stride = (kPlaneRows * a.row_bytes + 1023) / 1024 * 1024;
   a.slot_bytes = a.nchunks * a.chunk_stride;
-  a.um = p.Cout > 64 ? 128 : 64;
+  a.zstack = a.nz == 3 && a.row_bytes == 128 && a.nchunks == 1 && p.Cout <= 64 && getenv("S3D_NO_ZSTACK") == nullptr;
+  a.um = (p.Cout > 64 || a.zstack) ? 128 : 64;
   a.n_mtiles = p.Cout > 64 ? p.Cout / 128 : 1;
   a.tps = 128 / a.row_bytes;
   // weight map [taps][Cout][Cin]: a stage is a (kc, um, tps) box; rows beyond Cout / taps beyond ntaps
@@ -431,7 +506,7 @@ int conv_halo_launch(const S3dConvParams* p_in, const void* in, const void* w, c
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   int rc = encode_act_map(&map_x, in, esz, tf32, p.Cin, p.iW, p.iH, p.iD, p.N, box, estr, sw);
   if (rc != S3D_OK) return rc;
-  rc = encode_weight_map(&map_w, w, esz, tf32, p.Cin, p.Cout, p.ntaps, a.kc, a.um, sw, a.tps);
+  rc = encode_weight_map(&map_w, w, esz, tf32, p.Cin, p.Cout, p.ntaps, a.kc, a.zstack ? 64 : a.um, sw, a.tps);
   if (rc != S3D_OK) return rc;
 
   const int smem_bytes = a.ring * a.slot_bytes + a.w_stages * a.w_bytes + 1024;
