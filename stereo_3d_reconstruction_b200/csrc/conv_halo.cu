@@ -168,14 +168,19 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
           if (a.zstack) {
             for (int sv = 0; sv < 4; ++sv) {                    // stacked variant: rows 0-63 use kz = sv, rows 64-127 kz = sv-1
               if (sv == 2) while (issued < need) issue_plane(true);
-              for (int kyx = 0; kyx < 9; ++kyx) {
+              for (int kyx0 = 0; kyx0 < 9; kyx0 += a.tps) {       // one weight stage = up to tps stacked taps
                 if (issued < need_next) issue_plane(false);
+                const int nt = min(a.tps, 9 - kyx0);
                 ptx::mbar_wait(&ctrl.w_empty[ws], wphase ^ 1);
-                ptx::mbar_arrive_expect_tx(&ctrl.w_full[ws], a.w_tx);
+                ptx::mbar_arrive_expect_tx(&ctrl.w_full[ws], nt * 128 * a.row_bytes);
                 uint8_t* dst = smem_w + ws * a.w_bytes;
-                // a tap coordinate of `ntaps` is out of range: the TMA unit zero-fills that half
-                ptx::tma_load_3d(dst, &map_w, &ctrl.w_full[ws], 0, 0, sv <= 2 ? sv * 9 + kyx : ntaps);
-                ptx::tma_load_3d(dst + 64 * a.row_bytes, &map_w, &ctrl.w_full[ws], 0, 0, sv >= 1 ? (sv - 1) * 9 + kyx : ntaps);
+                for (int tt = 0; tt < nt; ++tt) {
+                  // a tap coordinate of `ntaps` is out of range: the TMA unit zero-fills that half
+                  const int kyx = kyx0 + tt;
+                  ptx::tma_load_3d(dst, &map_w, &ctrl.w_full[ws], 0, 0, sv <= 2 ? sv * 9 + kyx : ntaps);
+                  ptx::tma_load_3d(dst + 64 * a.row_bytes, &map_w, &ctrl.w_full[ws], 0, 0, sv >= 1 ? (sv - 1) * 9 + kyx : ntaps);
+                  dst += 128 * a.row_bytes;
+                }
                 if (++ws == a.w_stages) { ws = 0; wphase ^= 1; }
               }
             }
@@ -224,17 +229,21 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             ptx::tc_fence_after();
             const int slot = (j0 + sv) % ring;
             const uint32_t slot_lo = planes_u32 + slot * a.slot_bytes;
-            for (int kyx = 0; kyx < 9; ++kyx) {
-              const int ky = kyx / 3, kx = kyx - ky * 3;
+            for (int kyx0 = 0; kyx0 < 9; kyx0 += a.tps) {
+              const int nt = min(a.tps, 9 - kyx0);
               ptx::mbar_wait(&ctrl.w_full[ws], wphase);
               ptx::tc_fence_after();
-              const uint64_t wdesc = w_hi | desc_lo(w_u32 + ws * a.w_bytes);
-              const uint64_t xdesc = x_hi | desc_lo(slot_lo + (ky * kHX + kx) * rb);
+              const uint32_t wlo = desc_lo(w_u32 + ws * a.w_bytes);
               if (ptx::elect_one()) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  if (kTF32) ptx::mma_tf32(d_tmem, wdesc + 2 * k, xdesc + 2 * k, a.idesc, accum | k);
-                  else       ptx::mma_bf16(d_tmem, wdesc + 2 * k, xdesc + 2 * k, a.idesc, accum | k);
+                for (int tt = 0; tt < nt; ++tt) {
+                  const int kyx = kyx0 + tt;
+                  const int ky = kyx / 3, kx = kyx - ky * 3;
+                  const uint64_t wdesc = w_hi | (wlo + tt * ((128 * rb) >> 4));
+                  const uint64_t xdesc = x_hi | desc_lo(slot_lo + (ky * kHX + kx) * rb);
+                  for (int k = 0; k < kper; ++k) {
+                    if (kTF32) ptx::mma_tf32(d_tmem, wdesc + 2 * k, xdesc + 2 * k, a.idesc, accum | tt | k);
+                    else       ptx::mma_bf16(d_tmem, wdesc + 2 * k, xdesc + 2 * k, a.idesc, accum | tt | k);
+                  }
                 }
                 ptx::tc_commit(&ctrl.w_empty[ws]);
               }
@@ -477,7 +486,7 @@ int conv_halo_launch(const S3dConvParams* p_in, const void* in, const void* w, c
   a.nchunks = cin_bytes / a.row_bytes;
   a.chunk_stride = (kPlaneRows * a.row_bytes + 1023) / 1024 * 1024;
   a.slot_bytes = a.nchunks * a.chunk_stride;
-  a.zstack = a.nz == 3 && a.row_bytes == 128 && a.nchunks == 1 && p.Cout <= 64 && getenv("S3D_NO_ZSTACK") == nullptr;
+  a.zstack = a.nz == 3 && a.nchunks == 1 && p.Cout <= 64 && getenv("S3D_NO_ZSTACK") == nullptr;
   a.um = (p.Cout > 64 || a.zstack) ? 128 : 64;
   a.n_mtiles = p.Cout > 64 ? p.Cout / 128 : 1;
   a.tps = 128 / a.row_bytes;
@@ -506,7 +515,7 @@ int conv_halo_launch(const S3dConvParams* p_in, const void* in, const void* w, c
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   int rc = encode_act_map(&map_x, in, esz, tf32, p.Cin, p.iW, p.iH, p.iD, p.N, box, estr, sw);
   if (rc != S3D_OK) return rc;
-  rc = encode_weight_map(&map_w, w, esz, tf32, p.Cin, p.Cout, p.ntaps, a.kc, a.zstack ? 64 : a.um, sw, a.tps);
+  rc = encode_weight_map(&map_w, w, esz, tf32, p.Cin, p.Cout, p.ntaps, a.kc, a.zstack ? 64 : a.um, sw, a.zstack ? 1 : a.tps);
   if (rc != S3D_OK) return rc;
 
   const int smem_bytes = a.ring * a.slot_bytes + a.w_stages * a.w_bytes + 1024;
