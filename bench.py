@@ -235,7 +235,7 @@ def run_ours(args):
     n0 = lib.launches()
     with ClockSampler(local) as clk:
         ms = timed(step_resident, args.steps, args.warmup)
-    launches = (lib.launches() - n0) * args.steps // (args.steps + args.warmup)
+    launches = (lib.launches() - n0) // (args.steps + args.warmup)        # kernels of this library per step
     dom_ms = [a.elapsed_time(b) for a, b in dom_events[len(dom_layers) * args.warmup:]]
     model._conv = orig_conv
     ms_e2e = timed(step_e2e, args.steps, min(args.warmup, 2) or 1)
