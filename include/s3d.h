@@ -49,7 +49,7 @@ extern "C" {
 #define S3D_MAX_TAPS 64
 
 /* One convolution-like layer as an implicit GEMM:
- *   out[n, z*omz+ooz, y*omy+ooy, x*omx+oox, co] =
+ *   out[n*osN + (z*omz+ooz)*osD + (y*omy+ooy)*osH + (x*omx+oox)*osW + co*osC] =
  *     act( bias[co] + sum_{t<ntaps} sum_{ci<Cin}
  *            in[n, z*sz+dz[t], y*sy+dy[t], x*sx+dx[t], ci] * w[cls*ntaps+t, co, ci]  (+ residual) )
  * for (z,y,x) in the logical output grid oD x oH x oW; out-of-range input samples read 0.
@@ -62,13 +62,18 @@ typedef struct S3dConvParams {
   int32_t sz, sy, sx;               /* input stride per output step (1 or 2)            */
   int32_t ntaps, n_classes;         /* taps per class; 1 or 8 classes                   */
   int8_t  dz[S3D_MAX_TAPS], dy[S3D_MAX_TAPS], dx[S3D_MAX_TAPS]; /* [n_classes*ntaps]   */
-  int64_t osN, osD, osH, osW;       /* output element strides (channel stride is 1)     */
+  int64_t osN, osD, osH, osW;       /* output element strides of n, z, y, x              */
+  int64_t osC;                      /* output channel stride (1 = channels-last; h*w etc. = planar) */
   int32_t omz, omy, omx;            /* output coordinate multiplier                     */
   int32_t cout_store;               /* channels actually written (<= Cout)              */
   int32_t in_dtype, out_dtype;      /* S3D_DTYPE_*; weights have in_dtype               */
   int32_t act;  float act_param;
   int32_t tw, th, td, tn;           /* M-tile box, powers of two, tw*th*td*tn == 128    */
   int32_t bn;                       /* GEMM N tile: multiple of 16, <= 256, divides Cout */
+  /* Optional (may be NULL): weights of a stride-1 3x3x3 layer with Cout <= 64 pre-stacked for the
+   * z-stacked tensor-core tile, [4*9][128][Cin]: row block sv*9+kyx holds W[kz=sv,kyx] in rows 0..63
+   * and W[kz=sv-1,kyx] in rows 64..127 (zeros where kz is out of range or co >= Cout). */
+  const void* w_zstack;
 } S3dConvParams;
 
 const char* s3d_version(void);
@@ -100,8 +105,8 @@ int s3d_cost_volume_concat(const void* feat, void* vol, int B, int h, int w, int
 /* cost: fp32 [N,D,h,w] -> disp fp32 [N,h,w] = sum_d d*softmax_d(sign*cost).  sign=-1: soft-argmin. */
 int s3d_soft_argmin(const float* cost, float* disp, int N, int D, int h, int w, float sign,
                     void* stream);
-/* Cout=1 3x3x3 classifier conv + soft-argmin from per-tap planes.  taps: fp32 [N,D,h,w,tap_stride] with
- * taps[..., (kz*3+ky)*3+kx] = W[kz,ky,kx,:] . x[pixel,:] (a pointwise GEMM done by s3d_conv_igemm);
+/* Cout=1 3x3x3 classifier conv + soft-argmin from per-tap planes.  taps: fp32, line-planar [N,D,h,tap_stride,w] with
+ * taps[n,z,y,(kz*3+ky)*3+kx,x] = W[kz,ky,kx,:] . in[n,z,y,x,:] (a pointwise GEMM done by s3d_conv_igemm with osC=w);
  * cost[z,y,x] = sum_t taps[z+kz-1, y+ky-1, x+kx-1, t] (zero outside), disp = sum_z z*softmax_z(sign*cost).
  * cost_out may be NULL (debug: fp32 [N,D,h,w]). */
 int s3d_tap_gather_soft_argmin(const float* taps, float* disp, float* cost_out, int N, int D, int h, int w,

@@ -52,4 +52,7 @@ __device__ __forceinline__ float apply_act(float v, int act, float a) {
   }
 }
 
+// Out-of-line copy for epilogues that must stay small: 16 calls instead of 16 inlined switch bodies.
+static __device__ __noinline__ float apply_act_slow(float v, int act, float a) { return apply_act(v, act, a); }
+
 }  // namespace s3d

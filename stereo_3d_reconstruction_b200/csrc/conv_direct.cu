@@ -33,7 +33,7 @@ __global__ void conv_direct_kernel(const S3dConvParams p, const TIn* __restrict_
     if (bias) acc += bias[co];
     const int ooz = (cls >> 2) & 1, ooy = (cls >> 1) & 1, oox = cls & 1;
     const int64_t off = (int64_t)n * p.osN + (int64_t)(z * p.omz + ooz) * p.osD +
-                        (int64_t)(y * p.omy + ooy) * p.osH + (int64_t)(x * p.omx + oox) * p.osW + co;
+                        (int64_t)(y * p.omy + ooy) * p.osH + (int64_t)(x * p.omx + oox) * p.osW + (int64_t)co * p.osC;
     if (p.out_dtype == S3D_DTYPE_BF16) {
       if (residual) acc += __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(residual)[off]);
       reinterpret_cast<__nv_bfloat16*>(out)[off] = __float2bfloat16_rn(apply_act(acc, p.act, p.act_param));

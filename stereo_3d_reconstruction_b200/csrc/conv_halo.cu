@@ -60,6 +60,7 @@ struct HaloArgs {
   int ring;           // plane slots
   int um;             // UMMA M: 64 or 128 (output channels per tile)
   int zstack;         // 1: M = 128 = two output planes (z, z+1) x 64 channels stacked (3x3x3, Cout <= 64)
+  int prestacked;     // map_w is the host-stacked [36][128][Cin] tensor: one TMA box per weight stage
   int tps;            // taps per weight stage (128 / row_bytes)
   int w_stages, w_bytes, w_tx;
   int cols_x, cols_y, n_mtiles, total_cols;
@@ -172,14 +173,20 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
                 if (issued < need_next) issue_plane(false);
                 const int nt = min(a.tps, 9 - kyx0);
                 ptx::mbar_wait(&ctrl.w_empty[ws], wphase ^ 1);
-                ptx::mbar_arrive_expect_tx(&ctrl.w_full[ws], nt * 128 * a.row_bytes);
                 uint8_t* dst = smem_w + ws * a.w_bytes;
-                for (int tt = 0; tt < nt; ++tt) {
-                  // a tap coordinate of `ntaps` is out of range: the TMA unit zero-fills that half
-                  const int kyx = kyx0 + tt;
-                  ptx::tma_load_3d(dst, &map_w, &ctrl.w_full[ws], 0, 0, sv <= 2 ? sv * 9 + kyx : ntaps);
-                  ptx::tma_load_3d(dst + 64 * a.row_bytes, &map_w, &ctrl.w_full[ws], 0, 0, sv >= 1 ? (sv - 1) * 9 + kyx : ntaps);
-                  dst += 128 * a.row_bytes;
+                if (a.prestacked) {
+                  // one box of tps stacked taps (taps past kyx = 8 belong to the next variant / are zero-filled: unused)
+                  ptx::mbar_arrive_expect_tx(&ctrl.w_full[ws], a.w_tx);
+                  ptx::tma_load_3d(dst, &map_w, &ctrl.w_full[ws], 0, 0, sv * 9 + kyx0);
+                } else {
+                  ptx::mbar_arrive_expect_tx(&ctrl.w_full[ws], nt * 128 * a.row_bytes);
+                  for (int tt = 0; tt < nt; ++tt) {
+                    // a tap coordinate of `ntaps` is out of range: the TMA unit zero-fills that half
+                    const int kyx = kyx0 + tt;
+                    ptx::tma_load_3d(dst, &map_w, &ctrl.w_full[ws], 0, 0, sv <= 2 ? sv * 9 + kyx : ntaps);
+                    ptx::tma_load_3d(dst + 64 * a.row_bytes, &map_w, &ctrl.w_full[ws], 0, 0, sv >= 1 ? (sv - 1) * 9 + kyx : ntaps);
+                    dst += 128 * a.row_bytes;
+                  }
                 }
                 if (++ws == a.w_stages) { ws = 0; wphase ^= 1; }
               }
@@ -451,7 +458,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
 bool conv_halo_eligible(const S3dConvParams* p) {
   const int esz = p->in_dtype == S3D_DTYPE_F32 ? 4 : 2;
   if (p->n_classes != 1 || p->sx != 1 || p->sy != 1 || p->sz != 1) return false;
-  if (p->omx != 1 || p->omy != 1 || p->omz != 1) return false;
+  if (p->omx != 1 || p->omy != 1 || p->omz != 1 || p->osC != 1) return false;
   if (p->ntaps != 9 && p->ntaps != 27) return false;
   if (p->oD != p->iD || p->oH != p->iH || p->oW != p->iW) return false;
   if (p->ntaps == 9 && p->iD != 1) return false;
@@ -515,7 +522,9 @@ int conv_halo_launch(const S3dConvParams* p_in, const void* in, const void* w, c
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   int rc = encode_act_map(&map_x, in, esz, tf32, p.Cin, p.iW, p.iH, p.iD, p.N, box, estr, sw);
   if (rc != S3D_OK) return rc;
-  rc = encode_weight_map(&map_w, w, esz, tf32, p.Cin, p.Cout, p.ntaps, a.kc, a.zstack ? 64 : a.um, sw, a.zstack ? 1 : a.tps);
+  a.prestacked = a.zstack && p.w_zstack != nullptr && getenv("S3D_NO_PRESTACK") == nullptr;
+  if (a.prestacked) rc = encode_weight_map(&map_w, p.w_zstack, esz, tf32, p.Cin, 128, 36, a.kc, 128, sw, a.tps);
+  else rc = encode_weight_map(&map_w, w, esz, tf32, p.Cin, p.Cout, p.ntaps, a.kc, a.zstack ? 64 : a.um, sw, a.zstack ? 1 : a.tps);
   if (rc != S3D_OK) return rc;
 
   const int smem_bytes = a.ring * a.slot_bytes + a.w_stages * a.w_bytes + 1024;

@@ -180,7 +180,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const int dzr = (r >> (a.lw + a.lh)) & (a.p.td - 1);
     const int dnr = r >> (a.lw + a.lh + a.ld);
     const EpiParams epi = {a.bias, a.residual, a.out, a.p.cout_store, a.p.out_dtype == S3D_DTYPE_BF16, a.p.act,
-                           a.p.act_param};
+                           a.p.act_param, a.p.osC};
     int buf = 0;  uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(a, tile);

@@ -91,11 +91,15 @@ soft_argmin_kernel(const float* __restrict__ cost, float* __restrict__ disp, int
 __global__ void __launch_bounds__(128)
 tap_gather_soft_argmin_kernel(const float* __restrict__ P, float* __restrict__ disp, float* __restrict__ cost_out,
                               int N, int D, int h, int w, int ts, float sign) {
+  // taps are LINE-PLANAR: P[n][z][y][t][x]: for a fixed tap the lanes of a warp (consecutive x) read
+  // consecutive floats (one coalesced wavefront per load, neighbours reuse L1), while the producer
+  // writes each image line as one contiguous ts*w*4-byte block (DRAM-friendly).
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y, n = blockIdx.z;
   if (x >= w) return;
   const int64_t plane = (int64_t)h * w;
-  const float* Pn = P + (int64_t)n * D * plane * ts;
+  const float* Pn = P + (int64_t)n * D * ts * plane;
+  const int64_t tstride = w, lstride = (int64_t)ts * w;      // tap stride, line stride
   float m = -INFINITY, s = 0.f, t = 0.f;
   float c0 = 0.f, c1 = 0.f, c2 = 0.f;            // partial costs of output planes z'-1, z', z'+1
   auto retire = [&](int z, float c) {
@@ -105,7 +109,7 @@ tap_gather_soft_argmin_kernel(const float* __restrict__ P, float* __restrict__ d
     const float e = expf(v - m);  s += e;  t += e * (float)z;
   };
   for (int zi = 0; zi < D; ++zi) {
-    const float* Pz = Pn + (int64_t)zi * plane * ts;
+    const float* Pz = Pn + (int64_t)zi * ts * plane;
     float a0 = 0.f, a1 = 0.f, a2 = 0.f;          // contributions of input plane zi with kz = 2, 1, 0
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
@@ -115,10 +119,10 @@ tap_gather_soft_argmin_kernel(const float* __restrict__ P, float* __restrict__ d
       for (int kx = 0; kx < 3; ++kx) {
         const int xx = x + kx - 1;
         if (xx < 0 || xx >= w) continue;
-        const float* p = Pz + ((int64_t)yy * w + xx) * ts + ky * 3 + kx;
-        a0 += __ldg(p + 18);   // kz = 2: input plane zi feeds output plane zi - 1
-        a1 += __ldg(p + 9);    // kz = 1: output plane zi
-        a2 += __ldg(p);        // kz = 0: output plane zi + 1
+        const float* p = Pz + (int64_t)yy * lstride + (int64_t)(ky * 3 + kx) * tstride + xx;
+        a0 += __ldg(p + 18 * tstride);   // kz = 2: input plane zi feeds output plane zi - 1
+        a1 += __ldg(p + 9 * tstride);    // kz = 1: output plane zi
+        a2 += __ldg(p);                // kz = 0: output plane zi + 1
       }
     }
     c0 += a0;  c1 += a1;  c2 += a2;
@@ -333,8 +337,9 @@ extern "C" int s3d_tap_gather_soft_argmin(const float* taps, float* disp, float*
   if (!taps || !disp) { set_error("tap_gather_soft_argmin: null argument"); return S3D_ERR_INVALID; }
   S3D_CHECK_ARG(N > 0 && D > 0 && h > 0 && w > 0 && tap_stride >= 27 && h < 65536 && N < 65536,
                 "tap_gather_soft_argmin: bad shape");
-  dim3 grid(ceil_div(w, 128), h, N);
-  tap_gather_soft_argmin_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(taps, disp, cost_out, N, D, h, w,
+  const int threads = w <= 32 ? 32 : (w <= 64 ? 64 : 128);
+  dim3 grid(ceil_div(w, threads), h, N);
+  tap_gather_soft_argmin_kernel<<<grid, threads, 0, static_cast<cudaStream_t>(stream)>>>(taps, disp, cost_out, N, D, h, w,
                                                                                       tap_stride, sign);
   S3D_LAUNCH_CHECK();
   return S3D_OK;

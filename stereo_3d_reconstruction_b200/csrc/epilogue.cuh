@@ -15,82 +15,95 @@ struct EpiParams {
   int out_bf16;
   int act;
   float act_param;
+  int64_t osC;        // channel stride of the output (1 = channels-last)
 };
 
 // v: raw accumulator bits of columns [cg, cg+16); off: element offset of the row's channel 0.
+// Code size matters here (the epilogue is inlined into a kernel whose hot loop must stay in the
+// instruction cache): none / ReLU / LeakyReLU share one branch-free formula, sigmoid / tanh (two
+// layers in the whole network) go through a rolled loop.
 __device__ __forceinline__ void epilogue_store16(const EpiParams& e, int64_t off, int cg, const uint32_t (&v)[16]) {
   if (cg >= e.cout_store) return;
   float f[16];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    f[i] = __uint_as_float(v[i]);
-    if (e.bias) f[i] += __ldg(e.bias + cg + i);
+  for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+  if (e.bias) {
+    const float4* b4 = reinterpret_cast<const float4*>(e.bias + cg);       // bias is padded to Cout, 64-B aligned groups
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 b = __ldg(b4 + i);
+      f[4 * i] += b.x;  f[4 * i + 1] += b.y;  f[4 * i + 2] += b.z;  f[4 * i + 3] += b.w;
+    }
   }
   const bool full = cg + 16 <= e.cout_store;
-  if (e.out_bf16) {
-    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(e.out) + off + cg;
-    const __nv_bfloat16* rs = e.residual ? reinterpret_cast<const __nv_bfloat16*>(e.residual) + off + cg : nullptr;
-    const bool vec = full && ((reinterpret_cast<uintptr_t>(o) & 15) == 0) &&
-                     (!rs || (reinterpret_cast<uintptr_t>(rs) & 15) == 0);
-    if (vec) {
-      if (rs) {
-        uint4 r0 = __ldg(reinterpret_cast<const uint4*>(rs));
-        uint4 r1 = __ldg(reinterpret_cast<const uint4*>(rs) + 1);
-        const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&r0);
-        const __nv_bfloat162* h1 = reinterpret_cast<const __nv_bfloat162*>(&r1);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          float2 g0 = __bfloat1622float2(h0[i]), g1 = __bfloat1622float2(h1[i]);
-          f[2 * i] += g0.x;  f[2 * i + 1] += g0.y;
-          f[8 + 2 * i] += g1.x;  f[8 + 2 * i + 1] += g1.y;
-        }
-      }
-      uint4 w0, w1;
-      __nv_bfloat162* p0 = reinterpret_cast<__nv_bfloat162*>(&w0);
-      __nv_bfloat162* p1 = reinterpret_cast<__nv_bfloat162*>(&w1);
+  const bool planar = e.osC != 1;
+  const __nv_bfloat16* rs16 = reinterpret_cast<const __nv_bfloat16*>(e.residual);
+  const float* rs32 = reinterpret_cast<const float*>(e.residual);
+  __nv_bfloat16* o16 = reinterpret_cast<__nv_bfloat16*>(e.out);
+  float* o32 = reinterpret_cast<float*>(e.out);
+  const int64_t base = off + (planar ? (int64_t)cg * e.osC : (int64_t)cg);
+  const bool vec = !planar && full && (((e.out_bf16 ? (uintptr_t)(o16 + base) : (uintptr_t)(o32 + base)) & 15) == 0) &&
+                   (!e.residual || ((e.out_bf16 ? (uintptr_t)(rs16 + base) : (uintptr_t)(rs32 + base)) & 15) == 0);
+  // ---- residual
+  if (e.residual) {
+    if (vec && e.out_bf16) {
+      const uint4 r0 = __ldg(reinterpret_cast<const uint4*>(rs16 + base));
+      const uint4 r1 = __ldg(reinterpret_cast<const uint4*>(rs16 + base) + 1);
+      const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&r0);
+      const __nv_bfloat162* h1 = reinterpret_cast<const __nv_bfloat162*>(&r1);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        p0[i] = __floats2bfloat162_rn(apply_act(f[2 * i], e.act, e.act_param), apply_act(f[2 * i + 1], e.act, e.act_param));
-        p1[i] = __floats2bfloat162_rn(apply_act(f[8 + 2 * i], e.act, e.act_param),
-                                      apply_act(f[8 + 2 * i + 1], e.act, e.act_param));
+        const float2 g0 = __bfloat1622float2(h0[i]), g1 = __bfloat1622float2(h1[i]);
+        f[2 * i] += g0.x;  f[2 * i + 1] += g0.y;  f[8 + 2 * i] += g1.x;  f[8 + 2 * i + 1] += g1.y;
       }
-      reinterpret_cast<uint4*>(o)[0] = w0;
-      reinterpret_cast<uint4*>(o)[1] = w1;
-    } else {
+    } else if (vec) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        if (cg + i < e.cout_store) {
-          float s = f[i];
-          if (rs) s += __bfloat162float(rs[i]);
-          o[i] = __float2bfloat16_rn(apply_act(s, e.act, e.act_param));
-        }
+      for (int i = 0; i < 4; ++i) {
+        const float4 g = __ldg(reinterpret_cast<const float4*>(rs32 + base) + i);
+        f[4 * i] += g.x;  f[4 * i + 1] += g.y;  f[4 * i + 2] += g.z;  f[4 * i + 3] += g.w;
       }
+    } else {
+      const int64_t cs = planar ? e.osC : 1;
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (cg + i < e.cout_store) f[i] += e.out_bf16 ? __bfloat162float(rs16[base + i * cs]) : rs32[base + i * cs];
     }
+  }
+  // ---- activation
+  if (e.act <= S3D_ACT_LEAKY) {
+    const float slope = e.act == S3D_ACT_NONE ? 1.f : (e.act == S3D_ACT_LEAKY ? e.act_param : 0.f);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f) + slope * fminf(f[i], 0.f);
   } else {
-    float* o = reinterpret_cast<float*>(e.out) + off + cg;
-    const float* rs = e.residual ? reinterpret_cast<const float*>(e.residual) + off + cg : nullptr;
-    const bool vec = full && ((reinterpret_cast<uintptr_t>(o) & 15) == 0) &&
-                     (!rs || (reinterpret_cast<uintptr_t>(rs) & 15) == 0);
-    if (vec) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        float4 s = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
-        if (rs) {
-          float4 g = __ldg(reinterpret_cast<const float4*>(rs) + i);
-          s.x += g.x; s.y += g.y; s.z += g.z; s.w += g.w;
-        }
-        s.x = apply_act(s.x, e.act, e.act_param);  s.y = apply_act(s.y, e.act, e.act_param);
-        s.z = apply_act(s.z, e.act, e.act_param);  s.w = apply_act(s.w, e.act, e.act_param);
-        reinterpret_cast<float4*>(o)[i] = s;
-      }
-    } else {
+    for (int i = 0; i < 16; ++i)
+      if (cg + i < e.cout_store) f[i] = apply_act_slow(f[i], e.act, e.act_param);
+  }
+  // ---- store
+  if (vec && e.out_bf16) {
+    uint4 w0, w1;
+    __nv_bfloat162* p0 = reinterpret_cast<__nv_bfloat162*>(&w0);
+    __nv_bfloat162* p1 = reinterpret_cast<__nv_bfloat162*>(&w1);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        if (cg + i < e.cout_store) {
-          float s = f[i];
-          if (rs) s += rs[i];
-          o[i] = apply_act(s, e.act, e.act_param);
-        }
+    for (int i = 0; i < 4; ++i) {
+      p0[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+      p1[i] = __floats2bfloat162_rn(f[8 + 2 * i], f[8 + 2 * i + 1]);
+    }
+    reinterpret_cast<uint4*>(o16 + base)[0] = w0;
+    reinterpret_cast<uint4*>(o16 + base)[1] = w1;
+  } else if (vec) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      reinterpret_cast<float4*>(o32 + base)[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+  } else {
+    // channels-last tail / unaligned slice, or planar output (consecutive rows = consecutive x, so each
+    // channel is one coalesced warp store)
+    const int64_t cs = planar ? e.osC : 1;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      if (cg + i < e.cout_store) {
+        if (e.out_bf16) o16[base + i * cs] = __float2bfloat16_rn(f[i]);
+        else            o32[base + i * cs] = f[i];
       }
     }
   }

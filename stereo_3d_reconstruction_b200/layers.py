@@ -90,6 +90,19 @@ class PackedConv:
         self.bias = bp.to(device)
         self.taps = taps
         self.ksize, self.pad = tuple(ksize), tuple(pad)
+        # stride-1 3x3x3 layers with Cout <= 64: pre-stack the weights for the z-stacked UMMA tile
+        # (two output planes x 64 channels = M 128), see csrc/conv_halo.cu and include/s3d.h
+        self.weight_zs = None
+        if tuple(ksize) == (3, 3, 3) and tuple(pad) == (1, 1, 1) and tuple(stride) == (1, 1, 1) and \
+                self.n_classes == 1 and self.cout_pad <= 64:
+            zs = torch.zeros(4, 9, 128, self.cin_pad, dtype=torch.float32)
+            w3 = wp.view(3, 9, self.cout_pad, self.cin_pad)
+            for sv in range(4):
+                if sv <= 2:
+                    zs[sv, :, :self.cout_pad] = w3[sv]
+                if sv >= 1:
+                    zs[sv, :, 64:64 + self.cout_pad] = w3[sv - 1]
+            self.weight_zs = zs.view(36, 128, self.cin_pad).to(torch_dtype(dtype_code)).to(device).contiguous()
         self.bn = _choose_bn(self.cout_pad)
         self._cache = {}
 
@@ -171,13 +184,15 @@ class PackedConv:
             for (dz, dy, dx) in ct:
                 p.dz[i], p.dy[i], p.dx[i] = dz, dy, dx
                 i += 1
-        p.osN, p.osD, p.osH, p.osW = out_strides
+        p.osN, p.osD, p.osH, p.osW = out_strides[:4]
+        p.osC = out_strides[4] if len(out_strides) > 4 else 1
         p.omz, p.omy, p.omx = self.out_mult
         p.cout_store = self.cout_pad if cout_store is None else cout_store
         p.in_dtype, p.out_dtype = self.dtype_code, out_dtype_code
         p.act, p.act_param = self.act, self.act_param
         p.tw, p.th, p.td, p.tn = _choose_tile(N, oD, oH, oW, self.stride[2], self.stride[1], self.stride[0])
         p.bn = self.bn
+        p.w_zstack = self.weight_zs.data_ptr() if self.weight_zs is not None else None
         self._cache[key] = p
         return p
 
@@ -185,7 +200,8 @@ class PackedConv:
         """x: channels-last [N,D,H,W,Cin_pad] contiguous CUDA tensor.
 
         out: destination tensor (allocated if None) -- `out_view` optionally gives
-        (data_ptr_offset_elems, (osN, osD, osH, osW)) to write into a channel slice of a wider buffer."""
+        (data_ptr_offset_elems, (osN, osD, osH, osW[, osC])) to write into a channel slice of a wider buffer
+        or (osC != 1) a planar layout."""
         assert x.is_cuda and x.is_contiguous() and x.dim() == 5 and x.shape[-1] == self.cin_pad, \
             (tuple(x.shape), self.cin_pad)
         assert x.dtype == torch_dtype(self.dtype_code)

@@ -27,12 +27,14 @@ class S3dConvParams(ctypes.Structure):
         ('dz', ctypes.c_int8 * S3D_MAX_TAPS), ('dy', ctypes.c_int8 * S3D_MAX_TAPS),
         ('dx', ctypes.c_int8 * S3D_MAX_TAPS),
         ('osN', ctypes.c_int64), ('osD', ctypes.c_int64), ('osH', ctypes.c_int64), ('osW', ctypes.c_int64),
+        ('osC', ctypes.c_int64),
         ('omz', ctypes.c_int32), ('omy', ctypes.c_int32), ('omx', ctypes.c_int32),
         ('cout_store', ctypes.c_int32),
         ('in_dtype', ctypes.c_int32), ('out_dtype', ctypes.c_int32),
         ('act', ctypes.c_int32), ('act_param', ctypes.c_float),
         ('tw', ctypes.c_int32), ('th', ctypes.c_int32), ('td', ctypes.c_int32), ('tn', ctypes.c_int32),
         ('bn', ctypes.c_int32),
+        ('w_zstack', ctypes.c_void_p),
     ]
 
 

@@ -216,8 +216,9 @@ class _StereoBase(nn.Module):
             y = self._conv('dres1a', a, out=self._bufo('a2', 'dres1a', a))
             a = self._conv('dres1b', y, residual=a, out=self._bufo('a3', 'dres1b', y))
             c = self._conv('cls_a', a, out=self._bufo('a0', 'cls_a', a))
-            taps = self._conv('cls_b', c, out=self._buf('taps', (2 * B, D, h, w, self._packed['cls_b'].cout_pad),
-                                                        torch.float32))
+            S = self._packed['cls_b'].cout_pad                      # 27 taps padded to 32 planes
+            taps = self._buf('taps', (2 * B, D, h, S, w), torch.float32)   # line-planar: [.., y, tap, x]
+            self._conv('cls_b', c, out=taps, out_view=(0, (D * h * S * w, h * S * w, S * w, 1, w)), cout_store=S)
             ops.tap_gather_soft_argmin(taps, -1.0, out=disp_q)
         else:
             ops.corr_soft_argmin(feat, B, D, out=disp_q)

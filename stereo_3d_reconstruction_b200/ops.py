@@ -73,10 +73,10 @@ def soft_argmin(cost, sign=-1.0, out=None):
 
 
 def tap_gather_soft_argmin(taps, sign=-1.0, out=None, want_cost=False):
-    """taps fp32 [N,D,h,w,S>=27] (per-tap projections) -> disp fp32 [N,h,w]; see include/s3d.h."""
+    """taps fp32, line-planar [N,D,h,S>=27,w] (per-tap projections) -> disp fp32 [N,h,w]; see include/s3d.h."""
     _chk(taps, out)
     assert taps.dtype == torch.float32 and taps.dim() == 5
-    N, D, h, w, S = taps.shape
+    N, D, h, S, w = taps.shape
     if out is None:
         out = torch.empty((N, h, w), dtype=torch.float32, device=taps.device)
     cost = torch.empty((N, D, h, w), dtype=torch.float32, device=taps.device) if want_cost else None

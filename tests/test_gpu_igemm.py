@@ -83,8 +83,8 @@ def test_igemm_rejects_bad_shapes():
     pc = PackedConv.from_conv(conv, None, lib.ACT_NONE, lib.DTYPE_BF16, 'cuda')
     x = torch.zeros(1, 1, 8, 8, 16, dtype=torch.bfloat16).cuda()
     p = pc.params(1, 1, 8, 8, (8 * 8 * 16, 8 * 8 * 16, 8 * 16, 16), lib.DTYPE_BF16, 16)
-    import copy, ctypes
-    q = copy.copy(p); q.tw = 3
+    import ctypes
+    q = type(p).from_buffer_copy(p); q.tw = 3
     out = torch.zeros(1, 1, 8, 8, 16, dtype=torch.bfloat16).cuda()
     rc = lib.load().s3d_conv_igemm(ctypes.byref(q), x.data_ptr(), pc.weight.data_ptr(), None, None, out.data_ptr(), None)
     assert rc == -1 and b'tile' in lib.load().s3d_last_error()

@@ -147,8 +147,8 @@ def test_tap_gather_soft_argmin_equals_cout1_conv(N, C, D, h, w):
     wt = torch.randn(1, C, 3, 3, 3, generator=g) * 0.3
     cost_ref = F.conv3d(x, wt, padding=1).squeeze(1)
     ref = O.soft_argmin(cost_ref)
-    taps = torch.einsum('ncdhw,tc->ndhwt', x, wt[0].reshape(C, 27).t())
-    taps = torch.cat([taps, torch.zeros(N, D, h, w, 5)], -1).contiguous()        # stride 32
+    taps = torch.einsum('ncdhw,tc->ndhtw', x, wt[0].reshape(C, 27).t())          # line-planar [N,D,h,27,w]
+    taps = torch.cat([taps, torch.zeros(N, D, h, 5, w)], 3).contiguous()        # 32 tap rows per line
     got, cost = ops.tap_gather_soft_argmin(taps.cuda(), -1.0, want_cost=True)
     torch.testing.assert_close(cost.cpu(), cost_ref, rtol=1e-4, atol=1e-4)
     torch.testing.assert_close(got.cpu(), ref, rtol=1e-4, atol=1e-4)
