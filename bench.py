@@ -273,7 +273,9 @@ def run_ours(args):
                      'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,
                      'peak_source': '%s bf16_tflops_sustained (kernel timed inside a long step)' % pk['source'],
                      'ms_per_launch': dom, 'flops_per_launch': flops, 'share_of_step': dom * len(dom_layers) / (ms / args.steps),
-                     'traffic': None},
+                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel at this exact shape,
+                     # from the round-1 `ncu --set full` capture (profiles/r1_ncu_summary.md); algorithmic bytes = 4.295e9
+                     'traffic': 4.2536e9 if (B == 64 and args.precision == 'bf16' and (H, W, D) == (256, 256, 32)) else None},
         'model_tflops_per_step': total_flops / 1e12,
         'model_tflops_achieved': total_flops / (ms / args.steps / 1e3) / 1e12,
     }
