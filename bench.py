@@ -176,16 +176,39 @@ def run_ours(args):
             dist.all_reduce(stats)
         return vox
 
-    h_vox = torch.empty((B, cfg.CONST.N_VOX, cfg.CONST.N_VOX, cfg.CONST.N_VOX), dtype=torch.float32).pin_memory()
+    # ---- end-to-end path: pinned host inputs -> H2D -> forward -> D2H, every step inside the timed region.
+    # Double-buffered device inputs + a copy stream, so the H2D of step i+1 overlaps the compute of step i
+    # (what a serving loop does); all copies of the K timed steps are still issued and finished inside the region.
+    nv = cfg.CONST.N_VOX
+    h_vox = torch.empty((B, nv, nv, nv), dtype=torch.float32).pin_memory()
     h_stats = torch.empty(2 * T + 1, dtype=torch.int64).pin_memory()
-    d_l = torch.empty((B, 3, H, W), dtype=torch.float32, device=dev)
-    d_r = torch.empty_like(d_l)
-    d_g = torch.empty((B, cfg.CONST.N_VOX, cfg.CONST.N_VOX, cfg.CONST.N_VOX), dtype=torch.uint8, device=dev)
+    d_in = [(torch.empty((B, 3, H, W), dtype=torch.float32, device=dev), torch.empty((B, 3, H, W), dtype=torch.float32, device=dev),
+             torch.empty((B, nv, nv, nv), dtype=torch.uint8, device=dev)) for _ in range(2)]
+    copy_stream = torch.cuda.Stream(device=dev)
+    in_ready = [torch.cuda.Event() for _ in range(2)]
+    in_free = [torch.cuda.Event() for _ in range(2)]
+    e2e_state = {'primed': -1, 'first_timed': -1}
+
+    def stage_inputs(i):
+        hl, hr, hg = host_sets[i % n_sets]
+        slot = i & 1
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(in_free[slot])             # the forward that last read this slot has finished
+            d_in[slot][0].copy_(hl, non_blocking=True)
+            d_in[slot][1].copy_(hr, non_blocking=True)
+            d_in[slot][2].copy_(hg, non_blocking=True)
+            in_ready[slot].record(copy_stream)
 
     def step_e2e(i):
-        hl, hr, hg = host_sets[i % n_sets]
-        d_l.copy_(hl, non_blocking=True); d_r.copy_(hr, non_blocking=True); d_g.copy_(hg, non_blocking=True)
-        _, _, vox, iou = model(d_l, d_r, d_g)
+        cur = torch.cuda.current_stream()
+        if e2e_state['primed'] != i or i == e2e_state['first_timed']:
+            stage_inputs(i)      # first step of the timed region copies its own inputs INSIDE the region (no head start)
+        slot = i & 1
+        cur.wait_event(in_ready[slot])
+        stage_inputs(i + 1); e2e_state['primed'] = i + 1      # prefetch the next step's inputs
+        dl_, dr_, dg_ = d_in[slot]
+        _, _, vox, iou = model(dl_, dr_, dg_)
+        in_free[slot].record(cur)
         stats[:T] = iou[:, :, 0].sum(0)
         stats[T:2 * T] = iou[:, :, 1].sum(0)
         stats[2 * T] = B
@@ -238,7 +261,9 @@ def run_ours(args):
     launches = (lib.launches() - n0) // (args.steps + args.warmup)        # kernels of this library per step
     dom_ms = [a.elapsed_time(b) for a, b in dom_events[len(dom_layers) * args.warmup:]]
     model._conv = orig_conv
-    ms_e2e = timed(step_e2e, args.steps, min(args.warmup, 2) or 1)
+    warm_e2e = min(args.warmup, 2) or 1
+    e2e_state['first_timed'] = warm_e2e
+    ms_e2e = timed(step_e2e, args.steps, warm_e2e)
 
     if rank != 0:
         if world > 1:
