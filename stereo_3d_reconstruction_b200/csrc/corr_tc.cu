@@ -1,0 +1,253 @@
+// Fused correlation + soft-argmax on the tensor cores (rows V+S, correlation variant).
+//
+// The SIMT kernel in costvolume.cu is compute-bound (2*C*D flop per pixel against 2*C*e bytes: D/4
+// flop/B in fp32, beyond the fp32 ridge for D >= 32).  The correlation of one image row is a Gram
+// matrix, S = X_ref [w x C] . X_tgt^T [C x w], whose band S[x, x -/+ d] is the cost volume -- a dense
+// contraction, so it goes to tcgen05:
+//   tile      two image rows (y, y+1) of one volume n: M = 128 reference pixels (2 x 64, x padded to 64
+//             by TMA zero fill), N = 128 target pixels of the same two rows, K = C.  One TMA box per
+//             operand and K chunk; the accumulator [128 x 128] fp32 lives in TMEM (two buffers).
+//             Only the two 64 x 64 diagonal blocks are used (the off-diagonal blocks pair different
+//             image rows), and of those only the band -- the tensor pipe has ~50x headroom here.
+//   epilogue  thread = reference pixel (TMEM lane).  It reads the <= 64 target columns of its own row
+//             block, keeps those with 0 <= d < D, adds the closed-form contribution of the out-of-image
+//             disparities (cost 0, as in the oracle), and finishes softmax / expectation in registers.
+//             The cost volume never exists anywhere: per pixel 2*C*e bytes in, 4 bytes out.
+// Restrictions: bf16 features (fp32 features keep the exact SIMT kernel), w <= 64, C*2 a multiple of 32 B.
+#include <cuda.h>
+#include <string.h>
+#include <stdlib.h>
+#include "common.cuh"
+#include "ptx.cuh"
+#include "epilogue.cuh"
+
+namespace s3d {
+namespace {
+
+constexpr int kThreads = 384;      // warps 0-3: TMA / MMA / TMEM alloc / idle; warps 4-7 and 8-11: two epilogue groups
+constexpr int kWP = 64;            // padded row width
+constexpr int kRows = 2;           // image rows per tile
+constexpr int kM = kWP * kRows;    // 128
+constexpr int kMaxStages = 6;
+constexpr int kTmemCols = 256;
+
+struct CorrArgs {
+  float* disp;
+  int B, h, w, C, D;
+  int row_bytes, kc, nchunks;
+  int op_bytes;        // bytes of one operand tile per chunk: 128 * row_bytes
+  int stage_bytes;     // 2 * op_bytes
+  int stages;
+  int tiles_per_img, total_tiles;
+  float inv_c;
+  uint32_t idesc;
+};
+
+struct CorrCtrl {
+  uint64_t full[kMaxStages], empty[kMaxStages];
+  uint64_t acc_full[2], acc_empty[2];
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+corr_tc_kernel(const __grid_constant__ CUtensorMap map_f, const __grid_constant__ CorrArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ CorrCtrl ctrl;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) ptx::prefetch_tensormap(&map_f);
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kMaxStages; ++s) { ptx::mbar_init(&ctrl.full[s], 1); ptx::mbar_init(&ctrl.empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { ptx::mbar_init(&ctrl.acc_full[b], 1); ptx::mbar_init(&ctrl.acc_empty[b], 128); }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) ptx::tmem_alloc(&ctrl.tmem_base, kTmemCols);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = ctrl.tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;  uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+        const int n = tile / a.tiles_per_img, y0 = (tile % a.tiles_per_img) * kRows;
+        const int nt = n < a.B ? n + a.B : n - a.B;          // the other view is the target
+        for (int ch = 0; ch < a.nchunks; ++ch) {
+          ptx::mbar_wait(&ctrl.empty[stage], phase ^ 1);
+          uint8_t* s = smem + stage * a.stage_bytes;
+          ptx::mbar_arrive_expect_tx(&ctrl.full[stage], a.stage_bytes);
+          ptx::tma_load_5d(s, &map_f, &ctrl.full[stage], ch * a.kc, 0, y0, 0, n);
+          ptx::tma_load_5d(s + a.op_bytes, &map_f, &ctrl.full[stage], ch * a.kc, 0, y0, 0, nt);
+          if (++stage == a.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    int stage = 0;  uint32_t phase = 0;
+    int buf = 0;    uint32_t acc_phase = 0;
+    const int kper = a.row_bytes >> 5;
+    const uint64_t hi = ptx::make_smem_desc(0, a.row_bytes) & 0xFFFFFFFF00000000ull;
+    const uint32_t smem_u = ptx::smem_u32(smem);
+    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+      ptx::mbar_wait(&ctrl.acc_empty[buf], acc_phase ^ 1);
+      ptx::tc_fence_after();
+      const uint32_t d_tmem = tmem_base + buf * kM;
+      for (int ch = 0; ch < a.nchunks; ++ch) {
+        ptx::mbar_wait(&ctrl.full[stage], phase);
+        ptx::tc_fence_after();
+        const uint32_t sa = smem_u + stage * a.stage_bytes;
+        const uint64_t adesc = hi | ((sa >> 4) | (1u << 16));
+        const uint64_t bdesc = hi | (((sa + a.op_bytes) >> 4) | (1u << 16));
+        if (ptx::elect_one()) {
+          for (int k = 0; k < kper; ++k) ptx::mma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, a.idesc, (ch | k) != 0);
+          ptx::tc_commit(&ctrl.empty[stage]);
+        }
+        __syncwarp();
+        if (++stage == a.stages) { stage = 0; phase ^= 1; }
+      }
+      if (ptx::elect_one()) ptx::tc_commit(&ctrl.acc_full[buf]);
+      __syncwarp();
+      if (++buf == 2) { buf = 0; acc_phase ^= 1; }
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    const int rowblk = q >> 1;                 // image row of the tile this warp serves
+    const int x = (q & 1) * 32 + lane;         // reference pixel of this thread
+    const int xw0 = (q & 1) * 32;              // first x of the warp
+    const int D = a.D, w = a.w;
+    const float scale2 = a.inv_c * 1.4426950408889634f;     // 1/C * log2(e)
+    // two epilogue groups alternate tiles (group g owns accumulator buffer g): twice the warps per
+    // scheduler hide the dependent-issue latency of the softmax arithmetic
+    const int grp = (warp - 4) >> 2;
+    const int buf = grp;  uint32_t acc_phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
+      if ((it & 1) != grp) continue;
+      const int n = tile / a.tiles_per_img, y = (tile % a.tiles_per_img) * kRows + rowblk;
+      const bool left_ref = n < a.B;
+      // target columns this warp needs: left-ref xt in [xw0-D+1, xw0+31], right-ref xt in [xw0, xw0+31+D-1]
+      const int lo = left_ref ? max(0, xw0 - D + 1) : xw0;
+      const int hi_ = left_ref ? xw0 + 31 : min(kWP - 1, xw0 + 31 + D - 1);
+      const int c_lo = lo >> 4, c_hi = hi_ >> 4;          // 16-column chunks, warp-uniform
+      ptx::mbar_wait(&ctrl.acc_full[buf], acc_phase);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + buf * kM + rowblk * kWP + (static_cast<uint32_t>(q * 32) << 16);
+      // Everything below works in the base-2 exponent domain: v = S * (log2(e) / C).  Columns outside this
+      // thread's disparity window are set to -inf once, which makes both softmax passes branch-free
+      // (ex2(-inf) = 0); the expectation uses sum(e * xt) with compile-time xt and d = +/-(x - xt).
+      float v[4][16];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (c >= c_lo && c <= c_hi) {
+          uint32_t u[16];
+          ptx::tmem_ld16(taddr + c * 16, u);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[c][i] = __uint_as_float(u[i]) * scale2;
+        }
+      }
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&ctrl.acc_empty[buf]);             // accumulator is in registers: release it early
+      acc_phase ^= 1;
+
+      // out-of-image disparities keep cost 0 (oracle semantics): d in [dz0, D) where
+      //   left-ref : x - d < 0   <=>  d > x            right-ref: x + d >= w  <=>  d >= w - x
+      const int dz0 = left_ref ? min(D, x + 1) : min(D, max(0, w - x));
+      float m = dz0 < D ? 0.f : -INFINITY;
+      if (left_ref) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (c >= c_lo && c <= c_hi) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              v[c][i] = (unsigned)(x - (c * 16 + i)) < (unsigned)dz0 ? v[c][i] : -INFINITY;
+              m = fmaxf(m, v[c][i]);
+            }
+          }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (c >= c_lo && c <= c_hi) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              v[c][i] = (unsigned)((c * 16 + i) - x) < (unsigned)dz0 ? v[c][i] : -INFINITY;
+              m = fmaxf(m, v[c][i]);
+            }
+          }
+      }
+      float s = 0.f, tx = 0.f;                             // sum e, sum e * xt
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (c >= c_lo && c <= c_hi) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float e = exp2f(v[c][i] - m);
+            s += e;
+            tx = fmaf(e, (float)(c * 16 + i), tx);
+          }
+        }
+      float t = left_ref ? fmaf((float)x, s, -tx) : fmaf(-(float)x, s, tx);     // sum e * d
+      if (dz0 < D) {                                       // (D - dz0) terms of cost 0 at d = dz0 .. D-1
+        const float e0 = exp2f(-m), cnt = (float)(D - dz0);
+        s += e0 * cnt;
+        t += e0 * cnt * 0.5f * (float)(dz0 + D - 1);
+      }
+      if (x < w && y < a.h) a.disp[((int64_t)n * a.h + y) * w + x] = t / s;
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+}  // namespace
+
+bool corr_tc_eligible(int w, int C, int D, int dtype) {
+  return dtype == S3D_DTYPE_BF16 && w <= kWP && (C * 2) % 32 == 0 && D >= 1 && getenv("S3D_NO_CORR_TC") == nullptr;
+}
+
+int corr_tc_launch(const void* feat, float* disp, int B, int h, int w, int C, int D, cudaStream_t stream) {
+  CorrArgs a;
+  memset(&a, 0, sizeof(a));
+  a.disp = disp;  a.B = B;  a.h = h;  a.w = w;  a.C = C;  a.D = D;
+  const int cb = C * 2;
+  a.row_bytes = cb % 128 == 0 ? 128 : (cb % 64 == 0 ? 64 : 32);
+  a.kc = a.row_bytes / 2;
+  a.nchunks = cb / a.row_bytes;
+  a.op_bytes = kM * a.row_bytes;
+  a.stage_bytes = 2 * a.op_bytes;
+  a.stages = (200 * 1024) / a.stage_bytes;
+  if (a.stages > kMaxStages) a.stages = kMaxStages;
+  a.tiles_per_img = ceil_div(h, kRows);
+  const int64_t total = (int64_t)2 * B * a.tiles_per_img;
+  S3D_CHECK_ARG(total > 0 && total < (1ll << 31), "corr_tc: tile count out of range");
+  a.total_tiles = (int)total;
+  a.inv_c = 1.f / (float)C;
+  a.idesc = ptx::make_instr_desc(1, kM, kM);
+  const CUtensorMapSwizzle sw = a.row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                              : a.row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+  CUtensorMap map_f;
+  cuuint32_t box[5] = {(cuuint32_t)a.kc, kWP, kRows, 1, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  int rc = encode_act_map(&map_f, feat, 2, false, C, w, h, 1, 2 * B, box, estr, sw);
+  if (rc != S3D_OK) return rc;
+  const int smem_bytes = a.stages * a.stage_bytes + 1024;
+  static int attr_set = 0;
+  if (attr_set < smem_bytes) {
+    S3D_CUDA(cudaFuncSetAttribute(corr_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    attr_set = smem_bytes;
+  }
+  int grid = num_sms();
+  if (grid > a.total_tiles) grid = a.total_tiles;
+  corr_tc_kernel<<<grid, kThreads, smem_bytes, stream>>>(map_f, a);
+  S3D_LAUNCH_CHECK();
+  return S3D_OK;
+}
+
+}  // namespace s3d

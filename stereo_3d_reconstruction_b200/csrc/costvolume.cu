@@ -263,6 +263,11 @@ __global__ void upsample_disp_kernel(const float* __restrict__ q, float* __restr
 
 using namespace s3d;
 
+namespace s3d {
+bool corr_tc_eligible(int w, int C, int D, int dtype);
+int corr_tc_launch(const void* feat, float* disp, int B, int h, int w, int C, int D, cudaStream_t stream);
+}
+
 extern "C" int s3d_cost_volume_concat(const void* feat, void* vol, int B, int h, int w, int C, int D, int dtype,
                                       void* stream) {
   if (!feat || !vol) { set_error("cost_volume_concat: null argument"); return S3D_ERR_INVALID; }
@@ -295,8 +300,11 @@ extern "C" int s3d_corr_soft_argmin(const void* feat, float* disp, float* cost_o
                                     int dtype, void* stream) {
   if (!feat || !disp) { set_error("corr_soft_argmin: null argument"); return S3D_ERR_INVALID; }
   S3D_CHECK_ARG(dtype == S3D_DTYPE_F32 || dtype == S3D_DTYPE_BF16, "corr_soft_argmin: bad dtype");
-  S3D_CHECK_ARG(D >= 8 && D <= 128 && (D & (D - 1)) == 0, "corr_soft_argmin: D must be a power of two in [8,128]");
-  S3D_CHECK_ARG(B > 0 && h > 0 && w > 0 && C > 0, "corr_soft_argmin: bad shape");
+  S3D_CHECK_ARG(B > 0 && h > 0 && w > 0 && C > 0 && D > 0, "corr_soft_argmin: bad shape");
+  // bf16 features, rows of up to 64 pixels, no debug cost output: Gram-matrix kernel on the tensor cores (corr_tc.cu)
+  if (!cost_out && corr_tc_eligible(w, C, D, dtype))
+    return corr_tc_launch(feat, disp, B, h, w, C, D, static_cast<cudaStream_t>(stream));
+  S3D_CHECK_ARG(D >= 8 && D <= 128 && (D & (D - 1)) == 0, "corr_soft_argmin (SIMT path): D must be a power of two in [8,128]");
   const int WP = (w + 3) & ~3;
   const size_t smem = (size_t)C * ((WP + 4) + (WP + D + 16)) * sizeof(float);
   S3D_CHECK_ARG(smem <= 200 * 1024, "corr_soft_argmin: row too large for shared memory");

@@ -152,3 +152,15 @@ def test_tap_gather_soft_argmin_equals_cout1_conv(N, C, D, h, w):
     got, cost = ops.tap_gather_soft_argmin(taps.cuda(), -1.0, want_cost=True)
     torch.testing.assert_close(cost.cpu(), cost_ref, rtol=1e-4, atol=1e-4)
     torch.testing.assert_close(got.cpu(), ref, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize('B,C,h,w,D', [(2, 32, 8, 64, 32), (1, 16, 5, 21, 8), (1, 64, 3, 35, 64), (1, 32, 2, 40, 128),
+                                       (3, 32, 7, 64, 24), (1, 128, 4, 64, 48)])
+def test_corr_soft_argmin_tensor_core_path(B, C, h, w, D):
+    """bf16, w <= 64, no cost output -> corr_tc.cu (tcgen05 Gram matrix + band soft-argmax in the epilogue)."""
+    g = torch.Generator().manual_seed(12)
+    f = (torch.randn(2 * B, C, h, w, generator=g) * 1.5).to(torch.bfloat16).float()
+    cost_ref = torch.cat([O.build_corr_volume(f[:B], f[B:], D, -1), O.build_corr_volume(f[B:], f[:B], D, +1)], 0)
+    ref = O.soft_argmax(cost_ref)
+    got = ops.corr_soft_argmin(cl_feat(f).to(torch.bfloat16).cuda(), B, D)
+    torch.testing.assert_close(got.cpu(), ref, rtol=1e-3, atol=1e-3)
