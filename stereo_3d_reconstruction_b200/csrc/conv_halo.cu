@@ -65,7 +65,6 @@ struct HaloArgs {
   int w_stages, w_bytes, w_tx;
   int cols_x, cols_y, n_mtiles, total_cols;
   uint32_t idesc;
-  int debug;          // S3D_HALO_DEBUG timing experiments: 1 = no tap offsets, 2 = +aligned groups (SBO 1024), 3 = SBO 1024 only
 };
 
 struct HaloCtrl {
@@ -217,7 +216,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     const uint32_t planes_u32 = ptx::smem_u32(smem);
     const uint32_t w_u32 = ptx::smem_u32(smem_w);
     const int rb = a.row_bytes;
-    const uint64_t x_hi = desc_hi(a.debug >= 2 ? 8 * rb : kHX * rb, rb);   // pixel rows: 8-row groups one halo line (10 rows) apart
+    const uint64_t x_hi = desc_hi(kHX * rb, rb);              // pixel rows: 8-row groups one halo line (10 rows) apart
     const uint64_t w_hi = desc_hi(8 * rb, rb);                // weights: dense rows
     const int kper = rb >> 5;                                 // tcgen05.mma per tap per chunk (32 B of K each)
     const uint32_t w_tap_step = (a.um * rb) >> 4;             // next tap inside a weight stage
@@ -295,7 +294,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
                   const int kz = tap / 9, kyx = tap - kz * 9;
                   const int ky = kyx / 3, kx = kyx - ky * 3;
                   int slot = slot0 + kz;  if (slot >= ring) slot -= ring;
-                  const uint32_t xlo = desc_lo(planes_u32 + slot * a.slot_bytes + ch * a.chunk_stride + ((a.debug == 1 || a.debug == 2) ? 0 : (ky * kHX + kx) * rb));
+                  const uint32_t xlo = desc_lo(planes_u32 + slot * a.slot_bytes + ch * a.chunk_stride + (ky * kHX + kx) * rb);
                   const uint64_t wdesc = w_hi | (wlo + tt * w_tap_step);
                   const uint64_t xdesc = x_hi | xlo;
                   if (ptx::elect_one()) {
@@ -513,7 +512,6 @@ int conv_halo_launch(const S3dConvParams* p_in, const void* in, const void* w, c
   S3D_CHECK_ARG(total > 0 && total < (1ll << 31), "halo: column count out of range");
   a.total_cols = (int)total;
   a.idesc = ptx::make_instr_desc(tf32 ? 2 : 1, a.um, kPix);
-  { const char* dbg = getenv("S3D_HALO_DEBUG"); a.debug = dbg ? atoi(dbg) : 0; }
 
   const CUtensorMapSwizzle sw = a.row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                               : a.row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;

@@ -62,14 +62,16 @@ soft_argmin_kernel(const float* __restrict__ cost, float* __restrict__ disp, int
   const float* c = cost + n * D * plane + pix;
   float m = -INFINITY, s = 0.f, t = 0.f;
   int d = 0;
-  for (; d + 4 <= D; d += 4) {
-    float v[4];
+  for (; d + 8 <= D; d += 8) {                 // 8 independent plane loads in flight per thread
+    float v[8];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) v[k] = sign * __ldcs(c + (int64_t)(d + k) * plane);
-    const float mm = fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3]));
+    for (int k = 0; k < 8; ++k) v[k] = sign * __ldcs(c + (int64_t)(d + k) * plane);
+    float mm = v[0];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) mm = fmaxf(mm, v[k]);
     if (mm > m) { const float sc = expf(m - mm); s *= sc; t *= sc; m = mm; }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) { const float e = expf(v[k] - m); s += e; t += e * (float)(d + k); }
+    for (int k = 0; k < 8; ++k) { const float e = expf(v[k] - m); s += e; t += e * (float)(d + k); }
   }
   for (; d < D; ++d) {
     const float v = sign * __ldcs(c + (int64_t)d * plane);
