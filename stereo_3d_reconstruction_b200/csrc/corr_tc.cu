@@ -24,12 +24,13 @@
 namespace s3d {
 namespace {
 
-constexpr int kThreads = 384;      // warps 0-3: TMA / MMA / TMEM alloc / idle; warps 4-7 and 8-11: two epilogue groups
+constexpr int kGroups = 4;         // epilogue warp groups; group g owns TMEM accumulator buffer g
+constexpr int kThreads = 128 + kGroups * 128;   // warps 0-3: TMA / MMA / TMEM alloc / idle; then 4 warps per group
 constexpr int kWP = 64;            // padded row width
 constexpr int kRows = 2;           // image rows per tile
 constexpr int kM = kWP * kRows;    // 128
 constexpr int kMaxStages = 6;
-constexpr int kTmemCols = 256;
+constexpr int kTmemCols = kGroups * kM;   // 512
 
 struct CorrArgs {
   float* disp;
@@ -45,7 +46,7 @@ struct CorrArgs {
 
 struct CorrCtrl {
   uint64_t full[kMaxStages], empty[kMaxStages];
-  uint64_t acc_full[2], acc_empty[2];
+  uint64_t acc_full[kGroups], acc_empty[kGroups];
   uint32_t tmem_base;
 };
 
@@ -59,7 +60,7 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap map_f, const __grid_constant_
   if (warp == 0 && lane == 0) ptx::prefetch_tensormap(&map_f);
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kMaxStages; ++s) { ptx::mbar_init(&ctrl.full[s], 1); ptx::mbar_init(&ctrl.empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { ptx::mbar_init(&ctrl.acc_full[b], 1); ptx::mbar_init(&ctrl.acc_empty[b], 128); }
+    for (int b = 0; b < kGroups; ++b) { ptx::mbar_init(&ctrl.acc_full[b], 1); ptx::mbar_init(&ctrl.acc_empty[b], 128); }
     ptx::fence_barrier_init();
   }
   if (warp == 2) ptx::tmem_alloc(&ctrl.tmem_base, kTmemCols);
@@ -109,7 +110,7 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap map_f, const __grid_constant_
       }
       if (ptx::elect_one()) ptx::tc_commit(&ctrl.acc_full[buf]);
       __syncwarp();
-      if (++buf == 2) { buf = 0; acc_phase ^= 1; }
+      if (++buf == kGroups) { buf = 0; acc_phase ^= 1; }
     }
   } else if (warp >= 4) {
     const int q = warp & 3;
@@ -118,76 +119,59 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap map_f, const __grid_constant_
     const int xw0 = (q & 1) * 32;              // first x of the warp
     const int D = a.D, w = a.w;
     const float scale2 = a.inv_c * 1.4426950408889634f;     // 1/C * log2(e)
-    // two epilogue groups alternate tiles (group g owns accumulator buffer g): twice the warps per
-    // scheduler hide the dependent-issue latency of the softmax arithmetic
+    // kGroups epilogue groups take tiles round-robin (group g owns accumulator buffer g): several warps per
+    // scheduler hide the dependent-issue latency of the softmax arithmetic.  The softmax is ONLINE over
+    // 16-column chunks so only one chunk is live in registers (<= 102 registers per thread at 640 threads).
     const int grp = (warp - 4) >> 2;
     const int buf = grp;  uint32_t acc_phase = 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
-      if ((it & 1) != grp) continue;
+      if (it % kGroups != grp) continue;
       const int n = tile / a.tiles_per_img, y = (tile % a.tiles_per_img) * kRows + rowblk;
       const bool left_ref = n < a.B;
       // target columns this warp needs: left-ref xt in [xw0-D+1, xw0+31], right-ref xt in [xw0, xw0+31+D-1]
       const int lo = left_ref ? max(0, xw0 - D + 1) : xw0;
       const int hi_ = left_ref ? xw0 + 31 : min(kWP - 1, xw0 + 31 + D - 1);
       const int c_lo = lo >> 4, c_hi = hi_ >> 4;          // 16-column chunks, warp-uniform
+      // out-of-image disparities keep cost 0 (oracle semantics): d in [dz0, D) where
+      //   left-ref : x - d < 0   <=>  d > x            right-ref: x + d >= w  <=>  d >= w - x
+      const int dz0 = left_ref ? min(D, x + 1) : min(D, max(0, w - x));
+      // base-2 exponent domain: v = S * log2(e)/C.  Columns outside this thread's disparity window become
+      // -inf (ex2 -> 0); the running max starts at a finite floor so no (-inf) - (-inf) can occur.
+      float m = dz0 < D ? 0.f : -1e30f;
+      float s = 0.f, tx = 0.f;                             // sum e, sum e * xt  (xt is a compile-time column index)
       ptx::mbar_wait(&ctrl.acc_full[buf], acc_phase);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + buf * kM + rowblk * kWP + (static_cast<uint32_t>(q * 32) << 16);
-      // Everything below works in the base-2 exponent domain: v = S * (log2(e) / C).  Columns outside this
-      // thread's disparity window are set to -inf once, which makes both softmax passes branch-free
-      // (ex2(-inf) = 0); the expectation uses sum(e * xt) with compile-time xt and d = +/-(x - xt).
-      float v[4][16];
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         if (c >= c_lo && c <= c_hi) {
           uint32_t u[16];
           ptx::tmem_ld16(taddr + c * 16, u);
           ptx::tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[c][i] = __uint_as_float(u[i]) * scale2;
-        }
-      }
-      ptx::tc_fence_before();
-      ptx::mbar_arrive(&ctrl.acc_empty[buf]);             // accumulator is in registers: release it early
-      acc_phase ^= 1;
-
-      // out-of-image disparities keep cost 0 (oracle semantics): d in [dz0, D) where
-      //   left-ref : x - d < 0   <=>  d > x            right-ref: x + d >= w  <=>  d >= w - x
-      const int dz0 = left_ref ? min(D, x + 1) : min(D, max(0, w - x));
-      float m = dz0 < D ? 0.f : -INFINITY;
-      if (left_ref) {
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-          if (c >= c_lo && c <= c_hi) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              v[c][i] = (unsigned)(x - (c * 16 + i)) < (unsigned)dz0 ? v[c][i] : -INFINITY;
-              m = fmaxf(m, v[c][i]);
-            }
-          }
-      } else {
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-          if (c >= c_lo && c <= c_hi) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              v[c][i] = (unsigned)((c * 16 + i) - x) < (unsigned)dz0 ? v[c][i] : -INFINITY;
-              m = fmaxf(m, v[c][i]);
-            }
-          }
-      }
-      float s = 0.f, tx = 0.f;                             // sum e, sum e * xt
-#pragma unroll
-      for (int c = 0; c < 4; ++c)
-        if (c >= c_lo && c <= c_hi) {
+          float v[16];
+          float cm = -INFINITY;
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const float e = exp2f(v[c][i] - m);
+            const int xt = c * 16 + i;
+            const bool ok = left_ref ? (unsigned)(x - xt) < (unsigned)dz0 : (unsigned)(xt - x) < (unsigned)dz0;
+            v[i] = ok ? __uint_as_float(u[i]) * scale2 : -INFINITY;
+            cm = fmaxf(cm, v[i]);
+          }
+          const float mn = fmaxf(m, cm);
+          const float sc = exp2f(m - mn);
+          s *= sc;  tx *= sc;  m = mn;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float e = exp2f(v[i] - m);
             s += e;
             tx = fmaf(e, (float)(c * 16 + i), tx);
           }
         }
+      }
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&ctrl.acc_empty[buf]);
+      acc_phase ^= 1;
       float t = left_ref ? fmaf((float)x, s, -tx) : fmaf(-(float)x, s, tx);     // sum e * d
       if (dz0 < D) {                                       // (D - dz0) terms of cost 0 at d = dz0 .. D-1
         const float e0 = exp2f(-m), cnt = (float)(D - dz0);
