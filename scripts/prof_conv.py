@@ -11,6 +11,12 @@ if name == 'agg':          # the dominant layer: 64->64 3x3x3 at D=32, 64x64, 12
     conv = nn.Conv3d(64, 64, 3, 1, 1, bias=False); shape = (128, 32, 64, 64, 64)
 elif name == 'agg32':
     conv = nn.Conv3d(64, 64, 3, 1, 1, bias=False); shape = (32, 32, 64, 64, 64)
+elif name == 'mrg':
+    conv = nn.Conv3d(16, 16, 3, 1, 1, bias=False); shape = (128, 32, 32, 32, 16)
+elif name == 'mrg64':
+    conv = nn.Conv3d(64, 16, 3, 1, 1, bias=False); shape = (128, 32, 32, 32, 64)
+elif name == 'mrg_big':
+    conv = nn.Conv3d(16, 16, 3, 1, 1, bias=False); shape = (32, 32, 64, 64, 16)
 elif name == 'agg128':
     conv = nn.Conv3d(64, 128, 3, 1, 1, bias=False); shape = (32, 32, 64, 64, 64)
 elif name == 'pw_planar' or name == 'pw_cl':

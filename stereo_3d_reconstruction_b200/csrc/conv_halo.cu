@@ -43,7 +43,7 @@ constexpr int kTY = 32, kHY = kTY + 2;         // output y per patch, + halo
 constexpr int kPix = kTX * kTY;                // 256 = UMMA N
 constexpr int kPlaneRows = kHX * kHY;          // 340
 constexpr int kMaxRing = 4;
-constexpr int kMaxWStages = 6;
+constexpr int kMaxWStages = 12;
 constexpr int kTmemCols = 512;
 
 struct HaloArgs {
@@ -92,6 +92,196 @@ __device__ __forceinline__ uint64_t desc_hi(uint32_t sbo, int row_bytes) {
 }
 __device__ __forceinline__ uint32_t desc_lo(uint32_t addr) { return ((addr & 0x3FFFF) >> 4) | (1u << 16); }
 
+// Fast-path epilogue of one 16-pixel chunk (two patch lines of 8) for one output channel (= this thread):
+// bias, optional residual, none/ReLU/LeakyReLU as one branch-free formula, bf16 or fp32 store.
+struct FastEpi {
+  void* out;  const void* residual;  float bias, slope;  int osH;  int out_bf16;
+};
+__device__ __forceinline__ void fast_chunk(const FastEpi& e, int64_t zoff, int j0, const int (&xw)[8], const uint32_t (&v)[16]) {
+  const int l0 = (j0 >> 3) * e.osH, l1 = l0 + e.osH;
+  float f[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) + e.bias;
+  if (e.out_bf16) {
+    __nv_bfloat16* __restrict__ o = reinterpret_cast<__nv_bfloat16*>(e.out) + zoff;
+    if (e.residual) {
+      const __nv_bfloat16* __restrict__ rs = reinterpret_cast<const __nv_bfloat16*>(e.residual) + zoff;
+      __nv_bfloat16 r[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) r[i] = rs[(i < 8 ? l0 : l1) + xw[i & 7]];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) f[i] += __bfloat162float(r[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      o[(i < 8 ? l0 : l1) + xw[i & 7]] = __float2bfloat16_rn(fmaxf(f[i], 0.f) + e.slope * fminf(f[i], 0.f));
+  } else {
+    float* __restrict__ o = reinterpret_cast<float*>(e.out) + zoff;
+    if (e.residual) {
+      const float* __restrict__ rs = reinterpret_cast<const float*>(e.residual) + zoff;
+      float r[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) r[i] = rs[(i < 8 ? l0 : l1) + xw[i & 7]];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) f[i] += r[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) o[(i < 8 ? l0 : l1) + xw[i & 7]] = fmaxf(f[i], 0.f) + e.slope * fminf(f[i], 0.f);
+  }
+}
+
+// ---- z-stacked TMA producer ---------------------------------------------------------------------------
+// Profiling (ncu source page, round 1) showed the ORIGINAL producer loop -- ~100 dependent instructions per weight
+// stage: a runtime modulo for the ring slot, generic->shared address conversion of every barrier, arguments
+// re-read from constant memory, an ELECT loop around each UTMALDG -- to be the critical path of the whole
+// kernel (~770 cycles per stage; MMA count, weight bytes and ring depth made no difference).  This version keeps
+// ring slots / parities as incremental counters, uses pre-converted 32-bit barrier addresses, runs warp-uniform
+// and puts only the TMA issue under elect_one.
+struct ZsProd {
+  uint32_t planes_u32, w_u32;                      // shared-memory bases
+  uint32_t bar_pf, bar_pe, bar_wf, bar_we;         // first barrier of each array (8 bytes apart)
+  int slot_bytes, w_bytes, w_stages, ring, w_tx, plane_tx;
+  int nsteps, nplanes, total_cols;
+};
+
+template <int TPS>
+__device__ __forceinline__ void zstack_produce(const HaloArgs& a, const ZsProd& z, const CUtensorMap* map_x,
+                                               const CUtensorMap* map_w) {
+  int ws = 0;  uint32_t wphase = 0;
+  int pslot = 0;  uint32_t pphase = 0;             // next plane slot and the parity its `empty` barrier must have passed
+  int pcol = blockIdx.x, pj = 0, issued = 0;
+  Col pc = decode_col(a, pcol < z.total_cols ? pcol : 0);
+  auto issue_plane = [&](bool blocking) -> bool {
+    if (pcol >= z.total_cols) return false;
+    const uint32_t be = z.bar_pe + 8 * pslot, bf = z.bar_pf + 8 * pslot;
+    if (blocking) ptx::mbar_wait_u32(be, pphase ^ 1);
+    else if (!ptx::mbar_test_wait_u32(be, pphase ^ 1)) return false;
+    if (ptx::elect_one()) {
+      ptx::mbar_arrive_expect_tx_u32(bf, z.plane_tx);
+      ptx::tma_load_5d_u32(z.planes_u32 + pslot * z.slot_bytes, map_x, bf, 0, pc.x0 - 1, pc.y0 - 1, pj - 1, pc.n);
+    }
+    __syncwarp();
+    ++issued;
+    if (++pslot == z.ring) { pslot = 0; pphase ^= 1; }
+    if (++pj == z.nplanes) {
+      pj = 0;  pcol += gridDim.x;
+      if (pcol < z.total_cols) pc = decode_col(a, pcol);
+    }
+    return true;
+  };
+  int col_base = 0;
+  for (int col = blockIdx.x; col < z.total_cols; col += gridDim.x) {
+    for (int st = 0; st < z.nsteps; ++st) {
+      const int need = col_base + st * 2 + 4;                  // planes this step reads (global count)
+      while (issued < need - 2) issue_plane(true);
+      const int need_next = (st + 1 < z.nsteps) ? need + 2 : col_base + z.nplanes + 4;
+      for (int sv = 0; sv < 4; ++sv) {
+        if (sv == 2) while (issued < need) issue_plane(true);
+#pragma unroll
+        for (int kyx0 = 0; kyx0 < 9; kyx0 += TPS) {            // one weight stage = TPS stacked taps, one TMA box
+          if (issued < need_next) issue_plane(false);          // next step's planes, as soon as their slot frees up
+          const uint32_t be = z.bar_we + 8 * ws, bf = z.bar_wf + 8 * ws;
+          ptx::mbar_wait_u32(be, wphase ^ 1);
+          if (ptx::elect_one()) {
+            ptx::mbar_arrive_expect_tx_u32(bf, z.w_tx);
+            ptx::tma_load_3d_u32(z.w_u32 + ws * z.w_bytes, map_w, bf, 0, 0, sv * 9 + kyx0);
+          }
+          __syncwarp();
+          if (++ws == z.w_stages) { ws = 0; wphase ^= 1; }
+        }
+      }
+    }
+    col_base += z.nplanes;
+  }
+}
+
+// ---- z-stacked MMA issue loop -----------------------------------------------------------------------
+// Issue-side cost is the critical path of the narrow layers (one K=16 MMA per tap), and on this compiler a
+// tcgen05.mma only gets the cheap encoding (descriptors in uniform registers, no per-instruction ELECT loop)
+// when it sits in a SMALL straight-line elect_one region.  So: TPS (taps per weight stage) is a template
+// parameter, every tap / K step is unrolled with compile-time offsets, mbarrier waits stay outside the elect
+// region (warp-wide), and there is exactly one elect + __syncwarp per weight stage.
+struct ZsIssue {
+  uint32_t tmem_base, planes_u32, w_u32;
+  uint32_t bar_pf, bar_pe, bar_wf, bar_we, bar_af, bar_ae;   // 32-bit shared addresses of the barrier arrays
+  uint64_t x_hi, w_hi;
+  int slot_bytes, w_bytes, w_stages, ring;
+  uint32_t rb16;
+  uint32_t idesc;
+  int nsteps, nplanes, total_cols;
+};
+
+template <bool kTF32, int TPS>
+__device__ __forceinline__ void zstack_issue(const ZsIssue& z) {
+  constexpr int kPer = 4 / TPS;                  // tcgen05.mma per tap (TPS * row_bytes == 128)
+  int ws = 0;  uint32_t wphase = 0;
+  int buf = 0; uint32_t acc_phase = 0;
+  int pw = 0;  uint32_t pwphase = 0;             // plane slot / parity of the next plane this warp has not waited for yet
+  int waited = 0, col_base = 0;
+  int slot = 0;                                  // ring slot of input plane (col_base + 2*st + sv), kept incrementally
+  const uint32_t tap_step = 8 * z.rb16 * 16;     // 128 rows of one stacked tap, in 16-byte units
+  const uint32_t w_lo0 = desc_lo(z.w_u32), w_lo_step = z.w_bytes >> 4;
+  const uint32_t x_lo0 = desc_lo(z.planes_u32), x_lo_step = z.slot_bytes >> 4;
+  for (int col = blockIdx.x; col < z.total_cols; col += gridDim.x) {
+    for (int st = 0; st < z.nsteps; ++st) {
+      ptx::mbar_wait_u32(z.bar_ae + 8 * buf, acc_phase ^ 1);
+      const uint32_t d_tmem = z.tmem_base + buf * kPix;
+      const int j0 = col_base + st * 2;          // global index of input plane 2*st - 1
+      uint32_t accum = 0;
+      int sl = slot;
+      for (int sv = 0; sv < 4; ++sv) {
+        while (waited < j0 + sv + 1) {
+          ptx::mbar_wait_u32(z.bar_pf + 8 * pw, pwphase);
+          ++waited;
+          if (++pw == z.ring) { pw = 0; pwphase ^= 1; }
+        }
+        ptx::tc_fence_after();
+        const uint64_t xdesc0 = z.x_hi | (x_lo0 + sl * x_lo_step);
+#pragma unroll
+        for (int kyx0 = 0; kyx0 < 9; kyx0 += TPS) {            // one weight stage
+          ptx::mbar_wait_u32(z.bar_wf + 8 * ws, wphase);
+          ptx::tc_fence_after();
+          const uint64_t wdesc0 = z.w_hi | (w_lo0 + ws * w_lo_step);
+          if (ptx::elect_one()) {
+#pragma unroll
+            for (int tt = 0; tt < TPS; ++tt) {
+              const int kyx = kyx0 + tt;
+              if (kyx < 9) {
+                const uint32_t xoff = ((kyx / 3) * kHX + (kyx % 3)) * z.rb16;
+#pragma unroll
+                for (int k = 0; k < kPer; ++k) {
+                  const uint32_t acc = (tt == 0 && k == 0) ? accum : 1u;
+                  if (kTF32) ptx::mma_tf32(d_tmem, wdesc0 + tt * tap_step + 2 * k, xdesc0 + xoff + 2 * k, z.idesc, acc);
+                  else       ptx::mma_bf16(d_tmem, wdesc0 + tt * tap_step + 2 * k, xdesc0 + xoff + 2 * k, z.idesc, acc);
+                }
+              }
+            }
+            ptx::tc_commit_u32(z.bar_we + 8 * ws);
+          }
+          __syncwarp();
+          accum = 1;
+          if (++ws == z.w_stages) { ws = 0; wphase ^= 1; }
+        }
+        // input planes 2st-1 and 2st are dead once their 9 taps are issued; the other two feed the next
+        // step too, except at the end of the column
+        if (sv < 2 || st == z.nsteps - 1) {
+          if (ptx::elect_one()) ptx::tc_commit_u32(z.bar_pe + 8 * sl);
+          __syncwarp();
+        }
+        if (++sl == z.ring) sl = 0;
+      }
+      if (ptx::elect_one()) ptx::tc_commit_u32(z.bar_af + 8 * buf);
+      __syncwarp();
+      if (++buf == 2) { buf = 0; acc_phase ^= 1; }
+      // the next step starts two planes further on
+      slot += 2;  if (slot >= z.ring) slot -= z.ring;
+    }
+    // next column: its first plane is global plane col_base + nplanes = (last step's first plane) + 4
+    col_base += z.nplanes;
+    slot += 2;  if (slot >= z.ring) slot -= z.ring;          // (nplanes = 2*nsteps + 2: two more planes than 2 per step)
+  }
+}
+
 template <bool kTF32>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
@@ -131,8 +321,17 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
   ptx::tc_fence_after();
   const uint32_t tmem_base = ctrl.tmem_base;
 
-  if (warp == 0) {
-    // ================= TMA producer =================
+  if (warp == 0 && a.zstack && a.prestacked) {
+    // ================= TMA producer (z-stacked, host-stacked weights): lean warp-uniform loop =================
+    const ZsProd zp = {ptx::smem_u32(smem), ptx::smem_u32(smem_w),
+                       ptx::smem_u32(&ctrl.plane_full[0]), ptx::smem_u32(&ctrl.plane_empty[0]), ptx::smem_u32(&ctrl.w_full[0]),
+                       ptx::smem_u32(&ctrl.w_empty[0]), a.slot_bytes, a.w_bytes, a.w_stages, ring, a.w_tx, plane_tx,
+                       nsteps, nplanes, a.total_cols};
+    if (a.tps == 1) zstack_produce<1>(a, zp, &map_x, &map_w);
+    else if (a.tps == 2) zstack_produce<2>(a, zp, &map_x, &map_w);
+    else zstack_produce<4>(a, zp, &map_x, &map_w);
+  } else if (warp == 0) {
+    // ================= TMA producer (generic) =================
     if (lane == 0) {
       // plane iterator: next plane to issue = plane `pj` of column `pcol`; `issued` counts globally
       int pcol = blockIdx.x, pj = 0, issued = 0;
@@ -221,55 +420,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     const int kper = rb >> 5;                                 // tcgen05.mma per tap per chunk (32 B of K each)
     const uint32_t w_tap_step = (a.um * rb) >> 4;             // next tap inside a weight stage
     if (a.zstack) {
-      for (int col = blockIdx.x; col < a.total_cols; col += gridDim.x) {
-        for (int st = 0; st < nsteps; ++st) {
-          ptx::mbar_wait(&ctrl.acc_empty[buf], acc_phase ^ 1);
-          const uint32_t d_tmem = tmem_base + buf * kPix;
-          const int j0 = col_base + st * 2;                    // global index of input plane 2*st - 1
-          uint32_t accum = 0;
-          for (int sv = 0; sv < 4; ++sv) {
-            while (waited < j0 + sv + 1) {
-              ptx::mbar_wait(&ctrl.plane_full[waited % ring], (waited / ring) & 1);
-              ++waited;
-            }
-            ptx::tc_fence_after();
-            const int slot = (j0 + sv) % ring;
-            const uint32_t slot_lo = planes_u32 + slot * a.slot_bytes;
-            for (int kyx0 = 0; kyx0 < 9; kyx0 += a.tps) {
-              const int nt = min(a.tps, 9 - kyx0);
-              ptx::mbar_wait(&ctrl.w_full[ws], wphase);
-              ptx::tc_fence_after();
-              const uint32_t wlo = desc_lo(w_u32 + ws * a.w_bytes);
-              if (ptx::elect_one()) {
-                for (int tt = 0; tt < nt; ++tt) {
-                  const int kyx = kyx0 + tt;
-                  const int ky = kyx / 3, kx = kyx - ky * 3;
-                  const uint64_t wdesc = w_hi | (wlo + tt * ((128 * rb) >> 4));
-                  const uint64_t xdesc = x_hi | desc_lo(slot_lo + (ky * kHX + kx) * rb);
-                  for (int k = 0; k < kper; ++k) {
-                    if (kTF32) ptx::mma_tf32(d_tmem, wdesc + 2 * k, xdesc + 2 * k, a.idesc, accum | tt | k);
-                    else       ptx::mma_bf16(d_tmem, wdesc + 2 * k, xdesc + 2 * k, a.idesc, accum | tt | k);
-                  }
-                }
-                ptx::tc_commit(&ctrl.w_empty[ws]);
-              }
-              __syncwarp();
-              accum = 1;
-              if (++ws == a.w_stages) { ws = 0; wphase ^= 1; }
-            }
-            // input planes 2st-1 and 2st are dead once their 9 taps are issued; the other two feed the
-            // next step too, except at the end of the column
-            if (ptx::elect_one()) {
-              if (sv < 2 || st == nsteps - 1) ptx::tc_commit(&ctrl.plane_empty[slot]);
-            }
-            __syncwarp();
-          }
-          if (ptx::elect_one()) ptx::tc_commit(&ctrl.acc_full[buf]);
-          __syncwarp();
-          if (++buf == 2) { buf = 0; acc_phase ^= 1; }
-        }
-        col_base += nplanes;
-      }
+      ZsIssue zi = {tmem_base, planes_u32, w_u32,
+                    ptx::smem_u32(&ctrl.plane_full[0]), ptx::smem_u32(&ctrl.plane_empty[0]), ptx::smem_u32(&ctrl.w_full[0]),
+                    ptx::smem_u32(&ctrl.w_empty[0]), ptx::smem_u32(&ctrl.acc_full[0]), ptx::smem_u32(&ctrl.acc_empty[0]),
+                    x_hi, w_hi, a.slot_bytes, a.w_bytes, a.w_stages, ring, (uint32_t)(rb >> 4), a.idesc, nsteps, nplanes,
+                    a.total_cols};
+      if (a.tps == 1) zstack_issue<kTF32, 1>(zi);
+      else if (a.tps == 2) zstack_issue<kTF32, 2>(zi);
+      else zstack_issue<kTF32, 4>(zi);
     } else {
     for (int col = blockIdx.x; col < a.total_cols; col += gridDim.x) {
         for (int z = 0; z < D; ++z) {
@@ -361,46 +519,20 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         const int64_t zoff = col_off + (int64_t)z * a.p.osD;
         if (warp_any && z < D) {
           if (interior && simple_act) {
-            // fast path (interior patches): no bounds checks, no per-pixel branches; the dtype /
-            // residual variants are warp-uniform branches around fully unrolled bodies.
+            // fast path (interior patches): no bounds checks, no per-pixel branches.  The TMEM loads are
+            // software-pipelined: chunk j+1 is in flight while chunk j is converted and stored (layers with
+            // few output channels have only 1-2 busy epilogue warps, so the load latency must be hidden here).
+            const FastEpi fe = {a.out, a.residual, bias, slope, osH, out_bf16 ? 1 : 0};
+            uint32_t va[16], vb[16];
+            ptx::tmem_ld16(taddr, va);
 #pragma unroll 1
-            for (int j0 = 0; j0 < kPix; j0 += 16) {
-              uint32_t v[16];
-              ptx::tmem_ld16(taddr + j0, v);
+            for (int j0 = 0; j0 < kPix; j0 += 32) {
               ptx::tmem_ld_wait();
-              if (ch_ok) {
-                const int l0 = (j0 >> 3) * osH, l1 = l0 + osH;
-                float f[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) + bias;
-                if (out_bf16) {
-                  __nv_bfloat16* __restrict__ o = reinterpret_cast<__nv_bfloat16*>(a.out) + zoff;
-                  if (a.residual) {
-                    const __nv_bfloat16* __restrict__ rs = reinterpret_cast<const __nv_bfloat16*>(a.residual) + zoff;
-                    __nv_bfloat16 r[16];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) r[i] = rs[(i < 8 ? l0 : l1) + xw[i & 7]];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) f[i] += __bfloat162float(r[i]);
-                  }
-#pragma unroll
-                  for (int i = 0; i < 16; ++i)
-                    o[(i < 8 ? l0 : l1) + xw[i & 7]] = __float2bfloat16_rn(fmaxf(f[i], 0.f) + slope * fminf(f[i], 0.f));
-                } else {
-                  float* __restrict__ o = reinterpret_cast<float*>(a.out) + zoff;
-                  if (a.residual) {
-                    const float* __restrict__ rs = reinterpret_cast<const float*>(a.residual) + zoff;
-                    float r[16];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) r[i] = rs[(i < 8 ? l0 : l1) + xw[i & 7]];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) f[i] += r[i];
-                  }
-#pragma unroll
-                  for (int i = 0; i < 16; ++i)
-                    o[(i < 8 ? l0 : l1) + xw[i & 7]] = fmaxf(f[i], 0.f) + slope * fminf(f[i], 0.f);
-                }
-              }
+              ptx::tmem_ld16(taddr + j0 + 16, vb);
+              if (ch_ok) fast_chunk(fe, zoff, j0, xw, va);
+              ptx::tmem_ld_wait();
+              if (j0 + 32 < kPix) ptx::tmem_ld16(taddr + j0 + 32, va);
+              if (ch_ok) fast_chunk(fe, zoff, j0 + 16, xw, vb);
             }
           } else {
 #pragma unroll 1
@@ -503,7 +635,13 @@ int conv_halo_launch(const S3dConvParams* p_in, const void* in, const void* w, c
   const int budget_total = 225 * 1024;
   a.ring = (budget_total - 2 * a.w_bytes) / a.slot_bytes;
   if (a.ring > kMaxRing) a.ring = kMaxRing;
-  S3D_CHECK_ARG(a.ring >= a.nz + 1, "halo: not enough shared memory for the plane ring");
+  // z-stacked steps release input planes 2s-1 and 2s as soon as their 9 taps are issued, so 3 slots suffice
+  // (plane p reuses the slot of plane p-3, free well before p is needed).  The kernel is bound by the
+  // stage round trip (commit -> producer -> TMA -> MMA, ~1.3 us regardless of stage size: measured with
+  // S3D_HALO_SKIPK / S3D_HALO_HALFW), so shared memory is better spent on MORE weight stages in flight.
+  if (a.zstack && a.ring > 3 && getenv("S3D_HALO_RING4") == nullptr) a.ring = 3;
+  S3D_CHECK_ARG(a.ring >= (a.zstack ? 3 : a.nz + 1), "halo: not enough shared memory for the plane ring");
+
   a.w_stages = (budget_total - a.ring * a.slot_bytes) / a.w_bytes;
   if (a.w_stages > kMaxWStages) a.w_stages = kMaxWStages;
   S3D_CHECK_ARG(a.w_stages >= 2, "halo: not enough shared memory for the weight ring");
