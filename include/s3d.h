@@ -74,6 +74,9 @@ typedef struct S3dConvParams {
    * z-stacked tensor-core tile, [4*9][128][Cin]: row block sv*9+kyx holds W[kz=sv,kyx] in rows 0..63
    * and W[kz=sv-1,kyx] in rows 64..127 (zeros where kz is out of range or co >= Cout). */
   const void* w_zstack;
+  /* 1 if w_zstack holds two more row blocks, [36] = [I;0] and [37] = [0;I] (I = identity over the Cout channels):
+   * the kernel can then add `residual` on the tensor cores instead of in the epilogue. */
+  int32_t w_zstack_ident;
 } S3dConvParams;
 
 const char* s3d_version(void);

@@ -42,7 +42,7 @@ constexpr int kTX = 8, kHX = kTX + 2;          // output x per patch, + halo
 constexpr int kTY = 32, kHY = kTY + 2;         // output y per patch, + halo
 constexpr int kPix = kTX * kTY;                // 256 = UMMA N
 constexpr int kPlaneRows = kHX * kHY;          // 340
-constexpr int kMaxRing = 4;
+constexpr int kMaxRing = 8;
 constexpr int kMaxWStages = 12;
 constexpr int kTmemCols = 512;
 
@@ -60,7 +60,8 @@ struct HaloArgs {
   int ring;           // plane slots
   int um;             // UMMA M: 64 or 128 (output channels per tile)
   int zstack;         // 1: M = 128 = two output planes (z, z+1) x 64 channels stacked (3x3x3, Cout <= 64)
-  int prestacked;     // map_w is the host-stacked [36][128][Cin] tensor: one TMA box per weight stage
+  int prestacked;     // map_w is the host-stacked [36(+2)][128][Cin] tensor: one TMA box per weight stage
+  int res_tap;        // residual added on the tensor core: identity row blocks 36/37 x TMA-staged residual planes
   int tps;            // taps per weight stage (128 / row_bytes)
   int w_stages, w_bytes, w_tx;
   int cols_x, cols_y, n_mtiles, total_cols;
@@ -71,6 +72,7 @@ struct HaloCtrl {
   uint64_t plane_full[kMaxRing], plane_empty[kMaxRing];
   uint64_t w_full[kMaxWStages], w_empty[kMaxWStages];
   uint64_t acc_full[2], acc_empty[2];
+  uint64_t res_full, res_empty;          // residual plane buffer (res_tap)
   uint32_t tmem_base;
 };
 
@@ -92,41 +94,60 @@ __device__ __forceinline__ uint64_t desc_hi(uint32_t sbo, int row_bytes) {
 }
 __device__ __forceinline__ uint32_t desc_lo(uint32_t addr) { return ((addr & 0x3FFFF) >> 4) | (1u << 16); }
 
-// Fast-path epilogue of one 16-pixel chunk (two patch lines of 8) for one output channel (= this thread):
-// bias, optional residual, none/ReLU/LeakyReLU as one branch-free formula, bf16 or fp32 store.
+// Fast-path epilogue (interior patch, none/ReLU/LeakyReLU): thread = one output channel (TMEM lane), 256 pixel
+// columns in chunks of 16 (two patch lines of 8).  TMEM loads AND residual loads of chunk j+1 are in flight while
+// chunk j is converted and stored (software pipeline in registers).
 struct FastEpi {
-  void* out;  const void* residual;  float bias, slope;  int osH;  int out_bf16;
+  void* out;  const void* residual;  float bias, slope;  int osH;
 };
-__device__ __forceinline__ void fast_chunk(const FastEpi& e, int64_t zoff, int j0, const int (&xw)[8], const uint32_t (&v)[16]) {
+
+template <typename T> struct RawOf;
+template <> struct RawOf<__nv_bfloat16> { typedef unsigned short type; };
+template <> struct RawOf<float> { typedef float type; };
+
+template <typename T, bool kRes>
+__device__ __forceinline__ void fast_res_load(const FastEpi& e, int64_t zoff, int j0, const int (&xw)[8], T (&r)[16]) {
+  if (kRes) {
+    const T* __restrict__ rs = reinterpret_cast<const T*>(e.residual) + zoff;
+    const int l0 = (j0 >> 3) * e.osH, l1 = l0 + e.osH;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) r[i] = rs[(i < 8 ? l0 : l1) + xw[i & 7]];
+  }
+}
+
+template <typename T, bool kRes>
+__device__ __forceinline__ void fast_chunk(const FastEpi& e, int64_t zoff, int j0, const int (&xw)[8], const uint32_t (&v)[16],
+                                           const T (&r)[16]) {
+  T* __restrict__ o = reinterpret_cast<T*>(e.out) + zoff;
   const int l0 = (j0 >> 3) * e.osH, l1 = l0 + e.osH;
-  float f[16];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) + e.bias;
-  if (e.out_bf16) {
-    __nv_bfloat16* __restrict__ o = reinterpret_cast<__nv_bfloat16*>(e.out) + zoff;
-    if (e.residual) {
-      const __nv_bfloat16* __restrict__ rs = reinterpret_cast<const __nv_bfloat16*>(e.residual) + zoff;
-      __nv_bfloat16 r[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) r[i] = rs[(i < 8 ? l0 : l1) + xw[i & 7]];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) f[i] += __bfloat162float(r[i]);
+  for (int i = 0; i < 16; ++i) {
+    float f = __uint_as_float(v[i]) + e.bias;
+    if (kRes) f += to_f32<T>(r[i]);
+    o[(i < 8 ? l0 : l1) + xw[i & 7]] = from_f32<T>(fmaxf(f, 0.f) + e.slope * fminf(f, 0.f));
+  }
+}
+
+template <typename T, bool kRes>
+__device__ __forceinline__ void fast_epilogue(const FastEpi& e, uint32_t taddr, int64_t zoff, const int (&xw)[8], bool ch_ok) {
+  uint32_t va[16], vb[16];
+  T ra[16], rb[16];
+  ptx::tmem_ld16(taddr, va);
+  if (ch_ok) fast_res_load<T, kRes>(e, zoff, 0, xw, ra);
+#pragma unroll 1
+  for (int j0 = 0; j0 < kPix; j0 += 32) {
+    ptx::tmem_ld_wait();
+    ptx::tmem_ld16(taddr + j0 + 16, vb);
+    if (ch_ok) {
+      fast_res_load<T, kRes>(e, zoff, j0 + 16, xw, rb);
+      fast_chunk<T, kRes>(e, zoff, j0, xw, va, ra);
     }
-#pragma unroll
-    for (int i = 0; i < 16; ++i)
-      o[(i < 8 ? l0 : l1) + xw[i & 7]] = __float2bfloat16_rn(fmaxf(f[i], 0.f) + e.slope * fminf(f[i], 0.f));
-  } else {
-    float* __restrict__ o = reinterpret_cast<float*>(e.out) + zoff;
-    if (e.residual) {
-      const float* __restrict__ rs = reinterpret_cast<const float*>(e.residual) + zoff;
-      float r[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) r[i] = rs[(i < 8 ? l0 : l1) + xw[i & 7]];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) f[i] += r[i];
+    ptx::tmem_ld_wait();
+    if (j0 + 32 < kPix) {
+      ptx::tmem_ld16(taddr + j0 + 32, va);
+      if (ch_ok) fast_res_load<T, kRes>(e, zoff, j0 + 32, xw, ra);
     }
-#pragma unroll
-    for (int i = 0; i < 16; ++i) o[(i < 8 ? l0 : l1) + xw[i & 7]] = fmaxf(f[i], 0.f) + e.slope * fminf(f[i], 0.f);
+    if (ch_ok) fast_chunk<T, kRes>(e, zoff, j0 + 16, xw, vb, rb);
   }
 }
 
@@ -141,16 +162,43 @@ struct ZsProd {
   uint32_t planes_u32, w_u32;                      // shared-memory bases
   uint32_t bar_pf, bar_pe, bar_wf, bar_we;         // first barrier of each array (8 bytes apart)
   int slot_bytes, w_bytes, w_stages, ring, w_tx, plane_tx;
-  int nsteps, nplanes, total_cols;
+  int nsteps, nplanes, total_cols, lookahead;
+  int res_tap;  uint32_t res_u32, bar_rf, bar_re;       // residual plane buffer (32 KB) and its barrier pair
 };
 
 template <int TPS>
 __device__ __forceinline__ void zstack_produce(const HaloArgs& a, const ZsProd& z, const CUtensorMap* map_x,
-                                               const CUtensorMap* map_w) {
+                                               const CUtensorMap* map_w, const CUtensorMap* map_r) {
   int ws = 0;  uint32_t wphase = 0;
   int pslot = 0;  uint32_t pphase = 0;             // next plane slot and the parity its `empty` barrier must have passed
   int pcol = blockIdx.x, pj = 0, issued = 0;
   Col pc = decode_col(a, pcol < z.total_cols ? pcol : 0);
+  // residual-as-a-tap: ONE 32 KB buffer filled twice per step (plane 2st for the identity block [I;0] issued after
+  // sv 0, plane 2st+1 for [0;I] after sv 2).  Fill k+1 may only start when fill k has been consumed, so fills are
+  // issued opportunistically (test_wait) from the stage loop, like the input planes.
+  int r_issued = 0, rcol = blockIdx.x, rst = 0, rhalf = 0;
+  Col rc = pc;
+  auto issue_res = [&](bool blocking) -> bool {
+    if (rcol >= z.total_cols) return false;
+    const uint32_t par = ((uint32_t)r_issued & 1u) ^ 1u;
+    if (blocking) ptx::mbar_wait_u32(z.bar_re, par);
+    else if (!ptx::mbar_test_wait_u32(z.bar_re, par)) return false;
+    if (ptx::elect_one()) {
+      ptx::mbar_arrive_expect_tx_u32(z.bar_rf, kPix * 128);
+      ptx::tma_load_5d_u32(z.res_u32, map_r, z.bar_rf, 0, rc.x0, rc.y0, rst * 2 + rhalf, rc.n);   // z >= D: zero fill
+    }
+    __syncwarp();
+    ++r_issued;
+    if (++rhalf == 2) {
+      rhalf = 0;
+      if (++rst == z.nsteps) {
+        rst = 0;  rcol += gridDim.x;
+        if (rcol < z.total_cols) rc = decode_col(a, rcol);
+      }
+    }
+    return true;
+  };
+  int gstep = 0;
   auto issue_plane = [&](bool blocking) -> bool {
     if (pcol >= z.total_cols) return false;
     const uint32_t be = z.bar_pe + 8 * pslot, bf = z.bar_pf + 8 * pslot;
@@ -174,12 +222,15 @@ __device__ __forceinline__ void zstack_produce(const HaloArgs& a, const ZsProd& 
     for (int st = 0; st < z.nsteps; ++st) {
       const int need = col_base + st * 2 + 4;                  // planes this step reads (global count)
       while (issued < need - 2) issue_plane(true);
-      const int need_next = (st + 1 < z.nsteps) ? need + 2 : col_base + z.nplanes + 4;
+      // planes of the following step(s) (global numbering runs on into the next column) are requested as soon as
+      // their ring slot is free; how far ahead depends on the ring size (small planes -> deep ring)
+      const int need_next = need + z.lookahead;
       for (int sv = 0; sv < 4; ++sv) {
         if (sv == 2) while (issued < need) issue_plane(true);
 #pragma unroll
         for (int kyx0 = 0; kyx0 < 9; kyx0 += TPS) {            // one weight stage = TPS stacked taps, one TMA box
           if (issued < need_next) issue_plane(false);          // next step's planes, as soon as their slot frees up
+          if (TPS == 1 && z.res_tap && r_issued < 2 * gstep + 3) issue_res(false);
           const uint32_t be = z.bar_we + 8 * ws, bf = z.bar_wf + 8 * ws;
           ptx::mbar_wait_u32(be, wphase ^ 1);
           if (ptx::elect_one()) {
@@ -189,7 +240,20 @@ __device__ __forceinline__ void zstack_produce(const HaloArgs& a, const ZsProd& 
           __syncwarp();
           if (++ws == z.w_stages) { ws = 0; wphase ^= 1; }
         }
+        if (TPS == 1 && z.res_tap && (sv == 0 || sv == 2)) {   // identity stage: row block 36 ([I;0]) / 37 ([0;I])
+          const int half = sv >> 1;
+          while (r_issued < 2 * gstep + 1 + half) issue_res(true);
+          const uint32_t be = z.bar_we + 8 * ws, bf = z.bar_wf + 8 * ws;
+          ptx::mbar_wait_u32(be, wphase ^ 1);
+          if (ptx::elect_one()) {
+            ptx::mbar_arrive_expect_tx_u32(bf, z.w_tx);
+            ptx::tma_load_3d_u32(z.w_u32 + ws * z.w_bytes, map_w, bf, 0, 0, 36 + half);
+          }
+          __syncwarp();
+          if (++ws == z.w_stages) { ws = 0; wphase ^= 1; }
+        }
       }
+      ++gstep;
     }
     col_base += z.nplanes;
   }
@@ -209,15 +273,16 @@ struct ZsIssue {
   uint32_t rb16;
   uint32_t idesc;
   int nsteps, nplanes, total_cols;
+  int res_tap;  uint32_t res_u32, bar_rf, bar_re;
 };
 
-template <bool kTF32, int TPS>
+template <bool kTF32, int TPS, int kPer>          // TPS taps per weight stage, kPer = row_bytes / 32 MMAs per tap
 __device__ __forceinline__ void zstack_issue(const ZsIssue& z) {
-  constexpr int kPer = 4 / TPS;                  // tcgen05.mma per tap (TPS * row_bytes == 128)
   int ws = 0;  uint32_t wphase = 0;
   int buf = 0; uint32_t acc_phase = 0;
   int pw = 0;  uint32_t pwphase = 0;             // plane slot / parity of the next plane this warp has not waited for yet
   int waited = 0, col_base = 0;
+  uint32_t res_use = 0;                          // residual buffer fills consumed so far
   int slot = 0;                                  // ring slot of input plane (col_base + 2*st + sv), kept incrementally
   const uint32_t tap_step = 8 * z.rb16 * 16;     // 128 rows of one stacked tap, in 16-byte units
   const uint32_t w_lo0 = desc_lo(z.w_u32), w_lo_step = z.w_bytes >> 4;
@@ -269,6 +334,26 @@ __device__ __forceinline__ void zstack_issue(const ZsIssue& z) {
           __syncwarp();
         }
         if (++sl == z.ring) sl = 0;
+        if (TPS == 1 && z.res_tap && (sv == 0 || sv == 2)) {
+          // residual as one more tap: D += [I;0] (or [0;I]) x residual plane 2st (2st+1), 4 K steps of 16 channels
+          ptx::mbar_wait_u32(z.bar_wf + 8 * ws, wphase);
+          ptx::mbar_wait_u32(z.bar_rf, res_use & 1);
+          ptx::tc_fence_after();
+          const uint64_t wdesc0 = z.w_hi | (w_lo0 + ws * w_lo_step);
+          const uint64_t rdesc0 = z.w_hi | desc_lo(z.res_u32);            // dense 128-byte rows, like the weights
+          if (ptx::elect_one()) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              if (kTF32) ptx::mma_tf32(d_tmem, wdesc0 + 2 * k, rdesc0 + 2 * k, z.idesc, 1u);
+              else       ptx::mma_bf16(d_tmem, wdesc0 + 2 * k, rdesc0 + 2 * k, z.idesc, 1u);
+            }
+            ptx::tc_commit_u32(z.bar_we + 8 * ws);
+            ptx::tc_commit_u32(z.bar_re);
+          }
+          __syncwarp();
+          ++res_use;
+          if (++ws == z.w_stages) { ws = 0; wphase ^= 1; }
+        }
       }
       if (ptx::elect_one()) ptx::tc_commit_u32(z.bar_af + 8 * buf);
       __syncwarp();
@@ -285,7 +370,7 @@ __device__ __forceinline__ void zstack_issue(const ZsIssue& z) {
 template <bool kTF32>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
-                 const __grid_constant__ HaloArgs a) {
+                 const __grid_constant__ CUtensorMap map_r, const __grid_constant__ HaloArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_w = smem + a.ring * a.slot_bytes;
@@ -313,6 +398,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     for (int s = 0; s < kMaxRing; ++s) { ptx::mbar_init(&ctrl.plane_full[s], 1); ptx::mbar_init(&ctrl.plane_empty[s], 1); }
     for (int s = 0; s < kMaxWStages; ++s) { ptx::mbar_init(&ctrl.w_full[s], 1); ptx::mbar_init(&ctrl.w_empty[s], 1); }
     for (int b = 0; b < 2; ++b) { ptx::mbar_init(&ctrl.acc_full[b], 1); ptx::mbar_init(&ctrl.acc_empty[b], 128); }
+    ptx::mbar_init(&ctrl.res_full, 1);  ptx::mbar_init(&ctrl.res_empty, 1);
     ptx::fence_barrier_init();
   }
   if (warp == 2) ptx::tmem_alloc(&ctrl.tmem_base, kTmemCols);
@@ -326,10 +412,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     const ZsProd zp = {ptx::smem_u32(smem), ptx::smem_u32(smem_w),
                        ptx::smem_u32(&ctrl.plane_full[0]), ptx::smem_u32(&ctrl.plane_empty[0]), ptx::smem_u32(&ctrl.w_full[0]),
                        ptx::smem_u32(&ctrl.w_empty[0]), a.slot_bytes, a.w_bytes, a.w_stages, ring, a.w_tx, plane_tx,
-                       nsteps, nplanes, a.total_cols};
-    if (a.tps == 1) zstack_produce<1>(a, zp, &map_x, &map_w);
-    else if (a.tps == 2) zstack_produce<2>(a, zp, &map_x, &map_w);
-    else zstack_produce<4>(a, zp, &map_x, &map_w);
+                       nsteps, nplanes, a.total_cols, ring > 4 ? ring - 2 : 2,
+                       a.res_tap, ptx::smem_u32(smem_w + a.w_stages * a.w_bytes), ptx::smem_u32(&ctrl.res_full),
+                       ptx::smem_u32(&ctrl.res_empty)};
+    if (a.tps == 1) zstack_produce<1>(a, zp, &map_x, &map_w, &map_r);
+    else if (a.tps == 3) zstack_produce<3>(a, zp, &map_x, &map_w, &map_r);
+    else zstack_produce<9>(a, zp, &map_x, &map_w, &map_r);
   } else if (warp == 0) {
     // ================= TMA producer (generic) =================
     if (lane == 0) {
@@ -424,10 +512,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
                     ptx::smem_u32(&ctrl.plane_full[0]), ptx::smem_u32(&ctrl.plane_empty[0]), ptx::smem_u32(&ctrl.w_full[0]),
                     ptx::smem_u32(&ctrl.w_empty[0]), ptx::smem_u32(&ctrl.acc_full[0]), ptx::smem_u32(&ctrl.acc_empty[0]),
                     x_hi, w_hi, a.slot_bytes, a.w_bytes, a.w_stages, ring, (uint32_t)(rb >> 4), a.idesc, nsteps, nplanes,
-                    a.total_cols};
-      if (a.tps == 1) zstack_issue<kTF32, 1>(zi);
-      else if (a.tps == 2) zstack_issue<kTF32, 2>(zi);
-      else zstack_issue<kTF32, 4>(zi);
+                    a.total_cols, a.res_tap, ptx::smem_u32(smem_w + a.w_stages * a.w_bytes), ptx::smem_u32(&ctrl.res_full),
+                    ptx::smem_u32(&ctrl.res_empty)};
+      if (!a.prestacked) {                      // direct C callers without host-stacked weights: 128/row_bytes taps per stage
+        if (a.tps == 1) zstack_issue<kTF32, 1, 4>(zi);
+        else if (a.tps == 2) zstack_issue<kTF32, 2, 2>(zi);
+        else zstack_issue<kTF32, 4, 1>(zi);
+      } else if (a.tps == 1) zstack_issue<kTF32, 1, 4>(zi);
+      else if (a.tps == 3) zstack_issue<kTF32, 3, 2>(zi);
+      else zstack_issue<kTF32, 9, 1>(zi);
     } else {
     for (int col = blockIdx.x; col < a.total_cols; col += gridDim.x) {
         for (int z = 0; z < D; ++z) {
@@ -519,20 +612,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         const int64_t zoff = col_off + (int64_t)z * a.p.osD;
         if (warp_any && z < D) {
           if (interior && simple_act) {
-            // fast path (interior patches): no bounds checks, no per-pixel branches.  The TMEM loads are
-            // software-pipelined: chunk j+1 is in flight while chunk j is converted and stored (layers with
-            // few output channels have only 1-2 busy epilogue warps, so the load latency must be hidden here).
-            const FastEpi fe = {a.out, a.residual, bias, slope, osH, out_bf16 ? 1 : 0};
-            uint32_t va[16], vb[16];
-            ptx::tmem_ld16(taddr, va);
-#pragma unroll 1
-            for (int j0 = 0; j0 < kPix; j0 += 32) {
-              ptx::tmem_ld_wait();
-              ptx::tmem_ld16(taddr + j0 + 16, vb);
-              if (ch_ok) fast_chunk(fe, zoff, j0, xw, va);
-              ptx::tmem_ld_wait();
-              if (j0 + 32 < kPix) ptx::tmem_ld16(taddr + j0 + 32, va);
-              if (ch_ok) fast_chunk(fe, zoff, j0 + 16, xw, vb);
+            // fast path (interior patches): no bounds checks, no per-pixel branches, loads software-pipelined
+            const void* res_ep = a.res_tap ? nullptr : a.residual;     // res_tap: already in the accumulator
+            const FastEpi fe = {a.out, res_ep, bias, slope, osH};
+            if (out_bf16) {
+              if (res_ep) fast_epilogue<__nv_bfloat16, true>(fe, taddr, zoff, xw, ch_ok);
+              else            fast_epilogue<__nv_bfloat16, false>(fe, taddr, zoff, xw, ch_ok);
+            } else {
+              if (res_ep) fast_epilogue<float, true>(fe, taddr, zoff, xw, ch_ok);
+              else            fast_epilogue<float, false>(fe, taddr, zoff, xw, ch_ok);
             }
           } else {
 #pragma unroll 1
@@ -546,7 +634,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
                 for (int i = 0; i < 16; ++i) {           // batch the residual loads (independent, in flight together)
                   const int yl = (j0 >> 3) + (i >> 3), xl = i & 7;
                   r[i] = 0.f;
-                  if (a.residual && yl < ylim && xl < xlim) {
+                  if (a.residual && !a.res_tap && yl < ylim && xl < xlim) {
                     const int64_t off = zoff + yl * osH + xw[xl];
                     r[i] = out_bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(a.residual)[off])
                                     : reinterpret_cast<const float*>(a.residual)[off];
@@ -628,20 +716,33 @@ int conv_halo_launch(const S3dConvParams* p_in, const void* in, const void* w, c
   a.um = (p.Cout > 64 || a.zstack) ? 128 : 64;
   a.n_mtiles = p.Cout > 64 ? p.Cout / 128 : 1;
   a.tps = 128 / a.row_bytes;
+  a.prestacked = a.zstack && p.w_zstack != nullptr && getenv("S3D_NO_PRESTACK") == nullptr;
+  // host-stacked weights: a weight stage is a whole number of the 9 in-plane taps (fewer barrier round trips for
+  // narrow layers, where one tap is a single K=16 MMA): 1 / 3 / 9 taps for 128 / 64 / 32-byte rows
+  if (a.prestacked) a.tps = a.row_bytes == 128 ? 1 : (a.row_bytes == 64 ? 3 : 9);
+  // residual on the tensor core: needs the identity row blocks, 128-byte rows on both sides (residual channels ==
+  // Cin == Cout), bf16 (kind::tf32 would round an fp32 residual to 10 mantissa bits) and a dense channels-last output
+  a.res_tap = a.prestacked && residual != nullptr && p.w_zstack_ident && a.row_bytes == 128 && !tf32 &&
+              p.out_dtype == S3D_DTYPE_BF16 && p.Cout * esz == 128 && p.osW == p.Cout && p.osH == p.osW * p.oW &&
+              p.osD == p.osH * p.oH && p.osN == p.osD * p.oD && getenv("S3D_NO_RES_TAP") == nullptr;
+  const int res_bytes = a.res_tap ? kPix * 128 : 0;
   // weight map [taps][Cout][Cin]: a stage is a (kc, um, tps) box; rows beyond Cout / taps beyond ntaps
   // are zero-filled by the TMA unit (and still count towards the transaction bytes).
   a.w_tx = a.tps * a.um * a.row_bytes;
   a.w_bytes = (a.w_tx + 1023) / 1024 * 1024;
-  const int budget_total = 225 * 1024;
+  const int budget_total = 225 * 1024 - res_bytes;
   a.ring = (budget_total - 2 * a.w_bytes) / a.slot_bytes;
-  if (a.ring > kMaxRing) a.ring = kMaxRing;
-  // z-stacked steps release input planes 2s-1 and 2s as soon as their 9 taps are issued, so 3 slots suffice
-  // (plane p reuses the slot of plane p-3, free well before p is needed).  The kernel is bound by the
-  // stage round trip (commit -> producer -> TMA -> MMA, ~1.3 us regardless of stage size: measured with
-  // S3D_HALO_SKIPK / S3D_HALO_HALFW), so shared memory is better spent on MORE weight stages in flight.
-  if (a.zstack && a.ring > 3 && getenv("S3D_HALO_RING4") == nullptr) a.ring = 3;
+  if (a.ring > 4) a.ring = 4;
+  if (a.zstack) {
+    // z-stacked steps release input planes 2s-1 and 2s as soon as their 9 taps are issued, so 3 slots suffice
+    // (plane p reuses the slot of plane p-3).  Big planes (128-byte rows): 3 slots, the rest of shared memory
+    // goes to weight stages.  Small planes (narrow layers): a deep ring, because a step is then so short that the
+    // plane round trip (release -> TMA of 340 short rows -> full) would otherwise stall it.
+    const int deep = (budget_total - 4 * a.w_bytes) / a.slot_bytes;      // keep at least 4 weight stages
+    a.ring = deep > kMaxRing ? kMaxRing : (deep < 3 ? 3 : deep);
+    if (getenv("S3D_HALO_RING4") != nullptr) a.ring = 4;
+  }
   S3D_CHECK_ARG(a.ring >= (a.zstack ? 3 : a.nz + 1), "halo: not enough shared memory for the plane ring");
-
   a.w_stages = (budget_total - a.ring * a.slot_bytes) / a.w_bytes;
   if (a.w_stages > kMaxWStages) a.w_stages = kMaxWStages;
   S3D_CHECK_ARG(a.w_stages >= 2, "halo: not enough shared memory for the weight ring");
@@ -658,12 +759,17 @@ int conv_halo_launch(const S3dConvParams* p_in, const void* in, const void* w, c
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   int rc = encode_act_map(&map_x, in, esz, tf32, p.Cin, p.iW, p.iH, p.iD, p.N, box, estr, sw);
   if (rc != S3D_OK) return rc;
-  a.prestacked = a.zstack && p.w_zstack != nullptr && getenv("S3D_NO_PRESTACK") == nullptr;
-  if (a.prestacked) rc = encode_weight_map(&map_w, p.w_zstack, esz, tf32, p.Cin, 128, 36, a.kc, 128, sw, a.tps);
+  if (a.prestacked) rc = encode_weight_map(&map_w, p.w_zstack, esz, tf32, p.Cin, 128, p.w_zstack_ident ? 38 : 36, a.kc, 128, sw, a.tps);
   else rc = encode_weight_map(&map_w, w, esz, tf32, p.Cin, p.Cout, p.ntaps, a.kc, a.zstack ? 64 : a.um, sw, a.zstack ? 1 : a.tps);
   if (rc != S3D_OK) return rc;
 
-  const int smem_bytes = a.ring * a.slot_bytes + a.w_stages * a.w_bytes + 1024;
+  CUtensorMap map_r = map_x;                                   // placeholder when unused
+  if (a.res_tap) {
+    cuuint32_t rbox[5] = {(cuuint32_t)a.kc, kTX, kTY, 1, 1};   // the 32 x 8 output patch itself, no halo
+    rc = encode_act_map(&map_r, residual, esz, tf32, p.Cout, p.oW, p.oH, p.oD, p.N, rbox, estr, sw);
+    if (rc != S3D_OK) return rc;
+  }
+  const int smem_bytes = a.ring * a.slot_bytes + a.w_stages * a.w_bytes + res_bytes + 1024;
   auto kern = tf32 ? conv_halo_kernel<true> : conv_halo_kernel<false>;
   static int attr_set[2] = {0, 0};
   if (attr_set[tf32] < smem_bytes) {
@@ -672,7 +778,7 @@ int conv_halo_launch(const S3dConvParams* p_in, const void* in, const void* w, c
   }
   int grid = num_sms();
   if (grid > a.total_cols) grid = a.total_cols;
-  kern<<<grid, kThreads, smem_bytes, stream>>>(map_x, map_w, a);
+  kern<<<grid, kThreads, smem_bytes, stream>>>(map_x, map_w, map_r, a);
   S3D_LAUNCH_CHECK();
   return S3D_OK;
 }

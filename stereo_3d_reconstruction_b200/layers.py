@@ -95,14 +95,22 @@ class PackedConv:
         self.weight_zs = None
         if tuple(ksize) == (3, 3, 3) and tuple(pad) == (1, 1, 1) and tuple(stride) == (1, 1, 1) and \
                 self.n_classes == 1 and self.cout_pad <= 64:
-            zs = torch.zeros(4, 9, 128, self.cin_pad, dtype=torch.float32)
+            zs = torch.zeros(38, 128, self.cin_pad, dtype=torch.float32)
             w3 = wp.view(3, 9, self.cout_pad, self.cin_pad)
+            z4 = zs[:36].view(4, 9, 128, self.cin_pad)
             for sv in range(4):
                 if sv <= 2:
-                    zs[sv, :, :self.cout_pad] = w3[sv]
+                    z4[sv, :, :self.cout_pad] = w3[sv]
                 if sv >= 1:
-                    zs[sv, :, 64:64 + self.cout_pad] = w3[sv - 1]
-            self.weight_zs = zs.view(36, 128, self.cin_pad).to(torch_dtype(dtype_code)).to(device).contiguous()
+                    z4[sv, :, 64:64 + self.cout_pad] = w3[sv - 1]
+            # row blocks 36 / 37: identity onto output plane z / z+1, so a residual tensor (same channel count as
+            # the input) can be added by the tensor core as one more "tap"
+            self.zs_ident = self.cin_pad == self.cout_pad
+            if self.zs_ident:
+                eye = torch.eye(self.cout_pad)
+                zs[36, :self.cout_pad] = eye
+                zs[37, 64:64 + self.cout_pad] = eye
+            self.weight_zs = zs.to(torch_dtype(dtype_code)).to(device).contiguous()
         self.bn = _choose_bn(self.cout_pad)
         self._cache = {}
 
@@ -193,6 +201,7 @@ class PackedConv:
         p.tw, p.th, p.td, p.tn = _choose_tile(N, oD, oH, oW, self.stride[2], self.stride[1], self.stride[0])
         p.bn = self.bn
         p.w_zstack = self.weight_zs.data_ptr() if self.weight_zs is not None else None
+        p.w_zstack_ident = 1 if (self.weight_zs is not None and self.zs_ident) else 0
         self._cache[key] = p
         return p
 

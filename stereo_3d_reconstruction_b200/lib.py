@@ -35,6 +35,7 @@ class S3dConvParams(ctypes.Structure):
         ('tw', ctypes.c_int32), ('th', ctypes.c_int32), ('td', ctypes.c_int32), ('tn', ctypes.c_int32),
         ('bn', ctypes.c_int32),
         ('w_zstack', ctypes.c_void_p),
+        ('w_zstack_ident', ctypes.c_int32),
     ]
 
 

@@ -88,3 +88,16 @@ def test_igemm_rejects_bad_shapes():
     out = torch.zeros(1, 1, 8, 8, 16, dtype=torch.bfloat16).cuda()
     rc = lib.load().s3d_conv_igemm(ctypes.byref(q), x.data_ptr(), pc.weight.data_ptr(), None, None, out.data_ptr(), None)
     assert rc == -1 and b'tile' in lib.load().s3d_last_error()
+
+
+@pytest.mark.parametrize('D,H,W', [(4, 16, 16), (5, 37, 19), (2, 64, 64)])
+def test_conv3d_residual_on_tensor_core(D, H, W):
+    """64->64 3x3x3 bf16 with a residual: the halo kernel adds the residual as an identity 'tap' (TMA-staged
+    residual plane x [I;0] / [0;I] weight blocks) instead of loading it in the epilogue."""
+    torch.manual_seed(5)
+    conv = nn.Conv3d(64, 64, 3, 1, 1, bias=True)
+    x = torch.randn(2, 64, D, H, W)
+    res = torch.randn(2, 64, D, H, W).to(torch.bfloat16).float()
+    pc = PackedConv.from_conv(conv, None, lib.ACT_RELU, lib.DTYPE_BF16, 'cuda')
+    assert pc.zs_ident
+    _check(pc, x, F.relu(conv(x) + res), 'bf16', 64, residual=to_cl(res).to(torch.bfloat16).cuda())

@@ -58,12 +58,16 @@ def test_zstack_weights_layout():
     torch.manual_seed(0)
     conv = nn.Conv3d(16, 24, 3, 1, 1, bias=False)
     pc = PackedConv.from_conv(conv, None, lib.ACT_NONE, lib.DTYPE_F32, 'cpu')
-    zs = pc.weight_zs.view(4, 9, 128, pc.cin_pad)
+    assert pc.weight_zs.shape[0] == 38 and not pc.zs_ident and pc.weight_zs[36:].abs().sum() == 0      # Cin != Cout: no identity blocks
+    zs = pc.weight_zs[:36].view(4, 9, 128, pc.cin_pad)
     w = pc.weight.view(3, 9, pc.cout_pad, pc.cin_pad)
     for sv in range(4):
         top = w[sv] if sv <= 2 else torch.zeros_like(w[0])
         bot = w[sv - 1] if sv >= 1 else torch.zeros_like(w[0])
         assert torch.equal(zs[sv, :, :pc.cout_pad], top) and torch.equal(zs[sv, :, 64:64 + pc.cout_pad], bot)
         assert zs[sv, :, pc.cout_pad:64].abs().sum() == 0 and zs[sv, :, 64 + pc.cout_pad:].abs().sum() == 0
+    pc2 = PackedConv.from_conv(nn.Conv3d(32, 32, 3, 1, 1), None, lib.ACT_NONE, lib.DTYPE_F32, 'cpu')
+    assert pc2.zs_ident and torch.equal(pc2.weight_zs[36, :32], torch.eye(32)) and torch.equal(pc2.weight_zs[37, 64:96], torch.eye(32))
+    assert pc2.weight_zs[36, 32:].abs().sum() == 0 and pc2.weight_zs[37, :64].abs().sum() == 0
     conv2 = nn.Conv3d(16, 128, 3, 1, 1)
     assert PackedConv.from_conv(conv2, None, lib.ACT_NONE, lib.DTYPE_F32, 'cpu').weight_zs is None
