@@ -166,7 +166,7 @@ struct ZsProd {
   int res_tap;  uint32_t res_u32, bar_rf, bar_re;       // residual plane buffer (32 KB) and its barrier pair
 };
 
-template <int TPS>
+template <int TPS, bool kRes>                    // kRes: residual-as-a-tap stages (only with TPS == 1)
 __device__ __forceinline__ void zstack_produce(const HaloArgs& a, const ZsProd& z, const CUtensorMap* map_x,
                                                const CUtensorMap* map_w, const CUtensorMap* map_r) {
   int ws = 0;  uint32_t wphase = 0;
@@ -230,7 +230,7 @@ __device__ __forceinline__ void zstack_produce(const HaloArgs& a, const ZsProd& 
 #pragma unroll
         for (int kyx0 = 0; kyx0 < 9; kyx0 += TPS) {            // one weight stage = TPS stacked taps, one TMA box
           if (issued < need_next) issue_plane(false);          // next step's planes, as soon as their slot frees up
-          if (TPS == 1 && z.res_tap && r_issued < 2 * gstep + 3) issue_res(false);
+          if (kRes && r_issued < 2 * gstep + 3) issue_res(false);
           const uint32_t be = z.bar_we + 8 * ws, bf = z.bar_wf + 8 * ws;
           ptx::mbar_wait_u32(be, wphase ^ 1);
           if (ptx::elect_one()) {
@@ -240,7 +240,7 @@ __device__ __forceinline__ void zstack_produce(const HaloArgs& a, const ZsProd& 
           __syncwarp();
           if (++ws == z.w_stages) { ws = 0; wphase ^= 1; }
         }
-        if (TPS == 1 && z.res_tap && (sv == 0 || sv == 2)) {   // identity stage: row block 36 ([I;0]) / 37 ([0;I])
+        if (kRes && (sv == 0 || sv == 2)) {   // identity stage: row block 36 ([I;0]) / 37 ([0;I])
           const int half = sv >> 1;
           while (r_issued < 2 * gstep + 1 + half) issue_res(true);
           const uint32_t be = z.bar_we + 8 * ws, bf = z.bar_wf + 8 * ws;
@@ -276,7 +276,7 @@ struct ZsIssue {
   int res_tap;  uint32_t res_u32, bar_rf, bar_re;
 };
 
-template <bool kTF32, int TPS, int kPer>          // TPS taps per weight stage, kPer = row_bytes / 32 MMAs per tap
+template <bool kTF32, int TPS, int kPer, bool kRes>   // TPS taps per weight stage, kPer = row_bytes / 32 MMAs per tap
 __device__ __forceinline__ void zstack_issue(const ZsIssue& z) {
   int ws = 0;  uint32_t wphase = 0;
   int buf = 0; uint32_t acc_phase = 0;
@@ -334,7 +334,7 @@ __device__ __forceinline__ void zstack_issue(const ZsIssue& z) {
           __syncwarp();
         }
         if (++sl == z.ring) sl = 0;
-        if (TPS == 1 && z.res_tap && (sv == 0 || sv == 2)) {
+        if (kRes && (sv == 0 || sv == 2)) {
           // residual as one more tap: D += [I;0] (or [0;I]) x residual plane 2st (2st+1), 4 K steps of 16 channels
           ptx::mbar_wait_u32(z.bar_wf + 8 * ws, wphase);
           ptx::mbar_wait_u32(z.bar_rf, res_use & 1);
@@ -415,9 +415,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
                        nsteps, nplanes, a.total_cols, ring > 4 ? ring - 2 : 2,
                        a.res_tap, ptx::smem_u32(smem_w + a.w_stages * a.w_bytes), ptx::smem_u32(&ctrl.res_full),
                        ptx::smem_u32(&ctrl.res_empty)};
-    if (a.tps == 1) zstack_produce<1>(a, zp, &map_x, &map_w, &map_r);
-    else if (a.tps == 3) zstack_produce<3>(a, zp, &map_x, &map_w, &map_r);
-    else zstack_produce<9>(a, zp, &map_x, &map_w, &map_r);
+    if (a.tps == 1 && a.res_tap) zstack_produce<1, true>(a, zp, &map_x, &map_w, &map_r);
+    else if (a.tps == 1) zstack_produce<1, false>(a, zp, &map_x, &map_w, &map_r);
+    else if (a.tps == 3) zstack_produce<3, false>(a, zp, &map_x, &map_w, &map_r);
+    else zstack_produce<9, false>(a, zp, &map_x, &map_w, &map_r);
   } else if (warp == 0) {
     // ================= TMA producer (generic) =================
     if (lane == 0) {
@@ -515,12 +516,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
                     a.total_cols, a.res_tap, ptx::smem_u32(smem_w + a.w_stages * a.w_bytes), ptx::smem_u32(&ctrl.res_full),
                     ptx::smem_u32(&ctrl.res_empty)};
       if (!a.prestacked) {                      // direct C callers without host-stacked weights: 128/row_bytes taps per stage
-        if (a.tps == 1) zstack_issue<kTF32, 1, 4>(zi);
-        else if (a.tps == 2) zstack_issue<kTF32, 2, 2>(zi);
-        else zstack_issue<kTF32, 4, 1>(zi);
-      } else if (a.tps == 1) zstack_issue<kTF32, 1, 4>(zi);
-      else if (a.tps == 3) zstack_issue<kTF32, 3, 2>(zi);
-      else zstack_issue<kTF32, 9, 1>(zi);
+        if (a.tps == 1) zstack_issue<kTF32, 1, 4, false>(zi);
+        else if (a.tps == 2) zstack_issue<kTF32, 2, 2, false>(zi);
+        else zstack_issue<kTF32, 4, 1, false>(zi);
+      } else if (a.tps == 1 && a.res_tap) zstack_issue<kTF32, 1, 4, true>(zi);
+      else if (a.tps == 1) zstack_issue<kTF32, 1, 4, false>(zi);
+      else if (a.tps == 3) zstack_issue<kTF32, 3, 2, false>(zi);
+      else zstack_issue<kTF32, 9, 1, false>(zi);
     } else {
     for (int col = blockIdx.x; col < a.total_cols; col += gridDim.x) {
         for (int z = 0; z < D; ++z) {

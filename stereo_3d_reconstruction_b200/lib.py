@@ -9,7 +9,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libs3d_b200.so')
+LIB_PATH = os.environ.get('S3D_LIB_PATH') or os.path.join(_HERE, 'libs3d_b200.so')   # env override: A/B-testing builds
 
 S3D_MAX_TAPS = 64
 DTYPE_F32, DTYPE_BF16 = 0, 1
