@@ -15,16 +15,27 @@
 //     A operand (M = 64 or 128 output channels) and the pixels are the B operand with N = 256, which
 //     buys 128 math cycles per A read:  D[co, p] += sum_ci W_t[co, ci] * X[p + off_t, ci].
 //
+//  3. M = 64 issues at the M = 128 rate, so two output planes (z, z+1) x 64 channels are STACKED into one M = 128
+//     tile: input plane zeta meets the stacked weight block [W(kz = zeta-z+1) ; W(kz = zeta-z)] (out-of-range kz =
+//     zeros), 36 stacked taps per plane pair instead of 54.  Stacked blocks are built once on the host
+//     (S3dConvParams.w_zstack) so a weight stage is ONE TMA box.
+//  4. After 1-3 the kernel was bound by none of MMA count, weight bytes or ring depth but by the instruction stream
+//     of the TMA producer thread (~100 dependent instructions per stage), then by barrier round trips on narrow
+//     layers: see zstack_produce / zstack_issue below (templated, warp-uniform, pre-converted barrier addresses,
+//     incremental ring counters, small straight-line elect_one regions, whole tap groups per stage).
+//  5. A residual input is added on the tensor core as one more tap (identity blocks x TMA-staged residual plane).
+//
 //   CTA work item  a "column": one image/volume n, a 32(y) x 8(x) output patch (256 pixels = N),
-//                  marching over z.
+//                  marching over z (two planes per step when z-stacked).
 //   plane slot     input plane z' of the patch with halo, 34 x 10 rows of row_bytes (one 5-D TMA box,
-//                  out-of-image rows zero-filled), ring of up to 4 slots: planes z-1,z,z+1 feed output
-//                  plane z while z+2 streams in.  Every plane is fetched once per column.
-//   weights        [taps][Cout][Cin] streamed through a TMA ring of 128-byte-wide stages (1/2/4 taps
-//                  per stage for 128/64/32-byte rows), L2 resident.
+//                  out-of-image rows zero-filled).  z-stacked: 3 slots for 128-byte rows (a plane is released as
+//                  soon as its 9 taps are issued), up to 7 for narrow rows; otherwise nz+1 slots.  Every plane is
+//                  fetched once per column (DRAM traffic = 0.99x compulsory, measured).
+//   weights        streamed through a TMA ring: z-stacked 1 / 3 / 9 stacked taps per stage for 128 / 64 / 32-byte
+//                  rows (16-36 KB), L2 resident.
 //   accumulators   fp32 in TMEM, [channel lanes x 256 pixel columns], two buffers (512 columns).
-//   epilogue       thread = output channel (TMEM lane); a warp stores 32 (16 for M=64) consecutive
-//                  channels of one pixel per instruction.
+//   epilogue       thread = output channel (TMEM lane); TMEM loads software-pipelined; a warp stores 32 (16 for
+//                  M=64) consecutive channels of one pixel per instruction.
 //
 // Warp roles: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-7 epilogue.
 #include <cuda.h>
@@ -773,11 +784,8 @@ int conv_halo_launch(const S3dConvParams* p_in, const void* in, const void* w, c
   }
   const int smem_bytes = a.ring * a.slot_bytes + a.w_stages * a.w_bytes + res_bytes + 1024;
   auto kern = tf32 ? conv_halo_kernel<true> : conv_halo_kernel<false>;
-  static int attr_set[2] = {0, 0};
-  if (attr_set[tf32] < smem_bytes) {
-    S3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    attr_set[tf32] = smem_bytes;
-  }
+  // set on every launch: the attribute is per device and a process may use several (the call is a cheap host-side update)
+  S3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   int grid = num_sms();
   if (grid > a.total_cols) grid = a.total_cols;
   kern<<<grid, kThreads, smem_bytes, stream>>>(map_x, map_w, map_r, a);

@@ -285,11 +285,8 @@ int conv_igemm_launch(const S3dConvParams* p, const void* in, const void* w, con
 
   const int smem_bytes = a.stages * a.stage_bytes + 1024;
   auto kern = tf32 ? conv_igemm_kernel<true> : conv_igemm_kernel<false>;
-  static bool attr_set[2] = {false, false};
-  if (!attr_set[tf32]) {
-    S3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    attr_set[tf32] = true;
-  }
+  // set on every launch: the attribute is per device and a process may use several (the call is a cheap host-side update)
+  S3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   int grid = num_sms();
   if (grid > a.total_tiles) grid = a.total_tiles;
   kern<<<grid, kThreads, smem_bytes, stream>>>(map_a, map_b, a);

@@ -222,11 +222,7 @@ int corr_tc_launch(const void* feat, float* disp, int B, int h, int w, int C, in
   int rc = encode_act_map(&map_f, feat, 2, false, C, w, h, 1, 2 * B, box, estr, sw);
   if (rc != S3D_OK) return rc;
   const int smem_bytes = a.stages * a.stage_bytes + 1024;
-  static int attr_set = 0;
-  if (attr_set < smem_bytes) {
-    S3D_CUDA(cudaFuncSetAttribute(corr_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    attr_set = smem_bytes;
-  }
+  S3D_CUDA(cudaFuncSetAttribute(corr_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   int grid = num_sms();
   if (grid > a.total_tiles) grid = a.total_tiles;
   corr_tc_kernel<<<grid, kThreads, smem_bytes, stream>>>(map_f, a);

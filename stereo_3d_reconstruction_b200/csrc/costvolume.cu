@@ -280,8 +280,7 @@ extern "C" int s3d_cost_volume_concat(const void* feat, void* vol, int B, int h,
   const int vpp = C * esz / 16;
   const size_t smem = (size_t)2 * w * vpp * sizeof(uint4);
   S3D_CHECK_ARG(smem <= 200 * 1024, "cost_volume_concat: row too large for shared memory");
-  static bool attr = false;
-  if (!attr) { S3D_CUDA(cudaFuncSetAttribute(concat_volume_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
+  S3D_CUDA(cudaFuncSetAttribute(concat_volume_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   concat_volume_kernel<<<2 * B * h, 256, smem, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const uint4*>(feat), static_cast<uint4*>(vol), B, h, w, vpp, D);
   S3D_LAUNCH_CHECK();
@@ -316,13 +315,12 @@ extern "C" int s3d_corr_soft_argmin(const void* feat, float* disp, float* cost_o
   if (threads > 256) threads = 256;
   if (threads < 32) threads = 32;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  static bool attr[2] = {false, false};
   if (dtype == S3D_DTYPE_BF16) {
-    if (!attr[0]) { S3D_CUDA(cudaFuncSetAttribute(corr_soft_argmin_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr[0] = true; }
+    S3D_CUDA(cudaFuncSetAttribute(corr_soft_argmin_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     corr_soft_argmin_kernel<__nv_bfloat16><<<2 * B * h, threads, smem, st>>>(
         static_cast<const __nv_bfloat16*>(feat), disp, cost_out, B, h, w, C, D);
   } else {
-    if (!attr[1]) { S3D_CUDA(cudaFuncSetAttribute(corr_soft_argmin_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr[1] = true; }
+    S3D_CUDA(cudaFuncSetAttribute(corr_soft_argmin_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     corr_soft_argmin_kernel<float><<<2 * B * h, threads, smem, st>>>(
         static_cast<const float*>(feat), disp, cost_out, B, h, w, C, D);
   }

@@ -15,12 +15,10 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 int num_sms() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-      n = 148;
-  }
+  // per call: one process may drive several devices (cudaDeviceGetAttribute is a cached host-side lookup)
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+    n = 148;
   return n;
 }
 

@@ -101,3 +101,26 @@ def test_conv3d_residual_on_tensor_core(D, H, W):
     pc = PackedConv.from_conv(conv, None, lib.ACT_RELU, lib.DTYPE_BF16, 'cuda')
     assert pc.zs_ident
     _check(pc, x, F.relu(conv(x) + res), 'bf16', 64, residual=to_cl(res).to(torch.bfloat16).cuda())
+
+
+def test_zstack_without_host_stacked_weights():
+    """A direct C caller may leave w_zstack NULL: the kernel then assembles each stacked weight stage from two
+    TMA boxes of the plain [taps][Cout][Cin] tensor (out-of-range kz = TMA zero fill).  Same result."""
+    import ctypes
+    torch.manual_seed(6)
+    conv = nn.Conv3d(64, 48, 3, 1, 1, bias=True)
+    x = torch.randn(2, 64, 5, 19, 13)
+    pc = PackedConv.from_conv(conv, None, lib.ACT_RELU, lib.DTYPE_BF16, 'cuda')
+    xc = pad_c(to_cl(x), pc.cin_pad).to(torch.bfloat16).cuda()
+    ref = pc(xc, engine='igemm')
+    out = torch.zeros_like(ref)
+    C = out.shape[-1]
+    p = pc.params(2, 5, 19, 13, (5 * 19 * 13 * C, 19 * 13 * C, 13 * C, C), lib.DTYPE_BF16, C)
+    q = type(p).from_buffer_copy(p)
+    q.w_zstack = None
+    q.w_zstack_ident = 0
+    rc = lib.load().s3d_conv_igemm(ctypes.byref(q), xc.data_ptr(), pc.weight.data_ptr(), pc.bias.data_ptr(), None,
+                                   out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    assert rc == 0, lib.load().s3d_last_error()
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref)
