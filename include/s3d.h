@@ -77,6 +77,13 @@ typedef struct S3dConvParams {
   /* 1 if w_zstack holds two more row blocks, [36] = [I;0] and [37] = [0;I] (I = identity over the Cout channels):
    * the kernel can then add `residual` on the tensor cores instead of in the epilogue. */
   int32_t w_zstack_ident;
+  /* Optional fused 1x1 projection (may be NULL): after the activation, channel `proj_channel` of every output
+   * position is overwritten with proj_act(sum_{c<16} proj_w[c] * out[c]) (proj_w: 16 fp32 DEVICE values, zeros
+   * beyond the real channels).  Needs Cout == 16 (one accumulator group).  Used to fold the decoder's final
+   * 1x1x1 transposed conv + sigmoid into the last deconv layer.  Supported by s3d_conv_igemm's generic engine
+   * and by s3d_conv_direct. */
+  const float* proj_w;
+  int32_t proj_channel, proj_act;
 } S3dConvParams;
 
 const char* s3d_version(void);

@@ -21,25 +21,43 @@ __global__ void conv_direct_kernel(const S3dConvParams p, const TIn* __restrict_
     const int z = (int)(r % p.oD);  r /= p.oD;
     const int n = (int)(r % p.N);   r /= p.N;
     const int cls = (int)r;
-    float acc = 0.f;
-    for (int t = 0; t < p.ntaps; ++t) {
-      const int ti = cls * p.ntaps + t;
-      const int xi = x * p.sx + p.dx[ti], yi = y * p.sy + p.dy[ti], zi = z * p.sz + p.dz[ti];
-      if (xi < 0 || xi >= p.iW || yi < 0 || yi >= p.iH || zi < 0 || zi >= p.iD) continue;
-      const TIn* ip = in + ((((int64_t)n * p.iD + zi) * p.iH + yi) * p.iW + xi) * p.Cin;
-      const TIn* wp = w + ((int64_t)ti * p.Cout + co) * p.Cin;
-      for (int ci = 0; ci < p.Cin; ++ci) acc = fmaf(to_f32(ip[ci]), to_f32(wp[ci]), acc);
+    // conv output (bias + activation) of channel `c` at this position; the fused projection re-evaluates it for
+    // every input channel of the 1x1 (this engine is the exact validation path, not the fast one)
+    auto conv_at = [&](int c) -> float {
+      float a = 0.f;
+      for (int t = 0; t < p.ntaps; ++t) {
+        const int ti = cls * p.ntaps + t;
+        const int xi = x * p.sx + p.dx[ti], yi = y * p.sy + p.dy[ti], zi = z * p.sz + p.dz[ti];
+        if (xi < 0 || xi >= p.iW || yi < 0 || yi >= p.iH || zi < 0 || zi >= p.iD) continue;
+        const TIn* ip = in + ((((int64_t)n * p.iD + zi) * p.iH + yi) * p.iW + xi) * p.Cin;
+        const TIn* wp = w + ((int64_t)ti * p.Cout + c) * p.Cin;
+        for (int ci = 0; ci < p.Cin; ++ci) a = fmaf(to_f32(ip[ci]), to_f32(wp[ci]), a);
+      }
+      if (bias) a += bias[c];
+      return a;
+    };
+    float acc;
+    bool projected = false;
+    if (p.proj_w && co == p.proj_channel) {
+      float pr = 0.f;
+      for (int c = 0; c < p.Cout; ++c) {
+        const float wc = p.proj_w[c];
+        if (wc != 0.f) pr = fmaf(apply_act(conv_at(c), p.act, p.act_param), wc, pr);
+      }
+      acc = apply_act(pr, p.proj_act, 1.f);
+      projected = true;
+    } else {
+      acc = conv_at(co);
     }
-    if (bias) acc += bias[co];
     const int ooz = (cls >> 2) & 1, ooy = (cls >> 1) & 1, oox = cls & 1;
     const int64_t off = (int64_t)n * p.osN + (int64_t)(z * p.omz + ooz) * p.osD +
                         (int64_t)(y * p.omy + ooy) * p.osH + (int64_t)(x * p.omx + oox) * p.osW + (int64_t)co * p.osC;
     if (p.out_dtype == S3D_DTYPE_BF16) {
-      if (residual) acc += __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(residual)[off]);
-      reinterpret_cast<__nv_bfloat16*>(out)[off] = __float2bfloat16_rn(apply_act(acc, p.act, p.act_param));
+      if (residual && !projected) acc += __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(residual)[off]);
+      reinterpret_cast<__nv_bfloat16*>(out)[off] = __float2bfloat16_rn(projected ? acc : apply_act(acc, p.act, p.act_param));
     } else {
-      if (residual) acc += reinterpret_cast<const float*>(residual)[off];
-      reinterpret_cast<float*>(out)[off] = apply_act(acc, p.act, p.act_param);
+      if (residual && !projected) acc += reinterpret_cast<const float*>(residual)[off];
+      reinterpret_cast<float*>(out)[off] = projected ? acc : apply_act(acc, p.act, p.act_param);
     }
   }
 }

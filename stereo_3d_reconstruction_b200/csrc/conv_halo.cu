@@ -690,7 +690,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
 bool conv_halo_eligible(const S3dConvParams* p) {
   const int esz = p->in_dtype == S3D_DTYPE_F32 ? 4 : 2;
   if (p->n_classes != 1 || p->sx != 1 || p->sy != 1 || p->sz != 1) return false;
-  if (p->omx != 1 || p->omy != 1 || p->omz != 1 || p->osC != 1) return false;
+  if (p->omx != 1 || p->omy != 1 || p->omz != 1 || p->osC != 1 || p->proj_w) return false;
   if (p->ntaps != 9 && p->ntaps != 27) return false;
   if (p->oD != p->iD || p->oH != p->iH || p->oW != p->iW) return false;
   if (p->ntaps == 9 && p->iD != 1) return false;

@@ -180,7 +180,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const int dzr = (r >> (a.lw + a.lh)) & (a.p.td - 1);
     const int dnr = r >> (a.lw + a.lh + a.ld);
     const EpiParams epi = {a.bias, a.residual, a.out, a.p.cout_store, a.p.out_dtype == S3D_DTYPE_BF16, a.p.act,
-                           a.p.act_param, a.p.osC};
+                           a.p.act_param, a.p.osC, a.p.proj_w, a.p.proj_channel, a.p.proj_act};
     int buf = 0;  uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(a, tile);
@@ -234,6 +234,8 @@ int conv_igemm_validate(const S3dConvParams* p, const void* in, const void* w) {
   S3D_CHECK_ARG(p->cout_store >= 1 && p->cout_store <= p->Cout, "igemm: cout_store");
   S3D_CHECK_ARG((reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0,
                 "igemm: in / w must be 16 B aligned");
+  S3D_CHECK_ARG(!p->proj_w || (p->Cout == 16 && p->proj_channel >= 0 && p->proj_channel < 16 && p->osC == 1),
+                "igemm: fused projection needs Cout == 16, channels-last output");
   return S3D_OK;
 }
 

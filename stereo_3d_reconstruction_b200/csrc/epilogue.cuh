@@ -16,6 +16,7 @@ struct EpiParams {
   int act;
   float act_param;
   int64_t osC;        // channel stride of the output (1 = channels-last)
+  const float* proj_w;  int proj_channel, proj_act;     // optional fused 1x1 projection (see s3d.h)
 };
 
 // v: raw accumulator bits of columns [cg, cg+16); off: element offset of the row's channel 0.
@@ -78,6 +79,15 @@ __device__ __forceinline__ void epilogue_store16(const EpiParams& e, int64_t off
 #pragma unroll
     for (int i = 0; i < 16; ++i)
       if (cg + i < e.cout_store) f[i] = apply_act_slow(f[i], e.act, e.act_param);
+  }
+  // ---- optional fused 1x1 projection into one channel of this (single) group
+  if (e.proj_w) {
+    float pr = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) pr = fmaf(f[i], __ldg(e.proj_w + i), pr);
+    pr = apply_act_slow(pr, e.proj_act, 1.f);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) if (i == e.proj_channel) f[i] = pr;
   }
   // ---- store
   if (vec && e.out_bf16) {

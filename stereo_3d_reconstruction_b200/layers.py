@@ -112,6 +112,7 @@ class PackedConv:
                 zs[37, 64:64 + self.cout_pad] = eye
             self.weight_zs = zs.to(torch_dtype(dtype_code)).to(device).contiguous()
         self.bn = _choose_bn(self.cout_pad)
+        self.proj = None                 # optional fused 1x1 projection: (fp32[16] device tensor, channel, act)
         self._cache = {}
 
     # ---- constructors ------------------------------------------------------------------
@@ -169,6 +170,16 @@ class PackedConv:
         return cls(torch.stack(rows), b, [taps], (1, 1, 1), (1, 1, 1), C, w.shape[0], act, act_param, dtype_code,
                    device, ksize=(1, h, w_), pad=(0, 0, 0))
 
+    def set_projection(self, w_vec, channel, act):
+        """Fuse a 1x1 projection of this layer's (activated) outputs into channel `channel` of its own output
+        (include/s3d.h, proj_w).  Needs a single 16-channel accumulator group."""
+        assert self.cout_pad == 16 and self.cout <= channel < 16, (self.cout_pad, self.cout, channel)
+        v = torch.zeros(16, dtype=torch.float32)
+        v[:self.cout] = w_vec.detach().float().cpu().flatten()[:self.cout]
+        self.proj = (v.to(self.weight.device), int(channel), int(act))
+        self._cache = {}
+        return self
+
     # ---- launch ------------------------------------------------------------------------
     def out_grid(self, iD, iH, iW):
         """Logical output grid per class for an input of the given size."""
@@ -202,6 +213,8 @@ class PackedConv:
         p.bn = self.bn
         p.w_zstack = self.weight_zs.data_ptr() if self.weight_zs is not None else None
         p.w_zstack_ident = 1 if (self.weight_zs is not None and self.zs_ident) else 0
+        if self.proj is not None:
+            p.proj_w, p.proj_channel, p.proj_act = self.proj[0].data_ptr(), self.proj[1], self.proj[2]
         self._cache[key] = p
         return p
 

@@ -36,6 +36,7 @@ class S3dConvParams(ctypes.Structure):
         ('bn', ctypes.c_int32),
         ('w_zstack', ctypes.c_void_p),
         ('w_zstack_ident', ctypes.c_int32),
+        ('proj_w', ctypes.c_void_p), ('proj_channel', ctypes.c_int32), ('proj_act', ctypes.c_int32),
     ]
 
 

@@ -269,7 +269,13 @@ class Stereo2Voxel(_StereoBase):
         for i, seq in enumerate(self.decoder.layers):
             P['dec%d' % i] = PackedConv.from_deconv_k4s2p1(seq[0], seq[1], A.ACT_RELU, dc, dev)
         w = self.decoder.out.weight            # [Cin, 1, 1,1,1]
-        P['dec_out'] = PackedConv.from_pointwise(w.view(w.shape[0], 1).t(), None, None, A.ACT_SIGMOID, dc, dev)
+        last = P['dec%d' % (len(self.decoder.layers) - 1)]
+        self._fused_out = last.cout_pad == 16 and last.cout < 16
+        if self._fused_out:
+            # 1x1x1 transposed conv + sigmoid folded into the last deconv's epilogue: coarse volume -> channel `cout`
+            last.set_projection(w.view(-1), last.cout, A.ACT_SIGMOID)
+        else:
+            P['dec_out'] = PackedConv.from_pointwise(w.view(w.shape[0], 1).t(), None, None, A.ACT_SIGMOID, dc, dev)
         for i, seq in enumerate(self.merger.layers):
             P['mrg%d' % i] = PackedConv.from_conv(seq[0], seq[1], A.ACT_LEAKY, dc, dev,
                                                   act_param=self.cfg.NETWORK.LEAKY_VALUE)
@@ -303,10 +309,11 @@ class Stereo2Voxel(_StereoBase):
         cm = m_in.shape[-1]
         craw = cfg.NETWORK.DEC_CHANNELS[-1]
         assert m_in.shape[1] == nv and cm > craw
-        # coarse volume = sigmoid(1x1x1 transposed conv), written into channel `craw` of the same
-        # buffer (the conv's weights are zero for input channels >= craw, so the in-place write of
-        # channel `craw` cannot feed back).
-        self._conv('dec_out', m_in, out=m_in, out_view=(craw, (nv ** 3 * cm, nv * nv * cm, nv * cm, cm)), cout_store=1)
+        # coarse volume = sigmoid(1x1x1 transposed conv) lives in channel `craw` of the same buffer: normally
+        # produced by the last deconv's fused projection epilogue; otherwise by a pointwise launch (its weights
+        # are zero for input channels >= craw, so the in-place write of channel `craw` cannot feed back).
+        if not self._fused_out:
+            self._conv('dec_out', m_in, out=m_in, out_view=(craw, (nv ** 3 * cm, nv * nv * cm, nv * cm, cm)), cout_store=1)
         s = m_in
         for i in range(len(self.merger.layers)):
             s = self._conv('mrg%d' % i, s, out=self._bufo('m%d' % (i % 2), 'mrg%d' % i, s))
