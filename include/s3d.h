@@ -107,6 +107,11 @@ int s3d_conv_direct(const S3dConvParams* p, const void* in, const void* w, const
 int s3d_pack_image(const float* img, const float* disp, float disp_scale, void* out,
                    int B, int H, int W, int Cpad, int out_dtype, void* stream);
 
+/* Same, from decoded 8-bit images (the reference's inputs are PNG renders, README.md:73-74): img is uint8 HWC
+ * [B,H,W,3]; channels 0-2 = img * img_scale (1/255 for [0,1] images), channel 3 = disp * disp_scale. */
+int s3d_pack_image_u8(const uint8_t* img, const float* disp, float disp_scale, float img_scale, void* out,
+                      int B, int H, int W, int Cpad, int out_dtype, void* stream);
+
 /* --- cost volume / disparity (rows V, S) ---------------------------------------------- */
 /* feat: [2B,1,h,w,C] (left maps first, then right).  vol: [2B,D,h,w,2C]; entries [0,B) are
  * left-referenced (target sampled at x-d), [B,2B) right-referenced (target at x+d). */

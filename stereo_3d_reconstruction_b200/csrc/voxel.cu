@@ -53,6 +53,30 @@ __global__ void pack_image_kernel(const float* __restrict__ img, const float* __
   }
 }
 
+// uint8 HWC input (decoded PNG): 3 bytes per pixel, coalesced enough through L1; same output layout as above.
+template <typename T>
+__global__ void pack_image_u8_kernel(const uint8_t* __restrict__ img, const float* __restrict__ disp, float disp_scale,
+                                     float img_scale, T* __restrict__ out, int64_t total, int Cpad) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint8_t* ip = img + i * 3;
+    const float c0 = (float)ip[0] * img_scale, c1 = (float)ip[1] * img_scale, c2 = (float)ip[2] * img_scale;
+    const float c3 = disp ? disp[i] * disp_scale : 0.f;
+    T* o = out + i * Cpad;
+    if (sizeof(T) == 2 && (Cpad & 7) == 0) {
+      uint4 v0 = make_uint4(0, 0, 0, 0);
+      __nv_bfloat162 p01 = __floats2bfloat162_rn(c0, c1), p23 = __floats2bfloat162_rn(c2, c3);
+      v0.x = *reinterpret_cast<uint32_t*>(&p01);
+      v0.y = *reinterpret_cast<uint32_t*>(&p23);
+      uint4* o4 = reinterpret_cast<uint4*>(o);
+      o4[0] = v0;
+      for (int c = 1; c < Cpad / 8; ++c) o4[c] = make_uint4(0, 0, 0, 0);
+    } else {
+      o[0] = from_f32<T>(c0);  o[1] = from_f32<T>(c1);  o[2] = from_f32<T>(c2);  o[3] = from_f32<T>(c3);
+      for (int c = 4; c < Cpad; ++c) o[c] = from_f32<T>(0.f);
+    }
+  }
+}
+
 __device__ __forceinline__ void pool_bin(int i, int in, int out, int& s, int& e) {
   s = (i * in) / out;
   e = ((i + 1) * in + out - 1) / out;
@@ -165,6 +189,21 @@ extern "C" int s3d_pack_image(const float* img, const float* disp, float disp_sc
   else if (out_dtype == S3D_DTYPE_F32)
     pack_image_kernel<float><<<grid_for(total, 256), 256, 0, st>>>(img, disp, disp_scale, static_cast<float*>(out), B, H, W, Cpad);
   else { set_error("pack_image: bad dtype"); return S3D_ERR_INVALID; }
+  S3D_LAUNCH_CHECK();
+  return S3D_OK;
+}
+
+extern "C" int s3d_pack_image_u8(const uint8_t* img, const float* disp, float disp_scale, float img_scale, void* out,
+                                 int B, int H, int W, int Cpad, int out_dtype, void* stream) {
+  if (!img || !out) { set_error("pack_image_u8: null argument"); return S3D_ERR_INVALID; }
+  S3D_CHECK_ARG(B > 0 && H > 0 && W > 0 && Cpad >= 4, "pack_image_u8: bad shape");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t total = (int64_t)B * H * W;
+  if (out_dtype == S3D_DTYPE_BF16)
+    pack_image_u8_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, st>>>(img, disp, disp_scale, img_scale, static_cast<__nv_bfloat16*>(out), total, Cpad);
+  else if (out_dtype == S3D_DTYPE_F32)
+    pack_image_u8_kernel<float><<<grid_for(total, 256), 256, 0, st>>>(img, disp, disp_scale, img_scale, static_cast<float*>(out), total, Cpad);
+  else { set_error("pack_image_u8: bad dtype"); return S3D_ERR_INVALID; }
   S3D_LAUNCH_CHECK();
   return S3D_OK;
 }

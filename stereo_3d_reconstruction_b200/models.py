@@ -190,10 +190,14 @@ class _StereoBase(nn.Module):
         return self._packed[name](x, engine=self._engine(), **kw)
 
     # ---- stages ----------------------------------------------------------------------------
+    @staticmethod
+    def _bhw(img):
+        return (img.shape[0], img.shape[1], img.shape[2]) if img.dtype == torch.uint8 else (img.shape[0], img.shape[2], img.shape[3])
+
     def _disparity(self, left, right):
         """-> disp fp32 [2B,H,W] (left-referenced first), in input pixels."""
         cfg = self.cfg
-        B, _, H, W = left.shape
+        B, H, W = self._bhw(left)
         D = cfg.NETWORK.MAX_DISP
         dt = torch_dtype(self._dtype_code())
         x = self._buf('img', (2 * B, 1, H, W, 16), dt)
@@ -235,7 +239,7 @@ class _StereoBase(nn.Module):
 
     def _latent(self, left, right, disp):
         """RGB-D encoder on both views -> [2B,1,h',w',C_last] (before pooling)."""
-        B, _, H, W = left.shape
+        B, H, W = self._bhw(left)
         dt = torch_dtype(self._dtype_code())
         scale = 1.0 / (4.0 * self.cfg.NETWORK.MAX_DISP)
         x = self._buf('rgbd', (2 * B, 1, H, W, 16), dt)
@@ -250,6 +254,11 @@ class _StereoBase(nn.Module):
             self.pack()
         if not (left.is_cuda and right.is_cuda):
             raise _lib.S3dError('inputs must be CUDA tensors (no CPU fallback)')
+        if left.dtype == torch.uint8 and right.dtype == torch.uint8:
+            # decoded 8-bit images, HWC [B,H,W,3]: converted (x/255) inside the staging kernel, 4x less H2D traffic
+            if left.shape != right.shape or left.dim() != 4 or left.shape[3] != 3:
+                raise ValueError('expected uint8 left/right of shape [B,H,W,3], got %s / %s' % (tuple(left.shape), tuple(right.shape)))
+            return left.contiguous(), right.contiguous()
         if left.shape != right.shape or left.dim() != 4 or left.shape[1] != 3:
             raise ValueError('expected left/right of shape [B,3,H,W], got %s / %s' % (tuple(left.shape), tuple(right.shape)))
         return left.contiguous().float(), right.contiguous().float()
@@ -294,7 +303,7 @@ class Stereo2Voxel(_StereoBase):
 
     def _forward_chunk(self, left, right, gt):
         cfg = self.cfg
-        B, _, H, W = left.shape
+        B, H, W = self._bhw(left)
         nv = cfg.CONST.N_VOX
         disp, _ = self._disparity(left, right)
         x = self._latent(left, right, disp)

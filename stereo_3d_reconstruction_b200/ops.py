@@ -32,8 +32,20 @@ def _stream():
 
 
 def pack_image(img, disp=None, disp_scale=1.0, cpad=16, dtype=torch.bfloat16, out=None):
-    """img fp32 NCHW [B,3,H,W] (+ disp fp32 [B,H,W]) -> channels-last [B,1,H,W,cpad]."""
+    """img fp32 NCHW [B,3,H,W], or uint8 HWC [B,H,W,3] (decoded PNG; scaled by 1/255), (+ disp fp32 [B,H,W])
+    -> channels-last [B,1,H,W,cpad]."""
     _chk(img, disp, out)
+    if img.dtype == torch.uint8:
+        B, H, W, C = img.shape
+        assert C == 3
+        if out is None:
+            out = torch.empty((B, 1, H, W, cpad), dtype=dtype, device=img.device)
+        rc = _lib.load().s3d_pack_image_u8(img.data_ptr(), disp.data_ptr() if disp is not None else None,
+                                           float(disp_scale), 1.0 / 255.0, out.data_ptr(), B, H, W, cpad, _code(out),
+                                           _stream())
+        _lib.check(rc, 's3d_pack_image_u8')
+        _lib.count_launch()
+        return out
     B, C, H, W = img.shape
     assert C == 3 and img.dtype == torch.float32
     if out is None:

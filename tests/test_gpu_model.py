@@ -62,6 +62,31 @@ def test_stereo2point_matches_oracle(prec):
     assert (p.cpu() - rp).abs().max().item() <= (1e-4 if prec == 'fp32' else 3e-2)
 
 
+def test_uint8_inputs_match_float_inputs():
+    """Decoded 8-bit HWC images take the same path as their float NCHW equivalent (x/255), bit for bit."""
+    cfg = small_cfg(NETWORK__PRECISION='bf16')
+    oracle = O.make_model('Stereo2Voxel', cfg, seed=0)
+    model = M.build_model('Stereo2Voxel', cfg)
+    model.load_state_dict(oracle.state_dict())
+    model.cuda().pack()
+    left, right = _pair(cfg, 2)
+    l8 = (left.clamp(0, 1) * 255).round().to(torch.uint8).permute(0, 2, 3, 1).contiguous()
+    r8 = (right.clamp(0, 1) * 255).round().to(torch.uint8).permute(0, 2, 3, 1).contiguous()
+    lf = (l8.float() * (1.0 / 255.0)).permute(0, 3, 1, 2).contiguous()
+    rf = (r8.float() * (1.0 / 255.0)).permute(0, 3, 1, 2).contiguous()
+    with torch.no_grad():
+        a = [t.clone() for t in model(l8.cuda(), r8.cuda())[:3]]
+        b = [t.clone() for t in model(lf.cuda(), rf.cuda())[:3]]
+        rdl, _, rvox = oracle(lf, rf)
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
+    td, tv = TOLS['bf16']
+    assert (a[0].cpu() - rdl).abs().max().item() <= td * rdl.abs().max().item()
+    assert (a[2].cpu() - rvox).abs().max().item() <= tv
+    with pytest.raises(ValueError):
+        model(l8.permute(0, 3, 1, 2).contiguous().cuda(), r8.permute(0, 3, 1, 2).contiguous().cuda())
+
+
 def test_odd_input_size_fp32():
     cfg = small_cfg(NETWORK__PRECISION='fp32', CONST__IMG_H=70, CONST__IMG_W=50)
     oracle = O.make_model('Stereo2Voxel', cfg, seed=1)

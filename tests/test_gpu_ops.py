@@ -117,6 +117,19 @@ def test_pack_image():
     assert got[..., 4:].abs().max() == 0
 
 
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_pack_image_u8(dtype):
+    g = torch.Generator().manual_seed(9)
+    img = torch.randint(0, 256, (2, 9, 11, 3), generator=g, dtype=torch.uint8)       # decoded PNG layout (HWC)
+    disp = torch.rand(2, 9, 11, generator=g) * 30
+    got = ops.pack_image(img.cuda(), disp.cuda(), 0.25, dtype=dtype).cpu()
+    assert got.shape == (2, 1, 9, 11, 16)
+    ref = (img.float() * (1.0 / 255.0)).to(dtype)
+    assert torch.equal(got[:, 0, :, :, :3], ref)
+    assert torch.equal(got[:, 0, :, :, 3], (disp * 0.25).to(dtype))
+    assert got[..., 4:].abs().max() == 0
+
+
 # ---- SIMT conv (exact fp32 engine) vs torch.nn.functional --------------------------------------
 def _run(pc, x_nc, engine, dtype=torch.float32):
     x = pad_c(to_cl(x_nc), pc.cin_pad).to(dtype).cuda()
