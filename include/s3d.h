@@ -84,6 +84,12 @@ typedef struct S3dConvParams {
    * and by s3d_conv_direct. */
   const float* proj_w;
   int32_t proj_channel, proj_act;
+  /* Optional (may be NULL): weights of a stride-1 3x3x3 layer with Cout <= 64 pre-stacked for the plane-scatter
+   * kernel (csrc/conv_scatter.cu), a DEVICE tensor [4][9][3*Cout][Cin] in the layer's dtype.  Rotation r = 0..2
+   * (used for input plane p with p % 3 == r), in-plane tap kyx: row block s = 0..2 holds W[kz = (r+1-s) mod 3, kyx]
+   * (the slice that carries input plane p into output plane z = p+1-kz, which accumulates in slot z % 3 == s).
+   * Rotation 3 is rotation 0 with block 2 zeroed (p = 0: there is no output plane -1). */
+  const void* w_nstack;
 } S3dConvParams;
 
 const char* s3d_version(void);

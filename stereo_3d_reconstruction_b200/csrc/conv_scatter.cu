@@ -1,0 +1,567 @@
+// Plane-scatter implicit GEMM for stride-1 3x3x3 convolutions with Cout <= 64 (the five 64-wide cost-aggregation
+// layers = two thirds of the forward pass, and the fusion scorer's narrow 3-D layers).
+//
+// conv_halo.cu's z-stacked tile (two output planes x 64 channels on the M side) spends a quarter of its MMA rows on
+// structural zeros: of the four input planes a plane pair reads, the first and the last only feed one of the two
+// output planes.  Here the roles are turned round.  An INPUT plane p feeds exactly three output planes
+// (z = p+1, p, p-1 through kz = 0, 1, 2), so the pixels go on the M side (128 per tile) and the three kz slices of
+// the weights are stacked on the N side:
+//
+//     D[pixel, (slot, co)] += sum_ci X_p[pixel + (ky,kx), ci] * Wrot[(slot, co), ci]        N = 3 * Cout (192)
+//
+// Every MMA row and column is a useful product; an N = 192 MMA issues at the full tensor rate (96 cycles, measured
+// with scripts/mma_rate.cu, operands distinct per instruction).  The three 64-column accumulator "slots" of a tile
+// form a ring over output planes: out plane z lives in slot z % 3, receives input planes z-1, z, z+1 and is then
+// complete.  Which kz lands in which slot depends on p % 3, so the host packs three rotations of the stacked
+// weights (plus a fourth for p = 0 whose non-existent z = -1 block is zero, so that the first MMA of a column can
+// overwrite all three slots): S3dConvParams.w_nstack, [4][9][3*Cout][Cin].
+//
+//   CTA work item   a column: one volume n, a 32(y) x 8(x) patch = two tiles of 16 x 8 = 128 pixels, marching over z.
+//   plane slot      input plane p of the patch with halo (34 x 10 rows, one 5-D TMA box, zero fill outside); each
+//                   plane is fetched once per column and is the A operand of 9 taps x 2 tiles (descriptor start
+//                   moved by (ky*10 + kx) rows, 8-row groups one halo line apart -- as in conv_halo.cu).
+//   weights         one stage = TPS of the 9 in-plane taps of the current rotation (24 KB for 64 -> 64), used by
+//                   BOTH tiles, so the L2 -> SM weight stream is the same 32 B/clk/SM as the z-stacked kernel's.
+//   accumulators    TMEM columns [256 t + 64 s, +64) for tile t, slot s.
+//   epilogue        thread = pixel (TMEM lane).  When input plane p is done, out plane p-1 is complete: its slot is
+//                   read into registers, ZEROED (tcgen05.st; the slot's next user accumulates from its first MMA)
+//                   and handed back at once; bias / residual / activation / store then run from registers while
+//                   the tensor core is already on the next plane.  Tile 1 trails tile 0 by one weight stage so
+//                   that each tile's hand-back is hidden behind the other tile's MMAs.
+//
+// Warp roles: 0 TMA producer, 1 MMA issuer, 2 TMEM allocator, 4-7 epilogue of tile 0, 8-11 epilogue of tile 1.
+#include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
+#include "common.cuh"
+#include "ptx.cuh"
+#include "epilogue.cuh"
+
+namespace s3d {
+namespace {
+
+constexpr int kThreads = 384;
+constexpr int kTX = 8, kHX = kTX + 2;
+constexpr int kTY = 32, kHY = kTY + 2;
+constexpr int kTileY = 16;                     // rows of one M = 128 tile
+constexpr int kPlaneRows = kHX * kHY;          // 340
+constexpr int kMaxRing = 6;
+constexpr int kMaxW = 8;
+constexpr int kTmemCols = 512;
+constexpr int kTileCols = 256;                 // TMEM column pitch between the two tiles
+
+struct ScArgs {
+  S3dConvParams p;
+  const float* bias;
+  const void* residual;
+  void* out;
+  int row_bytes;      // Cin * esz: 32 / 64 / 128
+  int kc;             // channels per row
+  int slot_bytes;     // one input plane with halo, rounded to 1024
+  int ring;           // plane slots
+  int cp;             // accumulator columns per output plane (= Cout, multiple of 16)
+  int tps;            // in-plane taps per weight stage: 1, 3 or 9
+  int w_stages, w_bytes, w_tx;
+  int cols_x, cols_y, total_cols;
+  uint32_t idesc;
+  int fast_store;     // epilogue may use the transposed (coalesced) store path
+};
+
+struct ScCtrl {
+  uint64_t plane_full[kMaxRing], plane_empty[kMaxRing];
+  uint64_t w_full[kMaxW], w_empty[kMaxW];
+  uint64_t acc_full[2], acc_empty[2];
+  uint32_t tmem_base;
+};
+
+struct Col { int n, y0, x0; };
+
+__device__ __forceinline__ Col decode_col(const ScArgs& a, int c) {
+  Col r;
+  r.x0 = (c % a.cols_x) * kTX;  c /= a.cols_x;
+  r.y0 = (c % a.cols_y) * kTY;  c /= a.cols_y;
+  r.n = c;
+  return r;
+}
+
+__device__ __forceinline__ uint64_t desc_hi(uint32_t sbo, int row_bytes) {
+  const uint64_t layout = row_bytes == 128 ? 2ull : (row_bytes == 64 ? 4ull : 6ull);
+  return (static_cast<uint64_t>(sbo >> 4) << 32) | (1ull << 46) | (layout << 61);
+}
+__device__ __forceinline__ uint32_t desc_lo(uint32_t addr) { return ((addr & 0x3FFFF) >> 4) | (1u << 16); }
+
+// ---- TMA producer: warp-uniform, incremental ring counters, TMA issue under small elect_one regions -----------------
+template <int TPS>
+__device__ __forceinline__ void sc_produce(const ScArgs& a, ScCtrl& ctrl, uint32_t planes_u32, uint32_t w_u32,
+                                           const CUtensorMap* map_x, const CUtensorMap* map_w) {
+  constexpr int G = 9 / TPS;
+  const uint32_t bar_pf = ptx::smem_u32(&ctrl.plane_full[0]), bar_pe = ptx::smem_u32(&ctrl.plane_empty[0]);
+  const uint32_t bar_wf = ptx::smem_u32(&ctrl.w_full[0]), bar_we = ptx::smem_u32(&ctrl.w_empty[0]);
+  const int D = a.p.iD, ring = a.ring, w_stages = a.w_stages, total_cols = a.total_cols;
+  const int slot_bytes = a.slot_bytes, w_bytes = a.w_bytes, w_tx = a.w_tx;
+  const int plane_tx = kPlaneRows * a.row_bytes;
+  int ws = 0;  uint32_t wphase = 0;
+  int pslot = 0;  uint32_t pphase = 0;
+  int pcol = blockIdx.x, pj = 0, issued = 0;
+  Col pc = decode_col(a, pcol < total_cols ? pcol : 0);
+  auto issue_plane = [&](bool blocking) -> bool {
+    if (pcol >= total_cols) return false;
+    const uint32_t be = bar_pe + 8 * pslot, bf = bar_pf + 8 * pslot;
+    if (blocking) ptx::mbar_wait_u32(be, pphase ^ 1);
+    else if (!ptx::mbar_test_wait_u32(be, pphase ^ 1)) return false;
+    if (ptx::elect_one()) {
+      ptx::mbar_arrive_expect_tx_u32(bf, plane_tx);
+      ptx::tma_load_5d_u32(planes_u32 + pslot * slot_bytes, map_x, bf, 0, pc.x0 - 1, pc.y0 - 1, pj, pc.n);
+    }
+    __syncwarp();
+    ++issued;
+    if (++pslot == ring) { pslot = 0; pphase ^= 1; }
+    if (++pj == D) {
+      pj = 0;  pcol += gridDim.x;
+      if (pcol < total_cols) pc = decode_col(a, pcol);
+    }
+    return true;
+  };
+  int gp = 0;                                    // global index of the current plane
+  for (int col = blockIdx.x; col < total_cols; col += gridDim.x) {
+    int rot = 3;                                 // weight rotation: 3 for p = 0, then p % 3
+    for (int p = 0; p < D; ++p, ++gp) {
+      while (issued <= gp) issue_plane(true);
+      const int ahead = gp + ring;               // planes that may be in flight while plane gp is being read
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        if (issued < ahead) issue_plane(false);
+        const uint32_t be = bar_we + 8 * ws, bf = bar_wf + 8 * ws;
+        ptx::mbar_wait_u32(be, wphase ^ 1);
+        if (ptx::elect_one()) {
+          ptx::mbar_arrive_expect_tx_u32(bf, w_tx);
+          ptx::tma_load_3d_u32(w_u32 + ws * w_bytes, map_w, bf, 0, 0, rot * 9 + g * TPS);
+        }
+        __syncwarp();
+        if (++ws == w_stages) { ws = 0; wphase ^= 1; }
+      }
+      rot = (p == 0) ? 1 : (rot == 2 ? 0 : rot + 1);
+    }
+  }
+}
+
+// ---- MMA issuer -------------------------------------------------------------------------------------------------
+// Per input plane the weight groups g = 0..G-1 are issued as  T0g0, [T0g1, T1g0], [T0g2, T1g1], ..., T1g(G-1):
+// tile 1 trails tile 0 by one group, so a tile's accumulator hand-back (epilogue reads + zeroes the finished slot)
+// overlaps the other tile's MMAs.  Everything is warp-uniform; only MMAs and commits sit under elect_one, in small
+// straight-line regions with compile-time operand offsets (the cheap tcgen05.mma encoding, see conv_halo.cu).
+struct ScIssue {
+  uint32_t tmem_base, planes_u32, w_u32;
+  uint32_t bar_pf, bar_pe, bar_wf, bar_we, bar_af, bar_ae;
+  uint64_t x_hi, w_hi;
+  int slot_bytes, w_bytes, w_stages, ring;
+  uint32_t rb16, tap_step, tile_off;             // 16-byte units
+  uint32_t idesc;
+  int D, total_cols;
+};
+
+template <bool kTF32, int TPS, int kPer>
+__device__ __forceinline__ void sc_issue_group(const ScIssue& z, uint32_t d_tmem, uint64_t xdesc, uint64_t wdesc, int g,
+                                               uint32_t first) {
+#pragma unroll
+  for (int tt = 0; tt < TPS; ++tt) {
+    const int kyx = g * TPS + tt;
+    const uint32_t xoff = ((kyx / 3) * kHX + (kyx % 3)) * z.rb16;
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+      const uint32_t acc = (g == 0 && tt == 0 && k == 0) ? first : 1u;
+      if (kTF32) ptx::mma_tf32(d_tmem, xdesc + xoff + 2 * k, wdesc + tt * z.tap_step + 2 * k, z.idesc, acc);
+      else       ptx::mma_bf16(d_tmem, xdesc + xoff + 2 * k, wdesc + tt * z.tap_step + 2 * k, z.idesc, acc);
+    }
+  }
+}
+
+template <bool kTF32, int TPS, int kPer>
+__device__ __forceinline__ void sc_issue(const ScIssue& z) {
+  constexpr int G = 9 / TPS;
+  int ws = 0;  uint32_t wphase = 0;
+  int pw = 0;  uint32_t pwphase = 0;
+  uint32_t aphase = 0;
+  const uint32_t w_lo0 = desc_lo(z.w_u32), w_lo_step = z.w_bytes >> 4;
+  const uint32_t x_lo0 = desc_lo(z.planes_u32), x_lo_step = z.slot_bytes >> 4;
+  const uint32_t d0 = z.tmem_base, d1 = z.tmem_base + kTileCols;
+  for (int col = blockIdx.x; col < z.total_cols; col += gridDim.x) {
+    for (int p = 0; p < z.D; ++p) {
+      ptx::mbar_wait_u32(z.bar_pf + 8 * pw, pwphase);
+      const uint64_t xd0 = z.x_hi | (x_lo0 + pw * x_lo_step);
+      const uint64_t xd1 = xd0 + z.tile_off;
+      const uint32_t first = p == 0 ? 0u : 1u;     // the first MMA of a column overwrites all three slots
+      int ws_prev = 0;
+#pragma unroll
+      for (int g = 0; g <= G; ++g) {
+        if (g < G) {                               // tile 0, group g
+          ptx::mbar_wait_u32(z.bar_wf + 8 * ws, wphase);
+          if (g == 0) ptx::mbar_wait_u32(z.bar_ae, aphase ^ 1);
+          ptx::tc_fence_after();
+          const uint64_t wd = z.w_hi | (w_lo0 + ws * w_lo_step);
+          if (ptx::elect_one()) {
+            sc_issue_group<kTF32, TPS, kPer>(z, d0, xd0, wd, g, first);
+            if (g == G - 1) ptx::tc_commit_u32(z.bar_af);
+          }
+          __syncwarp();
+        }
+        if (g >= 1) {                              // tile 1, group g-1 (its stage was awaited one iteration ago)
+          if (g == 1) { ptx::mbar_wait_u32(z.bar_ae + 8, aphase ^ 1); ptx::tc_fence_after(); }
+          const uint64_t wd = z.w_hi | (w_lo0 + ws_prev * w_lo_step);
+          if (ptx::elect_one()) {
+            sc_issue_group<kTF32, TPS, kPer>(z, d1, xd1, wd, g - 1, first);
+            ptx::tc_commit_u32(z.bar_we + 8 * ws_prev);
+            if (g == G) { ptx::tc_commit_u32(z.bar_af + 8); ptx::tc_commit_u32(z.bar_pe + 8 * pw); }
+          }
+          __syncwarp();
+        }
+        if (g < G) {
+          ws_prev = ws;
+          if (++ws == z.w_stages) { ws = 0; wphase ^= 1; }
+        }
+      }
+      aphase ^= 1;
+      if (++pw == z.ring) { pw = 0; pwphase ^= 1; }
+    }
+  }
+}
+
+// ---- epilogue ------------------------------------------------------------------------------------------------------
+// A thread owns one pixel (TMEM lane) and all of its channels, i.e. a 128-byte run of the channels-last output; stored
+// directly, one warp instruction would touch 32 different lines with 16 bytes each.  ncu showed those scattered
+// stores filling 40 % of the L1 data pipe that also feeds the tensor core its shared-memory operands (56 %), which
+// cost 25 % of the kernel.  So the 16-byte chunks are transposed inside each group of NCH lanes first (butterfly of
+// warp shuffles): lane j of a group then holds chunk j of every pixel of the group, and one instruction writes whole
+// pixels contiguously (4 lines per instruction instead of 32).  Residual reads go the same way round.
+template <int NCH>
+__device__ __forceinline__ void chunk_transpose(uint4 (&c)[NCH], int lane) {
+#pragma unroll
+  for (int s = NCH / 2; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int a = 0; a < NCH; ++a) {
+      if (a & s) continue;
+      const uint4 send = up ? c[a] : c[a | s];
+      uint4 recv;
+      recv.x = __shfl_xor_sync(0xffffffffu, send.x, s);
+      recv.y = __shfl_xor_sync(0xffffffffu, send.y, s);
+      recv.z = __shfl_xor_sync(0xffffffffu, send.z, s);
+      recv.w = __shfl_xor_sync(0xffffffffu, send.w, s);
+      if (up) c[a] = recv; else c[a | s] = recv;
+    }
+  }
+}
+
+struct ScEpi {
+  const float* bias;  const void* residual;  void* out;
+  float slope;                 // none / ReLU / LeakyReLU as max(v,0) + slope * min(v,0)
+  int osW;
+};
+
+// Coalesced read of the residual chunks of this lane's group of pixels (then transposed back to "my pixel").
+template <int NCH, typename TOut>
+__device__ __forceinline__ void sc_res_load(const ScEpi& e, int64_t grp_off, int osW, int lane, uint32_t okmask, uint4 (&r)[NCH]) {
+  const int j = lane & (NCH - 1);
+  const TOut* rs = reinterpret_cast<const TOut*>(e.residual) + grp_off + j * (16 / (int)sizeof(TOut));
+#pragma unroll
+  for (int k = 0; k < NCH; ++k)
+    r[k] = ((okmask >> k) & 1u) ? __ldg(reinterpret_cast<const uint4*>(rs + k * osW)) : make_uint4(0, 0, 0, 0);
+}
+
+template <int CP, typename TOut, bool kRes, bool kRelu>
+__device__ __forceinline__ void sc_fast_store(const ScEpi& e, int64_t grp_off, int lane, uint32_t okmask,
+                                              const uint32_t (&v)[CP / 16][16], uint4 (&r)[CP * sizeof(TOut) / 16]) {
+  constexpr int NCH = CP * sizeof(TOut) / 16;
+  constexpr int CPC = 16 / sizeof(TOut);          // channels per chunk
+  uint4 c[NCH];
+  if (kRes) chunk_transpose<NCH>(r, lane);
+#pragma unroll
+  for (int jg = 0; jg < CP / 16; ++jg) {
+    float f[16];
+    const float4* b4 = reinterpret_cast<const float4*>(e.bias + 16 * jg);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 b = __ldg(b4 + i);
+      f[4 * i] = __uint_as_float(v[jg][4 * i]) + b.x;          f[4 * i + 1] = __uint_as_float(v[jg][4 * i + 1]) + b.y;
+      f[4 * i + 2] = __uint_as_float(v[jg][4 * i + 2]) + b.z;  f[4 * i + 3] = __uint_as_float(v[jg][4 * i + 3]) + b.w;
+    }
+    if (kRes) {
+      if (sizeof(TOut) == 2) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&r[2 * jg + h]);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float2 g = __bfloat1622float2(hp[i]);
+            f[8 * h + 2 * i] += g.x;  f[8 * h + 2 * i + 1] += g.y;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          const float4 g = *reinterpret_cast<const float4*>(&r[4 * jg + h]);
+          f[4 * h] += g.x;  f[4 * h + 1] += g.y;  f[4 * h + 2] += g.z;  f[4 * h + 3] += g.w;
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) f[i] = kRelu ? fmaxf(f[i], 0.f) : fmaxf(f[i], 0.f) + e.slope * fminf(f[i], 0.f);
+    if (sizeof(TOut) == 2) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        __nv_bfloat162* hp = reinterpret_cast<__nv_bfloat162*>(&c[2 * jg + h]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) hp[i] = __floats2bfloat162_rn(f[8 * h + 2 * i], f[8 * h + 2 * i + 1]);
+      }
+    } else {
+#pragma unroll
+      for (int h = 0; h < 4; ++h) c[4 * jg + h] = *reinterpret_cast<const uint4*>(&f[4 * h]);
+    }
+  }
+  chunk_transpose<NCH>(c, lane);
+  const int j = lane & (NCH - 1);
+  TOut* o = reinterpret_cast<TOut*>(e.out) + grp_off + j * CPC;
+#pragma unroll
+  for (int k = 0; k < NCH; ++k)
+    if ((okmask >> k) & 1u) *reinterpret_cast<uint4*>(o + k * e.osW) = c[k];
+}
+
+// One drained plane: residual chunks `r` (already loaded, still in group order) + accumulators -> coalesced stores.
+template <int CP, typename TOut>
+__device__ __forceinline__ void sc_fast_plane(const ScEpi& e, int64_t grp_off, int lane, uint32_t okmask,
+                                              const uint32_t (&v)[CP / 16][16], uint4 (&r)[CP * sizeof(TOut) / 16]) {
+  if (e.slope == 0.f) {                             // ReLU (every aggregation layer): one instruction per value
+    if (e.residual) sc_fast_store<CP, TOut, true, true>(e, grp_off, lane, okmask, v, r);
+    else            sc_fast_store<CP, TOut, false, true>(e, grp_off, lane, okmask, v, r);
+  } else {
+    if (e.residual) sc_fast_store<CP, TOut, true, false>(e, grp_off, lane, okmask, v, r);
+    else            sc_fast_store<CP, TOut, false, false>(e, grp_off, lane, okmask, v, r);
+  }
+}
+
+template <int CP, typename TOut, bool kFast>     // kFast: transposed stores (needs a power-of-two chunk count per pixel)
+__device__ __forceinline__ void sc_epilogue(const ScArgs& a, ScCtrl& ctrl, uint32_t tmem_base, int warp, int lane) {
+  constexpr int NCH = kFast ? CP * (int)sizeof(TOut) / 16 : 1;     // 16-byte chunks per pixel
+  const int t = (warp - 4) >> 2, q = warp & 3;
+  const EpiParams ep = {a.bias, a.residual, a.out, a.p.cout_store, sizeof(TOut) == 2, a.p.act, a.p.act_param, 1, nullptr, 0, 0};
+  const ScEpi fe = {a.bias, a.residual, a.out,
+                    a.p.act == S3D_ACT_NONE ? 1.f : (a.p.act == S3D_ACT_LEAKY ? a.p.act_param : 0.f), (int)a.p.osW};
+  const uint32_t bar_af = ptx::smem_u32(&ctrl.acc_full[t]), bar_ae = ptx::smem_u32(&ctrl.acc_empty[t]);
+  const uint32_t tbase = tmem_base + t * kTileCols + (static_cast<uint32_t>(q * 32) << 16);
+  const int yl = t * kTileY + q * 4 + (lane >> 3), xl = lane & 7;      // TMEM lane = 8 * row + x inside the tile
+  const int D = a.p.oD;
+  const int xb = xl & ~(NCH - 1);                     // first pixel of this lane's transpose group
+  uint32_t aphase = 0;
+  for (int col = blockIdx.x; col < a.total_cols; col += gridDim.x) {
+    const Col c = decode_col(a, col);
+    const bool rowok = c.y0 + yl < a.p.oH;
+    const bool ok = rowok && c.x0 + xl < a.p.oW;
+    const int64_t row_off = (int64_t)c.n * a.p.osN + (int64_t)(c.y0 + yl) * a.p.osH + (int64_t)c.x0 * a.p.osW;
+    const int64_t pix_off = row_off + (int64_t)xl * a.p.osW;
+    const int64_t grp_off = row_off + (int64_t)xb * a.p.osW;
+    uint32_t okmask = 0;                              // which pixels of the group exist
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) okmask |= (rowok && c.x0 + xb + k < a.p.oW) ? (1u << k) : 0u;
+    int slot = 0, z = 0;                              // next output plane to drain and its slot (z % 3)
+    for (int p = 0; p < D; ++p) {
+      // input plane p done => out plane p-1 is complete; after the last input plane so is out plane D-1
+      const int ndrain = (p >= 1 ? 1 : 0) + (p == D - 1 ? 1 : 0);
+      uint4 r[NCH];
+      if constexpr (kFast) {                          // residual of the plane about to be drained: in flight during the wait
+        if (a.residual && ndrain) sc_res_load<NCH, TOut>(fe, grp_off + (int64_t)z * a.p.osD, fe.osW, lane, okmask, r);
+      }
+      ptx::mbar_wait_u32(bar_af, aphase);
+      ptx::tc_fence_after();
+      if (ndrain == 0) {
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive_u32(bar_ae);
+      }
+      for (int i = 0; i < ndrain; ++i) {
+        uint32_t v[CP / 16][16];
+        const uint32_t taddr = tbase + slot * CP;
+#pragma unroll
+        for (int j = 0; j < CP / 16; ++j) ptx::tmem_ld16(taddr + 16 * j, v[j]);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < CP / 16; ++j) ptx::tmem_st16_zero(taddr + 16 * j);
+        ptx::tmem_st_wait();
+        if (i == ndrain - 1) {                        // hand the tile back before the arithmetic / stores
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive_u32(bar_ae);
+        }
+        const int64_t zo = (int64_t)z * a.p.osD;
+        if constexpr (kFast) {
+          // (second drain of the last plane: its residual could not be prefetched)
+          if (i == 1 && a.residual) sc_res_load<NCH, TOut>(fe, grp_off + zo, fe.osW, lane, okmask, r);
+          sc_fast_plane<CP, TOut>(fe, grp_off + zo, lane, okmask, v, r);
+        } else {
+          if (ok) {
+#pragma unroll
+            for (int j = 0; j < CP / 16; ++j) epilogue_store16(ep, pix_off + zo, 16 * j, v[j]);
+          }
+        }
+        ++z;
+        if (++slot == 3) slot = 0;
+      }
+      aphase ^= 1;
+    }
+  }
+}
+
+template <int CP>
+__device__ __forceinline__ void sc_epilogue_dispatch(const ScArgs& a, ScCtrl& ctrl, uint32_t tmem_base, int warp, int lane) {
+  constexpr bool kPow2_16 = CP == 16 || CP == 32 || CP == 64;      // bf16: CP / 8 chunks
+  constexpr bool kPow2_32 = CP == 16 || CP == 32;                  // fp32: CP / 4 chunks, at most 8
+  if (a.p.out_dtype == S3D_DTYPE_BF16) {
+    if (kPow2_16 && a.fast_store) sc_epilogue<CP, __nv_bfloat16, kPow2_16>(a, ctrl, tmem_base, warp, lane);
+    else sc_epilogue<CP, __nv_bfloat16, false>(a, ctrl, tmem_base, warp, lane);
+  } else {
+    if (kPow2_32 && a.fast_store) sc_epilogue<CP, float, kPow2_32>(a, ctrl, tmem_base, warp, lane);
+    else sc_epilogue<CP, float, false>(a, ctrl, tmem_base, warp, lane);
+  }
+}
+
+template <bool kTF32>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_scatter_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+                    const __grid_constant__ ScArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_w = smem + a.ring * a.slot_bytes;
+  __shared__ ScCtrl ctrl;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&map_x);
+    ptx::prefetch_tensormap(&map_w);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kMaxRing; ++s) { ptx::mbar_init(&ctrl.plane_full[s], 1); ptx::mbar_init(&ctrl.plane_empty[s], 1); }
+    for (int s = 0; s < kMaxW; ++s) { ptx::mbar_init(&ctrl.w_full[s], 1); ptx::mbar_init(&ctrl.w_empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { ptx::mbar_init(&ctrl.acc_full[b], 1); ptx::mbar_init(&ctrl.acc_empty[b], 4); }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) ptx::tmem_alloc(&ctrl.tmem_base, kTmemCols);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = ctrl.tmem_base;
+
+  if (warp == 0) {
+    const uint32_t planes_u32 = ptx::smem_u32(smem), w_u32 = ptx::smem_u32(smem_w);
+    if (a.tps == 1) sc_produce<1>(a, ctrl, planes_u32, w_u32, &map_x, &map_w);
+    else if (a.tps == 3) sc_produce<3>(a, ctrl, planes_u32, w_u32, &map_x, &map_w);
+    else sc_produce<9>(a, ctrl, planes_u32, w_u32, &map_x, &map_w);
+  } else if (warp == 1) {
+    const int rb = a.row_bytes;
+    const ScIssue zi = {tmem_base, ptx::smem_u32(smem), ptx::smem_u32(smem_w),
+                        ptx::smem_u32(&ctrl.plane_full[0]), ptx::smem_u32(&ctrl.plane_empty[0]), ptx::smem_u32(&ctrl.w_full[0]),
+                        ptx::smem_u32(&ctrl.w_empty[0]), ptx::smem_u32(&ctrl.acc_full[0]), ptx::smem_u32(&ctrl.acc_empty[0]),
+                        desc_hi(kHX * rb, rb), desc_hi(8 * rb, rb), a.slot_bytes, a.w_bytes, a.w_stages, a.ring,
+                        (uint32_t)(rb >> 4), (uint32_t)((3 * a.cp * rb) >> 4), (uint32_t)((kTileY * kHX * rb) >> 4), a.idesc,
+                        a.p.iD, a.total_cols};
+    if (rb == 128) sc_issue<kTF32, 1, 4>(zi);
+    else if (rb == 64) sc_issue<kTF32, 3, 2>(zi);
+    else if (a.tps == 3) sc_issue<kTF32, 3, 1>(zi);
+    else sc_issue<kTF32, 9, 1>(zi);
+  } else if (warp >= 4) {
+    if (a.cp == 64) sc_epilogue_dispatch<64>(a, ctrl, tmem_base, warp, lane);
+    else if (a.cp == 48) sc_epilogue_dispatch<48>(a, ctrl, tmem_base, warp, lane);
+    else if (a.cp == 32) sc_epilogue_dispatch<32>(a, ctrl, tmem_base, warp, lane);
+    else sc_epilogue_dispatch<16>(a, ctrl, tmem_base, warp, lane);
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+}  // namespace
+
+// stride-1 3x3x3, pad 1, canonical tap order, Cout <= 64, one K chunk per row, channels-last output, host-packed
+// rotations present.
+bool conv_scatter_eligible(const S3dConvParams* p) {
+  const int esz = p->in_dtype == S3D_DTYPE_F32 ? 4 : 2;
+  if (!p->w_nstack || getenv("S3D_NO_SCATTER") != nullptr) return false;
+  if (p->n_classes != 1 || p->sx != 1 || p->sy != 1 || p->sz != 1 || p->ntaps != 27) return false;
+  if (p->omx != 1 || p->omy != 1 || p->omz != 1 || p->osC != 1 || p->proj_w) return false;
+  if (p->oD != p->iD || p->oH != p->iH || p->oW != p->iW) return false;
+  for (int t = 0; t < 27; ++t)
+    if (p->dz[t] != t / 9 - 1 || p->dy[t] != (t % 9) / 3 - 1 || p->dx[t] != t % 3 - 1) return false;
+  const int cin_bytes = p->Cin * esz;
+  if (cin_bytes != 32 && cin_bytes != 64 && cin_bytes != 128) return false;
+  if (p->Cout > 64 || p->Cout % 16 != 0) return false;
+  return true;
+}
+
+int conv_scatter_launch(const S3dConvParams* p_in, const void* in, const float* bias, const void* residual, void* out,
+                        cudaStream_t stream) {
+  const S3dConvParams& p = *p_in;
+  const bool tf32 = p.in_dtype == S3D_DTYPE_F32;
+  const int esz = tf32 ? 4 : 2;
+  S3D_CHECK_ARG(p.cout_store >= 1 && p.cout_store <= p.Cout, "scatter: cout_store");
+  ScArgs a;
+  memset(&a, 0, sizeof(a));
+  a.p = p;  a.bias = bias;  a.residual = residual;  a.out = out;
+  a.row_bytes = p.Cin * esz;
+  a.kc = p.Cin;
+  a.slot_bytes = (kPlaneRows * a.row_bytes + 1023) / 1024 * 1024;
+  a.cp = p.Cout;
+  a.tps = a.row_bytes == 128 ? 1 : 3;
+  if (a.row_bytes == 32 && getenv("S3D_SCATTER_TPS9") != nullptr) a.tps = 9;
+  a.w_tx = a.tps * 3 * a.cp * a.row_bytes;
+  a.w_bytes = (a.w_tx + 1023) / 1024 * 1024;
+  const int budget = 227 * 1024 - 1024 - 512;                 // dynamic shared memory minus alignment slack and ScCtrl
+  // big planes: 2 slots and the rest for weight stages; small planes: a deeper ring (a plane is then consumed faster
+  // than its TMA round trip), keeping at least 4 weight stages
+  int ring = (budget - 4 * a.w_bytes) / a.slot_bytes;
+  if (ring > kMaxRing) ring = kMaxRing;
+  if (ring < 2) ring = 2;
+  if (a.row_bytes == 128 && ring > 2) ring = 2;       // 2 plane slots + 5 weight stages (weight latency is what stalls)
+  if (const char* e = getenv("S3D_SCATTER_RING")) { const int r = atoi(e); if (r >= 2 && r <= kMaxRing) ring = r; }
+  a.ring = ring;
+  a.w_stages = (budget - a.ring * a.slot_bytes) / a.w_bytes;
+  if (a.w_stages > kMaxW) a.w_stages = kMaxW;
+  S3D_CHECK_ARG(a.w_stages >= 3, "scatter: not enough shared memory for the weight ring");
+  a.cols_x = ceil_div(p.oW, kTX);  a.cols_y = ceil_div(p.oH, kTY);
+  const int64_t total = (int64_t)p.N * a.cols_x * a.cols_y;
+  S3D_CHECK_ARG(total > 0 && total < (1ll << 31), "scatter: column count out of range");
+  a.total_cols = (int)total;
+  a.idesc = ptx::make_instr_desc(tf32 ? 2 : 1, 128, 3 * a.cp);
+  {
+    const int oesz = p.out_dtype == S3D_DTYPE_BF16 ? 2 : 4;
+    const bool simple_act = p.act == S3D_ACT_NONE || p.act == S3D_ACT_RELU || p.act == S3D_ACT_LEAKY;
+    auto aligned = [&](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    auto dense16 = [&](int64_t st) { return (st * oesz) % 16 == 0; };
+    a.fast_store = simple_act && bias != nullptr && p.cout_store == p.Cout && aligned(out) && aligned(residual) &&
+                   dense16(p.osW) && dense16(p.osH) && dense16(p.osD) && dense16(p.osN) && p.osW < (1ll << 24) &&
+                   getenv("S3D_SCATTER_NO_TRANSPOSE") == nullptr;
+  }
+
+  const CUtensorMapSwizzle sw = a.row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                              : a.row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+  CUtensorMap map_x, map_w;
+  cuuint32_t box[5] = {(cuuint32_t)a.kc, kHX, kHY, 1, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  int rc = encode_act_map(&map_x, in, esz, tf32, p.Cin, p.iW, p.iH, p.iD, p.N, box, estr, sw);
+  if (rc != S3D_OK) return rc;
+  rc = encode_weight_map(&map_w, p.w_nstack, esz, tf32, p.Cin, 3 * a.cp, 36, a.kc, 3 * a.cp, sw, a.tps);
+  if (rc != S3D_OK) return rc;
+
+  const int smem_bytes = a.ring * a.slot_bytes + a.w_stages * a.w_bytes + 1024;
+  auto kern = tf32 ? conv_scatter_kernel<true> : conv_scatter_kernel<false>;
+  S3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+  int grid = num_sms();
+  if (grid > a.total_cols) grid = a.total_cols;
+  kern<<<grid, kThreads, smem_bytes, stream>>>(map_x, map_w, a);
+  S3D_LAUNCH_CHECK();
+  return S3D_OK;
+}
+
+}  // namespace s3d

@@ -93,6 +93,7 @@ class PackedConv:
         # stride-1 3x3x3 layers with Cout <= 64: pre-stack the weights for the z-stacked UMMA tile
         # (two output planes x 64 channels = M 128), see csrc/conv_halo.cu and include/s3d.h
         self.weight_zs = None
+        self.weight_ns = None
         if tuple(ksize) == (3, 3, 3) and tuple(pad) == (1, 1, 1) and tuple(stride) == (1, 1, 1) and \
                 self.n_classes == 1 and self.cout_pad <= 64:
             zs = torch.zeros(38, 128, self.cin_pad, dtype=torch.float32)
@@ -111,9 +112,23 @@ class PackedConv:
                 zs[36, :self.cout_pad] = eye
                 zs[37, 64:64 + self.cout_pad] = eye
             self.weight_zs = zs.to(torch_dtype(dtype_code)).to(device).contiguous()
+            self.weight_ns = self.pack_nstack(w3).to(torch_dtype(dtype_code)).to(device).contiguous()
         self.bn = _choose_bn(self.cout_pad)
         self.proj = None                 # optional fused 1x1 projection: (fp32[16] device tensor, channel, act)
         self._cache = {}
+
+    @staticmethod
+    def pack_nstack(w3):
+        """[3(kz), 9(kyx), Cout_pad, Cin_pad] -> [4, 9, 3*Cout_pad, Cin_pad]: the three kz slices stacked on the output
+        side in the four rotations of include/s3d.h (w_nstack): rotation r, block s = W[kz = (r + 1 - s) mod 3]."""
+        _, _, co, ci = w3.shape
+        ns = torch.zeros(4, 9, 3 * co, ci, dtype=torch.float32)
+        for r in range(4):
+            for s in range(3):
+                if r == 3 and s == 2:
+                    continue                      # input plane 0 has no output plane -1
+                ns[r, :, s * co:(s + 1) * co] = w3[((r % 3) + 1 - s) % 3]
+        return ns.view(36, 3 * co, ci)
 
     # ---- constructors ------------------------------------------------------------------
     @classmethod
@@ -213,6 +228,7 @@ class PackedConv:
         p.bn = self.bn
         p.w_zstack = self.weight_zs.data_ptr() if self.weight_zs is not None else None
         p.w_zstack_ident = 1 if (self.weight_zs is not None and self.zs_ident) else 0
+        p.w_nstack = self.weight_ns.data_ptr() if self.weight_ns is not None else None
         if self.proj is not None:
             p.proj_w, p.proj_channel, p.proj_act = self.proj[0].data_ptr(), self.proj[1], self.proj[2]
         self._cache[key] = p

@@ -37,6 +37,7 @@ class S3dConvParams(ctypes.Structure):
         ('w_zstack', ctypes.c_void_p),
         ('w_zstack_ident', ctypes.c_int32),
         ('proj_w', ctypes.c_void_p), ('proj_channel', ctypes.c_int32), ('proj_act', ctypes.c_int32),
+        ('w_nstack', ctypes.c_void_p),
     ]
 
 
