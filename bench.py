@@ -279,7 +279,8 @@ def run_ours(args):
     dom = sum(dom_ms) / max(len(dom_ms), 1)
     achieved = flops / (dom / 1e3) / 1e12
     peak = pk['bf16_tflops_sustained']
-    total_flops = sum(model._packed[k].flops(*shape) for k, shape in model_flop_shapes(cfg, B).items())
+    total_flops = sum(model._packed[k].flops(*shape) for k, shape in model_flop_shapes(cfg, B).items()
+                      if k in model._packed)     # dec_out is fused into dec3's epilogue when it fits
     line = {
         'metric': 'stereo pairs/sec Stereo2Voxel fwd', 'value': value, 'unit': 'pairs/s', 'n_gpus': world,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
@@ -294,13 +295,13 @@ def run_ours(args):
                 'd2h_bytes_per_step': B * cfg.CONST.N_VOX ** 3 * 4 + (2 * T + 1) * 8},
         'gpu_launches': launches,
         'clocks': clk.summary(),
-        'roofline': {'bound': 'tensor', 'kernel': 'conv_halo_kernel (3x3x3 64->64 cost aggregation, 4 of the 6 aggregation layers)',
+        'roofline': {'bound': 'tensor', 'kernel': 'conv_scatter_kernel (3x3x3 64->64 cost aggregation, 4 of the 6 aggregation layers)',
                      'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,
                      'peak_source': '%s bf16_tflops_sustained (kernel timed inside a long step)' % pk['source'],
                      'ms_per_launch': dom, 'flops_per_launch': flops, 'share_of_step': dom * len(dom_layers) / (ms / args.steps),
                      # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel at this exact shape,
                      # from the round-1 `ncu --set full` capture (profiles/r1_ncu_summary.md); algorithmic bytes = 4.295e9
-                     'traffic': 4.2536e9 if (B == 64 and args.precision == 'bf16' and (H, W, D) == (256, 256, 32)) else None},
+                     'traffic': 4.2810e9 if (B == 64 and args.precision == 'bf16' and (H, W, D) == (256, 256, 32)) else None},
         'model_tflops_per_step': total_flops / 1e12,
         'model_tflops_achieved': total_flops / (ms / args.steps / 1e3) / 1e12,
     }

@@ -46,7 +46,7 @@ constexpr int kTY = 32, kHY = kTY + 2;
 constexpr int kTileY = 16;                     // rows of one M = 128 tile
 constexpr int kPlaneRows = kHX * kHY;          // 340
 constexpr int kMaxRing = 6;
-constexpr int kMaxW = 8;
+constexpr int kMaxW = 12;
 constexpr int kTmemCols = 512;
 constexpr int kTileCols = 256;                 // TMEM column pitch between the two tiles
 
@@ -63,6 +63,8 @@ struct ScArgs {
   int tps;            // in-plane taps per weight stage: 1, 3 or 9
   int w_stages, w_bytes, w_tx;
   int cols_x, cols_y, total_cols;
+  int pair;           // 1: CTA pairs (cta_group::2, M = 256): each CTA keeps its own pixels, half of the weight rows
+  int ncols_max;      // pair mode: columns every CTA walks (phantom columns beyond total_cols compute on zeros)
   uint32_t idesc;
   int fast_store;     // epilogue may use the transposed (coalesced) store path
 };
@@ -84,6 +86,12 @@ __device__ __forceinline__ Col decode_col(const ScArgs& a, int c) {
   return r;
 }
 
+// Columns this CTA walks.  The two CTAs of a pair run the same MMAs, so in pair mode every CTA walks ncols_max
+// columns; a column index >= total_cols decodes to n >= N (TMA zero fill, nothing stored).
+__device__ __forceinline__ int cta_cols(const ScArgs& a) {
+  return a.pair ? a.ncols_max : (a.total_cols - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+}
+
 __device__ __forceinline__ uint64_t desc_hi(uint32_t sbo, int row_bytes) {
   const uint64_t layout = row_bytes == 128 ? 2ull : (row_bytes == 64 ? 4ull : 6ull);
   return (static_cast<uint64_t>(sbo >> 4) << 32) | (1ull << 46) | (layout << 61);
@@ -91,39 +99,49 @@ __device__ __forceinline__ uint64_t desc_hi(uint32_t sbo, int row_bytes) {
 __device__ __forceinline__ uint32_t desc_lo(uint32_t addr) { return ((addr & 0x3FFFF) >> 4) | (1u << 16); }
 
 // ---- TMA producer: warp-uniform, incremental ring counters, TMA issue under small elect_one regions -----------------
-template <int TPS>
+template <int TPS, bool kPair>
 __device__ __forceinline__ void sc_produce(const ScArgs& a, ScCtrl& ctrl, uint32_t planes_u32, uint32_t w_u32,
                                            const CUtensorMap* map_x, const CUtensorMap* map_w) {
   constexpr int G = 9 / TPS;
   const uint32_t bar_pf = ptx::smem_u32(&ctrl.plane_full[0]), bar_pe = ptx::smem_u32(&ctrl.plane_empty[0]);
   const uint32_t bar_wf = ptx::smem_u32(&ctrl.w_full[0]), bar_we = ptx::smem_u32(&ctrl.w_empty[0]);
-  const int D = a.p.iD, ring = a.ring, w_stages = a.w_stages, total_cols = a.total_cols;
+  const int D = a.p.iD, ring = a.ring, w_stages = a.w_stages, ncols = cta_cols(a);
   const int slot_bytes = a.slot_bytes, w_bytes = a.w_bytes, w_tx = a.w_tx;
+  // pair mode: this CTA stages its own planes and ITS half of the weight rows; every load signals the leader's `full`
+  // barrier, on which the leader's producer expects the bytes of both CTAs
+  const int crank = kPair ? (int)ptx::cluster_ctarank() : 0;
+  const bool leader = crank == 0;
+  const int w_row0 = kPair ? crank * (3 * a.cp / 2) : 0;
   const int plane_tx = kPlaneRows * a.row_bytes;
   int ws = 0;  uint32_t wphase = 0;
   int pslot = 0;  uint32_t pphase = 0;
-  int pcol = blockIdx.x, pj = 0, issued = 0;
-  Col pc = decode_col(a, pcol < total_cols ? pcol : 0);
+  int pci = 0, pj = 0, issued = 0;
+  Col pc = decode_col(a, blockIdx.x);
   auto issue_plane = [&](bool blocking) -> bool {
-    if (pcol >= total_cols) return false;
+    if (pci >= ncols) return false;
     const uint32_t be = bar_pe + 8 * pslot, bf = bar_pf + 8 * pslot;
     if (blocking) ptx::mbar_wait_u32(be, pphase ^ 1);
     else if (!ptx::mbar_test_wait_u32(be, pphase ^ 1)) return false;
     if (ptx::elect_one()) {
-      ptx::mbar_arrive_expect_tx_u32(bf, plane_tx);
-      ptx::tma_load_5d_u32(planes_u32 + pslot * slot_bytes, map_x, bf, 0, pc.x0 - 1, pc.y0 - 1, pj, pc.n);
+      if (kPair) {
+        if (leader) ptx::mbar_arrive_expect_tx_u32(bf, 2 * plane_tx);
+        ptx::tma_load_5d_2sm_u32(planes_u32 + pslot * slot_bytes, map_x, bf, 0, pc.x0 - 1, pc.y0 - 1, pj, pc.n);
+      } else {
+        ptx::mbar_arrive_expect_tx_u32(bf, plane_tx);
+        ptx::tma_load_5d_u32(planes_u32 + pslot * slot_bytes, map_x, bf, 0, pc.x0 - 1, pc.y0 - 1, pj, pc.n);
+      }
     }
     __syncwarp();
     ++issued;
     if (++pslot == ring) { pslot = 0; pphase ^= 1; }
     if (++pj == D) {
-      pj = 0;  pcol += gridDim.x;
-      if (pcol < total_cols) pc = decode_col(a, pcol);
+      pj = 0;  ++pci;
+      if (pci < ncols) pc = decode_col(a, blockIdx.x + pci * gridDim.x);
     }
     return true;
   };
   int gp = 0;                                    // global index of the current plane
-  for (int col = blockIdx.x; col < total_cols; col += gridDim.x) {
+  for (int ci = 0; ci < ncols; ++ci) {
     int rot = 3;                                 // weight rotation: 3 for p = 0, then p % 3
     for (int p = 0; p < D; ++p, ++gp) {
       while (issued <= gp) issue_plane(true);
@@ -134,8 +152,13 @@ __device__ __forceinline__ void sc_produce(const ScArgs& a, ScCtrl& ctrl, uint32
         const uint32_t be = bar_we + 8 * ws, bf = bar_wf + 8 * ws;
         ptx::mbar_wait_u32(be, wphase ^ 1);
         if (ptx::elect_one()) {
-          ptx::mbar_arrive_expect_tx_u32(bf, w_tx);
-          ptx::tma_load_3d_u32(w_u32 + ws * w_bytes, map_w, bf, 0, 0, rot * 9 + g * TPS);
+          if (kPair) {
+            if (leader) ptx::mbar_arrive_expect_tx_u32(bf, 2 * w_tx);
+            ptx::tma_load_3d_2sm_u32(w_u32 + ws * w_bytes, map_w, bf, 0, w_row0, rot * 9 + g * TPS);
+          } else {
+            ptx::mbar_arrive_expect_tx_u32(bf, w_tx);
+            ptx::tma_load_3d_u32(w_u32 + ws * w_bytes, map_w, bf, 0, 0, rot * 9 + g * TPS);
+          }
         }
         __syncwarp();
         if (++ws == w_stages) { ws = 0; wphase ^= 1; }
@@ -157,10 +180,16 @@ struct ScIssue {
   int slot_bytes, w_bytes, w_stages, ring;
   uint32_t rb16, tap_step, tile_off;             // 16-byte units
   uint32_t idesc;
-  int D, total_cols;
+  int D, ncols;
 };
 
-template <bool kTF32, int TPS, int kPer>
+template <bool kPair>
+__device__ __forceinline__ void sc_commit(uint32_t bar) {
+  if (kPair) ptx::tc_commit_2sm_u32(bar, 3);       // same barrier in both CTAs of the pair
+  else       ptx::tc_commit_u32(bar);
+}
+
+template <bool kTF32, int TPS, int kPer, bool kPair>
 __device__ __forceinline__ void sc_issue_group(const ScIssue& z, uint32_t d_tmem, uint64_t xdesc, uint64_t wdesc, int g,
                                                uint32_t first) {
 #pragma unroll
@@ -170,13 +199,14 @@ __device__ __forceinline__ void sc_issue_group(const ScIssue& z, uint32_t d_tmem
 #pragma unroll
     for (int k = 0; k < kPer; ++k) {
       const uint32_t acc = (g == 0 && tt == 0 && k == 0) ? first : 1u;
-      if (kTF32) ptx::mma_tf32(d_tmem, xdesc + xoff + 2 * k, wdesc + tt * z.tap_step + 2 * k, z.idesc, acc);
-      else       ptx::mma_bf16(d_tmem, xdesc + xoff + 2 * k, wdesc + tt * z.tap_step + 2 * k, z.idesc, acc);
+      const uint64_t ad = xdesc + xoff + 2 * k, bd = wdesc + tt * z.tap_step + 2 * k;
+      if (kPair) { if (kTF32) ptx::mma_tf32_2sm(d_tmem, ad, bd, z.idesc, acc); else ptx::mma_bf16_2sm(d_tmem, ad, bd, z.idesc, acc); }
+      else       { if (kTF32) ptx::mma_tf32(d_tmem, ad, bd, z.idesc, acc);     else ptx::mma_bf16(d_tmem, ad, bd, z.idesc, acc); }
     }
   }
 }
 
-template <bool kTF32, int TPS, int kPer>
+template <bool kTF32, int TPS, int kPer, bool kPair>
 __device__ __forceinline__ void sc_issue(const ScIssue& z) {
   constexpr int G = 9 / TPS;
   int ws = 0;  uint32_t wphase = 0;
@@ -185,7 +215,7 @@ __device__ __forceinline__ void sc_issue(const ScIssue& z) {
   const uint32_t w_lo0 = desc_lo(z.w_u32), w_lo_step = z.w_bytes >> 4;
   const uint32_t x_lo0 = desc_lo(z.planes_u32), x_lo_step = z.slot_bytes >> 4;
   const uint32_t d0 = z.tmem_base, d1 = z.tmem_base + kTileCols;
-  for (int col = blockIdx.x; col < z.total_cols; col += gridDim.x) {
+  for (int ci = 0; ci < z.ncols; ++ci) {
     for (int p = 0; p < z.D; ++p) {
       ptx::mbar_wait_u32(z.bar_pf + 8 * pw, pwphase);
       const uint64_t xd0 = z.x_hi | (x_lo0 + pw * x_lo_step);
@@ -200,8 +230,8 @@ __device__ __forceinline__ void sc_issue(const ScIssue& z) {
           ptx::tc_fence_after();
           const uint64_t wd = z.w_hi | (w_lo0 + ws * w_lo_step);
           if (ptx::elect_one()) {
-            sc_issue_group<kTF32, TPS, kPer>(z, d0, xd0, wd, g, first);
-            if (g == G - 1) ptx::tc_commit_u32(z.bar_af);
+            sc_issue_group<kTF32, TPS, kPer, kPair>(z, d0, xd0, wd, g, first);
+            if (g == G - 1) sc_commit<kPair>(z.bar_af);
           }
           __syncwarp();
         }
@@ -209,9 +239,9 @@ __device__ __forceinline__ void sc_issue(const ScIssue& z) {
           if (g == 1) { ptx::mbar_wait_u32(z.bar_ae + 8, aphase ^ 1); ptx::tc_fence_after(); }
           const uint64_t wd = z.w_hi | (w_lo0 + ws_prev * w_lo_step);
           if (ptx::elect_one()) {
-            sc_issue_group<kTF32, TPS, kPer>(z, d1, xd1, wd, g - 1, first);
-            ptx::tc_commit_u32(z.bar_we + 8 * ws_prev);
-            if (g == G) { ptx::tc_commit_u32(z.bar_af + 8); ptx::tc_commit_u32(z.bar_pe + 8 * pw); }
+            sc_issue_group<kTF32, TPS, kPer, kPair>(z, d1, xd1, wd, g - 1, first);
+            sc_commit<kPair>(z.bar_we + 8 * ws_prev);
+            if (g == G) { sc_commit<kPair>(z.bar_af + 8); sc_commit<kPair>(z.bar_pe + 8 * pw); }
           }
           __syncwarp();
         }
@@ -352,9 +382,10 @@ __device__ __forceinline__ void sc_epilogue(const ScArgs& a, ScCtrl& ctrl, uint3
   const int D = a.p.oD;
   const int xb = xl & ~(NCH - 1);                     // first pixel of this lane's transpose group
   uint32_t aphase = 0;
-  for (int col = blockIdx.x; col < a.total_cols; col += gridDim.x) {
-    const Col c = decode_col(a, col);
-    const bool rowok = c.y0 + yl < a.p.oH;
+  const int ncols = cta_cols(a);
+  for (int ci = 0; ci < ncols; ++ci) {
+    const Col c = decode_col(a, blockIdx.x + ci * gridDim.x);
+    const bool rowok = c.y0 + yl < a.p.oH && c.n < a.p.N;
     const bool ok = rowok && c.x0 + xl < a.p.oW;
     const int64_t row_off = (int64_t)c.n * a.p.osN + (int64_t)(c.y0 + yl) * a.p.osH + (int64_t)c.x0 * a.p.osW;
     const int64_t pix_off = row_off + (int64_t)xl * a.p.osW;
@@ -375,7 +406,7 @@ __device__ __forceinline__ void sc_epilogue(const ScArgs& a, ScCtrl& ctrl, uint3
       if (ndrain == 0) {
         ptx::tc_fence_before();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive_u32(bar_ae);
+        if (lane == 0) { if (a.pair) ptx::mbar_arrive_cluster_u32(bar_ae, 0); else ptx::mbar_arrive_u32(bar_ae); }
       }
       for (int i = 0; i < ndrain; ++i) {
         uint32_t v[CP / 16][16];
@@ -389,7 +420,7 @@ __device__ __forceinline__ void sc_epilogue(const ScArgs& a, ScCtrl& ctrl, uint3
         if (i == ndrain - 1) {                        // hand the tile back before the arithmetic / stores
           ptx::tc_fence_before();
           __syncwarp();
-          if (lane == 0) ptx::mbar_arrive_u32(bar_ae);
+          if (lane == 0) { if (a.pair) ptx::mbar_arrive_cluster_u32(bar_ae, 0); else ptx::mbar_arrive_u32(bar_ae); }
         }
         const int64_t zo = (int64_t)z * a.p.osD;
         if constexpr (kFast) {
@@ -423,7 +454,7 @@ __device__ __forceinline__ void sc_epilogue_dispatch(const ScArgs& a, ScCtrl& ct
   }
 }
 
-template <bool kTF32>
+template <bool kTF32, bool kPair>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_scatter_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                     const __grid_constant__ ScArgs a) {
@@ -441,32 +472,34 @@ conv_scatter_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kMaxRing; ++s) { ptx::mbar_init(&ctrl.plane_full[s], 1); ptx::mbar_init(&ctrl.plane_empty[s], 1); }
     for (int s = 0; s < kMaxW; ++s) { ptx::mbar_init(&ctrl.w_full[s], 1); ptx::mbar_init(&ctrl.w_empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { ptx::mbar_init(&ctrl.acc_full[b], 1); ptx::mbar_init(&ctrl.acc_empty[b], 4); }
+    // accumulator hand-back: one arrival per epilogue warp of the tile -- of both CTAs in pair mode (on the leader's barrier)
+    for (int b = 0; b < 2; ++b) { ptx::mbar_init(&ctrl.acc_full[b], 1); ptx::mbar_init(&ctrl.acc_empty[b], kPair ? 8 : 4); }
     ptx::fence_barrier_init();
   }
-  if (warp == 2) ptx::tmem_alloc(&ctrl.tmem_base, kTmemCols);
+  if (warp == 2) { if (kPair) ptx::tmem_alloc_2sm(&ctrl.tmem_base, kTmemCols); else ptx::tmem_alloc(&ctrl.tmem_base, kTmemCols); }
   ptx::tc_fence_before();
   __syncthreads();
+  if (kPair) ptx::cluster_sync_all();              // the peer's barriers exist before anything is signalled at them
   ptx::tc_fence_after();
   const uint32_t tmem_base = ctrl.tmem_base;
 
   if (warp == 0) {
     const uint32_t planes_u32 = ptx::smem_u32(smem), w_u32 = ptx::smem_u32(smem_w);
-    if (a.tps == 1) sc_produce<1>(a, ctrl, planes_u32, w_u32, &map_x, &map_w);
-    else if (a.tps == 3) sc_produce<3>(a, ctrl, planes_u32, w_u32, &map_x, &map_w);
-    else sc_produce<9>(a, ctrl, planes_u32, w_u32, &map_x, &map_w);
-  } else if (warp == 1) {
+    if (a.tps == 1) sc_produce<1, kPair>(a, ctrl, planes_u32, w_u32, &map_x, &map_w);
+    else if (a.tps == 3) sc_produce<3, kPair>(a, ctrl, planes_u32, w_u32, &map_x, &map_w);
+    else sc_produce<9, kPair>(a, ctrl, planes_u32, w_u32, &map_x, &map_w);
+  } else if (warp == 1 && (!kPair || ptx::cluster_ctarank() == 0)) {      // pair mode: the leader issues for both CTAs
     const int rb = a.row_bytes;
     const ScIssue zi = {tmem_base, ptx::smem_u32(smem), ptx::smem_u32(smem_w),
                         ptx::smem_u32(&ctrl.plane_full[0]), ptx::smem_u32(&ctrl.plane_empty[0]), ptx::smem_u32(&ctrl.w_full[0]),
                         ptx::smem_u32(&ctrl.w_empty[0]), ptx::smem_u32(&ctrl.acc_full[0]), ptx::smem_u32(&ctrl.acc_empty[0]),
                         desc_hi(kHX * rb, rb), desc_hi(8 * rb, rb), a.slot_bytes, a.w_bytes, a.w_stages, a.ring,
-                        (uint32_t)(rb >> 4), (uint32_t)((3 * a.cp * rb) >> 4), (uint32_t)((kTileY * kHX * rb) >> 4), a.idesc,
-                        a.p.iD, a.total_cols};
-    if (rb == 128) sc_issue<kTF32, 1, 4>(zi);
-    else if (rb == 64) sc_issue<kTF32, 3, 2>(zi);
-    else if (a.tps == 3) sc_issue<kTF32, 3, 1>(zi);
-    else sc_issue<kTF32, 9, 1>(zi);
+                        (uint32_t)(rb >> 4), (uint32_t)(((kPair ? 3 * a.cp / 2 : 3 * a.cp) * rb) >> 4), (uint32_t)((kTileY * kHX * rb) >> 4), a.idesc,
+                        a.p.iD, cta_cols(a)};
+    if (rb == 128) sc_issue<kTF32, 1, 4, kPair>(zi);
+    else if (rb == 64) sc_issue<kTF32, 3, 2, kPair>(zi);
+    else if (a.tps == 3) sc_issue<kTF32, 3, 1, kPair>(zi);
+    else sc_issue<kTF32, 9, 1, kPair>(zi);
   } else if (warp >= 4) {
     if (a.cp == 64) sc_epilogue_dispatch<64>(a, ctrl, tmem_base, warp, lane);
     else if (a.cp == 48) sc_epilogue_dispatch<48>(a, ctrl, tmem_base, warp, lane);
@@ -476,9 +509,10 @@ conv_scatter_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
 
   ptx::tc_fence_before();
   __syncthreads();
+  if (kPair) ptx::cluster_sync_all();              // no CTA leaves while its peer may still signal its barriers
   if (warp == 2) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, kTmemCols);
+    if (kPair) ptx::tmem_dealloc_2sm(tmem_base, kTmemCols); else ptx::tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -515,25 +549,36 @@ int conv_scatter_launch(const S3dConvParams* p_in, const void* in, const float* 
   a.cp = p.Cout;
   a.tps = a.row_bytes == 128 ? 1 : 3;
   if (a.row_bytes == 32 && getenv("S3D_SCATTER_TPS9") != nullptr) a.tps = 9;
-  a.w_tx = a.tps * 3 * a.cp * a.row_bytes;
+  a.cols_x = ceil_div(p.oW, kTX);  a.cols_y = ceil_div(p.oH, kTY);
+  const int64_t total = (int64_t)p.N * a.cols_x * a.cols_y;
+  S3D_CHECK_ARG(total > 0 && total < (1ll << 31), "scatter: column count out of range");
+  a.total_cols = (int)total;
+  // CTA pairs (cta_group::2): the two SMs of a TPC run one M = 256 MMA, each on its own 128 pixels, and each keeps only
+  // HALF of the weight rows in shared memory.  That halves the B-operand reads and the weight TMA writes per SM -- the
+  // single-CTA kernel saturates the shared-memory pipe (A 4 KB + B 6 KB per 96-cycle MMA, plus the TMA fills).
+  int grid = num_sms();
+  a.pair = ((3 * a.cp / 2) % 8 == 0 && total >= 2 && grid >= 2 && getenv("S3D_SCATTER_NO_PAIR") == nullptr) ? 1 : 0;
+  if (a.pair) {
+    if ((int64_t)grid > total) grid = (int)((total + 1) / 2 * 2);
+    grid -= grid % 2;
+    a.ncols_max = (int)((total + grid - 1) / grid);
+  } else if ((int64_t)grid > total) grid = (int)total;
+  const int w_rows = a.pair ? 3 * a.cp / 2 : 3 * a.cp;          // weight rows staged per CTA
+  a.w_tx = a.tps * w_rows * a.row_bytes;
   a.w_bytes = (a.w_tx + 1023) / 1024 * 1024;
   const int budget = 227 * 1024 - 1024 - 512;                 // dynamic shared memory minus alignment slack and ScCtrl
-  // big planes: 2 slots and the rest for weight stages; small planes: a deeper ring (a plane is then consumed faster
-  // than its TMA round trip), keeping at least 4 weight stages
+  // big planes: 2 slots and the rest for weight stages (weight latency is what stalls); small planes: a deeper ring
+  // (a plane is then consumed faster than its TMA round trip), keeping at least 4 weight stages
   int ring = (budget - 4 * a.w_bytes) / a.slot_bytes;
   if (ring > kMaxRing) ring = kMaxRing;
   if (ring < 2) ring = 2;
-  if (a.row_bytes == 128 && ring > 2) ring = 2;       // 2 plane slots + 5 weight stages (weight latency is what stalls)
+  if (a.row_bytes == 128 && ring > (a.pair ? 3 : 2)) ring = a.pair ? 3 : 2;
   if (const char* e = getenv("S3D_SCATTER_RING")) { const int r = atoi(e); if (r >= 2 && r <= kMaxRing) ring = r; }
   a.ring = ring;
   a.w_stages = (budget - a.ring * a.slot_bytes) / a.w_bytes;
   if (a.w_stages > kMaxW) a.w_stages = kMaxW;
   S3D_CHECK_ARG(a.w_stages >= 3, "scatter: not enough shared memory for the weight ring");
-  a.cols_x = ceil_div(p.oW, kTX);  a.cols_y = ceil_div(p.oH, kTY);
-  const int64_t total = (int64_t)p.N * a.cols_x * a.cols_y;
-  S3D_CHECK_ARG(total > 0 && total < (1ll << 31), "scatter: column count out of range");
-  a.total_cols = (int)total;
-  a.idesc = ptx::make_instr_desc(tf32 ? 2 : 1, 128, 3 * a.cp);
+  a.idesc = ptx::make_instr_desc(tf32 ? 2 : 1, a.pair ? 256 : 128, 3 * a.cp);
   {
     const int oesz = p.out_dtype == S3D_DTYPE_BF16 ? 2 : 4;
     const bool simple_act = p.act == S3D_ACT_NONE || p.act == S3D_ACT_RELU || p.act == S3D_ACT_LEAKY;
@@ -551,15 +596,25 @@ int conv_scatter_launch(const S3dConvParams* p_in, const void* in, const float* 
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   int rc = encode_act_map(&map_x, in, esz, tf32, p.Cin, p.iW, p.iH, p.iD, p.N, box, estr, sw);
   if (rc != S3D_OK) return rc;
-  rc = encode_weight_map(&map_w, p.w_nstack, esz, tf32, p.Cin, 3 * a.cp, 36, a.kc, 3 * a.cp, sw, a.tps);
+  rc = encode_weight_map(&map_w, p.w_nstack, esz, tf32, p.Cin, 3 * a.cp, 36, a.kc, w_rows, sw, a.tps);
   if (rc != S3D_OK) return rc;
 
   const int smem_bytes = a.ring * a.slot_bytes + a.w_stages * a.w_bytes + 1024;
-  auto kern = tf32 ? conv_scatter_kernel<true> : conv_scatter_kernel<false>;
+  auto kern = a.pair ? (tf32 ? conv_scatter_kernel<true, true> : conv_scatter_kernel<false, true>)
+                     : (tf32 ? conv_scatter_kernel<true, false> : conv_scatter_kernel<false, false>);
   S3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-  int grid = num_sms();
-  if (grid > a.total_cols) grid = a.total_cols;
-  kern<<<grid, kThreads, smem_bytes, stream>>>(map_x, map_w, a);
+  if (a.pair) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);  cfg.blockDim = dim3(kThreads);  cfg.dynamicSmemBytes = smem_bytes;  cfg.stream = stream;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2;  attr.val.clusterDim.y = 1;  attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;  cfg.numAttrs = 1;
+    S3D_CUDA(cudaLaunchKernelEx(&cfg, kern, map_x, map_w, a));
+  } else {
+    kern<<<grid, kThreads, smem_bytes, stream>>>(map_x, map_w, a);
+  }
   S3D_LAUNCH_CHECK();
   return S3D_OK;
 }
