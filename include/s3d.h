@@ -132,6 +132,11 @@ int s3d_soft_argmin(const float* cost, float* disp, int N, int D, int h, int w, 
  * cost_out may be NULL (debug: fp32 [N,D,h,w]). */
 int s3d_tap_gather_soft_argmin(const float* taps, float* disp, float* cost_out, int N, int D, int h, int w,
                                int tap_stride, float sign, void* stream);
+/* The same classifier + soft-argmin in ONE pass over the aggregated volume, no per-tap tensor (csrc/cls_fused.cu):
+ * x: bf16 channels-last [N,D,h,w,C], C in {16,32,64}; w_taps: bf16 [32][C], row t = (kz*3+ky)*3+kx holds W[kz,ky,kx,:]
+ * (rows 27..31 zero) -- the weight tensor of the pointwise layer above; disp: fp32 [N,h,w]. */
+int s3d_cls_soft_argmin(const void* x, const void* w_taps, float* disp, int N, int D, int h, int w, int C,
+                        float sign, void* stream);
 /* Fused correlation + soft-argmax; the [2B,D,h,w] cost is never materialised.
  * disp: fp32 [2B,h,w]; cost_out may be NULL (debug: fp32 [2B,D,h,w]). */
 int s3d_corr_soft_argmin(const void* feat, float* disp, float* cost_out, int B, int h, int w,

@@ -56,6 +56,7 @@ SIGNATURES = {
     's3d_cost_volume_concat': ([_vp, _vp, _i, _i, _i, _i, _i, _i, _vp], _i),
     's3d_soft_argmin': ([_vp, _vp, _i, _i, _i, _i, _f, _vp], _i),
     's3d_tap_gather_soft_argmin': ([_vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp], _i),
+    's3d_cls_soft_argmin': ([_vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp], _i),
     's3d_corr_soft_argmin': ([_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp], _i),
     's3d_upsample_disp': ([_vp, _vp, _i, _i, _i, _i, _i, _f, _vp], _i),
     's3d_latent_to_vox': ([_vp, _vp, _i, _i, _i, _i, _i, _i, _vp], _i),

@@ -11,6 +11,8 @@ The torch.nn layers below are PARAMETER CONTAINERS only -- their forward is neve
 folds BatchNorm and re-lays every weight for the tcgen05 implicit-GEMM engine once; `forward()` is a
 sequence of C-ABI calls (include/s3d.h) on the current CUDA stream, with no torch math on the path.
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -221,9 +223,14 @@ class _StereoBase(nn.Module):
             a = self._conv('dres1b', y, residual=a, out=self._bufo('a3', 'dres1b', y))
             c = self._conv('cls_a', a, out=self._bufo('a0', 'cls_a', a))
             S = self._packed['cls_b'].cout_pad                      # 27 taps padded to 32 planes
-            taps = self._buf('taps', (2 * B, D, h, S, w), torch.float32)   # line-planar: [.., y, tap, x]
-            self._conv('cls_b', c, out=taps, out_view=(0, (D * h * S * w, h * S * w, S * w, 1, w)), cout_store=S)
-            ops.tap_gather_soft_argmin(taps, -1.0, out=disp_q)
+            if c.dtype == torch.bfloat16 and c.shape[-1] in (16, 32, 64) and S == 32 and \
+                    os.environ.get('S3D_NO_CLS_FUSED') is None:
+                # classifier + soft-argmin in one pass over the volume (csrc/cls_fused.cu)
+                ops.cls_soft_argmin(c, self._packed['cls_b'].weight, -1.0, out=disp_q)
+            else:
+                taps = self._buf('taps', (2 * B, D, h, S, w), torch.float32)   # line-planar: [.., y, tap, x]
+                self._conv('cls_b', c, out=taps, out_view=(0, (D * h * S * w, h * S * w, S * w, 1, w)), cout_store=S)
+                ops.tap_gather_soft_argmin(taps, -1.0, out=disp_q)
         else:
             ops.corr_soft_argmin(feat, B, D, out=disp_q)
         disp = ops.upsample_disp(disp_q, H, W, 4.0, out=self._buf('disp', (2 * B, H, W), torch.float32))

@@ -99,6 +99,22 @@ def tap_gather_soft_argmin(taps, sign=-1.0, out=None, want_cost=False):
     return (out, cost) if want_cost else out
 
 
+def cls_soft_argmin(x, w_taps, sign=-1.0, out=None):
+    """x bf16 [N,D,h,w,C] (aggregated volume), w_taps bf16 [32,C] (27 classifier taps) -> disp fp32 [N,h,w]: the Cout=1
+    3x3x3 classifier and the soft-argmin in one pass (include/s3d.h, s3d_cls_soft_argmin)."""
+    _chk(x, w_taps, out)
+    assert x.dtype == torch.bfloat16 and w_taps.dtype == torch.bfloat16 and x.dim() == 5 and x.is_contiguous()
+    N, D, h, w, C = x.shape
+    assert w_taps.numel() == 32 * C and w_taps.is_contiguous()
+    if out is None:
+        out = torch.empty((N, h, w), dtype=torch.float32, device=x.device)
+    rc = _lib.load().s3d_cls_soft_argmin(x.data_ptr(), w_taps.data_ptr(), out.data_ptr(), N, D, h, w, C, float(sign),
+                                         _stream())
+    _lib.check(rc, 's3d_cls_soft_argmin')
+    _lib.count_launch()
+    return out
+
+
 def corr_soft_argmin(feat, B, D, out=None, want_cost=False):
     """feat [2B,1,h,w,C] -> disp fp32 [2B,h,w] (fused correlation + soft-argmax)."""
     _chk(feat, out)

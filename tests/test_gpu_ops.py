@@ -38,6 +38,27 @@ def test_soft_argmin(N, D, h, w):
     torch.testing.assert_close(got, ref, rtol=1e-4, atol=1e-4)
 
 
+@pytest.mark.parametrize('N,C,D,h,w', [(2, 16, 8, 9, 13), (1, 64, 32, 16, 16), (1, 32, 1, 3, 3), (1, 16, 2, 1, 5),
+                                       (3, 64, 5, 40, 21), (2, 32, 9, 64, 64)])
+def test_cls_soft_argmin_fused_equals_cout1_conv(N, C, D, h, w):
+    """One-pass classifier (cls_fused.cu): tcgen05 projections + in-kernel gather + online softmax
+    == Conv3d(C,1,3,1,1) -> soft-argmin on the same bf16-rounded inputs, and == the unfused two-kernel path."""
+    g = torch.Generator().manual_seed(13)
+    x = torch.randn(N, C, D, h, w, generator=g).to(torch.bfloat16)
+    wt = (torch.randn(1, C, 3, 3, 3, generator=g) * 0.3).to(torch.bfloat16)
+    cost_ref = F.conv3d(x.float(), wt.float(), padding=1).squeeze(1)
+    ref = O.soft_argmin(cost_ref)
+    w_taps = torch.zeros(32, C, dtype=torch.bfloat16)
+    w_taps[:27] = wt[0].reshape(C, 27).t()
+    xc = x.permute(0, 2, 3, 4, 1).contiguous().cuda()                              # [N,D,h,w,C]
+    got = ops.cls_soft_argmin(xc, w_taps.cuda(), -1.0)
+    torch.testing.assert_close(got.cpu(), ref, rtol=2e-4, atol=2e-4 * max(D, 1))
+    # the two-kernel path on the same inputs
+    taps = torch.einsum('ncdhw,tc->ndhtw', x.float(), w_taps.float()).contiguous()
+    two = ops.tap_gather_soft_argmin(taps.cuda(), -1.0)
+    torch.testing.assert_close(got, two, rtol=1e-4, atol=1e-4 * max(D, 1))
+
+
 @pytest.mark.parametrize('dtype,tol', [(torch.float32, 1e-3), (torch.bfloat16, 1e-3)])
 @pytest.mark.parametrize('B,C,h,w,D', [(2, 32, 8, 64, 32), (1, 16, 5, 21, 8), (1, 64, 3, 35, 64), (1, 32, 2, 40, 128)])
 def test_corr_soft_argmin(dtype, tol, B, C, h, w, D):
