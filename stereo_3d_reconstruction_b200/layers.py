@@ -11,6 +11,7 @@ At weight-load time every conv-like layer is folded and packed ONCE (SURVEY.md 8
 The forward then has zero layout work: one C-ABI call per layer.
 """
 import ctypes
+import os
 import itertools
 
 import torch
@@ -116,6 +117,20 @@ class PackedConv:
         self.bn = _choose_bn(self.cout_pad)
         self.proj = None                 # optional fused 1x1 projection: (fp32[16] device tensor, channel, act)
         self._cache = {}
+        # stride-1 3x3 2-D layers with Cout <= 64: a batch of images is a VOLUME whose kz = 0 / 2 weight slices are zero,
+        # so the plane-scatter kernel (csrc/conv_scatter.cu: pixel-major, coalesced epilogue, marches over the images
+        # of a column without per-image pipeline bubbles) runs them; its zero N blocks are free while N <= 96 (an MMA
+        # costs ~51 cycles for its A operand anyway).  `vol` is the 27-tap twin of this layer.
+        self.vol = None
+        esz = 2 if dtype_code == _lib.DTYPE_BF16 else 4
+        if tuple(ksize) == (1, 3, 3) and tuple(pad) == (0, 1, 1) and tuple(stride) == (1, 1, 1) and \
+                self.n_classes == 1 and self.cout_pad <= 64 and self.cin_pad * esz in (32, 64, 128) and \
+                [tuple(t) for t in taps[0]] == [(0, dy, dx) for dy in (-1, 0, 1) for dx in (-1, 0, 1)]:
+            w27 = torch.zeros(27, cout, cin, dtype=torch.float32)
+            w27[9:18] = w_rows.cpu()
+            taps27 = [[(dz, dy, dx) for dz in (-1, 0, 1) for dy in (-1, 0, 1) for dx in (-1, 0, 1)]]
+            self.vol = PackedConv(w27, bias, taps27, (1, 1, 1), (1, 1, 1), cin, cout, act, act_param, dtype_code, device,
+                                  ksize=(3, 3, 3), pad=(1, 1, 1))
 
     @staticmethod
     def pack_nstack(w3):
@@ -250,6 +265,10 @@ class PackedConv:
         if out is None:
             out = torch.empty((N, oD * m[0], oH * m[1], oW * m[2], self.cout_pad), dtype=odt, device=x.device)
         code = _lib.DTYPE_BF16 if out.dtype == torch.bfloat16 else _lib.DTYPE_F32
+        if self.vol is not None and engine == 'igemm' and iD == 1 and self.proj is None and \
+                (out_view is None or len(out_view[1]) == 4) and os.environ.get('S3D_NO_VOL2D') is None and \
+                os.environ.get('S3D_NO_SCATTER') is None:
+            return self._call_as_volume(x, out, residual, cout_store, out_view)
         if out_view is None:
             assert out.is_contiguous() and out.dim() == 5
             C = out.shape[-1]
@@ -272,6 +291,27 @@ class PackedConv:
                 out.data_ptr() + off * esz, torch.cuda.current_stream().cuda_stream)
         _lib.check(rc, 's3d_conv_%s' % engine)
         _lib.count_launch()
+        return out
+
+    def _call_as_volume(self, x, out, residual, cout_store, out_view):
+        """Run a batch of images [N,1,H,W,C] through the 27-tap twin as G volumes of N/G planes (see __init__)."""
+        N, _, H, W, C = x.shape
+        patches = -(-H // 32) * -(-W // 8)                     # columns per volume in conv_scatter.cu
+        # G volumes of N/G images: minimise waves x (planes per column + pipeline fill/drain), 148 columns per wave
+        G = min((g for g in range(1, N + 1) if N % g == 0),
+                key=lambda g: (-(-g * patches // 148) * (N // g + 2), g))
+        Dv = N // G
+        if out_view is None:
+            assert out.is_contiguous() and out.dim() == 5
+            Co = out.shape[-1]
+            sN, sH, sW = out.shape[2] * out.shape[3] * Co, out.shape[3] * Co, Co
+            off = 0
+            if cout_store is None:
+                cout_store = min(self.cout_pad, Co)
+        else:
+            off, (sN, _, sH, sW) = out_view
+        self.vol(x.view(G, Dv, H, W, C), out=out, residual=residual, cout_store=cout_store,
+                 out_view=(off, (Dv * sN, sN, sH, sW)))
         return out
 
     def flops(self, N, iD, iH, iW):
