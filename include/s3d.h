@@ -118,6 +118,15 @@ int s3d_pack_image(const float* img, const float* disp, float disp_scale, void* 
 int s3d_pack_image_u8(const uint8_t* img, const float* disp, float disp_scale, float img_scale, void* out,
                       int B, int H, int W, int Cpad, int out_dtype, void* stream);
 
+/* First layer of the 2-D encoders, direct: Conv2d(cin, Cout, 3, stride 2, pad 1) + bias + activation straight from the
+ * raw image -- img fp32 NCHW [B,3,H,W] (img_u8 = 0) or uint8 HWC [B,H,W,3] scaled by 1/255 (img_u8 = 1), plus for
+ * cin = 4 the channel disp[B,H,W] * disp_scale -- to channels-last [B,1,oH,oW,cout_pad] (oH = (H-1)/2+1) of `dtype`.
+ * w: the layer's packed weights [9][cout_pad][cin_pad] of `dtype` (only ci < cin is read); bias fp32[cout_pad] or NULL.
+ * Same arithmetic as s3d_pack_image + s3d_conv_igemm (inputs/weights rounded to `dtype`, fp32 accumulate). */
+int s3d_conv_first(const void* img, int img_u8, const float* disp, float disp_scale, const void* w, const float* bias,
+                   void* out, int B, int H, int W, int cin, int cin_pad, int cout_pad, int dtype, int act,
+                   float act_param, void* stream);
+
 /* --- cost volume / disparity (rows V, S) ---------------------------------------------- */
 /* feat: [2B,1,h,w,C] (left maps first, then right).  vol: [2B,D,h,w,2C]; entries [0,B) are
  * left-referenced (target sampled at x-d), [B,2B) right-referenced (target at x+d). */

@@ -202,10 +202,7 @@ class _StereoBase(nn.Module):
         B, H, W = self._bhw(left)
         D = cfg.NETWORK.MAX_DISP
         dt = torch_dtype(self._dtype_code())
-        x = self._buf('img', (2 * B, 1, H, W, 16), dt)
-        ops.pack_image(left, out=x[:B])
-        ops.pack_image(right, out=x[B:])
-        x = self._conv('enc0', x, out=self._bufo('e0', 'enc0', x))
+        x = self._first('enc0', 'e0', 'img', left, right, None, 1.0)
         x = self._conv('enc1', x, out=self._bufo('e1', 'enc1', x))
         x = self._conv('enc2', x, out=self._bufo('e2', 'enc2', x))
         y = self._conv('enc3', x, out=self._bufo('e3', 'enc3', x))
@@ -249,12 +246,28 @@ class _StereoBase(nn.Module):
         B, H, W = self._bhw(left)
         dt = torch_dtype(self._dtype_code())
         scale = 1.0 / (4.0 * self.cfg.NETWORK.MAX_DISP)
-        x = self._buf('rgbd', (2 * B, 1, H, W, 16), dt)
-        ops.pack_image(left, disp[:B], scale, out=x[:B])
-        ops.pack_image(right, disp[B:], scale, out=x[B:])
-        for i in range(len(self.rgbd_encoder.layers)):
+        x = self._first('rec0', 'r0', 'rgbd', left, right, disp, scale)
+        for i in range(1, len(self.rgbd_encoder.layers)):
             x = self._conv('rec%d' % i, x, out=self._bufo('r%d' % i, 'rec%d' % i, x))
         return x
+
+    def _first(self, layer, out_name, stage_name, left, right, disp, scale):
+        """First layer of an encoder on both views: straight from the raw images (csrc/conv_first.cu) when it is the
+        3x3 stride-2 layer that kernel implements, else staged channels-last copy + the general conv engine."""
+        B, H, W = self._bhw(left)
+        pc = self._packed[layer]
+        dt = torch_dtype(self._dtype_code())
+        if pc.ksize == (1, 3, 3) and pc.stride == (1, 2, 2) and pc.pad == (0, 1, 1) and pc.cout_pad in (16, 32, 64) and \
+                os.environ.get('S3D_NO_CONV_FIRST') is None:
+            oH, oW = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+            out = self._buf(out_name, (2 * B, 1, oH, oW, pc.cout_pad), dt)
+            ops.conv_first(left, pc, None if disp is None else disp[:B], scale, out=out[:B])
+            ops.conv_first(right, pc, None if disp is None else disp[B:], scale, out=out[B:])
+            return out
+        x = self._buf(stage_name, (2 * B, 1, H, W, 16), dt)
+        ops.pack_image(left, None if disp is None else disp[:B], scale, out=x[:B])
+        ops.pack_image(right, None if disp is None else disp[B:], scale, out=x[B:])
+        return self._conv(layer, x, out=self._bufo(out_name, layer, x))
 
     def _check_inputs(self, left, right):
         if self._packed is None:

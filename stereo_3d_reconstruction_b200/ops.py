@@ -99,6 +99,33 @@ def tap_gather_soft_argmin(taps, sign=-1.0, out=None, want_cost=False):
     return (out, cost) if want_cost else out
 
 
+def conv_first(img, pc, disp=None, disp_scale=1.0, out=None):
+    """First encoder layer straight from the raw image: img fp32 NCHW [B,3,H,W] or uint8 HWC [B,H,W,3] (+ disp fp32 [B,H,W]
+    as a 4th channel) through PackedConv `pc` (3x3, stride 2, pad 1) -> channels-last [B,1,oH,oW,cout_pad]."""
+    _chk(img, disp, out)
+    u8 = img.dtype == torch.uint8
+    if u8:
+        B, H, W, C = img.shape
+    else:
+        B, C, H, W = img.shape
+        assert img.dtype == torch.float32
+    assert C == 3 and img.is_contiguous()
+    assert pc.ksize == (1, 3, 3) and pc.stride == (1, 2, 2) and pc.pad == (0, 1, 1) and pc.n_classes == 1
+    cin = 4 if disp is not None else 3
+    assert pc.cin == cin, (pc.cin, cin)
+    oH, oW = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    dt = pc.weight.dtype
+    if out is None:
+        out = torch.empty((B, 1, oH, oW, pc.cout_pad), dtype=dt, device=img.device)
+    assert out.dtype == dt and out.is_contiguous() and out.shape[-1] == pc.cout_pad
+    rc = _lib.load().s3d_conv_first(img.data_ptr(), 1 if u8 else 0, disp.data_ptr() if disp is not None else None,
+                                    float(disp_scale), pc.weight.data_ptr(), pc.bias.data_ptr(), out.data_ptr(), B, H, W, cin,
+                                    pc.cin_pad, pc.cout_pad, pc.dtype_code, pc.act, pc.act_param, _stream())
+    _lib.check(rc, 's3d_conv_first')
+    _lib.count_launch()
+    return out
+
+
 def cls_soft_argmin(x, w_taps, sign=-1.0, out=None):
     """x bf16 [N,D,h,w,C] (aggregated volume), w_taps bf16 [32,C] (27 classifier taps) -> disp fp32 [N,h,w]: the Cout=1
     3x3x3 classifier and the soft-argmin in one pass (include/s3d.h, s3d_cls_soft_argmin)."""

@@ -151,6 +151,39 @@ def test_pack_image_u8(dtype):
     assert got[..., 4:].abs().max() == 0
 
 
+@pytest.mark.parametrize('dtype_code,dtype,tol', [(lib.DTYPE_F32, torch.float32, 1e-5), (lib.DTYPE_BF16, torch.bfloat16, 2e-2)])
+@pytest.mark.parametrize('with_disp,u8,H,W,cout', [(False, False, 16, 20, 32), (True, False, 9, 11, 16), (False, True, 12, 12, 64),
+                                                    (True, True, 7, 5, 32)])
+def test_conv_first_direct_from_raw_image(dtype_code, dtype, tol, with_disp, u8, H, W, cout):
+    """conv_first.cu == Conv2d(3|4, cout, 3, stride 2, pad 1) + bias + ReLU on the raw image (fp32 NCHW or uint8 HWC)."""
+    g = torch.Generator().manual_seed(21)
+    cin = 4 if with_disp else 3
+    conv = nn.Conv2d(cin, cout, 3, 2, 1)
+    with torch.no_grad():
+        conv.weight.copy_(torch.randn(conv.weight.shape, generator=g) * 0.3)
+        conv.bias.copy_(torch.randn(cout, generator=g) * 0.1)
+    if u8:
+        raw = torch.randint(0, 256, (2, H, W, 3), generator=g, dtype=torch.uint8)
+        img = (raw.float() * (1.0 / 255.0)).permute(0, 3, 1, 2).contiguous()
+    else:
+        raw = img = torch.rand(2, 3, H, W, generator=g)
+    disp = torch.rand(2, H, W, generator=g) * 20 if with_disp else None
+    x = img if disp is None else torch.cat([img, (disp * 0.05).unsqueeze(1)], 1)
+    pc = PackedConv.from_conv(conv, None, lib.ACT_RELU, dtype_code, 'cuda')
+    if dtype == torch.bfloat16:           # the kernel rounds inputs and weights to the storage type, like the engine it replaces
+        x = x.to(dtype).float()
+        ref = F.relu(F.conv2d(x, conv.weight.to(dtype).float(), conv.bias, 2, 1))
+    else:
+        ref = F.relu(conv(x))
+    got = ops.conv_first(raw.cuda(), pc, None if disp is None else disp.cuda(), 0.05)
+    assert got.shape == (2, 1, (H - 1) // 2 + 1, (W - 1) // 2 + 1, pc.cout_pad) and got.dtype == dtype
+    torch.testing.assert_close(got[:, 0, :, :, :cout].float().cpu(), ref.permute(0, 2, 3, 1), rtol=tol, atol=tol)
+    # and against the path it replaces (staged copy + implicit-GEMM / SIMT engine), same rounding points
+    staged = ops.pack_image(raw.cuda(), None if disp is None else disp.cuda(), 0.05, dtype=dtype)
+    old = pc(staged, engine='igemm' if dtype == torch.bfloat16 else 'direct')
+    torch.testing.assert_close(got.float(), old.float(), rtol=tol, atol=tol)
+
+
 # ---- SIMT conv (exact fp32 engine) vs torch.nn.functional --------------------------------------
 def _run(pc, x_nc, engine, dtype=torch.float32):
     x = pad_c(to_cl(x_nc), pc.cin_pad).to(dtype).cuda()
