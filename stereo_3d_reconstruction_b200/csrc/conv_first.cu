@@ -1,7 +1,7 @@
 // First layer of both 2-D encoders: 3x3, stride 2, pad 1 on the raw image (3 channels, +1 disparity channel for the
 // RGB-D encoder).  K = 27 or 36 is no shape for the tensor core: through the implicit-GEMM engine the layer cost
 // 0.34 ms (on a zero-padded 16-channel copy of the image that a staging kernel had to write first).  Here one thread
-// computes one output pixel x all output channels with fp32 FMAs straight from the NCHW fp32 (or HWC uint8) image:
+// computes two adjacent output pixels x all output channels with fp32 FMAs straight from the NCHW fp32 (or HWC uint8) image:
 // the layer reads the image once and writes its channels-last output once.
 // Arithmetic matches the tensor-core path it replaces: inputs and weights rounded to the storage type (bf16), fp32
 // accumulation, bias + activation in fp32, output rounded to the storage type.
@@ -10,81 +10,97 @@
 namespace s3d {
 namespace {
 
-constexpr int kMaxCin = 4;
-
-template <int CO, typename TW, typename TOut, bool kU8>
+template <int CO, int CIN, typename TW, typename TOut, bool kU8>
 __global__ void __launch_bounds__(128)
 conv_first_kernel(const void* __restrict__ img_, const float* __restrict__ disp, float disp_scale, float img_scale,
                   const TW* __restrict__ w, int cin_pad, const float* __restrict__ bias, TOut* __restrict__ out,
-                  int B, int H, int W, int oH, int oW, int cin, int act, float act_param) {
+                  int B, int H, int W, int oH, int oW, int act, float act_param) {
   // weights as fp32 [tap][ci][co]
-  __shared__ __align__(16) float ws[9 * kMaxCin * CO];
+  __shared__ __align__(16) float ws[9 * CIN * CO];
   __shared__ __align__(16) float bs[CO];
-  for (int i = threadIdx.x; i < 9 * kMaxCin * CO; i += blockDim.x) {
-    const int co = i % CO, ci = (i / CO) % kMaxCin, t = i / (CO * kMaxCin);
-    ws[i] = ci < cin ? to_f32(w[((int64_t)t * CO + co) * cin_pad + ci]) : 0.f;
+  for (int i = threadIdx.x; i < 9 * CIN * CO; i += blockDim.x) {
+    const int co = i % CO, ci = (i / CO) % CIN, t = i / (CO * CIN);
+    ws[i] = to_f32(w[((int64_t)t * CO + co) * cin_pad + ci]);
   }
   for (int i = threadIdx.x; i < CO; i += blockDim.x) bs[i] = bias ? bias[i] : 0.f;
   __syncthreads();
-  const int64_t total = (int64_t)B * oH * oW;
+  // a thread computes TWO horizontally adjacent output pixels (x = 2j, 2j+1): they share every weight read and the
+  // middle input column
+  const int oW2 = (oW + 1) >> 1;
+  const int64_t total = (int64_t)B * oH * oW2;
   const float slope = act == S3D_ACT_NONE ? 1.f : (act == S3D_ACT_LEAKY ? act_param : 0.f);
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-    const int ox = (int)(idx % oW), oy = (int)((idx / oW) % oH), n = (int)(idx / ((int64_t)oW * oH));
-    float acc[CO];
+    const int j = (int)(idx % oW2), oy = (int)((idx / oW2) % oH), n = (int)(idx / ((int64_t)oW2 * oH));
+    const int ox = 2 * j;
+    float acc[2][CO];
 #pragma unroll
-    for (int c = 0; c < CO; ++c) acc[c] = bs[c];
+    for (int c = 0; c < CO; ++c) { acc[0][c] = bs[c]; acc[1][c] = bs[c]; }
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
       const int iy = 2 * oy + ky - 1;
       if (iy < 0 || iy >= H) continue;
+      // input columns 2*ox-1 .. 2*ox+3: pixel 0 uses columns 0..2 of this window, pixel 1 columns 2..4
+      float v[5][CIN];
 #pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        const int ix = 2 * ox + kx - 1;
-        if (ix < 0 || ix >= W) continue;
-        float v[kMaxCin];
+      for (int cx = 0; cx < 5; ++cx) {
+        const int ix = 2 * ox + cx - 1;
+        const bool in = ix >= 0 && ix < W;
         if (kU8) {
           const uint8_t* ip = reinterpret_cast<const uint8_t*>(img_) + (((int64_t)n * H + iy) * W + ix) * 3;
-          v[0] = (float)ip[0] * img_scale;  v[1] = (float)ip[1] * img_scale;  v[2] = (float)ip[2] * img_scale;
+#pragma unroll
+          for (int ci = 0; ci < 3; ++ci) v[cx][ci] = in ? (float)ip[ci] * img_scale : 0.f;
         } else {
           const float* ip = reinterpret_cast<const float*>(img_) + ((int64_t)n * 3 * H + iy) * W + ix;
-          v[0] = __ldg(ip);  v[1] = __ldg(ip + (int64_t)H * W);  v[2] = __ldg(ip + 2 * (int64_t)H * W);
-        }
-        v[3] = (cin > 3 && disp) ? __ldg(disp + ((int64_t)n * H + iy) * W + ix) * disp_scale : 0.f;
-        const float* wt = ws + (ky * 3 + kx) * kMaxCin * CO;
 #pragma unroll
-        for (int ci = 0; ci < kMaxCin; ++ci) {
-          const float x = to_f32(from_f32<TW>(v[ci]));            // the rounding of the staged copy this kernel replaces
+          for (int ci = 0; ci < 3; ++ci) v[cx][ci] = in ? __ldg(ip + ci * (int64_t)H * W) : 0.f;
+        }
+        if (CIN > 3) v[cx][3] = in ? __ldg(disp + ((int64_t)n * H + iy) * W + ix) * disp_scale : 0.f;
+#pragma unroll
+        for (int ci = 0; ci < CIN; ++ci) v[cx][ci] = to_f32(from_f32<TW>(v[cx][ci]));   // rounding of the staged copy it replaces
+      }
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const float* wt = ws + (ky * 3 + kx) * CIN * CO;
+#pragma unroll
+        for (int ci = 0; ci < CIN; ++ci) {
+          const float x0 = v[kx][ci], x1 = v[kx + 2][ci];
           const float4* w4 = reinterpret_cast<const float4*>(wt + ci * CO);
 #pragma unroll
           for (int c4 = 0; c4 < CO / 4; ++c4) {
             const float4 q = w4[c4];
-            acc[4 * c4] = fmaf(x, q.x, acc[4 * c4]);          acc[4 * c4 + 1] = fmaf(x, q.y, acc[4 * c4 + 1]);
-            acc[4 * c4 + 2] = fmaf(x, q.z, acc[4 * c4 + 2]);  acc[4 * c4 + 3] = fmaf(x, q.w, acc[4 * c4 + 3]);
+            acc[0][4 * c4] = fmaf(x0, q.x, acc[0][4 * c4]);          acc[0][4 * c4 + 1] = fmaf(x0, q.y, acc[0][4 * c4 + 1]);
+            acc[0][4 * c4 + 2] = fmaf(x0, q.z, acc[0][4 * c4 + 2]);  acc[0][4 * c4 + 3] = fmaf(x0, q.w, acc[0][4 * c4 + 3]);
+            acc[1][4 * c4] = fmaf(x1, q.x, acc[1][4 * c4]);          acc[1][4 * c4 + 1] = fmaf(x1, q.y, acc[1][4 * c4 + 1]);
+            acc[1][4 * c4 + 2] = fmaf(x1, q.z, acc[1][4 * c4 + 2]);  acc[1][4 * c4 + 3] = fmaf(x1, q.w, acc[1][4 * c4 + 3]);
           }
         }
       }
     }
-    TOut* o = out + idx * CO;
-    if (act <= S3D_ACT_LEAKY) {
 #pragma unroll
-      for (int c = 0; c < CO; ++c) acc[c] = fmaxf(acc[c], 0.f) + slope * fminf(acc[c], 0.f);
-    } else {
+    for (int px = 0; px < 2; ++px) {
+      if (ox + px >= oW) break;
+      TOut* o = out + (((int64_t)n * oH + oy) * oW + ox + px) * CO;
+      if (act <= S3D_ACT_LEAKY) {
 #pragma unroll
-      for (int c = 0; c < CO; ++c) acc[c] = apply_act(acc[c], act, act_param);
-    }
-    if (sizeof(TOut) == 2) {
+        for (int c = 0; c < CO; ++c) acc[px][c] = fmaxf(acc[px][c], 0.f) + slope * fminf(acc[px][c], 0.f);
+      } else {
 #pragma unroll
-      for (int c8 = 0; c8 < CO / 8; ++c8) {
-        uint4 pk;
-        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(acc[8 * c8 + 2 * i], acc[8 * c8 + 2 * i + 1]);
-        reinterpret_cast<uint4*>(o)[c8] = pk;
+        for (int c = 0; c < CO; ++c) acc[px][c] = apply_act(acc[px][c], act, act_param);
       }
-    } else {
+      if (sizeof(TOut) == 2) {
 #pragma unroll
-      for (int c4 = 0; c4 < CO / 4; ++c4)
-        reinterpret_cast<float4*>(o)[c4] = make_float4(acc[4 * c4], acc[4 * c4 + 1], acc[4 * c4 + 2], acc[4 * c4 + 3]);
+        for (int c8 = 0; c8 < CO / 8; ++c8) {
+          uint4 pk;
+          __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(acc[px][8 * c8 + 2 * i], acc[px][8 * c8 + 2 * i + 1]);
+          reinterpret_cast<uint4*>(o)[c8] = pk;
+        }
+      } else {
+#pragma unroll
+        for (int c4 = 0; c4 < CO / 4; ++c4)
+          reinterpret_cast<float4*>(o)[c4] = make_float4(acc[px][4 * c4], acc[px][4 * c4 + 1], acc[px][4 * c4 + 2], acc[px][4 * c4 + 3]);
+      }
     }
   }
 }
@@ -93,16 +109,16 @@ template <int CO, typename TW, typename TOut>
 int launch_first(const void* img, int img_u8, const float* disp, float disp_scale, float img_scale, const void* w, int cin_pad,
                  const float* bias, void* out, int B, int H, int W, int oH, int oW, int cin, int act, float act_param,
                  cudaStream_t st) {
-  const int64_t total = (int64_t)B * oH * oW;
+  const int64_t total = (int64_t)B * oH * ((oW + 1) / 2);
   int64_t blocks = ceil_div64(total, 128);
   const int64_t cap = (int64_t)num_sms() * 16;
   if (blocks > cap) blocks = cap;
-  if (img_u8)
-    conv_first_kernel<CO, TW, TOut, true><<<(int)blocks, 128, 0, st>>>(img, disp, disp_scale, img_scale, static_cast<const TW*>(w),
-        cin_pad, bias, static_cast<TOut*>(out), B, H, W, oH, oW, cin, act, act_param);
-  else
-    conv_first_kernel<CO, TW, TOut, false><<<(int)blocks, 128, 0, st>>>(img, disp, disp_scale, img_scale, static_cast<const TW*>(w),
-        cin_pad, bias, static_cast<TOut*>(out), B, H, W, oH, oW, cin, act, act_param);
+#define S3D_FIRST_LAUNCH(CIN, U8)                                                                                          \
+  conv_first_kernel<CO, CIN, TW, TOut, U8><<<(int)blocks, 128, 0, st>>>(img, disp, disp_scale, img_scale, static_cast<const TW*>(w), \
+      cin_pad, bias, static_cast<TOut*>(out), B, H, W, oH, oW, act, act_param)
+  if (cin == 3) { if (img_u8) S3D_FIRST_LAUNCH(3, true); else S3D_FIRST_LAUNCH(3, false); }
+  else          { if (img_u8) S3D_FIRST_LAUNCH(4, true); else S3D_FIRST_LAUNCH(4, false); }
+#undef S3D_FIRST_LAUNCH
   S3D_LAUNCH_CHECK();
   return S3D_OK;
 }
