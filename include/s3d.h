@@ -162,6 +162,12 @@ int s3d_latent_to_vox(const void* x, void* out, int N, int H, int W, int C, int 
 /* Generic adaptive average pool, channels-last [N,1,H,W,C] -> [N,1,L,L,C]. */
 int s3d_avg_pool(const void* x, void* out, int N, int H, int W, int C, int L, int dtype,
                  void* stream);
+/* Depth-to-space after a transposed conv computed as a blocked stride-1 conv: in [N,d,h,w,64] with channel
+ * (class, c) = (cz*4 + cy*2 + cx)*8 + c  ->  out [N,2d,2h,2w,Cpad], out[n, 2z+cz, 2y+cy, 2x+cx, c] for c < 8.
+ * If Cpad > 8: channel 8 = proj_act(sum_c proj_w[c] * feature c) (proj_w: 8 fp32 DEVICE values; NULL -> 0), channels
+ * 9.. = 0 -- the decoder's final 1x1x1 transposed conv + sigmoid. */
+int s3d_depth_to_space(const void* in, void* out, const float* proj_w, int proj_act, int N, int d, int h, int w,
+                       int Cpad, int dtype, void* stream);
 /* Context-aware fusion epilogue + IoU.  score, vol: [V*B, 32^3] planes with element strides
  * score_stride / vol_stride (view-major); fused[b,v] = clamp(sum_v softmax_v(score)*vol, 0, 1).
  * gt (uint8 [B,32^3]) and iou (int64 [B,T,2] = intersection, union) may be NULL. */

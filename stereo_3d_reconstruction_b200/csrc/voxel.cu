@@ -208,6 +208,75 @@ extern "C" int s3d_pack_image_u8(const uint8_t* img, const float* disp, float di
   return S3D_OK;
 }
 
+// Depth-to-space after a blocked transposed conv (layers.py::from_deconv_k4s2p1_blocked): in[n, j, (class, c)] ->
+// out[n, 2j + class, c], c < 8, plus an optional 1x1x1 projection of the 8 features into channel 8 and zeros above.
+template <typename T>
+__global__ void depth_to_space_kernel(const T* __restrict__ in, T* __restrict__ out, const float* __restrict__ proj_w,
+                                      int proj_act, int N, int d, int h, int w, int Cpad) {
+  const int64_t total = (int64_t)N * d * h * w * 8;
+  float pw[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) pw[c] = proj_w ? __ldg(proj_w + c) : 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    // consecutive threads = consecutive 16-byte (bf16) chunks of the input: coalesced reads
+    const int cls = (int)(i & 7);
+    int64_t r = i >> 3;
+    const int x = (int)(r % w);  r /= w;
+    const int y = (int)(r % h);  r /= h;
+    const int z = (int)(r % d);  r /= d;
+    const int n = (int)r;
+    float f[8];
+    const T* ip = in + i * 8;
+    const int oz = 2 * z + (cls >> 2), oy = 2 * y + ((cls >> 1) & 1), ox = 2 * x + (cls & 1);
+    T* op = out + ((((int64_t)n * 2 * d + oz) * 2 * h + oy) * 2 * w + ox) * Cpad;
+    if (sizeof(T) == 2 && Cpad == 16) {
+      // bf16, 16 output channels: one 16-byte load, two 16-byte stores
+      const uint4 raw = __ldg(reinterpret_cast<const uint4*>(ip));
+      const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&raw);
+      float pr = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float2 g = __bfloat1622float2(hp[c]);
+        pr = fmaf(g.x, pw[2 * c], pr);  pr = fmaf(g.y, pw[2 * c + 1], pr);
+      }
+      uint4 hi = make_uint4(0, 0, 0, 0);
+      const __nv_bfloat16 pb = __float2bfloat16_rn(proj_w ? apply_act(pr, proj_act, 1.f) : 0.f);
+      hi.x = (uint32_t)(*reinterpret_cast<const unsigned short*>(&pb));
+      reinterpret_cast<uint4*>(op)[0] = raw;
+      reinterpret_cast<uint4*>(op)[1] = hi;
+      continue;
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) f[c] = to_f32(ip[c]);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) op[c] = from_f32<T>(f[c]);
+    if (Cpad > 8) {
+      float pr = 0.f;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) pr = fmaf(f[c], pw[c], pr);
+      op[8] = from_f32<T>(proj_w ? apply_act(pr, proj_act, 1.f) : 0.f);
+      for (int c = 9; c < Cpad; ++c) op[c] = from_f32<T>(0.f);
+    }
+  }
+}
+
+extern "C" int s3d_depth_to_space(const void* in, void* out, const float* proj_w, int proj_act, int N, int d, int h, int w,
+                                  int Cpad, int dtype, void* stream) {
+  if (!in || !out) { set_error("depth_to_space: null argument"); return S3D_ERR_INVALID; }
+  S3D_CHECK_ARG(N > 0 && d > 0 && h > 0 && w > 0 && Cpad >= 8 && (Cpad == 8 || Cpad >= 9), "depth_to_space: bad shape");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t total = (int64_t)N * d * h * w * 8;
+  if (dtype == S3D_DTYPE_BF16)
+    depth_to_space_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(in),
+        static_cast<__nv_bfloat16*>(out), proj_w, proj_act, N, d, h, w, Cpad);
+  else if (dtype == S3D_DTYPE_F32)
+    depth_to_space_kernel<float><<<grid_for(total, 256), 256, 0, st>>>(static_cast<const float*>(in), static_cast<float*>(out),
+        proj_w, proj_act, N, d, h, w, Cpad);
+  else { set_error("depth_to_space: bad dtype"); return S3D_ERR_INVALID; }
+  S3D_LAUNCH_CHECK();
+  return S3D_OK;
+}
+
 static int pool_launch(const void* x, void* out, int N, int H, int W, int C, int L, int dtype, int to_vox, void* stream) {
   if (!x || !out) { set_error("pool: null argument"); return S3D_ERR_INVALID; }
   S3D_CHECK_ARG(N > 0 && H > 0 && W > 0 && C > 0 && L > 0, "pool: bad shape");

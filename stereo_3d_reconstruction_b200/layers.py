@@ -182,6 +182,33 @@ class PackedConv:
         return cls(torch.stack(rows), b, taps, (1, 1, 1), (2, 2, 2), cin, cout, act, act_param, dtype_code, device)
 
     @classmethod
+    def from_deconv_k4s2p1_blocked(cls, deconv, bn, act, dtype_code, device, act_param=0.0):
+        """The same transposed conv as ONE stride-1 3x3x3 conv over the INPUT grid with 8*Cout output channels: channel
+        (class, co) of input position j is output voxel 2j + class (class = (cz,cy,cx) parity) -- a depth-to-space
+        layout.  Each class uses 2 of the 3 offsets per dimension, so 8 of its 27 taps are non-zero; as a dense
+        3x3x3 layer it runs on the plane-scatter kernel (every input plane fetched once, N = 3*8*Cout) instead of
+        8 classes x 8 re-fetched taps in the generic engine.  ops.depth_to_space() restores [.., 2d, 2h, 2w, C]."""
+        assert tuple(deconv.kernel_size) == (4, 4, 4) and tuple(deconv.stride) == (2, 2, 2) and \
+            tuple(deconv.padding) == (1, 1, 1) and tuple(deconv.output_padding) == (0, 0, 0)
+        w, b = _fold_bn(deconv.weight.transpose(0, 1), deconv.bias, bn)   # -> [Cout, Cin, 4,4,4]
+        cout, cin = w.shape[0], w.shape[1]
+        kof = {0: {0: 1, -1: 3}, 1: {1: 0, 0: 2}}                    # parity -> {input offset: kernel index}
+        taps, rows = [], []
+        for dz, dy, dx in itertools.product((-1, 0, 1), repeat=3):
+            m = torch.zeros(8 * cout, cin, dtype=w.dtype)
+            for cz, cy, cx in itertools.product(range(2), repeat=3):
+                if dz in kof[cz] and dy in kof[cy] and dx in kof[cx]:
+                    c = (cz * 2 + cy) * 2 + cx
+                    m[c * cout:(c + 1) * cout] = w[:, :, kof[cz][dz], kof[cy][dy], kof[cx][dx]]
+            taps.append((dz, dy, dx))
+            rows.append(m)
+        pc = cls(torch.stack(rows), b.repeat(8), [taps], (1, 1, 1), (1, 1, 1), cin, 8 * cout, act, act_param, dtype_code,
+                 device, ksize=(3, 3, 3), pad=(1, 1, 1))
+        pc.ntaps_algo = 8                                          # non-zero taps per output channel (for flops())
+        pc.block_cout = cout
+        return pc
+
+    @classmethod
     def from_pointwise(cls, w_out_in, bias, bn, act, dtype_code, device, act_param=0.0):
         """1x1(x1) conv / transposed conv given as a [Cout, Cin] matrix."""
         w, b = _fold_bn(w_out_in, bias, bn)
@@ -317,4 +344,4 @@ class PackedConv:
     def flops(self, N, iD, iH, iW):
         """Algorithmic (unpadded) FLOPs: 2 * outputs * Cout * Cin * taps-that-hit."""
         oD, oH, oW = self.out_grid(iD, iH, iW)
-        return 2.0 * N * oD * oH * oW * self.n_classes * self.cout * self.cin * self.ntaps
+        return 2.0 * N * oD * oH * oW * self.n_classes * self.cout * self.cin * getattr(self, 'ntaps_algo', self.ntaps)

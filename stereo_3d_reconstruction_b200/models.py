@@ -298,9 +298,23 @@ class Stereo2Voxel(_StereoBase):
         for i, seq in enumerate(self.decoder.layers):
             P['dec%d' % i] = PackedConv.from_deconv_k4s2p1(seq[0], seq[1], A.ACT_RELU, dc, dev)
         w = self.decoder.out.weight            # [Cin, 1, 1,1,1]
-        last = P['dec%d' % (len(self.decoder.layers) - 1)]
-        self._fused_out = last.cout_pad == 16 and last.cout < 16
-        if self._fused_out:
+        nl = len(self.decoder.layers)
+        last = P['dec%d' % (nl - 1)]
+        # last deconv (8 output channels): one blocked 3x3x3 conv on the plane-scatter kernel + depth-to-space, which
+        # also applies the final 1x1x1 transposed conv + sigmoid (coarse volume -> channel 8)
+        self._d2s = None
+        self._fused_out = False
+        esz = 2 if dc == A.DTYPE_BF16 else 4
+        seq = self.decoder.layers[nl - 1]
+        if last.cout == 8 and last.cin_pad * esz in (32, 64, 128) and self.precision != 'fp32' and \
+                os.environ.get('S3D_NO_D2S') is None:
+            P['dec%d' % (nl - 1)] = PackedConv.from_deconv_k4s2p1_blocked(seq[0], seq[1], A.ACT_RELU, dc, dev)
+            pw = torch.zeros(8, dtype=torch.float32)
+            pw[:] = w.detach().float().cpu().view(-1)[:8]
+            self._d2s = pw.to(dev)
+            self._fused_out = True
+        elif last.cout_pad == 16 and last.cout < 16:
+            self._fused_out = True
             # 1x1x1 transposed conv + sigmoid folded into the last deconv's epilogue: coarse volume -> channel `cout`
             last.set_projection(w.view(-1), last.cout, A.ACT_SIGMOID)
         else:
@@ -334,7 +348,11 @@ class Stereo2Voxel(_StereoBase):
         nl = len(self.decoder.layers)
         for i in range(nl):
             x = self._conv('dec%d' % i, x, out=self._bufo('d%d' % i, 'dec%d' % i, x))
-        m_in = x                                                   # [2B,32,32,32,16]: ch 0-7 raw, 8.. zero
+        if self._d2s is not None:
+            # x is the blocked output [2B,16,16,16,8 classes x 8]: depth-to-space + coarse-volume projection
+            n2, dd, hh, ww, _ = x.shape
+            x = ops.depth_to_space(x, 16, self._d2s, A.ACT_SIGMOID, out=self._buf('d2s', (n2, 2 * dd, 2 * hh, 2 * ww, 16), x.dtype))
+        m_in = x                                                   # [2B,32,32,32,16]: ch 0-7 raw, 8 coarse volume, 9.. zero
         cm = m_in.shape[-1]
         craw = cfg.NETWORK.DEC_CHANNELS[-1]
         assert m_in.shape[1] == nv and cm > craw

@@ -99,6 +99,24 @@ def tap_gather_soft_argmin(taps, sign=-1.0, out=None, want_cost=False):
     return (out, cost) if want_cost else out
 
 
+def depth_to_space(x, cpad=16, proj_w=None, proj_act=0, out=None):
+    """x [N,d,h,w,64] (channel = parity class * 8 + c, from PackedConv.from_deconv_k4s2p1_blocked) -> [N,2d,2h,2w,cpad];
+    optional projection of the 8 features into channel 8 (include/s3d.h, s3d_depth_to_space)."""
+    _chk(x, proj_w, out)
+    assert x.dim() == 5 and x.shape[-1] == 64 and x.is_contiguous()
+    N, d, h, w, _ = x.shape
+    if out is None:
+        out = torch.empty((N, 2 * d, 2 * h, 2 * w, cpad), dtype=x.dtype, device=x.device)
+    assert out.dtype == x.dtype and out.is_contiguous() and out.shape == (N, 2 * d, 2 * h, 2 * w, cpad)
+    if proj_w is not None:
+        assert proj_w.dtype == torch.float32 and proj_w.numel() >= 8
+    rc = _lib.load().s3d_depth_to_space(x.data_ptr(), out.data_ptr(), proj_w.data_ptr() if proj_w is not None else None,
+                                        int(proj_act), N, d, h, w, cpad, _code(x), _stream())
+    _lib.check(rc, 's3d_depth_to_space')
+    _lib.count_launch()
+    return out
+
+
 def conv_first(img, pc, disp=None, disp_scale=1.0, out=None):
     """First encoder layer straight from the raw image: img fp32 NCHW [B,3,H,W] or uint8 HWC [B,H,W,3] (+ disp fp32 [B,H,W]
     as a 4th channel) through PackedConv `pc` (3x3, stride 2, pad 1) -> channels-last [B,1,oH,oW,cout_pad]."""

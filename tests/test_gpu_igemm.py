@@ -63,6 +63,39 @@ def test_deconv(prec, cin, cout, S, N):
 
 
 @pytest.mark.parametrize('prec', ['bf16', 'tf32'])
+@pytest.mark.parametrize('shape', [(2, 5, 6, 7), (3, 16, 16, 16), (1, 1, 1, 1)])
+def test_deconv_blocked_plus_depth_to_space(prec, shape):
+    """ConvTranspose3d(32, 8, 4, 2, 1) + BN + ReLU as ONE 3x3x3 conv with 8 parity classes x 8 channels on the
+    plane-scatter kernel, then depth-to-space with the 1x1x1 + sigmoid projection in channel 8."""
+    from stereo_3d_reconstruction_b200 import ops
+    torch.manual_seed(5)
+    N, d, h, w = shape
+    dc = nn.ConvTranspose3d(32, 8, 4, 2, 1, bias=False)
+    bn = nn.BatchNorm3d(8).eval()
+    with torch.no_grad():
+        bn.running_mean.normal_(0, 0.1);  bn.running_var.uniform_(0.5, 1.5);  bn.weight.uniform_(0.8, 1.2);  bn.bias.normal_(0, 0.1)
+    x = torch.randn(N, 32, d, h, w)
+    with torch.no_grad():
+        ref = to_cl(F.relu(bn(dc(x))))                                # [N,2d,2h,2w,8]
+    pw = torch.randn(8) * 0.5
+    dt = torch.bfloat16 if prec == 'bf16' else torch.float32
+    pc = PackedConv.from_deconv_k4s2p1_blocked(dc, bn, lib.ACT_RELU, _code(prec), 'cuda')
+    y = pc(pad_c(to_cl(x), pc.cin_pad).to(dt).cuda(), engine='igemm')     # [N,d,h,w,64]
+    assert y.shape == (N, d, h, w, 64)
+    out = ops.depth_to_space(y, 16, pw.cuda(), lib.ACT_SIGMOID).float().cpu()
+    assert out.shape == (N, 2 * d, 2 * h, 2 * w, 16)
+    scale = ref.abs().max().item() + 1e-6
+    assert (out[..., :8] - ref).abs().max().item() <= TOL[prec] * scale
+    proj_ref = torch.sigmoid((out[..., :8] * pw).sum(-1))                 # from the stored (rounded) features
+    assert (out[..., 8] - proj_ref).abs().max().item() <= (1e-2 if prec == 'bf16' else 1e-5)
+    assert out[..., 9:].abs().max().item() == 0.0
+    # same layer through the generic engine's 8-class formulation
+    pc8 = PackedConv.from_deconv_k4s2p1(dc, bn, lib.ACT_RELU, _code(prec), 'cuda')
+    old = pc8(pad_c(to_cl(x), pc8.cin_pad).to(dt).cuda(), engine='igemm').float().cpu()
+    assert (out[..., :8] - old[..., :8]).abs().max().item() <= TOL[prec] * scale
+
+
+@pytest.mark.parametrize('prec', ['bf16', 'tf32'])
 def test_residual_and_linear(prec):
     torch.manual_seed(3)
     conv = nn.Conv2d(32, 32, 3, 1, 1)
