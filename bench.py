@@ -57,6 +57,26 @@ class ClockSampler:
         self._t = threading.Thread(target=self._run, daemon=True)
 
     def _run(self):
+        # NVML in-process (a query takes ~0.1 ms, so even a 150 ms timed region gets dozens of samples);
+        # nvidia-smi subprocesses (~80 ms each) only as a fallback
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self._index)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            bits = {'hw_slowdown': 0x8, 'hw_thermal_slowdown': 0x40, 'sw_thermal_slowdown': 0x20, 'sw_power_cap': 0x4}
+            get_reasons = getattr(nv, 'nvmlDeviceGetCurrentClocksEventReasons', None) or \
+                getattr(nv, 'nvmlDeviceGetCurrentClocksThrottleReasons')
+            while not self._stop.is_set():
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                r = get_reasons(h)
+                for n, b in bits.items():
+                    if r & b:
+                        self.reasons.add(n)
+                self._stop.wait(0.004)
+            return
+        except Exception:
+            pass
         q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
              'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']

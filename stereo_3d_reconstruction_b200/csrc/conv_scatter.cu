@@ -67,6 +67,7 @@ struct ScArgs {
   int ncols_max;      // pair mode: columns every CTA walks (phantom columns beyond total_cols compute on zeros)
   uint32_t idesc;
   int fast_store;     // epilogue may use the transposed (coalesced) store path
+  int res_direct;
 };
 
 struct ScCtrl {
@@ -286,25 +287,37 @@ struct ScEpi {
   const float* bias;  const void* residual;  void* out;
   float slope;                 // none / ReLU / LeakyReLU as max(v,0) + slope * min(v,0)
   int osW;
+  int res_direct;              // residual read per own pixel (no transpose) instead of per transpose group
 };
 
 // Coalesced read of the residual chunks of this lane's group of pixels (then transposed back to "my pixel").
 template <int NCH, typename TOut>
 __device__ __forceinline__ void sc_res_load(const ScEpi& e, int64_t grp_off, int osW, int lane, uint32_t okmask, uint4 (&r)[NCH]) {
   const int j = lane & (NCH - 1);
+  if (e.res_direct) {
+    const int own = (lane & 7) & (NCH - 1);            // this lane's pixel inside its group
+    const TOut* rs = reinterpret_cast<const TOut*>(e.residual) + grp_off + own * osW;
+    const bool ok = (okmask >> own) & 1u;
+#pragma unroll
+    for (int k = 0; k < NCH; ++k)
+      r[k] = ok ? __ldg(reinterpret_cast<const uint4*>(rs) + k) : make_uint4(0, 0, 0, 0);
+    return;
+  }
   const TOut* rs = reinterpret_cast<const TOut*>(e.residual) + grp_off + j * (16 / (int)sizeof(TOut));
 #pragma unroll
   for (int k = 0; k < NCH; ++k)
     r[k] = ((okmask >> k) & 1u) ? __ldg(reinterpret_cast<const uint4*>(rs + k * osW)) : make_uint4(0, 0, 0, 0);
 }
 
-template <int CP, typename TOut, bool kRes, bool kRelu>
+// kAct: 0 ReLU, 2 general slope (none / leaky).  (An identity variant that skips the three slope instructions was
+// measured SLOWER on the residual layer, 2.85 vs 2.70 ms, and grew the kernel; it is not instantiated.)
+template <int CP, typename TOut, bool kRes, int kAct>
 __device__ __forceinline__ void sc_fast_store(const ScEpi& e, int64_t grp_off, int lane, uint32_t okmask,
                                               const uint32_t (&v)[CP / 16][16], uint4 (&r)[CP * sizeof(TOut) / 16]) {
   constexpr int NCH = CP * sizeof(TOut) / 16;
   constexpr int CPC = 16 / sizeof(TOut);          // channels per chunk
   uint4 c[NCH];
-  if (kRes) chunk_transpose<NCH>(r, lane);
+  if (kRes && !e.res_direct) chunk_transpose<NCH>(r, lane);
 #pragma unroll
   for (int jg = 0; jg < CP / 16; ++jg) {
     float f[16];
@@ -335,7 +348,7 @@ __device__ __forceinline__ void sc_fast_store(const ScEpi& e, int64_t grp_off, i
       }
     }
 #pragma unroll
-    for (int i = 0; i < 16; ++i) f[i] = kRelu ? fmaxf(f[i], 0.f) : fmaxf(f[i], 0.f) + e.slope * fminf(f[i], 0.f);
+    for (int i = 0; i < 16; ++i) f[i] = kAct == 0 ? fmaxf(f[i], 0.f) : (kAct == 1 ? f[i] : fmaxf(f[i], 0.f) + e.slope * fminf(f[i], 0.f));
     if (sizeof(TOut) == 2) {
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
@@ -360,22 +373,24 @@ __device__ __forceinline__ void sc_fast_store(const ScEpi& e, int64_t grp_off, i
 template <int CP, typename TOut>
 __device__ __forceinline__ void sc_fast_plane(const ScEpi& e, int64_t grp_off, int lane, uint32_t okmask,
                                               const uint32_t (&v)[CP / 16][16], uint4 (&r)[CP * sizeof(TOut) / 16]) {
-  if (e.slope == 0.f) {                             // ReLU (every aggregation layer): one instruction per value
-    if (e.residual) sc_fast_store<CP, TOut, true, true>(e, grp_off, lane, okmask, v, r);
-    else            sc_fast_store<CP, TOut, false, true>(e, grp_off, lane, okmask, v, r);
+  if (e.slope == 0.f) {                             // ReLU (the aggregation layers): one instruction per value
+    if (e.residual) sc_fast_store<CP, TOut, true, 0>(e, grp_off, lane, okmask, v, r);
+    else            sc_fast_store<CP, TOut, false, 0>(e, grp_off, lane, okmask, v, r);
   } else {
-    if (e.residual) sc_fast_store<CP, TOut, true, false>(e, grp_off, lane, okmask, v, r);
-    else            sc_fast_store<CP, TOut, false, false>(e, grp_off, lane, okmask, v, r);
+    if (e.residual) sc_fast_store<CP, TOut, true, 2>(e, grp_off, lane, okmask, v, r);
+    else            sc_fast_store<CP, TOut, false, 2>(e, grp_off, lane, okmask, v, r);
   }
 }
 
-template <int CP, typename TOut, bool kFast>     // kFast: transposed stores (needs a power-of-two chunk count per pixel)
+// kFast: transposed stores (needs a power-of-two chunk count per pixel).  kSRes / kSAct >= 0: residual / activation fixed at
+// compile time (the specialised kernels below), -1: decided at run time.
+template <int CP, typename TOut, bool kFast, int kSRes = -1, int kSAct = -1>
 __device__ __forceinline__ void sc_epilogue(const ScArgs& a, ScCtrl& ctrl, uint32_t tmem_base, int warp, int lane) {
   constexpr int NCH = kFast ? CP * (int)sizeof(TOut) / 16 : 1;     // 16-byte chunks per pixel
   const int t = (warp - 4) >> 2, q = warp & 3;
   const EpiParams ep = {a.bias, a.residual, a.out, a.p.cout_store, sizeof(TOut) == 2, a.p.act, a.p.act_param, 1, nullptr, 0, 0};
   const ScEpi fe = {a.bias, a.residual, a.out,
-                    a.p.act == S3D_ACT_NONE ? 1.f : (a.p.act == S3D_ACT_LEAKY ? a.p.act_param : 0.f), (int)a.p.osW};
+                    a.p.act == S3D_ACT_NONE ? 1.f : (a.p.act == S3D_ACT_LEAKY ? a.p.act_param : 0.f), (int)a.p.osW, a.res_direct};
   const uint32_t bar_af = ptx::smem_u32(&ctrl.acc_full[t]), bar_ae = ptx::smem_u32(&ctrl.acc_empty[t]);
   const uint32_t tbase = tmem_base + t * kTileCols + (static_cast<uint32_t>(q * 32) << 16);
   const int yl = t * kTileY + q * 4 + (lane >> 3), xl = lane & 7;      // TMEM lane = 8 * row + x inside the tile
@@ -426,7 +441,8 @@ __device__ __forceinline__ void sc_epilogue(const ScArgs& a, ScCtrl& ctrl, uint3
         if constexpr (kFast) {
           // (second drain of the last plane: its residual could not be prefetched)
           if (i == 1 && a.residual) sc_res_load<NCH, TOut>(fe, grp_off + zo, fe.osW, lane, okmask, r);
-          sc_fast_plane<CP, TOut>(fe, grp_off + zo, lane, okmask, v, r);
+          if constexpr (kSRes >= 0) sc_fast_store<CP, TOut, kSRes != 0, kSAct>(fe, grp_off + zo, lane, okmask, v, r);
+          else sc_fast_plane<CP, TOut>(fe, grp_off + zo, lane, okmask, v, r);
         } else {
           if (ok) {
 #pragma unroll
@@ -454,7 +470,11 @@ __device__ __forceinline__ void sc_epilogue_dispatch(const ScArgs& a, ScCtrl& ct
   }
 }
 
-template <bool kTF32, bool kPair>
+// RB != 0: a kernel specialised for ONE layer shape (bf16 rows of RB bytes, CP output channels, residual, activation).
+// Every variant of producer / issuer / epilogue is inlined into the kernel, and the kernel is sensitive to its own code
+// size (measured: two more epilogue variants in the all-in-one kernel cost 4 % of the whole forward), so the layer
+// shapes of the network each get a kernel that contains only their own code.  RB == 0: all-in-one, run-time dispatch.
+template <bool kTF32, bool kPair, int RB = 0, int CP = 0, int kSRes = -1, int kSAct = -1>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_scatter_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                     const __grid_constant__ ScArgs a) {
@@ -485,7 +505,9 @@ conv_scatter_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
 
   if (warp == 0) {
     const uint32_t planes_u32 = ptx::smem_u32(smem), w_u32 = ptx::smem_u32(smem_w);
-    if (a.tps == 1) sc_produce<1, kPair>(a, ctrl, planes_u32, w_u32, &map_x, &map_w);
+    if constexpr (RB == 128) sc_produce<1, kPair>(a, ctrl, planes_u32, w_u32, &map_x, &map_w);
+    else if constexpr (RB != 0) sc_produce<3, kPair>(a, ctrl, planes_u32, w_u32, &map_x, &map_w);
+    else if (a.tps == 1) sc_produce<1, kPair>(a, ctrl, planes_u32, w_u32, &map_x, &map_w);
     else if (a.tps == 3) sc_produce<3, kPair>(a, ctrl, planes_u32, w_u32, &map_x, &map_w);
     else sc_produce<9, kPair>(a, ctrl, planes_u32, w_u32, &map_x, &map_w);
   } else if (warp == 1 && (!kPair || ptx::cluster_ctarank() == 0)) {      // pair mode: the leader issues for both CTAs
@@ -496,12 +518,16 @@ conv_scatter_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                         desc_hi(kHX * rb, rb), desc_hi(8 * rb, rb), a.slot_bytes, a.w_bytes, a.w_stages, a.ring,
                         (uint32_t)(rb >> 4), (uint32_t)(((kPair ? 3 * a.cp / 2 : 3 * a.cp) * rb) >> 4), (uint32_t)((kTileY * kHX * rb) >> 4), a.idesc,
                         a.p.iD, cta_cols(a)};
-    if (rb == 128) sc_issue<kTF32, 1, 4, kPair>(zi);
+    if constexpr (RB == 128) sc_issue<kTF32, 1, 4, kPair>(zi);
+    else if constexpr (RB == 64) sc_issue<kTF32, 3, 2, kPair>(zi);
+    else if constexpr (RB == 32) sc_issue<kTF32, 3, 1, kPair>(zi);
+    else if (rb == 128) sc_issue<kTF32, 1, 4, kPair>(zi);
     else if (rb == 64) sc_issue<kTF32, 3, 2, kPair>(zi);
     else if (a.tps == 3) sc_issue<kTF32, 3, 1, kPair>(zi);
     else sc_issue<kTF32, 9, 1, kPair>(zi);
   } else if (warp >= 4) {
-    if (a.cp == 64) sc_epilogue_dispatch<64>(a, ctrl, tmem_base, warp, lane);
+    if constexpr (RB != 0) sc_epilogue<CP, __nv_bfloat16, true, kSRes, kSAct>(a, ctrl, tmem_base, warp, lane);
+    else if (a.cp == 64) sc_epilogue_dispatch<64>(a, ctrl, tmem_base, warp, lane);
     else if (a.cp == 48) sc_epilogue_dispatch<48>(a, ctrl, tmem_base, warp, lane);
     else if (a.cp == 32) sc_epilogue_dispatch<32>(a, ctrl, tmem_base, warp, lane);
     else sc_epilogue_dispatch<16>(a, ctrl, tmem_base, warp, lane);
@@ -579,6 +605,9 @@ int conv_scatter_launch(const S3dConvParams* p_in, const void* in, const float* 
   if (a.w_stages > kMaxW) a.w_stages = kMaxW;
   S3D_CHECK_ARG(a.w_stages >= 3, "scatter: not enough shared memory for the weight ring");
   a.idesc = ptx::make_instr_desc(tf32 ? 2 : 1, a.pair ? 256 : 128, 3 * a.cp);
+  // residual: each thread reads its own pixel's 128 bytes directly (measured 2.58 vs 2.71 ms on the residual layer against
+  // coalesced group loads + a second shuffle transpose -- with CTA pairs the L1 data pipe has room for the scattered reads)
+  a.res_direct = getenv("S3D_SCATTER_RES_TRANSPOSE") == nullptr;
   {
     const int oesz = p.out_dtype == S3D_DTYPE_BF16 ? 2 : 4;
     const bool simple_act = p.act == S3D_ACT_NONE || p.act == S3D_ACT_RELU || p.act == S3D_ACT_LEAKY;
@@ -600,8 +629,21 @@ int conv_scatter_launch(const S3dConvParams* p_in, const void* in, const float* 
   if (rc != S3D_OK) return rc;
 
   const int smem_bytes = a.ring * a.slot_bytes + a.w_stages * a.w_bytes + 1024;
-  auto kern = a.pair ? (tf32 ? conv_scatter_kernel<true, true> : conv_scatter_kernel<false, true>)
-                     : (tf32 ? conv_scatter_kernel<true, false> : conv_scatter_kernel<false, false>);
+  typedef void (*KernFn)(CUtensorMap, CUtensorMap, ScArgs);
+  KernFn kern = a.pair ? (tf32 ? conv_scatter_kernel<true, true> : conv_scatter_kernel<false, true>)
+                       : (tf32 ? conv_scatter_kernel<true, false> : conv_scatter_kernel<false, false>);
+  // the network's own layer shapes (bf16, CTA pairs, coalesced epilogue) each have a lean kernel
+  if (a.pair && !tf32 && p.out_dtype == S3D_DTYPE_BF16 && a.fast_store && (a.row_bytes == 128 || a.tps == 3) &&
+      getenv("S3D_SCATTER_GENERIC") == nullptr) {
+    const int rb = a.row_bytes, cp = a.cp;
+    const bool res = residual != nullptr, relu = p.act == S3D_ACT_RELU;     // anything else: slope formula (kSAct = 2)
+    if (rb == 128 && cp == 64 && !res && relu)       kern = conv_scatter_kernel<false, true, 128, 64, 0, 0>;   // aggregation
+    else if (rb == 128 && cp == 64 && res && !relu)  kern = conv_scatter_kernel<false, true, 128, 64, 1, 2>;   // residual layers
+    else if (rb == 32 && cp == 16 && !res && !relu)  kern = conv_scatter_kernel<false, true, 32, 16, 0, 2>;    // fusion scorer
+    else if (rb == 64 && cp == 32 && !res && relu)   kern = conv_scatter_kernel<false, true, 64, 32, 0, 0>;    // enc1
+    else if (rb == 128 && cp == 32 && !res && !relu) kern = conv_scatter_kernel<false, true, 128, 32, 0, 2>;   // enc5
+    else if (rb == 64 && cp == 64 && !res && relu)   kern = conv_scatter_kernel<false, true, 64, 64, 0, 0>;    // blocked deconv
+  }
   S3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   if (a.pair) {
     cudaLaunchConfig_t cfg;
