@@ -470,6 +470,13 @@ __device__ __forceinline__ void sc_epilogue_dispatch(const ScArgs& a, ScCtrl& ct
   }
 }
 
+// Taps per weight stage.  Narrow layers take all 9 in-plane taps in one stage when that fits 28 KB: a tile's accumulator
+// hand-back hides behind the OTHER tile's current stage, and a stage of 3 one-MMA taps (~180 cycles) is too short for
+// it (fusion scorer: 0.148 -> 0.100 ms per layer).
+__host__ __device__ constexpr int spec_tps(int rb, int cp) {
+  return rb == 128 ? 1 : (9 * (3 * cp / 2) * rb <= 28 * 1024 ? 9 : 3);
+}
+
 // RB != 0: a kernel specialised for ONE layer shape (bf16 rows of RB bytes, CP output channels, residual, activation).
 // Every variant of producer / issuer / epilogue is inlined into the kernel, and the kernel is sensitive to its own code
 // size (measured: two more epilogue variants in the all-in-one kernel cost 4 % of the whole forward), so the layer
@@ -506,7 +513,7 @@ conv_scatter_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
   if (warp == 0) {
     const uint32_t planes_u32 = ptx::smem_u32(smem), w_u32 = ptx::smem_u32(smem_w);
     if constexpr (RB == 128) sc_produce<1, kPair>(a, ctrl, planes_u32, w_u32, &map_x, &map_w);
-    else if constexpr (RB != 0) sc_produce<3, kPair>(a, ctrl, planes_u32, w_u32, &map_x, &map_w);
+    else if constexpr (RB != 0) sc_produce<spec_tps(RB, CP), kPair>(a, ctrl, planes_u32, w_u32, &map_x, &map_w);
     else if (a.tps == 1) sc_produce<1, kPair>(a, ctrl, planes_u32, w_u32, &map_x, &map_w);
     else if (a.tps == 3) sc_produce<3, kPair>(a, ctrl, planes_u32, w_u32, &map_x, &map_w);
     else sc_produce<9, kPair>(a, ctrl, planes_u32, w_u32, &map_x, &map_w);
@@ -519,9 +526,10 @@ conv_scatter_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                         (uint32_t)(rb >> 4), (uint32_t)(((kPair ? 3 * a.cp / 2 : 3 * a.cp) * rb) >> 4), (uint32_t)((kTileY * kHX * rb) >> 4), a.idesc,
                         a.p.iD, cta_cols(a)};
     if constexpr (RB == 128) sc_issue<kTF32, 1, 4, kPair>(zi);
-    else if constexpr (RB == 64) sc_issue<kTF32, 3, 2, kPair>(zi);
-    else if constexpr (RB == 32) sc_issue<kTF32, 3, 1, kPair>(zi);
+    else if constexpr (RB == 64) sc_issue<kTF32, spec_tps(RB, CP), 2, kPair>(zi);
+    else if constexpr (RB == 32) sc_issue<kTF32, spec_tps(RB, CP), 1, kPair>(zi);
     else if (rb == 128) sc_issue<kTF32, 1, 4, kPair>(zi);
+    else if (rb == 64 && a.tps == 9) sc_issue<kTF32, 9, 2, kPair>(zi);
     else if (rb == 64) sc_issue<kTF32, 3, 2, kPair>(zi);
     else if (a.tps == 3) sc_issue<kTF32, 3, 1, kPair>(zi);
     else sc_issue<kTF32, 9, 1, kPair>(zi);
@@ -573,8 +581,8 @@ int conv_scatter_launch(const S3dConvParams* p_in, const void* in, const float* 
   a.kc = p.Cin;
   a.slot_bytes = (kPlaneRows * a.row_bytes + 1023) / 1024 * 1024;
   a.cp = p.Cout;
-  a.tps = a.row_bytes == 128 ? 1 : 3;
-  if (a.row_bytes == 32 && getenv("S3D_SCATTER_TPS9") != nullptr) a.tps = 9;
+  a.tps = spec_tps(a.row_bytes, a.cp);
+  if (getenv("S3D_SCATTER_TPS3") != nullptr && a.tps == 9) a.tps = 3;
   a.cols_x = ceil_div(p.oW, kTX);  a.cols_y = ceil_div(p.oH, kTY);
   const int64_t total = (int64_t)p.N * a.cols_x * a.cols_y;
   S3D_CHECK_ARG(total > 0 && total < (1ll << 31), "scatter: column count out of range");
@@ -633,7 +641,7 @@ int conv_scatter_launch(const S3dConvParams* p_in, const void* in, const float* 
   KernFn kern = a.pair ? (tf32 ? conv_scatter_kernel<true, true> : conv_scatter_kernel<false, true>)
                        : (tf32 ? conv_scatter_kernel<true, false> : conv_scatter_kernel<false, false>);
   // the network's own layer shapes (bf16, CTA pairs, coalesced epilogue) each have a lean kernel
-  if (a.pair && !tf32 && p.out_dtype == S3D_DTYPE_BF16 && a.fast_store && (a.row_bytes == 128 || a.tps == 3) &&
+  if (a.pair && !tf32 && p.out_dtype == S3D_DTYPE_BF16 && a.fast_store && a.tps == spec_tps(a.row_bytes, a.cp) &&
       getenv("S3D_SCATTER_GENERIC") == nullptr) {
     const int rb = a.row_bytes, cp = a.cp;
     const bool res = residual != nullptr, relu = p.act == S3D_ACT_RELU;     // anything else: slope formula (kSAct = 2)
