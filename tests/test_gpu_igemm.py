@@ -123,8 +123,47 @@ def test_igemm_rejects_bad_shapes():
     assert rc == -1 and b'tile' in lib.load().s3d_last_error()
 
 
+@pytest.mark.parametrize('knob', [None, 'S3D_SCATTER_NO_PAIR', 'S3D_SCATTER_GENERIC', 'S3D_SCATTER_NO_TRANSPOSE',
+                                  'S3D_SCATTER_RES_TRANSPOSE', 'S3D_SCATTER_TPS3', 'S3D_NO_SCATTER'])
+@pytest.mark.parametrize('prec,N,cin,cout,D,H,W,res,act', [
+    ('bf16', 1, 64, 64, 1, 8, 8, False, 'relu'),        # one column, one plane (no CTA pair possible)
+    ('bf16', 1, 64, 64, 2, 33, 9, True, 'none'),        # ragged patches in y and x, residual, 2 planes
+    ('bf16', 3, 64, 48, 3, 40, 20, False, 'relu'),      # 48 channels: 6 chunks per pixel, non-transposed epilogue
+    ('bf16', 2, 16, 16, 7, 32, 32, False, 'leaky'),     # fusion-scorer shape (32-byte rows, 9-tap stages)
+    ('bf16', 1, 32, 32, 4, 70, 70, True, 'relu'),       # 64-byte rows, odd number of columns
+    ('bf16', 5, 64, 64, 6, 16, 24, True, 'none'),       # the residual layer's kernel
+    ('bf16', 2, 64, 32, 5, 24, 16, False, 'none'),
+    ('tf32', 2, 32, 32, 5, 20, 12, True, 'relu'),       # fp32 storage, 128-byte rows
+    ('tf32', 1, 16, 64, 3, 9, 33, False, 'leaky'),
+])
+def test_conv3d_plane_scatter_shapes(monkeypatch, knob, prec, N, cin, cout, D, H, W, res, act):
+    """conv_scatter.cu over edge shapes, in every mode its knobs select (CTA pairs / single CTA, lean per-shape kernels /
+    all-in-one kernel, transposed / direct stores and residual reads, 9- / 3-tap stages) and the z-stacked fallback."""
+    if knob:
+        monkeypatch.setenv(knob, '1')
+    torch.manual_seed(7)
+    conv = nn.Conv3d(cin, cout, 3, 1, 1, bias=True)
+    x = torch.randn(N, cin, D, H, W)
+    dt = torch.bfloat16 if prec == 'bf16' else torch.float32
+    code = {'relu': lib.ACT_RELU, 'none': lib.ACT_NONE, 'leaky': lib.ACT_LEAKY}[act]
+    fn = {'relu': F.relu, 'none': lambda t: t, 'leaky': lambda t: F.leaky_relu(t, 0.2)}[act]
+    pc = PackedConv.from_conv(conv, None, code, _code(prec), 'cuda', act_param=0.2)
+    kw = {}
+    ref = conv(x)
+    if res:
+        r = torch.randn(N, cout, D, H, W).to(dt).float()
+        ref = ref + r
+        kw['residual'] = pad_c(to_cl(r), pc.cout_pad).to(dt).cuda()
+    _check(pc, x, fn(ref), prec, cout, **kw)
+
+
 @pytest.mark.parametrize('D,H,W', [(4, 16, 16), (5, 37, 19), (2, 64, 64)])
-def test_conv3d_residual_on_tensor_core(D, H, W):
+def test_conv3d_residual_on_tensor_core(D, H, W, monkeypatch):
+    monkeypatch.setenv('S3D_NO_SCATTER', '1')           # the z-stacked kernel is the fallback of conv_scatter.cu now
+    _conv3d_residual_on_tensor_core(D, H, W)
+
+
+def _conv3d_residual_on_tensor_core(D, H, W):
     """64->64 3x3x3 bf16 with a residual: the halo kernel adds the residual as an identity 'tap' (TMA-staged
     residual plane x [I;0] / [0;I] weight blocks) instead of loading it in the epilogue."""
     torch.manual_seed(5)
