@@ -200,8 +200,13 @@ def run_ours(args):
     # Double-buffered device inputs + a copy stream, so the H2D of step i+1 overlaps the compute of step i
     # (what a serving loop does); all copies of the K timed steps are still issued and finished inside the region.
     nv = cfg.CONST.N_VOX
-    h_vox = torch.empty((B, nv, nv, nv), dtype=torch.float32).pin_memory()
-    h_stats = torch.empty(2 * T + 1, dtype=torch.int64).pin_memory()
+    h_vox = [torch.empty((B, nv, nv, nv), dtype=torch.float32).pin_memory() for _ in range(2)]
+    h_stats = [torch.empty(2 * T + 1, dtype=torch.int64).pin_memory() for _ in range(2)]
+    d_vox = [torch.empty((B, nv, nv, nv), dtype=torch.float32, device=dev) for _ in range(2)]
+    d_stats = [torch.empty(2 * T + 1, dtype=torch.int64, device=dev) for _ in range(2)]
+    out_stream = torch.cuda.Stream(device=dev)
+    out_ready = [torch.cuda.Event() for _ in range(2)]
+    out_done = [torch.cuda.Event() for _ in range(2)]
     d_in = [(torch.empty((B, 3, H, W), dtype=torch.float32, device=dev), torch.empty((B, 3, H, W), dtype=torch.float32, device=dev),
              torch.empty((B, nv, nv, nv), dtype=torch.uint8, device=dev)) for _ in range(2)]
     copy_stream = torch.cuda.Stream(device=dev)
@@ -234,15 +239,29 @@ def run_ours(args):
         stats[2 * T] = B
         if world > 1:
             dist.all_reduce(stats)
-        h_vox.copy_(vox, non_blocking=True)
-        h_stats.copy_(stats, non_blocking=True)
+        # results leave through a device staging slot and a second stream, so the D2H of step i overlaps the compute of
+        # step i+1 (the model's output buffer is reused by the next forward); e2e_finish() joins the last copies
+        cur.wait_event(out_done[slot])
+        d_vox[slot].copy_(vox, non_blocking=True)
+        d_stats[slot].copy_(stats, non_blocking=True)
+        out_ready[slot].record(cur)
+        with torch.cuda.stream(out_stream):
+            out_stream.wait_event(out_ready[slot])
+            h_vox[slot].copy_(d_vox[slot], non_blocking=True)
+            h_stats[slot].copy_(d_stats[slot], non_blocking=True)
+            out_done[slot].record(out_stream)
+
+    def e2e_finish():
+        cur = torch.cuda.current_stream()
+        for ev in out_done:
+            cur.wait_event(ev)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup):
+    def timed(fn, steps, warmup, finish=None):
         for i in range(warmup):
             fn(i)
         barrier()
@@ -250,6 +269,8 @@ def run_ours(args):
         e0.record()
         for i in range(steps):
             fn(warmup + i)
+        if finish is not None:
+            finish()                 # the timed region ends only when every step's results are on the host
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -283,7 +304,7 @@ def run_ours(args):
     model._conv = orig_conv
     warm_e2e = min(args.warmup, 2) or 1
     e2e_state['first_timed'] = warm_e2e
-    ms_e2e = timed(step_e2e, args.steps, warm_e2e)
+    ms_e2e = timed(step_e2e, args.steps, warm_e2e, e2e_finish)
 
     if rank != 0:
         if world > 1:
