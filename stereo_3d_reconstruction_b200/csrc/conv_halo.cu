@@ -9,9 +9,10 @@
 //     tap (ky,kx) is the same swizzled buffer read from a start address (ky*10 + kx) rows further on,
 //     with the 8-row groups 10 rows apart (the hardware applies the swizzle XOR to absolute smem
 //     address bits, so an unaligned start inside a 1024-byte aligned buffer is legal; measured).
-//  2. A tcgen05.mma in SS mode pays a fixed ~95 cycles to read its 128-row A operand whatever N is,
-//     while B rows stream at full shared-memory bandwidth.  With pixels on the M side and Cout = 64 on
-//     the N side that read is 3x the 32 math cycles.  So the operands are SWAPPED: the weights are the
+//  2. In this kernel's first form (pixels on the M side, Cout = 64 on the N side) an MMA took ~95-110 cycles whatever
+//     N was, 3x the 32 math cycles of N = 64 (later pinned down with scripts/mma_rate.cu: the A operand costs a fixed
+//     ~51 cycles per MMA, the rest was the issue loop; N >= 128 runs at the full rate -- which is what
+//     conv_scatter.cu, the successor of this kernel for Cout <= 64, builds on).  Here the operands are SWAPPED: the weights are the
 //     A operand (M = 64 or 128 output channels) and the pixels are the B operand with N = 256, which
 //     buys 128 math cycles per A read:  D[co, p] += sum_ci W_t[co, ci] * X[p + off_t, ci].
 //
