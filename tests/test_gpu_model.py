@@ -87,6 +87,28 @@ def test_uint8_inputs_match_float_inputs():
         model(l8.permute(0, 3, 1, 2).contiguous().cuda(), r8.permute(0, 3, 1, 2).contiguous().cuda())
 
 
+@pytest.mark.parametrize('name', ['Stereo2Voxel', 'Stereo2Point'])
+def test_graphed_forward_replays_bit_identical(name):
+    """model.graphed(): the forward captured into a CUDA graph and replayed with new inputs == the eager forward."""
+    cfg = small_cfg(NETWORK__PRECISION='bf16')
+    model = M.build_model(name, cfg, seed=3).cuda().pack()
+    outs = []
+    for seed in (0, 1, 2):
+        left, right = synthetic.stereo_pair(2, cfg.CONST.IMG_H, cfg.CONST.IMG_W, 8, seed=seed)[:2]
+        left, right = left.cuda(), right.cuda()
+        args = (left, right)
+        if name == 'Stereo2Voxel':
+            args = args + (synthetic.gt_volume(2, seed=seed).cuda(),)
+        with torch.no_grad():
+            eager = [t.clone() for t in model(*args)]
+            graphed = [t.clone() for t in model.graphed(*args)]
+        assert len(model._graphs) == 1                       # captured once, replayed afterwards
+        for a, b in zip(eager, graphed):
+            assert torch.equal(a, b)
+        outs.append(eager[2])
+    assert not torch.equal(outs[0], outs[1])                 # different inputs did produce different outputs
+
+
 def test_odd_input_size_fp32():
     cfg = small_cfg(NETWORK__PRECISION='fp32', CONST__IMG_H=70, CONST__IMG_W=50)
     oracle = O.make_model('Stereo2Voxel', cfg, seed=1)
