@@ -55,8 +55,10 @@ struct ScArgs {
   const float* bias;
   const void* residual;
   void* out;
-  int row_bytes;      // Cin * esz: 32 / 64 / 128
-  int kc;             // channels per row
+  int row_bytes;      // bytes of one K chunk of a pixel row: 32 / 64 / 128
+  int kc;             // channels per K chunk
+  int nchunks;        // K chunks per row: 1, or 2 for 256-byte rows (64 fp32 channels: the tf32 aggregation layers)
+  int chunk_stride;   // bytes between the chunks of a plane slot
   int slot_bytes;     // one input plane with halo, rounded to 1024
   int ring;           // plane slots
   int cp;             // accumulator columns per output plane (= Cout, multiple of 16)
@@ -100,10 +102,10 @@ __device__ __forceinline__ uint64_t desc_hi(uint32_t sbo, int row_bytes) {
 __device__ __forceinline__ uint32_t desc_lo(uint32_t addr) { return ((addr & 0x3FFFF) >> 4) | (1u << 16); }
 
 // ---- TMA producer: warp-uniform, incremental ring counters, TMA issue under small elect_one regions -----------------
-template <int TPS, bool kPair>
+template <int TPS, bool kPair, int NK = 1>       // NK = 2: 256-byte rows as two 128-byte K chunks, one weight stage per (tap, chunk)
 __device__ __forceinline__ void sc_produce(const ScArgs& a, ScCtrl& ctrl, uint32_t planes_u32, uint32_t w_u32,
                                            const CUtensorMap* map_x, const CUtensorMap* map_w) {
-  constexpr int G = 9 / TPS;
+  constexpr int G = 9 * NK / TPS;
   const uint32_t bar_pf = ptx::smem_u32(&ctrl.plane_full[0]), bar_pe = ptx::smem_u32(&ctrl.plane_empty[0]);
   const uint32_t bar_wf = ptx::smem_u32(&ctrl.w_full[0]), bar_we = ptx::smem_u32(&ctrl.w_empty[0]);
   const int D = a.p.iD, ring = a.ring, w_stages = a.w_stages, ncols = cta_cols(a);
@@ -113,7 +115,8 @@ __device__ __forceinline__ void sc_produce(const ScArgs& a, ScCtrl& ctrl, uint32
   const int crank = kPair ? (int)ptx::cluster_ctarank() : 0;
   const bool leader = crank == 0;
   const int w_row0 = kPair ? crank * (3 * a.cp / 2) : 0;
-  const int plane_tx = kPlaneRows * a.row_bytes;
+  const int plane_tx = NK * kPlaneRows * a.row_bytes;
+  const int kc = a.kc, chunk_stride = a.chunk_stride;
   int ws = 0;  uint32_t wphase = 0;
   int pslot = 0;  uint32_t pphase = 0;
   int pci = 0, pj = 0, issued = 0;
@@ -126,10 +129,14 @@ __device__ __forceinline__ void sc_produce(const ScArgs& a, ScCtrl& ctrl, uint32
     if (ptx::elect_one()) {
       if (kPair) {
         if (leader) ptx::mbar_arrive_expect_tx_u32(bf, 2 * plane_tx);
-        ptx::tma_load_5d_2sm_u32(planes_u32 + pslot * slot_bytes, map_x, bf, 0, pc.x0 - 1, pc.y0 - 1, pj, pc.n);
+#pragma unroll
+        for (int ch = 0; ch < NK; ++ch)
+          ptx::tma_load_5d_2sm_u32(planes_u32 + pslot * slot_bytes + ch * chunk_stride, map_x, bf, ch * kc, pc.x0 - 1, pc.y0 - 1, pj, pc.n);
       } else {
         ptx::mbar_arrive_expect_tx_u32(bf, plane_tx);
-        ptx::tma_load_5d_u32(planes_u32 + pslot * slot_bytes, map_x, bf, 0, pc.x0 - 1, pc.y0 - 1, pj, pc.n);
+#pragma unroll
+        for (int ch = 0; ch < NK; ++ch)
+          ptx::tma_load_5d_u32(planes_u32 + pslot * slot_bytes + ch * chunk_stride, map_x, bf, ch * kc, pc.x0 - 1, pc.y0 - 1, pj, pc.n);
       }
     }
     __syncwarp();
@@ -153,12 +160,14 @@ __device__ __forceinline__ void sc_produce(const ScArgs& a, ScCtrl& ctrl, uint32
         const uint32_t be = bar_we + 8 * ws, bf = bar_wf + 8 * ws;
         ptx::mbar_wait_u32(be, wphase ^ 1);
         if (ptx::elect_one()) {
+          // NK = 2: group g = (tap g / 2, chunk g % 2)
+          const int tap = rot * 9 + (NK == 2 ? g / 2 : g * TPS), c0 = NK == 2 ? (g & 1) * kc : 0;
           if (kPair) {
             if (leader) ptx::mbar_arrive_expect_tx_u32(bf, 2 * w_tx);
-            ptx::tma_load_3d_2sm_u32(w_u32 + ws * w_bytes, map_w, bf, 0, w_row0, rot * 9 + g * TPS);
+            ptx::tma_load_3d_2sm_u32(w_u32 + ws * w_bytes, map_w, bf, c0, w_row0, tap);
           } else {
             ptx::mbar_arrive_expect_tx_u32(bf, w_tx);
-            ptx::tma_load_3d_u32(w_u32 + ws * w_bytes, map_w, bf, 0, 0, rot * 9 + g * TPS);
+            ptx::tma_load_3d_u32(w_u32 + ws * w_bytes, map_w, bf, c0, 0, tap);
           }
         }
         __syncwarp();
@@ -179,7 +188,7 @@ struct ScIssue {
   uint32_t bar_pf, bar_pe, bar_wf, bar_we, bar_af, bar_ae;
   uint64_t x_hi, w_hi;
   int slot_bytes, w_bytes, w_stages, ring;
-  uint32_t rb16, tap_step, tile_off;             // 16-byte units
+  uint32_t rb16, tap_step, tile_off, chunk_step; // 16-byte units
   uint32_t idesc;
   int D, ncols;
 };
@@ -190,13 +199,13 @@ __device__ __forceinline__ void sc_commit(uint32_t bar) {
   else       ptx::tc_commit_u32(bar);
 }
 
-template <bool kTF32, int TPS, int kPer, bool kPair>
+template <bool kTF32, int TPS, int kPer, bool kPair, int NK>
 __device__ __forceinline__ void sc_issue_group(const ScIssue& z, uint32_t d_tmem, uint64_t xdesc, uint64_t wdesc, int g,
                                                uint32_t first) {
 #pragma unroll
   for (int tt = 0; tt < TPS; ++tt) {
-    const int kyx = g * TPS + tt;
-    const uint32_t xoff = ((kyx / 3) * kHX + (kyx % 3)) * z.rb16;
+    const int kyx = NK == 2 ? g / 2 : g * TPS + tt;
+    const uint32_t xoff = ((kyx / 3) * kHX + (kyx % 3)) * z.rb16 + (NK == 2 ? (g & 1) * z.chunk_step : 0u);
 #pragma unroll
     for (int k = 0; k < kPer; ++k) {
       const uint32_t acc = (g == 0 && tt == 0 && k == 0) ? first : 1u;
@@ -207,9 +216,9 @@ __device__ __forceinline__ void sc_issue_group(const ScIssue& z, uint32_t d_tmem
   }
 }
 
-template <bool kTF32, int TPS, int kPer, bool kPair>
+template <bool kTF32, int TPS, int kPer, bool kPair, int NK = 1>
 __device__ __forceinline__ void sc_issue(const ScIssue& z) {
-  constexpr int G = 9 / TPS;
+  constexpr int G = 9 * NK / TPS;
   int ws = 0;  uint32_t wphase = 0;
   int pw = 0;  uint32_t pwphase = 0;
   uint32_t aphase = 0;
@@ -231,7 +240,7 @@ __device__ __forceinline__ void sc_issue(const ScIssue& z) {
           ptx::tc_fence_after();
           const uint64_t wd = z.w_hi | (w_lo0 + ws * w_lo_step);
           if (ptx::elect_one()) {
-            sc_issue_group<kTF32, TPS, kPer, kPair>(z, d0, xd0, wd, g, first);
+            sc_issue_group<kTF32, TPS, kPer, kPair, NK>(z, d0, xd0, wd, g, first);
             if (g == G - 1) sc_commit<kPair>(z.bar_af);
           }
           __syncwarp();
@@ -240,7 +249,7 @@ __device__ __forceinline__ void sc_issue(const ScIssue& z) {
           if (g == 1) { ptx::mbar_wait_u32(z.bar_ae + 8, aphase ^ 1); ptx::tc_fence_after(); }
           const uint64_t wd = z.w_hi | (w_lo0 + ws_prev * w_lo_step);
           if (ptx::elect_one()) {
-            sc_issue_group<kTF32, TPS, kPer, kPair>(z, d1, xd1, wd, g - 1, first);
+            sc_issue_group<kTF32, TPS, kPer, kPair, NK>(z, d1, xd1, wd, g - 1, first);
             sc_commit<kPair>(z.bar_we + 8 * ws_prev);
             if (g == G) { sc_commit<kPair>(z.bar_af + 8); sc_commit<kPair>(z.bar_pe + 8 * pw); }
           }
@@ -514,6 +523,7 @@ conv_scatter_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     const uint32_t planes_u32 = ptx::smem_u32(smem), w_u32 = ptx::smem_u32(smem_w);
     if constexpr (RB == 128) sc_produce<1, kPair>(a, ctrl, planes_u32, w_u32, &map_x, &map_w);
     else if constexpr (RB != 0) sc_produce<spec_tps(RB, CP), kPair>(a, ctrl, planes_u32, w_u32, &map_x, &map_w);
+    else if (a.nchunks == 2) sc_produce<1, kPair, 2>(a, ctrl, planes_u32, w_u32, &map_x, &map_w);
     else if (a.tps == 1) sc_produce<1, kPair>(a, ctrl, planes_u32, w_u32, &map_x, &map_w);
     else if (a.tps == 3) sc_produce<3, kPair>(a, ctrl, planes_u32, w_u32, &map_x, &map_w);
     else sc_produce<9, kPair>(a, ctrl, planes_u32, w_u32, &map_x, &map_w);
@@ -523,11 +533,12 @@ conv_scatter_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                         ptx::smem_u32(&ctrl.plane_full[0]), ptx::smem_u32(&ctrl.plane_empty[0]), ptx::smem_u32(&ctrl.w_full[0]),
                         ptx::smem_u32(&ctrl.w_empty[0]), ptx::smem_u32(&ctrl.acc_full[0]), ptx::smem_u32(&ctrl.acc_empty[0]),
                         desc_hi(kHX * rb, rb), desc_hi(8 * rb, rb), a.slot_bytes, a.w_bytes, a.w_stages, a.ring,
-                        (uint32_t)(rb >> 4), (uint32_t)(((kPair ? 3 * a.cp / 2 : 3 * a.cp) * rb) >> 4), (uint32_t)((kTileY * kHX * rb) >> 4), a.idesc,
+                        (uint32_t)(rb >> 4), (uint32_t)(((kPair ? 3 * a.cp / 2 : 3 * a.cp) * rb) >> 4), (uint32_t)((kTileY * kHX * rb) >> 4), (uint32_t)(a.chunk_stride >> 4), a.idesc,
                         a.p.iD, cta_cols(a)};
     if constexpr (RB == 128) sc_issue<kTF32, 1, 4, kPair>(zi);
     else if constexpr (RB == 64) sc_issue<kTF32, spec_tps(RB, CP), 2, kPair>(zi);
     else if constexpr (RB == 32) sc_issue<kTF32, spec_tps(RB, CP), 1, kPair>(zi);
+    else if (a.nchunks == 2) sc_issue<kTF32, 1, 4, kPair, 2>(zi);
     else if (rb == 128) sc_issue<kTF32, 1, 4, kPair>(zi);
     else if (rb == 64 && a.tps == 9) sc_issue<kTF32, 9, 2, kPair>(zi);
     else if (rb == 64) sc_issue<kTF32, 3, 2, kPair>(zi);
@@ -563,7 +574,7 @@ bool conv_scatter_eligible(const S3dConvParams* p) {
   for (int t = 0; t < 27; ++t)
     if (p->dz[t] != t / 9 - 1 || p->dy[t] != (t % 9) / 3 - 1 || p->dx[t] != t % 3 - 1) return false;
   const int cin_bytes = p->Cin * esz;
-  if (cin_bytes != 32 && cin_bytes != 64 && cin_bytes != 128) return false;
+  if (cin_bytes != 32 && cin_bytes != 64 && cin_bytes != 128 && cin_bytes != 256) return false;
   if (p->Cout > 64 || p->Cout % 16 != 0) return false;
   return true;
 }
@@ -577,9 +588,11 @@ int conv_scatter_launch(const S3dConvParams* p_in, const void* in, const float* 
   ScArgs a;
   memset(&a, 0, sizeof(a));
   a.p = p;  a.bias = bias;  a.residual = residual;  a.out = out;
-  a.row_bytes = p.Cin * esz;
-  a.kc = p.Cin;
-  a.slot_bytes = (kPlaneRows * a.row_bytes + 1023) / 1024 * 1024;
+  a.nchunks = p.Cin * esz == 256 ? 2 : 1;
+  a.row_bytes = p.Cin * esz / a.nchunks;
+  a.kc = p.Cin / a.nchunks;
+  a.chunk_stride = (kPlaneRows * a.row_bytes + 1023) / 1024 * 1024;
+  a.slot_bytes = a.nchunks * a.chunk_stride;
   a.cp = p.Cout;
   a.tps = spec_tps(a.row_bytes, a.cp);
   if (getenv("S3D_SCATTER_TPS3") != nullptr && a.tps == 9) a.tps = 3;
@@ -606,12 +619,12 @@ int conv_scatter_launch(const S3dConvParams* p_in, const void* in, const float* 
   int ring = (budget - 4 * a.w_bytes) / a.slot_bytes;
   if (ring > kMaxRing) ring = kMaxRing;
   if (ring < 2) ring = 2;
-  if (a.row_bytes == 128 && ring > (a.pair ? 3 : 2)) ring = a.pair ? 3 : 2;
+  if (a.row_bytes == 128 && ring > (a.pair && a.nchunks == 1 ? 3 : 2)) ring = a.pair && a.nchunks == 1 ? 3 : 2;
   if (const char* e = getenv("S3D_SCATTER_RING")) { const int r = atoi(e); if (r >= 2 && r <= kMaxRing) ring = r; }
   a.ring = ring;
   a.w_stages = (budget - a.ring * a.slot_bytes) / a.w_bytes;
   if (a.w_stages > kMaxW) a.w_stages = kMaxW;
-  S3D_CHECK_ARG(a.w_stages >= 3, "scatter: not enough shared memory for the weight ring");
+  S3D_CHECK_ARG(a.w_stages >= 2, "scatter: not enough shared memory for the weight ring");   // 2 works (no prefetch), >= 3 is the norm
   a.idesc = ptx::make_instr_desc(tf32 ? 2 : 1, a.pair ? 256 : 128, 3 * a.cp);
   // residual: each thread reads its own pixel's 128 bytes directly (measured 2.58 vs 2.71 ms on the residual layer against
   // coalesced group loads + a second shuffle transpose -- with CTA pairs the L1 data pipe has room for the scattered reads)
@@ -641,7 +654,7 @@ int conv_scatter_launch(const S3dConvParams* p_in, const void* in, const float* 
   KernFn kern = a.pair ? (tf32 ? conv_scatter_kernel<true, true> : conv_scatter_kernel<false, true>)
                        : (tf32 ? conv_scatter_kernel<true, false> : conv_scatter_kernel<false, false>);
   // the network's own layer shapes (bf16, CTA pairs, coalesced epilogue) each have a lean kernel
-  if (a.pair && !tf32 && p.out_dtype == S3D_DTYPE_BF16 && a.fast_store && a.tps == spec_tps(a.row_bytes, a.cp) &&
+  if (a.pair && !tf32 && a.nchunks == 1 && p.out_dtype == S3D_DTYPE_BF16 && a.fast_store && a.tps == spec_tps(a.row_bytes, a.cp) &&
       getenv("S3D_SCATTER_GENERIC") == nullptr) {
     const int rb = a.row_bytes, cp = a.cp;
     const bool res = residual != nullptr, relu = p.act == S3D_ACT_RELU;     // anything else: slope formula (kSAct = 2)

@@ -135,6 +135,8 @@ def test_igemm_rejects_bad_shapes():
     ('bf16', 2, 64, 32, 5, 24, 16, False, 'none'),
     ('tf32', 2, 32, 32, 5, 20, 12, True, 'relu'),       # fp32 storage, 128-byte rows
     ('tf32', 1, 16, 64, 3, 9, 33, False, 'leaky'),
+    ('tf32', 2, 64, 64, 5, 20, 12, True, 'relu'),       # 256-byte rows: two K chunks per tap (the tf32 aggregation layers)
+    ('bf16', 1, 128, 64, 3, 16, 16, False, 'relu'),     # 128 bf16 channels: two K chunks as well
 ])
 def test_conv3d_plane_scatter_shapes(monkeypatch, knob, prec, N, cin, cout, D, H, W, res, act):
     """conv_scatter.cu over edge shapes, in every mode its knobs select (CTA pairs / single CTA, lean per-shape kernels /
