@@ -35,7 +35,7 @@ conv_first_kernel(const void* __restrict__ img_, const float* __restrict__ disp,
     float acc[2][CO];
 #pragma unroll
     for (int c = 0; c < CO; ++c) { acc[0][c] = bs[c]; acc[1][c] = bs[c]; }
-#pragma unroll
+#pragma unroll 1                                       // (kept rolled: the fully unrolled body made this file the slowest to compile)
     for (int ky = 0; ky < 3; ++ky) {
       const int iy = 2 * oy + ky - 1;
       if (iy < 0 || iy >= H) continue;
