@@ -168,6 +168,10 @@ int s3d_avg_pool(const void* x, void* out, int N, int H, int W, int C, int L, in
  * 9.. = 0 -- the decoder's final 1x1x1 transposed conv + sigmoid. */
 int s3d_depth_to_space(const void* in, void* out, const float* proj_w, int proj_act, int N, int d, int h, int w,
                        int Cpad, int dtype, void* stream);
+/* Operand split of the 'tf32x3' precision mode: hi = x with the low 13 mantissa bits cleared (exactly representable
+ * in TF32), lo = x - hi (exact).  conv(x, w) ~= conv(hi, w_hi) + conv(lo, w_hi) + conv(hi, w_lo) on kind::tf32 tensor
+ * cores with fp32 accumulation reproduces fp32 to ~1e-6 relative.  n (elements) must be a multiple of 4. */
+int s3d_split_tf32(const float* x, float* hi, float* lo, int64_t n, void* stream);
 /* Context-aware fusion epilogue + IoU.  score, vol: [V*B, 32^3] planes with element strides
  * score_stride / vol_stride (view-major); fused[b,v] = clamp(sum_v softmax_v(score)*vol, 0, 1).
  * gt (uint8 [B,32^3]) and iou (int64 [B,T,2] = intersection, union) may be NULL. */

@@ -22,7 +22,7 @@ def smoke_cfg(prec):
 for label, mk in (('small', lambda p, cv: small_cfg(NETWORK__PRECISION=p, NETWORK__COST_VOLUME=cv)),
                   ('smoke', lambda p, cv: smoke_cfg(p))):
     for cv in (('concat', 'corr') if label == 'small' else ('concat',)):
-        for prec in ('fp32', 'tf32', 'bf16'):
+        for prec in ('fp32', 'tf32x3', 'tf32', 'bf16'):
             for seed in (0, 1, 2):
                 cfg = mk(prec, cv)
                 oracle = O.make_model('Stereo2Voxel', cfg, seed=seed)

@@ -277,6 +277,31 @@ extern "C" int s3d_depth_to_space(const void* in, void* out, const float* proj_w
   return S3D_OK;
 }
 
+// x = hi + lo with hi exactly representable in TF32 (low 13 mantissa bits cleared) and lo = x - hi (exact in fp32):
+// the operand split of the 3-pass 'tf32x3' precision mode (hi*hi + lo*hi + hi*lo on kind::tf32 MMAs, fp32 accumulation).
+__global__ void split_tf32_kernel(const float4* __restrict__ x, float4* __restrict__ hi, float4* __restrict__ lo, int64_t n4) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(x + i);
+    float4 h, l;
+    h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);  l.x = v.x - h.x;
+    h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);  l.y = v.y - h.y;
+    h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);  l.z = v.z - h.z;
+    h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);  l.w = v.w - h.w;
+    hi[i] = h;  lo[i] = l;
+  }
+}
+
+extern "C" int s3d_split_tf32(const float* x, float* hi, float* lo, int64_t n, void* stream) {
+  if (!x || !hi || !lo) { set_error("split_tf32: null argument"); return S3D_ERR_INVALID; }
+  S3D_CHECK_ARG(n > 0 && n % 4 == 0, "split_tf32: element count must be a positive multiple of 4");
+  S3D_CHECK_ARG(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(hi) | reinterpret_cast<uintptr_t>(lo)) & 15) == 0,
+                "split_tf32: pointers must be 16-byte aligned");
+  split_tf32_kernel<<<grid_for(n / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(hi), reinterpret_cast<float4*>(lo), n / 4);
+  S3D_LAUNCH_CHECK();
+  return S3D_OK;
+}
+
 static int pool_launch(const void* x, void* out, int N, int H, int W, int C, int L, int dtype, int to_vox, void* stream) {
   if (!x || !out) { set_error("pool: null argument"); return S3D_ERR_INVALID; }
   S3D_CHECK_ARG(N > 0 && H > 0 && W > 0 && C > 0 && L > 0, "pool: bad shape");

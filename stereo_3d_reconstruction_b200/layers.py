@@ -74,6 +74,8 @@ class PackedConv:
     def __init__(self, w_rows, bias, taps, stride, out_mult, cin, cout, act, act_param, dtype_code, device,
                  ksize=(1, 1, 1), pad=(0, 0, 0)):
         # w_rows: fp32 [n_classes*ntaps, cout, cin]
+        self._ctor = (w_rows.detach().float().cpu().clone(), bias.detach().float().cpu().clone(), taps, stride, out_mult, cin,
+                      cout, act, act_param, dtype_code, device, tuple(ksize), tuple(pad))      # for derive()
         self.n_classes = len(taps)
         self.ntaps = len(taps[0])
         assert self.n_classes * self.ntaps <= _lib.S3D_MAX_TAPS
@@ -131,6 +133,15 @@ class PackedConv:
             taps27 = [[(dz, dy, dx) for dz in (-1, 0, 1) for dy in (-1, 0, 1) for dx in (-1, 0, 1)]]
             self.vol = PackedConv(w27, bias, taps27, (1, 1, 1), (1, 1, 1), cin, cout, act, act_param, dtype_code, device,
                                   ksize=(3, 3, 3), pad=(1, 1, 1))
+
+    def derive(self, w_rows, bias, act):
+        """The same layer geometry with other weights / bias / activation (used by SplitConv)."""
+        _, _, taps, stride, out_mult, cin, cout, _, act_param, dtype_code, device, ksize, pad = self._ctor
+        pc = PackedConv(w_rows, bias, taps, stride, out_mult, cin, cout, act, act_param, dtype_code, device, ksize=ksize, pad=pad)
+        for k in ('ntaps_algo', 'block_cout'):
+            if hasattr(self, k):
+                setattr(pc, k, getattr(self, k))
+        return pc
 
     @staticmethod
     def pack_nstack(w3):
@@ -345,3 +356,39 @@ class PackedConv:
         """Algorithmic (unpadded) FLOPs: 2 * outputs * Cout * Cin * taps-that-hit."""
         oD, oH, oW = self.out_grid(iD, iH, iW)
         return 2.0 * N * oD * oH * oW * self.n_classes * self.cout * self.cin * getattr(self, 'ntaps_algo', self.ntaps)
+
+
+class SplitConv:
+    """'tf32x3' precision: fp32 accuracy from TF32 tensor cores.  Weights and activations are split into a part that is
+    exactly representable in TF32 and the remainder (w = w_hi + w_lo, x = x_hi + x_lo; include/s3d.h, s3d_split_tf32), and
+
+        conv(x, w) ~= conv(x_hi, w_hi) + conv(x_lo, w_hi) + conv(x_hi, w_lo)            (the lo*lo term is ~2^-22)
+
+    runs as three passes of the same kernels, accumulating in fp32 IN the output tensor through the engines' residual
+    input (pass 1 adds the layer's own residual; bias and activation are applied by pass 3 only)."""
+
+    def __init__(self, pc):
+        assert pc.dtype_code == _lib.DTYPE_F32 and pc.proj is None
+        w, b = pc._ctor[0], pc._ctor[1]
+        w_hi = (w.view(torch.int32) & -8192).view(torch.float32)          # clear the low 13 mantissa bits
+        self.full = pc                                                     # geometry, flops()
+        self.hi = pc.derive(w_hi, torch.zeros_like(b), _lib.ACT_NONE)
+        self.lo = pc.derive(w - w_hi, b, pc.act)
+        for k in ('cin', 'cout', 'cin_pad', 'cout_pad', 'ksize', 'stride', 'pad', 'n_classes', 'out_mult', 'act', 'act_param',
+                  'dtype_code', 'weight', 'bias', 'proj'):
+            setattr(self, k, getattr(pc, k))
+
+    def out_grid(self, *a):
+        return self.full.out_grid(*a)
+
+    def flops(self, *a):
+        return self.full.flops(*a)
+
+    def __call__(self, x, out=None, residual=None, engine='igemm', **kw):
+        from . import ops
+        assert engine == 'igemm' and x.dtype == torch.float32
+        x_hi, x_lo = ops.split_tf32(x)
+        out = self.hi(x_hi, out=out, residual=residual, **kw)
+        self.hi(x_lo, out=out, residual=out, **kw)
+        self.lo(x_hi, out=out, residual=out, **kw)
+        return out

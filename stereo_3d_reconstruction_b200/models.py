@@ -18,7 +18,7 @@ import torch.nn as nn
 
 from . import lib as _lib
 from . import ops
-from .layers import PackedConv, pad_to, torch_dtype
+from .layers import PackedConv, SplitConv, pad_to, torch_dtype
 
 A = _lib  # activation / dtype codes
 
@@ -203,6 +203,9 @@ class _StereoBase(nn.Module):
         for i, seq in enumerate(self.rgbd_encoder.layers):
             P['rec%d' % i] = PackedConv.from_conv(seq[0], seq[1], A.ACT_RELU, dc, dev)
         self._pack_head(P, dc, dev)
+        if self.precision == 'tf32x3':
+            # every conv as three TF32 passes over split operands (layers.py::SplitConv): fp32 accuracy on the tensor cores
+            P = {k: SplitConv(v) for k, v in P.items()}
         self._packed = P
         self._ws = {}
         self._graphs = {}
@@ -364,7 +367,7 @@ class Stereo2Voxel(_StereoBase):
             pw[:] = w.detach().float().cpu().view(-1)[:8]
             self._d2s = pw.to(dev)
             self._fused_out = True
-        elif last.cout_pad == 16 and last.cout < 16:
+        elif last.cout_pad == 16 and last.cout < 16 and self.precision != 'tf32x3':     # (a projection epilogue cannot be split)
             self._fused_out = True
             # 1x1x1 transposed conv + sigmoid folded into the last deconv's epilogue: coarse volume -> channel `cout`
             last.set_projection(w.view(-1), last.cout, A.ACT_SIGMOID)

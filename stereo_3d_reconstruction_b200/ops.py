@@ -99,6 +99,18 @@ def tap_gather_soft_argmin(taps, sign=-1.0, out=None, want_cost=False):
     return (out, cost) if want_cost else out
 
 
+def split_tf32(x, hi=None, lo=None):
+    """fp32 x -> (hi, lo): hi representable in TF32 (low 13 mantissa bits cleared), lo = x - hi (include/s3d.h)."""
+    _chk(x, hi, lo)
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.numel() % 4 == 0
+    hi = torch.empty_like(x) if hi is None else hi
+    lo = torch.empty_like(x) if lo is None else lo
+    rc = _lib.load().s3d_split_tf32(x.data_ptr(), hi.data_ptr(), lo.data_ptr(), x.numel(), _stream())
+    _lib.check(rc, 's3d_split_tf32')
+    _lib.count_launch()
+    return hi, lo
+
+
 def depth_to_space(x, cpad=16, proj_w=None, proj_act=0, out=None):
     """x [N,d,h,w,64] (channel = parity class * 8 + c, from PackedConv.from_deconv_k4s2p1_blocked) -> [N,2d,2h,2w,cpad];
     optional projection of the 8 features into channel 8 (include/s3d.h, s3d_depth_to_space)."""

@@ -14,14 +14,16 @@ pytestmark = pytest.mark.gpu
 # mantissa) measures 3-4e-3 on disparity and 5-9e-3 max on occupancy through the 12-conv stack, so it states
 # (1e-2, 2e-2); bf16 measures 1.0-1.4e-2 / 1.5-3.7e-2 max (mean 1-2e-3) and states (3e-2, 6e-2).
 # Measured values per seed: profiles/r1_parity_report.txt (scripts/parity_report.py).
-TOLS = {'fp32': (1e-4, 1e-4), 'tf32': (1e-2, 2e-2), 'bf16': (3e-2, 6e-2)}
+# 'tf32x3' (three TF32 passes over split operands, layers.py::SplitConv) is the tensor-core mode that meets the north_star's
+# 1e-3 (stated 5e-4; measured ~1e-5).
+TOLS = {'fp32': (1e-4, 1e-4), 'tf32x3': (5e-4, 5e-4), 'tf32': (1e-2, 2e-2), 'bf16': (3e-2, 6e-2)}
 
 
 def _pair(cfg, B):
     return synthetic.stereo_pair(B, cfg.CONST.IMG_H, cfg.CONST.IMG_W, 4 * cfg.NETWORK.MAX_DISP // 2, seed=0)[:2]
 
 
-@pytest.mark.parametrize('prec', ['fp32', 'tf32', 'bf16'])
+@pytest.mark.parametrize('prec', ['fp32', 'tf32x3', 'tf32', 'bf16'])
 @pytest.mark.parametrize('cv', ['concat', 'corr'])
 def test_stereo2voxel_matches_oracle(prec, cv):
     cfg = small_cfg(NETWORK__PRECISION=prec, NETWORK__COST_VOLUME=cv)
