@@ -246,6 +246,18 @@ __global__ void depth_to_space_kernel(const T* __restrict__ in, T* __restrict__ 
       reinterpret_cast<uint4*>(op)[1] = hi;
       continue;
     }
+    if (sizeof(T) == 4 && Cpad == 16) {
+      // fp32, 16 output channels: two 16-byte loads, four 16-byte stores
+      const float4 a = __ldg(reinterpret_cast<const float4*>(ip)), b = __ldg(reinterpret_cast<const float4*>(ip) + 1);
+      float pr = a.x * pw[0];
+      pr = fmaf(a.y, pw[1], pr);  pr = fmaf(a.z, pw[2], pr);  pr = fmaf(a.w, pw[3], pr);
+      pr = fmaf(b.x, pw[4], pr);  pr = fmaf(b.y, pw[5], pr);  pr = fmaf(b.z, pw[6], pr);  pr = fmaf(b.w, pw[7], pr);
+      float4* o4 = reinterpret_cast<float4*>(op);
+      o4[0] = a;  o4[1] = b;
+      o4[2] = make_float4(proj_w ? apply_act(pr, proj_act, 1.f) : 0.f, 0.f, 0.f, 0.f);
+      o4[3] = make_float4(0.f, 0.f, 0.f, 0.f);
+      continue;
+    }
 #pragma unroll
     for (int c = 0; c < 8; ++c) f[c] = to_f32(ip[c]);
 #pragma unroll
