@@ -74,7 +74,7 @@ class PackedConv:
     def __init__(self, w_rows, bias, taps, stride, out_mult, cin, cout, act, act_param, dtype_code, device,
                  ksize=(1, 1, 1), pad=(0, 0, 0)):
         # w_rows: fp32 [n_classes*ntaps, cout, cin]
-        self._ctor = (w_rows.detach().float().cpu().clone(), bias.detach().float().cpu().clone(), taps, stride, out_mult, cin,
+        self._ctor = (w_rows.detach().float().cpu(), bias.detach().float().cpu(), taps, stride, out_mult, cin,
                       cout, act, act_param, dtype_code, device, tuple(ksize), tuple(pad))      # for derive()
         self.n_classes = len(taps)
         self.ntaps = len(taps[0])
