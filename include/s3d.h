@@ -128,6 +128,12 @@ int s3d_conv_first(const void* img, int img_u8, const float* disp, float disp_sc
                    float act_param, void* stream);
 
 /* --- cost volume / disparity (rows V, S) ---------------------------------------------- */
+/* Cost volume + first aggregation layer fused (csrc/conv_scatter_concat.cu): the stride-1 3x3x3 conv `p` (N = 2B volumes,
+ * iD = D, Cin = 2C, Cout <= 64, w_nstack set) over the concat volume of s3d_cost_volume_concat, WITHOUT materialising it.
+ * feat: channels-last feature maps [2B, h, feat_pitch, C] whose real pixels start at column feat_pad and whose margins
+ * (>= D-1 pixels on both sides) are ZERO; left images first.  Bit-identical to s3d_cost_volume_concat + s3d_conv_igemm. */
+int s3d_conv_concat_volume(const S3dConvParams* p, const void* feat, int feat_pitch, int feat_pad, const float* bias,
+                           void* out, void* stream);
 /* feat: [2B,1,h,w,C] (left maps first, then right).  vol: [2B,D,h,w,2C]; entries [0,B) are
  * left-referenced (target sampled at x-d), [B,2B) right-referenced (target at x+d). */
 int s3d_cost_volume_concat(const void* feat, void* vol, int B, int h, int w, int C, int D,

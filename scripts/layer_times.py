@@ -26,7 +26,7 @@ def wrap(name, fn):
     return f
 oc = model._conv
 model._conv = lambda name, x, **kw: wrap(name, oc)(name, x, **kw)
-for n in ('pack_image', 'conv_first', 'depth_to_space', 'cost_volume_concat', 'soft_argmin', 'tap_gather_soft_argmin', 'cls_soft_argmin', 'corr_soft_argmin', 'upsample_disp', 'latent_to_vox', 'fuse_views'):
+for n in ('pack_image', 'conv_first', 'conv_concat_volume', 'depth_to_space', 'cost_volume_concat', 'soft_argmin', 'tap_gather_soft_argmin', 'cls_soft_argmin', 'corr_soft_argmin', 'upsample_disp', 'latent_to_vox', 'fuse_views'):
     setattr(ops, n, wrap(n, getattr(ops, n)))
 t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 t0.record(); model(l, r, gt); t1.record(); torch.cuda.synchronize()

@@ -1,0 +1,395 @@
+// Cost volume + first aggregation layer in one kernel: the plane-scatter 3x3x3 conv (conv_scatter.cuh) reading a concat
+// volume that is never written.  Plane d of volume n is [ ref(y, x) | tgt(y, x -/+ d) ] (the reference half
+// is the SAME feature map for every d, the target half is the other view shifted by d, zero outside the image), so
+//   * the reference half of a 32x8 patch is staged ONCE per column (two buffers, so the next column's is in flight) and is
+//     the K-chunk 0 operand of all D planes;
+//   * the target half of plane d is one TMA box of the other view's feature map through a SKEWED tensor map: the map's X
+//     and D dimensions have the same stride (one pixel), i.e. coordinate (x, d) addresses pixel x + d (right reference)
+//     or, with d counted downwards from a base moved D-1 pixels left, pixel x - d (left reference).  X keeps its real
+//     bound, so both conv halos are TMA zero fill; the shifted-out pixels land in the zero margins the feature rows are
+//     stored with (pad >= D-1 pixels on both sides).  Checked stand-alone with scripts/tma_skew.cu.
+// The 2.1 GB volume (B = 64), its write (0.34 ms at 96 % of HBM peak) and its read by the conv disappear; the MMA
+// sequence is the K-chunked one of conv_scatter.cuh (chunk 0 = reference channels, chunk 1 = target channels), so the
+// result is bit-identical to concat_volume_kernel + conv_scatter_kernel.
+#include "conv_scatter.cuh"
+
+namespace s3d {
+namespace scatter {
+
+struct CcCtrl {
+  ScCtrl c;
+  uint64_t ref_full[2], ref_empty[2];
+};
+
+struct CcArgs {
+  ScArgs a;
+  int n_half;          // B: volumes [0, B) are left-referenced, [B, 2B) right-referenced
+  int D;
+};
+
+template <bool kPair>
+__device__ __forceinline__ void cc_produce(const CcArgs& ca, CcCtrl& ctrl, uint32_t ref_u32, uint32_t planes_u32, uint32_t w_u32,
+                                           const CUtensorMap* map_ref, const CUtensorMap* map_tl, const CUtensorMap* map_tr,
+                                           const CUtensorMap* map_w) {
+  const ScArgs& a = ca.a;
+  constexpr int G = 9;                             // one weight stage per tap: [reference-channel rows][target-channel rows]
+  const uint32_t bar_pf = ptx::smem_u32(&ctrl.c.plane_full[0]), bar_pe = ptx::smem_u32(&ctrl.c.plane_empty[0]);
+  const uint32_t bar_wf = ptx::smem_u32(&ctrl.c.w_full[0]), bar_we = ptx::smem_u32(&ctrl.c.w_empty[0]);
+  const uint32_t bar_rf = ptx::smem_u32(&ctrl.ref_full[0]), bar_re = ptx::smem_u32(&ctrl.ref_empty[0]);
+  const int D = ca.D, ring = a.ring, w_stages = a.w_stages, ncols = cta_cols(a);
+  const int slot_bytes = a.slot_bytes, w_bytes = a.w_bytes, w_tx = a.w_tx, kc = a.kc, B = ca.n_half;
+  const int crank = kPair ? (int)ptx::cluster_ctarank() : 0;
+  const bool leader = crank == 0;
+  const int w_row0 = kPair ? crank * (3 * a.cp / 2) : 0;
+  const int plane_tx = kPlaneRows * a.row_bytes;
+  const uint32_t mult = kPair ? 2u : 1u;           // the leader's barriers collect the bytes of both CTAs
+  int ws = 0;  uint32_t wphase = 0;
+  int pslot = 0;  uint32_t pphase = 0;
+  int pci = 0, pj = 0, issued = 0;
+  Col pc = decode_col(a, blockIdx.x);
+  auto load = [&](uint32_t dst, const CUtensorMap* m, uint32_t bf, int c1, int c2, int c3, int c4) {
+    if (kPair) ptx::tma_load_5d_2sm_u32(dst, m, bf, 0, c1, c2, c3, c4);
+    else       ptx::tma_load_5d_u32(dst, m, bf, 0, c1, c2, c3, c4);
+  };
+  auto issue_plane = [&](bool blocking) -> bool {
+    if (pci >= ncols) return false;
+    if (pj == 0) {
+      // first plane of a column: its reference half goes out first (buffer pci & 1, free once column pci-2 is done);
+      // only when called blocking, so that an opportunistic call never stalls the weight stream on it
+      const int rb_ = pci & 1;
+      const uint32_t rpar = ((uint32_t)(pci >> 1) & 1u) ^ 1u;
+      if (blocking) ptx::mbar_wait_u32(bar_re + 8 * rb_, rpar);
+      else if (!ptx::mbar_test_wait_u32(bar_re + 8 * rb_, rpar)) return false;
+    }
+    const uint32_t be = bar_pe + 8 * pslot, bf = bar_pf + 8 * pslot;
+    if (blocking) ptx::mbar_wait_u32(be, pphase ^ 1);
+    else if (!ptx::mbar_test_wait_u32(be, pphase ^ 1)) return false;
+    if (ptx::elect_one()) {
+      if (pj == 0) {
+        const uint32_t rf = bar_rf + 8 * (pci & 1);
+        if (leader) ptx::mbar_arrive_expect_tx_u32(rf, mult * plane_tx);
+        load(ref_u32 + (pci & 1) * slot_bytes, map_ref, rf, pc.x0 - 1, pc.y0 - 1, 0, pc.n);          // dims (C, X, Y, 1, 2B)
+      }
+      if (leader) ptx::mbar_arrive_expect_tx_u32(bf, mult * plane_tx);
+      // target half: dims (C, X, D, Y, B).  Left reference: pixel x - d = (x, D-1-d) on the map based D-1 pixels to the left
+      if (pc.n < B) load(planes_u32 + pslot * slot_bytes, map_tl, bf, pc.x0 - 1, D - 1 - pj, pc.y0 - 1, pc.n);
+      else          load(planes_u32 + pslot * slot_bytes, map_tr, bf, pc.x0 - 1, pj, pc.y0 - 1, pc.n - B);
+    }
+    __syncwarp();
+    ++issued;
+    if (++pslot == ring) { pslot = 0; pphase ^= 1; }
+    if (++pj == D) {
+      pj = 0;  ++pci;
+      if (pci < ncols) pc = decode_col(a, blockIdx.x + pci * gridDim.x);
+    }
+    return true;
+  };
+  int gp = 0;
+  for (int ci = 0; ci < ncols; ++ci) {
+    int rot = 3;
+    for (int p = 0; p < D; ++p, ++gp) {
+      while (issued <= gp) issue_plane(true);
+      const int ahead = gp + ring;
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        if (issued < ahead) issue_plane(false);
+        const uint32_t be = bar_we + 8 * ws, bf = bar_wf + 8 * ws;
+        ptx::mbar_wait_u32(be, wphase ^ 1);
+        if (ptx::elect_one()) {
+          if (leader) ptx::mbar_arrive_expect_tx_u32(bf, mult * w_tx);
+#pragma unroll
+          for (int ch = 0; ch < 2; ++ch) {
+            if (kPair) ptx::tma_load_3d_2sm_u32(w_u32 + ws * w_bytes + ch * (w_tx >> 1), map_w, bf, ch * kc, w_row0, rot * 9 + g);
+            else       ptx::tma_load_3d_u32(w_u32 + ws * w_bytes + ch * (w_tx >> 1), map_w, bf, ch * kc, 0, rot * 9 + g);
+          }
+        }
+        __syncwarp();
+        if (++ws == w_stages) { ws = 0; wphase ^= 1; }
+      }
+      rot = (p == 0) ? 1 : (rot == 2 ? 0 : rot + 1);
+    }
+  }
+}
+
+struct CcIssue {
+  ScIssue z;
+  uint32_t ref_u32, bar_rf, bar_re;
+};
+
+// One tap = one weight stage: kPer MMAs on the reference buffer (K chunk 0), then kPer on the target slot (K chunk 1).
+template <bool kTF32, int kPer, bool kPair>
+__device__ __forceinline__ void cc_issue_group(const ScIssue& z, uint32_t d_tmem, uint64_t rdesc, uint64_t xdesc, uint64_t wdesc, int g,
+                                               uint32_t first) {
+  const uint32_t xoff = ((g / 3) * kHX + (g % 3)) * z.rb16;
+#pragma unroll
+  for (int ch = 0; ch < 2; ++ch) {
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+      const uint32_t acc = (g == 0 && ch == 0 && k == 0) ? first : 1u;
+      const uint64_t ad = (ch ? xdesc : rdesc) + xoff + 2 * k, bd = wdesc + ch * z.chunk_step + 2 * k;
+      if (kPair) { if (kTF32) ptx::mma_tf32_2sm(d_tmem, ad, bd, z.idesc, acc); else ptx::mma_bf16_2sm(d_tmem, ad, bd, z.idesc, acc); }
+      else       { if (kTF32) ptx::mma_tf32(d_tmem, ad, bd, z.idesc, acc);     else ptx::mma_bf16(d_tmem, ad, bd, z.idesc, acc); }
+    }
+  }
+}
+
+// Same schedule as sc_issue (tile 1 trails tile 0 by one weight stage); K chunk 0 of every tap reads the column's
+// reference buffer, chunk 1 the plane's target slot.
+template <bool kTF32, int kPer, bool kPair>
+__device__ __forceinline__ void cc_issue(const CcIssue& ci_) {
+  const ScIssue& z = ci_.z;
+  constexpr int G = 9;
+  int ws = 0;  uint32_t wphase = 0;
+  int pw = 0;  uint32_t pwphase = 0;
+  uint32_t aphase = 0;
+  const uint32_t w_lo0 = desc_lo(z.w_u32), w_lo_step = z.w_bytes >> 4;
+  const uint32_t x_lo0 = desc_lo(z.planes_u32), x_lo_step = z.slot_bytes >> 4;
+  const uint32_t r_lo0 = desc_lo(ci_.ref_u32);
+  const uint32_t d0 = z.tmem_base, d1 = z.tmem_base + kTileCols;
+  for (int ci = 0; ci < z.ncols; ++ci) {
+    const int rbuf = ci & 1;
+    ptx::mbar_wait_u32(ci_.bar_rf + 8 * rbuf, (uint32_t)(ci >> 1) & 1u);
+    const uint64_t rd0 = z.x_hi | (r_lo0 + rbuf * x_lo_step), rd1 = rd0 + z.tile_off;
+    for (int p = 0; p < z.D; ++p) {
+      ptx::mbar_wait_u32(z.bar_pf + 8 * pw, pwphase);
+      const uint64_t xd0 = z.x_hi | (x_lo0 + pw * x_lo_step), xd1 = xd0 + z.tile_off;
+      const uint32_t first = p == 0 ? 0u : 1u;
+      const bool last_plane = p == z.D - 1;
+      int ws_prev = 0;
+#pragma unroll
+      for (int g = 0; g <= G; ++g) {
+        if (g < G) {
+          ptx::mbar_wait_u32(z.bar_wf + 8 * ws, wphase);
+          if (g == 0) ptx::mbar_wait_u32(z.bar_ae, aphase ^ 1);
+          ptx::tc_fence_after();
+          const uint64_t wd = z.w_hi | (w_lo0 + ws * w_lo_step);
+          if (ptx::elect_one()) {
+            cc_issue_group<kTF32, kPer, kPair>(z, d0, rd0, xd0, wd, g, first);
+            if (g == G - 1) sc_commit<kPair>(z.bar_af);
+          }
+          __syncwarp();
+        }
+        if (g >= 1) {
+          if (g == 1) { ptx::mbar_wait_u32(z.bar_ae + 8, aphase ^ 1); ptx::tc_fence_after(); }
+          const uint64_t wd = z.w_hi | (w_lo0 + ws_prev * w_lo_step);
+          if (ptx::elect_one()) {
+            cc_issue_group<kTF32, kPer, kPair>(z, d1, rd1, xd1, wd, g - 1, first);
+            sc_commit<kPair>(z.bar_we + 8 * ws_prev);
+            if (g == G) {
+              sc_commit<kPair>(z.bar_af + 8);
+              sc_commit<kPair>(z.bar_pe + 8 * pw);
+              if (last_plane) sc_commit<kPair>(ci_.bar_re + 8 * rbuf);      // the column's reference buffer is free
+            }
+          }
+          __syncwarp();
+        }
+        if (g < G) {
+          ws_prev = ws;
+          if (++ws == z.w_stages) { ws = 0; wphase ^= 1; }
+        }
+      }
+      aphase ^= 1;
+      if (++pw == z.ring) { pw = 0; pwphase ^= 1; }
+    }
+  }
+}
+
+template <bool kTF32, bool kPair, int kPer, bool kLean>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_scatter_concat_kernel(const __grid_constant__ CUtensorMap map_ref, const __grid_constant__ CUtensorMap map_tl,
+                           const __grid_constant__ CUtensorMap map_tr, const __grid_constant__ CUtensorMap map_w,
+                           const __grid_constant__ CcArgs ca) {
+  const ScArgs& a = ca.a;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_planes = smem + 2 * a.slot_bytes;              // [ref 0][ref 1][target ring][weights]
+  uint8_t* smem_w = smem_planes + a.ring * a.slot_bytes;
+  __shared__ CcCtrl ctrl;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&map_ref);  ptx::prefetch_tensormap(&map_tl);
+    ptx::prefetch_tensormap(&map_tr);   ptx::prefetch_tensormap(&map_w);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kMaxRing; ++s) { ptx::mbar_init(&ctrl.c.plane_full[s], 1); ptx::mbar_init(&ctrl.c.plane_empty[s], 1); }
+    for (int s = 0; s < kMaxW; ++s) { ptx::mbar_init(&ctrl.c.w_full[s], 1); ptx::mbar_init(&ctrl.c.w_empty[s], 1); }
+    for (int b = 0; b < 2; ++b) {
+      ptx::mbar_init(&ctrl.c.acc_full[b], 1);  ptx::mbar_init(&ctrl.c.acc_empty[b], kPair ? 8 : 4);
+      ptx::mbar_init(&ctrl.ref_full[b], 1);    ptx::mbar_init(&ctrl.ref_empty[b], 1);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) { if (kPair) ptx::tmem_alloc_2sm(&ctrl.c.tmem_base, kTmemCols); else ptx::tmem_alloc(&ctrl.c.tmem_base, kTmemCols); }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (kPair) ptx::cluster_sync_all();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = ctrl.c.tmem_base;
+
+  if (warp == 0) {
+    cc_produce<kPair>(ca, ctrl, ptx::smem_u32(smem), ptx::smem_u32(smem_planes), ptx::smem_u32(smem_w), &map_ref, &map_tl, &map_tr,
+                      &map_w);
+  } else if (warp == 1 && (!kPair || ptx::cluster_ctarank() == 0)) {
+    const int rb = a.row_bytes;
+    const CcIssue zi = {{tmem_base, ptx::smem_u32(smem_planes), ptx::smem_u32(smem_w),
+                         ptx::smem_u32(&ctrl.c.plane_full[0]), ptx::smem_u32(&ctrl.c.plane_empty[0]), ptx::smem_u32(&ctrl.c.w_full[0]),
+                         ptx::smem_u32(&ctrl.c.w_empty[0]), ptx::smem_u32(&ctrl.c.acc_full[0]), ptx::smem_u32(&ctrl.c.acc_empty[0]),
+                         desc_hi(kHX * rb, rb), desc_hi(8 * rb, rb), a.slot_bytes, a.w_bytes, a.w_stages, a.ring,
+                         (uint32_t)(rb >> 4), 0u, (uint32_t)((kTileY * kHX * rb) >> 4), (uint32_t)(a.w_tx >> 5), a.idesc, ca.D, cta_cols(a)},
+                        ptx::smem_u32(smem), ptx::smem_u32(&ctrl.ref_full[0]), ptx::smem_u32(&ctrl.ref_empty[0])};
+    cc_issue<kTF32, kPer, kPair>(zi);
+  } else if (warp >= 4) {
+    if constexpr (kLean) sc_epilogue<64, __nv_bfloat16, true, 0, 0>(a, ctrl.c, tmem_base, warp, lane);
+    else if (a.cp == 64) sc_epilogue_dispatch<64>(a, ctrl.c, tmem_base, warp, lane);
+    else if (a.cp == 48) sc_epilogue_dispatch<48>(a, ctrl.c, tmem_base, warp, lane);
+    else if (a.cp == 32) sc_epilogue_dispatch<32>(a, ctrl.c, tmem_base, warp, lane);
+    else sc_epilogue_dispatch<16>(a, ctrl.c, tmem_base, warp, lane);
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (kPair) ptx::cluster_sync_all();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    if (kPair) ptx::tmem_dealloc_2sm(tmem_base, kTmemCols); else ptx::tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+static int encode5(CUtensorMap* m, const void* base, bool f32, const cuuint64_t dims[5], const cuuint64_t strides[4],
+                   const cuuint32_t box[5], CUtensorMapSwizzle sw) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return S3D_ERR_CUDA; }
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims,
+                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(concat view) failed: %d", (int)r); return S3D_ERR_CUDA; }
+  return S3D_OK;
+}
+
+}  // namespace scatter
+}  // namespace s3d
+
+extern "C" int s3d_conv_concat_volume(const S3dConvParams* p_in, const void* feat, int feat_pitch, int feat_pad, const float* bias,
+                                      void* out, void* stream) {
+  using namespace s3d;
+  using namespace s3d::scatter;
+  if (!p_in || !feat || !out) { set_error("conv_concat_volume: null argument"); return S3D_ERR_INVALID; }
+  const S3dConvParams& p = *p_in;
+  const bool tf32 = p.in_dtype == S3D_DTYPE_F32;
+  const int esz = tf32 ? 4 : 2;
+  S3D_CHECK_ARG(p.w_nstack != nullptr, "conv_concat_volume: the layer needs host-packed rotations (w_nstack)");
+  S3D_CHECK_ARG(p.n_classes == 1 && p.ntaps == 27 && p.sx == 1 && p.sy == 1 && p.sz == 1 && p.omx == 1 && p.omy == 1 && p.omz == 1 &&
+                p.osC == 1 && !p.proj_w && p.oD == p.iD && p.oH == p.iH && p.oW == p.iW, "conv_concat_volume: not a stride-1 3x3x3 layer");
+  for (int t = 0; t < 27; ++t)
+    S3D_CHECK_ARG(p.dz[t] == t / 9 - 1 && p.dy[t] == (t % 9) / 3 - 1 && p.dx[t] == t % 3 - 1, "conv_concat_volume: tap order");
+  S3D_CHECK_ARG(p.N % 2 == 0 && p.Cin % 2 == 0, "conv_concat_volume: N = 2B volumes, Cin = 2C channels");
+  const int C = p.Cin / 2, B = p.N / 2, D = p.iD, h = p.iH, w = p.iW;
+  const int rb = C * esz;
+  S3D_CHECK_ARG(rb == 32 || rb == 64 || rb == 128, "conv_concat_volume: C * element size must be 32, 64 or 128 bytes");
+  S3D_CHECK_ARG(p.Cout <= 64 && p.Cout % 16 == 0, "conv_concat_volume: Cout");
+  S3D_CHECK_ARG(feat_pad >= D - 1 && feat_pitch >= w + 2 * feat_pad, "conv_concat_volume: feature rows need >= D-1 zero pixels on both sides");
+  S3D_CHECK_ARG((reinterpret_cast<uintptr_t>(feat) & 15) == 0, "conv_concat_volume: feat alignment");
+  S3D_CHECK_ARG(p.cout_store >= 1 && p.cout_store <= p.Cout, "conv_concat_volume: cout_store");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+  CcArgs ca;
+  memset(&ca, 0, sizeof(ca));
+  ScArgs& a = ca.a;
+  a.p = p;  a.bias = bias;  a.residual = nullptr;  a.out = out;
+  ca.n_half = B;  ca.D = D;
+  a.nchunks = 2;  a.row_bytes = rb;  a.kc = C;
+  a.chunk_stride = (kPlaneRows * rb + 1023) / 1024 * 1024;
+  a.slot_bytes = a.chunk_stride;                               // a slot holds ONE half (reference buffers / target ring)
+  a.cp = p.Cout;  a.tps = 1;
+  a.cols_x = ceil_div(w, kTX);  a.cols_y = ceil_div(h, kTY);
+  const int64_t total = (int64_t)p.N * a.cols_x * a.cols_y;
+  S3D_CHECK_ARG(total > 0 && total < (1ll << 31), "conv_concat_volume: column count out of range");
+  a.total_cols = (int)total;
+  int grid = num_sms();
+  a.pair = ((3 * a.cp / 2) % 8 == 0 && total >= 2 && grid >= 2 && getenv("S3D_SCATTER_NO_PAIR") == nullptr) ? 1 : 0;
+  if (a.pair) {
+    if ((int64_t)grid > total) grid = (int)((total + 1) / 2 * 2);
+    grid -= grid % 2;
+    a.ncols_max = (int)((total + grid - 1) / grid);
+  } else if ((int64_t)grid > total) grid = (int)total;
+  const int w_rows = a.pair ? 3 * a.cp / 2 : 3 * a.cp;
+  a.w_tx = 2 * w_rows * rb;                                   // one stage = one tap, both K chunks
+  a.w_bytes = (a.w_tx + 1023) / 1024 * 1024;
+  const int budget = 227 * 1024 - 1024 - 640;
+  int ring = 4;
+  while (ring > 2 && (2 + ring) * a.slot_bytes + 4 * a.w_bytes > budget) --ring;
+  a.ring = ring;
+  a.w_stages = (budget - (2 + a.ring) * a.slot_bytes) / a.w_bytes;
+  if (a.w_stages > kMaxW) a.w_stages = kMaxW;
+  S3D_CHECK_ARG(a.w_stages >= 2, "conv_concat_volume: not enough shared memory");
+  a.idesc = ptx::make_instr_desc(tf32 ? 2 : 1, a.pair ? 256 : 128, 3 * a.cp);
+  a.res_direct = 1;
+  {
+    const int oesz = p.out_dtype == S3D_DTYPE_BF16 ? 2 : 4;
+    const bool simple_act = p.act == S3D_ACT_NONE || p.act == S3D_ACT_RELU || p.act == S3D_ACT_LEAKY;
+    auto dense16 = [&](int64_t s_) { return (s_ * oesz) % 16 == 0; };
+    a.fast_store = simple_act && bias != nullptr && p.cout_store == p.Cout && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+                   dense16(p.osW) && dense16(p.osH) && dense16(p.osD) && dense16(p.osN) && p.osW < (1ll << 24);
+  }
+
+  const CUtensorMapSwizzle sw = rb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : rb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+  const uint8_t* fb = static_cast<const uint8_t*>(feat);
+  const cuuint64_t px = (cuuint64_t)C * esz, row = (cuuint64_t)feat_pitch * px, img = (cuuint64_t)h * row;
+  CUtensorMap map_ref, map_tl, map_tr, map_w;
+  {
+    // reference half: plain view of the real pixels, dims (C, X, Y, 1, 2B)
+    const cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)w, (cuuint64_t)h, 1, (cuuint64_t)p.N};
+    const cuuint64_t strides[4] = {px, row, img, img};
+    const cuuint32_t box[5] = {(cuuint32_t)C, kHX, kHY, 1, 1};
+    int rc = encode5(&map_ref, fb + (size_t)feat_pad * px, tf32, dims, strides, box, sw);
+    if (rc != S3D_OK) return rc;
+  }
+  {
+    // target halves: skewed views, dims (C, X, D, Y, B) with stride(X) == stride(D) == one pixel
+    const cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)w, (cuuint64_t)D, (cuuint64_t)h, (cuuint64_t)B};
+    const cuuint64_t strides[4] = {px, px, row, img};
+    const cuuint32_t box[5] = {(cuuint32_t)C, kHX, 1, kHY, 1};
+    // left-referenced volumes read the RIGHT images (feat[B..2B)) at x - d: coordinate (x, D-1-d) from a base D-1 pixels left
+    int rc = encode5(&map_tl, fb + (size_t)B * img + (size_t)(feat_pad - (D - 1)) * px, tf32, dims, strides, box, sw);
+    if (rc != S3D_OK) return rc;
+    // right-referenced volumes read the LEFT images (feat[0..B)) at x + d: coordinate (x, d)
+    rc = encode5(&map_tr, fb + (size_t)feat_pad * px, tf32, dims, strides, box, sw);
+    if (rc != S3D_OK) return rc;
+  }
+  int rc = encode_weight_map(&map_w, p.w_nstack, esz, tf32, p.Cin, 3 * a.cp, 36, C, w_rows, sw, 1);
+  if (rc != S3D_OK) return rc;
+
+  const int smem_bytes = (2 + a.ring) * a.slot_bytes + a.w_stages * a.w_bytes + 1024;
+  typedef void (*Kern)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, CcArgs);
+  const bool lean = a.pair && !tf32 && p.out_dtype == S3D_DTYPE_BF16 && a.fast_store && a.cp == 64 && p.act == S3D_ACT_RELU && rb == 64;
+  Kern kern = nullptr;
+  if (lean) kern = conv_scatter_concat_kernel<false, true, 2, true>;
+  else if (a.pair) {
+    kern = tf32 ? (rb == 128 ? conv_scatter_concat_kernel<true, true, 4, false> : rb == 64 ? conv_scatter_concat_kernel<true, true, 2, false>
+                                                                                          : conv_scatter_concat_kernel<true, true, 1, false>)
+                : (rb == 128 ? conv_scatter_concat_kernel<false, true, 4, false> : rb == 64 ? conv_scatter_concat_kernel<false, true, 2, false>
+                                                                                            : conv_scatter_concat_kernel<false, true, 1, false>);
+  } else {
+    kern = tf32 ? (rb == 128 ? conv_scatter_concat_kernel<true, false, 4, false> : rb == 64 ? conv_scatter_concat_kernel<true, false, 2, false>
+                                                                                           : conv_scatter_concat_kernel<true, false, 1, false>)
+                : (rb == 128 ? conv_scatter_concat_kernel<false, false, 4, false> : rb == 64 ? conv_scatter_concat_kernel<false, false, 2, false>
+                                                                                             : conv_scatter_concat_kernel<false, false, 1, false>);
+  }
+  S3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+  if (a.pair) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);  cfg.blockDim = dim3(kThreads);  cfg.dynamicSmemBytes = smem_bytes;  cfg.stream = st;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2;  attr.val.clusterDim.y = 1;  attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;  cfg.numAttrs = 1;
+    S3D_CUDA(cudaLaunchKernelEx(&cfg, kern, map_ref, map_tl, map_tr, map_w, ca));
+  } else {
+    kern<<<grid, kThreads, smem_bytes, st>>>(map_ref, map_tl, map_tr, map_w, ca);
+  }
+  S3D_LAUNCH_CHECK();
+  return S3D_OK;
+}

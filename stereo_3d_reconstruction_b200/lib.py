@@ -54,6 +54,7 @@ SIGNATURES = {
     's3d_pack_image': ([_vp, _vp, _f, _vp, _i, _i, _i, _i, _i, _vp], _i),
     's3d_pack_image_u8': ([_vp, _vp, _f, _f, _vp, _i, _i, _i, _i, _i, _vp], _i),
     's3d_conv_first': ([_vp, _i, _vp, _f, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp], _i),
+    's3d_conv_concat_volume': ([ctypes.POINTER(S3dConvParams), _vp, _i, _i, _vp, _vp, _vp], _i),
     's3d_cost_volume_concat': ([_vp, _vp, _i, _i, _i, _i, _i, _i, _vp], _i),
     's3d_soft_argmin': ([_vp, _vp, _i, _i, _i, _i, _f, _vp], _i),
     's3d_tap_gather_soft_argmin': ([_vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp], _i),

@@ -242,14 +242,29 @@ class _StereoBase(nn.Module):
         x = self._conv('enc2', x, out=self._bufo('e2', 'enc2', x))
         y = self._conv('enc3', x, out=self._bufo('e3', 'enc3', x))
         x = self._conv('enc4', y, residual=x, out=self._bufo('e4', 'enc4', y))
-        feat = self._conv('enc5', x, out=self._bufo('e5', 'enc5', x))
-        h, w = feat.shape[2], feat.shape[3]
+        h, w = x.shape[2], x.shape[3]
+        C = cfg.NETWORK.FEAT_CHANNELS
+        p5, p0 = self._packed['enc5'], self._packed.get('dres0a')
+        fuse_volume = (cfg.NETWORK.COST_VOLUME == 'concat' and self.precision in ('bf16', 'tf32') and p5.cout_pad == C and
+                       isinstance(p0, PackedConv) and p0.weight_ns is not None and C * x.element_size() in (32, 64) and
+                       os.environ.get('S3D_NO_CONCAT_FUSE') is None and os.environ.get('S3D_NO_SCATTER') is None)
+        if fuse_volume:
+            # features go into rows with D zero pixels on both sides: the fused cost-volume + dres0a kernel reads the shifted
+            # target view of every disparity plane straight out of them (csrc/conv_scatter_concat.cu), no volume is written
+            pad, P = D, w + 2 * D
+            featp = self._buf('featp', (2 * B, 1, h, P, C), dt, zero=True)
+            self._conv('enc5', x, out=featp, out_view=(pad * C, (h * P * C, h * P * C, P * C, C)), cout_store=C)
+            feat = None
+        else:
+            feat = self._conv('enc5', x, out=self._bufo('e5', 'enc5', x))
         disp_q = self._buf('disp_q', (2 * B, h, w), torch.float32)
         if cfg.NETWORK.COST_VOLUME == 'concat':
-            C = cfg.NETWORK.FEAT_CHANNELS
-            assert feat.shape[-1] == C, 'FEAT_CHANNELS must be a multiple of 16'
-            vol = ops.cost_volume_concat(feat, B, D, out=self._buf('vol', (2 * B, D, h, w, 2 * C), dt))
-            a = self._conv('dres0a', vol, out=self._bufo('a0', 'dres0a', vol))
+            if fuse_volume:
+                a = ops.conv_concat_volume(p0, featp, B, D, pad, out=self._buf('a0', (2 * B, D, h, w, p0.cout_pad), dt))
+            else:
+                assert feat.shape[-1] == C, 'FEAT_CHANNELS must be a multiple of 16'
+                vol = ops.cost_volume_concat(feat, B, D, out=self._buf('vol', (2 * B, D, h, w, 2 * C), dt))
+                a = self._conv('dres0a', vol, out=self._bufo('a0', 'dres0a', vol))
             a = self._conv('dres0b', a, out=self._bufo('a1', 'dres0b', a))
             y = self._conv('dres1a', a, out=self._bufo('a2', 'dres1a', a))
             a = self._conv('dres1b', y, residual=a, out=self._bufo('a3', 'dres1b', y))

@@ -156,6 +156,28 @@ def conv_first(img, pc, disp=None, disp_scale=1.0, out=None):
     return out
 
 
+def conv_concat_volume(pc, featp, B, D, pad, out=None):
+    """Concat cost volume + the 3x3x3 conv `pc` (PackedConv over 2C channels) in one kernel, the volume never written.
+    featp: [2B,1,h,pitch,C] feature maps stored with `pad` >= D-1 ZERO pixels on both sides of every row (real pixels in
+    columns pad .. pitch-pad-1), left images first.  -> [2B,D,h,w,cout_pad].  include/s3d.h, s3d_conv_concat_volume."""
+    import ctypes
+    _chk(featp, out)
+    n2, one, h, pitch, C = featp.shape
+    assert n2 == 2 * B and one == 1 and featp.is_contiguous() and pc.cin_pad == 2 * C and pad >= D - 1
+    w = pitch - 2 * pad
+    assert w > 0
+    if out is None:
+        out = torch.empty((2 * B, D, h, w, pc.cout_pad), dtype=featp.dtype, device=featp.device)
+    assert out.is_contiguous() and out.shape == (2 * B, D, h, w, pc.cout_pad)
+    Co = pc.cout_pad
+    p = pc.params(2 * B, D, h, w, (D * h * w * Co, h * w * Co, w * Co, Co), _code(out), Co)
+    rc = _lib.load().s3d_conv_concat_volume(ctypes.byref(p), featp.data_ptr(), pitch, pad, pc.bias.data_ptr(), out.data_ptr(),
+                                            _stream())
+    _lib.check(rc, 's3d_conv_concat_volume')
+    _lib.count_launch()
+    return out
+
+
 def cls_soft_argmin(x, w_taps, sign=-1.0, out=None):
     """x bf16 [N,D,h,w,C] (aggregated volume), w_taps bf16 [32,C] (27 classifier taps) -> disp fp32 [N,h,w]: the Cout=1
     3x3x3 classifier and the soft-argmin in one pass (include/s3d.h, s3d_cls_soft_argmin)."""

@@ -159,6 +159,46 @@ def test_conv3d_plane_scatter_shapes(monkeypatch, knob, prec, N, cin, cout, D, H
     _check(pc, x, fn(ref), prec, cout, **kw)
 
 
+@pytest.mark.parametrize('knob', [None, 'S3D_SCATTER_NO_PAIR'])
+@pytest.mark.parametrize('prec,B,C,cout,D,h,w', [
+    ('bf16', 2, 32, 64, 8, 16, 16),       # the network's shape (64-byte halves, lean kernel)
+    ('bf16', 1, 16, 32, 5, 9, 13),        # ragged patches, 32-byte halves
+    ('bf16', 3, 32, 64, 32, 40, 64),      # D = 32 planes, two patch rows
+    ('bf16', 1, 64, 48, 3, 33, 10),       # 128-byte halves, 48 output channels
+    ('bf16', 2, 32, 64, 1, 8, 8),         # a single disparity plane
+    ('tf32', 1, 32, 64, 4, 20, 12),       # fp32 storage: 128-byte halves
+    ('tf32', 2, 16, 32, 6, 12, 24),
+])
+def test_conv_concat_volume_fused_is_bit_identical(monkeypatch, knob, prec, B, C, cout, D, h, w):
+    """conv_scatter_concat.cu: cost volume (never written) + 3x3x3 conv == s3d_cost_volume_concat + the same conv, bit for
+    bit (same MMA sequence), and == the oracle's volume + conv3d within the engine's tolerance."""
+    from stereo_3d_reconstruction_b200 import ops
+    from oracle import models as O
+    dt = torch.bfloat16 if prec == 'bf16' else torch.float32
+    if knob:
+        if C * (2 if prec == 'bf16' else 4) == 128:
+            pytest.skip('128-byte halves need CTA pairs (a single CTA cannot hold two weight stages of 36-48 KB)')
+        monkeypatch.setenv(knob, '1')
+    torch.manual_seed(9)
+    conv = nn.Conv3d(2 * C, cout, 3, 1, 1, bias=True)
+    pc = PackedConv.from_conv(conv, None, lib.ACT_RELU, _code(prec), 'cuda')
+    f = torch.randn(2 * B, C, h, w)
+    feat = to_cl(f).to(dt).cuda()                                         # [2B,1,h,w,C]
+    pad, P = D, w + 2 * D
+    featp = torch.zeros(2 * B, 1, h, P, C, dtype=dt, device='cuda')
+    featp[:, :, :, pad:pad + w] = feat
+    got = ops.conv_concat_volume(pc, featp, B, D, pad)
+    vol = ops.cost_volume_concat(feat, B, D)
+    two = pc(vol, engine='igemm')
+    assert got.shape == two.shape == (2 * B, D, h, w, pc.cout_pad)
+    assert torch.equal(got, two)
+    fr = feat.float().cpu()[:, 0].permute(0, 3, 1, 2)                     # rounded features, NCHW
+    ref_vol = torch.cat([O.build_concat_volume(fr[:B], fr[B:], D, -1), O.build_concat_volume(fr[B:], fr[:B], D, +1)], 0)
+    ref = to_cl(F.relu(conv(ref_vol)))
+    err = (got.float().cpu()[..., :cout] - ref).abs().max().item()
+    assert err <= TOL[prec] * (ref.abs().max().item() + 1e-6)
+
+
 @pytest.mark.parametrize('D,H,W', [(4, 16, 16), (5, 37, 19), (2, 64, 64)])
 def test_conv3d_residual_on_tensor_core(D, H, W, monkeypatch):
     monkeypatch.setenv('S3D_NO_SCATTER', '1')           # the z-stacked kernel is the fallback of conv_scatter.cu now
