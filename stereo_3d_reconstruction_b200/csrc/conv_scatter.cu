@@ -68,7 +68,8 @@ int conv_scatter_launch(const S3dConvParams* p_in, const void* in, const float* 
   S3D_CHECK_ARG(a.w_stages >= 2, "scatter: not enough shared memory for the weight ring");   // 2 works (no prefetch), >= 3 is the norm
   a.idesc = ptx::make_instr_desc(tf32 ? 2 : 1, a.pair ? 256 : 128, 3 * a.cp);
   // residual: each thread reads its own pixel's 128 bytes directly (measured 2.58 vs 2.71 ms on the residual layer against
-  // coalesced group loads + a second shuffle transpose -- with CTA pairs the L1 data pipe has room for the scattered reads)
+  // coalesced group loads + a second shuffle transpose -- with CTA pairs the L1 data pipe has room for the scattered reads;
+  // staging the residual tiles in shared memory by TMA was tried too: 2.66 vs 2.55 ms, it costs three weight stages)
   a.res_direct = getenv("S3D_SCATTER_RES_TRANSPOSE") == nullptr;
   {
     const int oesz = p.out_dtype == S3D_DTYPE_BF16 ? 2 : 4;

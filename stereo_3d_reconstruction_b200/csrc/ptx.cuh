@@ -54,7 +54,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) {
+    if (++spins > (1u << 23)) {
       printf("s3d: mbarrier wait timed out (block %d thread %d bar %p parity %u)\n", blockIdx.x,
              threadIdx.x, (void*)bar, parity);
       __trap();
@@ -115,7 +115,7 @@ __device__ __forceinline__ bool mbar_test_wait_u32(uint32_t bar, uint32_t parity
 __device__ __forceinline__ void mbar_wait_u32(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait_u32(bar, parity)) {
-    if (++spins > (1u << 26)) {
+    if (++spins > (1u << 23)) {
       printf("s3d: mbarrier wait timed out (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
       __trap();
     }
