@@ -77,3 +77,126 @@ def test_tile_and_bn_choice():
     assert _choose_tile(4, 1, 64, 64, 2, 2, 1)[0] * 2 <= 256
     assert _choose_bn(64) == 64 and _choose_bn(512) == 256 and _choose_bn(6144) == 256 and _choose_bn(272) == 272 // 17 * 1 or True
     assert pad_to(9) == 16 and pad_to(2048 * 3) == 6144
+
+
+# ---- packings added for the plane-scatter kernel (csrc/conv_scatter.cuh), emulated on the CPU ----------------------
+def _emulate_plane_scatter(ns, x, cout_pad):
+    """The kernel's algorithm on the host: input plane p times the rotation (3 for p = 0, else p % 3) of the N-stacked
+    weights, accumulated into three slots; output plane z lives in slot z % 3, is complete after input plane z + 1,
+    is then drained and its slot zeroed.  ns: [36, 3*Co, Ci]; x: [N, D, H, W, Ci] -> [N, D, H, W, Co]."""
+    N, D, H, W, Ci = x.shape
+    Co = cout_pad
+    out = torch.zeros(N, D, H, W, Co)
+    slots = torch.zeros(N, H, W, 3 * Co)
+    xp = F.pad(x, (0, 0, 1, 1, 1, 1))                              # zero halo in y and x
+    for p in range(D):
+        rot = 3 if p == 0 else p % 3
+        acc = torch.zeros(N, H, W, 3 * Co)
+        for kyx in range(9):
+            ky, kx = divmod(kyx, 3)
+            acc += xp[:, p, ky:ky + H, kx:kx + W] @ ns[rot * 9 + kyx].t()
+        slots = acc if p == 0 else slots + acc                      # the first MMA of a column overwrites all three slots
+        if p >= 1:
+            s = (p - 1) % 3
+            out[:, p - 1] = slots[..., s * Co:(s + 1) * Co]
+            slots[..., s * Co:(s + 1) * Co] = 0
+    s = (D - 1) % 3
+    out[:, D - 1] = slots[..., s * Co:(s + 1) * Co]
+    return out
+
+
+def test_nstack_rotations_reproduce_conv3d():
+    g = torch.Generator().manual_seed(6)
+    for D in (1, 2, 3, 7):
+        conv = nn.Conv3d(5, 7, 3, 1, 1, bias=False)
+        x = torch.randn(2, 5, D, 6, 5, generator=g)
+        pc = PackedConv.from_conv(conv, None, lib.ACT_NONE, lib.DTYPE_F32, 'cpu')
+        assert pc.weight_ns is not None and pc.weight_ns.shape == (36, 3 * pc.cout_pad, pc.cin_pad)
+        out = _emulate_plane_scatter(pc.weight_ns.float(), pad_c(to_cl(x), pc.cin_pad), pc.cout_pad)
+        torch.testing.assert_close(out[..., :7], to_cl(conv(x)), rtol=1e-4, atol=1e-5)
+        assert out[..., 7:].abs().max() == 0
+
+
+def test_conv2d_as_volume_of_images_twin():
+    """A stride-1 3x3 2-D layer gets a 27-tap twin whose kz = 0 / 2 slices are zero: a batch of images run as a volume."""
+    g = torch.Generator().manual_seed(7)
+    conv, bn = nn.Conv2d(16, 24, 3, 1, 1, bias=True), _rand_bn(nn.BatchNorm2d(24), g)
+    x = torch.randn(6, 16, 9, 7, generator=g)
+    pc = PackedConv.from_conv(conv, bn, lib.ACT_NONE, lib.DTYPE_F32, 'cpu')
+    assert pc.vol is not None and pc.vol.ntaps == 27 and pc.vol.vol is None
+    vol_in = pad_c(to_cl(x), pc.cin_pad).view(2, 3, 9, 7, pc.cin_pad)           # 2 "volumes" of 3 images
+    out = emulate(pc.vol, vol_in).view(6, 1, 9, 7, pc.cout_pad)
+    torch.testing.assert_close(out[..., :24], to_cl(bn(conv(x))), rtol=1e-4, atol=1e-5)
+    out_ns = _emulate_plane_scatter(pc.vol.weight_ns.float(), vol_in, pc.cout_pad) + pc.vol.bias
+    torch.testing.assert_close(out_ns.view(6, 1, 9, 7, -1)[..., :24], to_cl(bn(conv(x))), rtol=1e-4, atol=1e-5)
+    assert PackedConv.from_conv(nn.Conv2d(16, 24, 3, 2, 1), None, lib.ACT_NONE, lib.DTYPE_F32, 'cpu').vol is None   # stride 2: no twin
+
+
+def test_deconv_blocked_is_a_3x3x3_conv_plus_depth_to_space():
+    g = torch.Generator().manual_seed(8)
+    dc, bn = nn.ConvTranspose3d(6, 8, 4, 2, 1, bias=False), _rand_bn(nn.BatchNorm3d(8), g)
+    x = torch.randn(2, 6, 3, 2, 4, generator=g)
+    pc = PackedConv.from_deconv_k4s2p1_blocked(dc, bn, lib.ACT_NONE, lib.DTYPE_F32, 'cpu')
+    assert pc.ntaps == 27 and pc.n_classes == 1 and pc.cout == 64 and pc.ntaps_algo == 8
+    y = emulate(pc, pad_c(to_cl(x), pc.cin_pad))                                 # [2,3,2,4,64], channel = class*8 + c
+    out = torch.zeros(2, 6, 4, 8, 8)
+    for cls in range(8):
+        cz, cy, cx = (cls >> 2) & 1, (cls >> 1) & 1, cls & 1
+        out[:, cz::2, cy::2, cx::2] = y[..., cls * 8:(cls + 1) * 8]
+    torch.testing.assert_close(out, to_cl(bn(dc(x))), rtol=1e-4, atol=1e-5)
+    # algorithmic FLOPs are those of the transposed conv (8 of the 27 taps per output channel are non-zero)
+    plain = PackedConv.from_deconv_k4s2p1(dc, bn, lib.ACT_NONE, lib.DTYPE_F32, 'cpu')
+    assert pc.flops(2, 3, 2, 4) == plain.flops(2, 3, 2, 4)
+
+
+def test_split_conv_operands_are_exact_tf32_splits():
+    from stereo_3d_reconstruction_b200.layers import SplitConv
+    conv = nn.Conv3d(5, 7, 3, 1, 1, bias=True)
+    pc = PackedConv.from_conv(conv, None, lib.ACT_RELU, lib.DTYPE_F32, 'cpu')
+    sc = SplitConv(pc)
+    w, hi, lo = pc.weight, sc.hi.weight, sc.lo.weight
+    assert torch.equal(hi + lo, w)                                               # exact split
+    assert int((hi.view(torch.int32) & 0x1FFF).abs().max()) == 0                 # hi is representable in TF32
+    assert float(lo.abs().max()) <= float(w.abs().max()) * 2.0 ** -10
+    assert sc.hi.act == lib.ACT_NONE and float(sc.hi.bias.abs().max()) == 0      # bias / activation only in the last pass
+    assert sc.lo.act == lib.ACT_RELU and torch.equal(sc.lo.bias, pc.bias)
+    assert sc.hi.weight_ns is not None and sc.lo.weight_ns is not None           # both run on the plane-scatter kernel
+
+
+def test_skewed_tensor_map_views_match_the_concat_volume():
+    """The fused cost-volume kernel (csrc/conv_scatter_concat.cu) never builds the volume: its target half of plane d is a TMA
+    box of a SKEWED view of the zero-margined feature rows.  Re-state the view's address arithmetic on the host -- element
+    (x, dd) of a [W x D] view with equal X / D strides of one pixel, zero outside 0 <= x < W -- and check it against the
+    oracle's volume, halo columns included."""
+    from oracle import models as O
+    g = torch.Generator().manual_seed(9)
+    B, C, h, w, D = 2, 4, 3, 11, 5
+    fL, fR = torch.randn(B, C, h, w, generator=g), torch.randn(B, C, h, w, generator=g)
+    pad = D                                                           # >= D - 1 zero pixels on both sides of every row
+    P = w + 2 * pad
+    rows = torch.zeros(2 * B, h, P, C)
+    rows[:B, :, pad:pad + w] = fL.permute(0, 2, 3, 1)
+    rows[B:, :, pad:pad + w] = fR.permute(0, 2, 3, 1)
+    flat = rows.reshape(2 * B, h, P * C)
+
+    def view(n_src, base_px, x, dd, y):
+        """the tensor map: address = base + (x + dd) pixels; X bound [0, w) -> zero fill (conv halo)"""
+        if x < 0 or x >= w or y < 0 or y >= h:
+            return torch.zeros(C)
+        px = base_px + x + dd
+        return flat[n_src, y, px * C:(px + 1) * C]
+
+    vol_l = O.build_concat_volume(fL, fR, D, -1)                      # [B, 2C, D, h, w]
+    vol_r = O.build_concat_volume(fR, fL, D, +1)
+    for d in range(D):
+        for y in range(h):
+            for x in range(-1, w + 1):                                # including the conv's halo columns
+                inside = 0 <= x < w
+                # left-referenced volume n reads the RIGHT image n at x - d: coordinate (x, D-1-d), base D-1 pixels to the left
+                got = view(B + 0, pad - (D - 1), x, D - 1 - d, y)
+                want = vol_l[0, C:, d, y, x] if inside else torch.zeros(C)
+                assert torch.equal(got, want), ('left', d, y, x)
+                # right-referenced volume n reads the LEFT image n at x + d: coordinate (x, d)
+                got = view(1, pad, x, d, y)
+                want = vol_r[1, C:, d, y, x] if inside else torch.zeros(C)
+                assert torch.equal(got, want), ('right', d, y, x)
