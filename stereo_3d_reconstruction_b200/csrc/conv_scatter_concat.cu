@@ -288,6 +288,7 @@ extern "C" int s3d_conv_concat_volume(const S3dConvParams* p_in, const void* fea
   const int C = p.Cin / 2, B = p.N / 2, D = p.iD, h = p.iH, w = p.iW;
   const int rb = C * esz;
   S3D_CHECK_ARG(rb == 32 || rb == 64 || rb == 128, "conv_concat_volume: C * element size must be 32, 64 or 128 bytes");
+  S3D_CHECK_ARG(!(tf32 && rb == 32), "conv_concat_volume: fp32 features need C >= 16");
   S3D_CHECK_ARG(p.Cout <= 64 && p.Cout % 16 == 0, "conv_concat_volume: Cout");
   S3D_CHECK_ARG(feat_pad >= D - 1 && feat_pitch >= w + 2 * feat_pad, "conv_concat_volume: feature rows need >= D-1 zero pixels on both sides");
   S3D_CHECK_ARG((reinterpret_cast<uintptr_t>(feat) & 15) == 0, "conv_concat_volume: feat alignment");
@@ -323,7 +324,7 @@ extern "C" int s3d_conv_concat_volume(const S3dConvParams* p_in, const void* fea
   a.ring = ring;
   a.w_stages = (budget - (2 + a.ring) * a.slot_bytes) / a.w_bytes;
   if (a.w_stages > kMaxW) a.w_stages = kMaxW;
-  S3D_CHECK_ARG(a.w_stages >= 2, "conv_concat_volume: not enough shared memory");
+  S3D_CHECK_ARG(a.w_stages >= 2 && (a.pair || rb < 128), "conv_concat_volume: not enough shared memory (128-byte halves need CTA pairs)");
   a.idesc = ptx::make_instr_desc(tf32 ? 2 : 1, a.pair ? 256 : 128, 3 * a.cp);
   a.res_direct = 1;
   {
@@ -367,15 +368,13 @@ extern "C" int s3d_conv_concat_volume(const S3dConvParams* p_in, const void* fea
   Kern kern = nullptr;
   if (lean) kern = conv_scatter_concat_kernel<false, true, 2, true>;
   else if (a.pair) {
-    kern = tf32 ? (rb == 128 ? conv_scatter_concat_kernel<true, true, 4, false> : rb == 64 ? conv_scatter_concat_kernel<true, true, 2, false>
-                                                                                          : conv_scatter_concat_kernel<true, true, 1, false>)
+    kern = tf32 ? (rb == 128 ? conv_scatter_concat_kernel<true, true, 4, false> : conv_scatter_concat_kernel<true, true, 2, false>)
                 : (rb == 128 ? conv_scatter_concat_kernel<false, true, 4, false> : rb == 64 ? conv_scatter_concat_kernel<false, true, 2, false>
                                                                                             : conv_scatter_concat_kernel<false, true, 1, false>);
   } else {
-    kern = tf32 ? (rb == 128 ? conv_scatter_concat_kernel<true, false, 4, false> : rb == 64 ? conv_scatter_concat_kernel<true, false, 2, false>
-                                                                                           : conv_scatter_concat_kernel<true, false, 1, false>)
-                : (rb == 128 ? conv_scatter_concat_kernel<false, false, 4, false> : rb == 64 ? conv_scatter_concat_kernel<false, false, 2, false>
-                                                                                             : conv_scatter_concat_kernel<false, false, 1, false>);
+    // a single CTA cannot hold two weight stages of 128-byte halves (checked above through w_stages), so no kPer = 4 here
+    kern = tf32 ? conv_scatter_concat_kernel<true, false, 2, false>
+                : (rb == 64 ? conv_scatter_concat_kernel<false, false, 2, false> : conv_scatter_concat_kernel<false, false, 1, false>);
   }
   S3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   if (a.pair) {
