@@ -111,18 +111,25 @@ def test_graphed_forward_replays_bit_identical(name):
     assert not torch.equal(outs[0], outs[1])                 # different inputs did produce different outputs
 
 
-def test_odd_input_size_fp32():
-    cfg = small_cfg(NETWORK__PRECISION='fp32', CONST__IMG_H=70, CONST__IMG_W=50)
+@pytest.mark.parametrize('prec', ['fp32', 'tf32x3', 'bf16'])
+@pytest.mark.parametrize('H,W,B', [(70, 50, 2), (37, 101, 1)])
+def test_odd_input_sizes(prec, H, W, B):
+    """Sizes that are multiples of nothing: ragged patches in every kernel (first-layer pairs of pixels, plane-scatter
+    tiles, fused cost volume margins, fused classifier halo), odd batch."""
+    cfg = small_cfg(NETWORK__PRECISION=prec, CONST__IMG_H=H, CONST__IMG_W=W)
     oracle = O.make_model('Stereo2Voxel', cfg, seed=1)
     model = M.build_model('Stereo2Voxel', cfg)
     model.load_state_dict(oracle.state_dict())
     model.cuda().pack()
-    left, right = _pair(cfg, 2)
+    left, right = _pair(cfg, B)
     with torch.no_grad():
-        rdl, _, rvox = oracle(left, right)
-        dl, _, vox = model(left.cuda(), right.cuda())
-    assert (dl.cpu() - rdl).abs().max().item() <= 1e-4 * rdl.abs().max().item()
-    assert (vox.cpu() - rvox).abs().max().item() <= 1e-4
+        rdl, rdr, rvox = oracle(left, right)
+        dl, dr, vox = model(left.cuda(), right.cuda())
+    td, tv = TOLS[prec]
+    assert dl.shape == rdl.shape and vox.shape == rvox.shape
+    assert (dl.cpu() - rdl).abs().max().item() <= td * rdl.abs().max().item()
+    assert (dr.cpu() - rdr).abs().max().item() <= td * rdl.abs().max().item()
+    assert (vox.cpu() - rvox).abs().max().item() <= tv
 
 
 def test_cpu_inputs_fail_loudly():
