@@ -339,6 +339,9 @@ def run_ours(args):
         'roofline': {'bound': 'tensor', 'kernel': 'conv_scatter_kernel (3x3x3 64->64 cost aggregation, 4 of the 6 aggregation layers)',
                      'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,
                      'peak_source': '%s bf16_tflops_sustained (kernel timed inside a long step)' % pk['source'],
+                     # the same against the BURST cuBLAS figure: the kernel runs at the tensor pipe's ceiling for the clock the
+                     # power cap allows (ncu: 96.7 % tensor-pipe active) and draws less than cuBLAS, hence frac > 1 above
+                     'peak_burst': pk['bf16_tflops'], 'frac_of_burst': achieved / pk['bf16_tflops'],
                      'ms_per_launch': dom, 'flops_per_launch': flops, 'share_of_step': dom * len(dom_layers) / (ms / args.steps),
                      # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel at this exact shape,
                      # from the round-1 `ncu --set full` capture (profiles/r1_ncu_summary.md); algorithmic bytes = 4.295e9
