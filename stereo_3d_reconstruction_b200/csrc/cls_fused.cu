@@ -153,7 +153,7 @@ cls_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     const int g = threadIdx.x - 128;               // output pixel of this thread inside the patch
     const int yl = g >> 3, xl = g & 7;
     const uint32_t bar_af = ptx::smem_u32(&ctrl.acc_full[0]), bar_ae = ptx::smem_u32(&ctrl.acc_empty[0]);
-    const int tg_off = yl * kHX + xl;              // tap (ky,kx) of this pixel: Tg[tap * kTS + ky * kHX + kx]
+    const float* Tg = T + yl * kHX + xl;           // tap (ky,kx) of this pixel: Tg[tap * kTS + ky * kHX + kx]
     int buf = 0;  uint32_t aphase = 0;
     for (int ci = 0; ci < ncols; ++ci) {
       const Col c = decode_col(a, blockIdx.x + ci * gridDim.x);
@@ -181,22 +181,16 @@ cls_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive_u32(bar_ae + 8 * buf);
-#ifdef S3D_CLS_DOUBLE
-        float* Tb = T + buf * (kTaps * kTS);
-#else
-        float* Tb = T;
         // everyone has finished gathering the previous plane before its projections are overwritten
         asm volatile("bar.sync 1, 256;" ::: "memory");
-#endif
         const int r0 = tile0 * 128 + q * 32 + lane, r1 = tile1 * 128 + q * 32 + lane;
 #pragma unroll
-        for (int tp = 0; tp < kTaps; ++tp) Tb[tp * kTS + r0] = __uint_as_float(v0[tp >> 4][tp & 15]);
+        for (int tp = 0; tp < kTaps; ++tp) T[tp * kTS + r0] = __uint_as_float(v0[tp >> 4][tp & 15]);
         if (tile1 < kTiles && r1 < kRows) {
 #pragma unroll
-          for (int tp = 0; tp < kTaps; ++tp) Tb[tp * kTS + r1] = __uint_as_float(v1[tp >> 4][tp & 15]);
+          for (int tp = 0; tp < kTaps; ++tp) T[tp * kTS + r1] = __uint_as_float(v1[tp >> 4][tp & 15]);
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
-        const float* Tg = Tb + tg_off;
         float a0 = 0.f, a1 = 0.f, a2 = 0.f;        // contributions of input plane p through kz = 2, 1, 0
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
@@ -243,11 +237,7 @@ extern "C" int s3d_cls_soft_argmin(const void* x, const void* w_taps, float* dis
   a.disp = disp;  a.sign = sign;  a.N = N;  a.D = D;  a.h = h;  a.w = w;
   a.row_bytes = C * 2;
   a.slot_bytes = kTiles * 128 * a.row_bytes;                // 384 rows; multiple of 1024
-#ifdef S3D_CLS_DOUBLE
-  const int fixed = 4096 + 2 * kTaps * kTS * 4 + 1024;
-#else
   const int fixed = 4096 + kTaps * kTS * 4 + 1024;          // weights + projection buffer + alignment slack
-#endif
   int ring = (227 * 1024 - 512 - fixed) / a.slot_bytes;
   if (ring > kMaxRing) ring = kMaxRing;
   S3D_CHECK_ARG(ring >= 2, "cls_soft_argmin: not enough shared memory");
