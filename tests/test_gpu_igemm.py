@@ -166,6 +166,7 @@ def test_conv3d_plane_scatter_shapes(monkeypatch, knob, prec, N, cin, cout, D, H
     ('bf16', 3, 32, 64, 32, 40, 64),      # D = 32 planes, two patch rows
     ('bf16', 1, 64, 48, 3, 33, 10),       # 128-byte halves, 48 output channels
     ('bf16', 2, 32, 64, 1, 8, 8),         # a single disparity plane
+    ('bf16', 1, 32, 64, 12, 8, 8),        # more disparities than pixels in a row: planes d >= w have an all-zero target half
     ('tf32', 1, 32, 64, 4, 20, 12),       # fp32 storage: 128-byte halves
     ('tf32', 2, 16, 32, 6, 12, 24),
 ])
