@@ -150,8 +150,11 @@ cls_fused_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     // ================= projections -> shared memory -> gather + online softmax =================
     const int ew = warp - 4;                       // 0..7; TMEM lane quarter = warp % 4 = ew % 4
     const int q = ew & 3;
-    const int g = threadIdx.x - 128;               // output pixel of this thread inside the patch
-    const int yl = g >> 3, xl = g & 7;
+    // output pixel of this thread inside the patch.  A warp takes rows b, b+4, b+8, b+12 (not 4 consecutive rows): a tap
+    // line of the projection buffer has a pitch of 10 floats, so rows 4 apart start 8 banks apart and the warp's 27 gather
+    // loads are conflict-free (4 consecutive rows overlap on 6 banks: 2 wavefronts per load)
+    const int xl = lane & 7;
+    const int yl = (ew & 3) + 16 * (ew >> 2) + 4 * (lane >> 3);
     const uint32_t bar_af = ptx::smem_u32(&ctrl.acc_full[0]), bar_ae = ptx::smem_u32(&ctrl.acc_empty[0]);
     const float* Tg = T + yl * kHX + xl;           // tap (ky,kx) of this pixel: Tg[tap * kTS + ky * kHX + kx]
     int buf = 0;  uint32_t aphase = 0;
