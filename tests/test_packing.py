@@ -200,3 +200,33 @@ def test_skewed_tensor_map_views_match_the_concat_volume():
                 got = view(1, pad, x, d, y)
                 want = vol_r[1, C:, d, y, x] if inside else torch.zeros(C)
                 assert torch.equal(got, want), ('right', d, y, x)
+
+
+def test_tf32x3_three_pass_algebra_reaches_fp32_accuracy():
+    """SplitConv's claim, checked on the CPU: with every MMA operand truncated to TF32 (10 mantissa bits), the single pass
+    errs at ~1e-3 while hi*hi + lo*hi + hi*lo (operands split exactly, fp32 accumulation) reproduces the fp64 conv to ~1e-6."""
+    from stereo_3d_reconstruction_b200.layers import SplitConv
+    g = torch.Generator().manual_seed(10)
+    conv = nn.Conv3d(16, 16, 3, 1, 1, bias=True)
+    x = torch.randn(1, 16, 4, 6, 5, generator=g)
+    ref = to_cl(F.conv3d(x.double(), conv.weight.double(), conv.bias.double(), padding=1)).float()
+    pc = PackedConv.from_conv(conv, None, lib.ACT_NONE, lib.DTYPE_F32, 'cpu')
+    sc = SplitConv(pc)
+
+    def tf32(t):                                                    # what a kind::tf32 MMA keeps of an fp32 operand
+        return (t.view(torch.int32) & -8192).view(torch.float32)
+
+    def mma_pass(p, xin):                                           # emulate() with TF32-truncated operands, fp32 accumulate
+        q = p.derive(tf32(p._ctor[0]), p._ctor[1], lib.ACT_NONE)
+        return emulate(q, tf32(xin))
+
+    xc = pad_c(to_cl(x), pc.cin_pad)
+    x_hi = tf32(xc)
+    x_lo = xc - x_hi
+    one = mma_pass(pc, xc)
+    three = mma_pass(sc.hi, x_hi) + (mma_pass(sc.hi, x_lo) - sc.hi.bias) + (mma_pass(sc.lo, x_hi))
+    scale = ref.abs().max().item()
+    e1 = (one[..., :16] - ref).abs().max().item() / scale
+    e3 = (three[..., :16] - ref).abs().max().item() / scale
+    assert 1e-5 < e1 < 5e-3, e1                                     # single-pass TF32: ~1e-3
+    assert e3 < 5e-6, e3                                            # three passes: fp32-level
