@@ -10,6 +10,16 @@
 namespace s3d {
 namespace {
 
+// Packed fp32 FMA (sm_100 FFMA2): two lanes per instruction -- this kernel is bound by FMA issue slots.
+__device__ __forceinline__ void ffma2(float& d0, float& d1, float x, float w0, float w1) {
+  unsigned long long rd, ra, rb, rc;
+  asm("mov.b64 %0, {%1, %1};" : "=l"(ra) : "f"(x));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(w0), "f"(w1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(d0), "f"(d1));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(rd));
+}
+
 template <int CO, int CIN, typename TW, typename TOut, bool kU8>
 __global__ void __launch_bounds__(128)
 conv_first_kernel(const void* __restrict__ img_, const float* __restrict__ disp, float disp_scale, float img_scale,
@@ -68,10 +78,10 @@ conv_first_kernel(const void* __restrict__ img_, const float* __restrict__ disp,
 #pragma unroll
           for (int c4 = 0; c4 < CO / 4; ++c4) {
             const float4 q = w4[c4];
-            acc[0][4 * c4] = fmaf(x0, q.x, acc[0][4 * c4]);          acc[0][4 * c4 + 1] = fmaf(x0, q.y, acc[0][4 * c4 + 1]);
-            acc[0][4 * c4 + 2] = fmaf(x0, q.z, acc[0][4 * c4 + 2]);  acc[0][4 * c4 + 3] = fmaf(x0, q.w, acc[0][4 * c4 + 3]);
-            acc[1][4 * c4] = fmaf(x1, q.x, acc[1][4 * c4]);          acc[1][4 * c4 + 1] = fmaf(x1, q.y, acc[1][4 * c4 + 1]);
-            acc[1][4 * c4 + 2] = fmaf(x1, q.z, acc[1][4 * c4 + 2]);  acc[1][4 * c4 + 3] = fmaf(x1, q.w, acc[1][4 * c4 + 3]);
+            ffma2(acc[0][4 * c4], acc[0][4 * c4 + 1], x0, q.x, q.y);
+            ffma2(acc[0][4 * c4 + 2], acc[0][4 * c4 + 3], x0, q.z, q.w);
+            ffma2(acc[1][4 * c4], acc[1][4 * c4 + 1], x1, q.x, q.y);
+            ffma2(acc[1][4 * c4 + 2], acc[1][4 * c4 + 3], x1, q.z, q.w);
           }
         }
       }
