@@ -39,6 +39,13 @@ extern "C" {
 
 #define S3D_DTYPE_F32   0
 #define S3D_DTYPE_BF16  1
+/* Split bf16 pair ('bf16x3' precision mode): a value v is stored as hi = bf16(v) and lo = bf16(v - hi), v ~= hi + lo to
+ * 2^-17 relative.  A tensor with C logical channels has 2*C bf16 channels per position, [hi(C) | lo(C)]; weights are
+ * [rows][Cout][hi(Cin) | lo(Cin)].  The tensor-core engines compute x*w as hi*hi + lo*hi + hi*lo: three kind::f16 MMAs
+ * per K step into the same fp32 TMEM accumulator (~2^-16 per product, i.e. fp32-grade results at the bf16 MMA rate / 3;
+ * no split kernel, no partial sums through HBM).  Channel counts and strides of such tensors are in bf16 ELEMENTS of
+ * the physical tensor; S3dConvParams.Cin / Cout stay LOGICAL. */
+#define S3D_DTYPE_BF16X2 2
 
 #define S3D_ACT_NONE     0
 #define S3D_ACT_RELU     1
@@ -64,19 +71,13 @@ typedef struct S3dConvParams {
   int8_t  dz[S3D_MAX_TAPS], dy[S3D_MAX_TAPS], dx[S3D_MAX_TAPS]; /* [n_classes*ntaps]   */
   int64_t osN, osD, osH, osW;       /* output element strides of n, z, y, x              */
   int64_t osC;                      /* output channel stride (1 = channels-last; h*w etc. = planar) */
+  int64_t os_lo;                    /* out_dtype BF16X2: element offset from a channel's hi to its lo part (0 = Cout) */
   int32_t omz, omy, omx;            /* output coordinate multiplier                     */
   int32_t cout_store;               /* channels actually written (<= Cout)              */
-  int32_t in_dtype, out_dtype;      /* S3D_DTYPE_*; weights have in_dtype               */
+  int32_t in_dtype, out_dtype;      /* S3D_DTYPE_*; weights have in_dtype.  BF16X2 in: bf16 / fp32 / BF16X2 out  */
   int32_t act;  float act_param;
   int32_t tw, th, td, tn;           /* M-tile box, powers of two, tw*th*td*tn == 128    */
   int32_t bn;                       /* GEMM N tile: multiple of 16, <= 256, divides Cout */
-  /* Optional (may be NULL): weights of a stride-1 3x3x3 layer with Cout <= 64 pre-stacked for the
-   * z-stacked tensor-core tile, [4*9][128][Cin]: row block sv*9+kyx holds W[kz=sv,kyx] in rows 0..63
-   * and W[kz=sv-1,kyx] in rows 64..127 (zeros where kz is out of range or co >= Cout). */
-  const void* w_zstack;
-  /* 1 if w_zstack holds two more row blocks, [36] = [I;0] and [37] = [0;I] (I = identity over the Cout channels):
-   * the kernel can then add `residual` on the tensor cores instead of in the epilogue. */
-  int32_t w_zstack_ident;
   /* Optional fused 1x1 projection (may be NULL): after the activation, channel `proj_channel` of every output
    * position is overwritten with proj_act(sum_{c<16} proj_w[c] * out[c]) (proj_w: 16 fp32 DEVICE values, zeros
    * beyond the real channels).  Needs Cout == 16 (one accumulator group).  Used to fold the decoder's final
@@ -97,10 +98,19 @@ const char* s3d_version(void);
 const char* s3d_last_error(void);
 /* 0 if device `dev` is usable (compute capability 10.x), else a negative code. */
 int s3d_device_check(int dev);
+/* A/B switches of the launchers ("no_scatter", "scatter_no_pair", "scatter_generic", "scatter_tps3", "scatter_ring",
+ * "scatter_res_transpose", "scatter_no_transpose", "no_corr_tc"; all 0 by default = the shipped path).  They are
+ * initialised ONCE from the environment variables S3D_<NAME> when the library is first used and are never read from
+ * the environment on the launch path; s3d_set_knob overrides one at run time.  Process-wide, not thread-safe against
+ * concurrent launches. */
+int s3d_set_knob(const char* name, int value);
+int s3d_get_knob(const char* name);
 
 /* --- convolution engines ------------------------------------------------------------ */
 /* tcgen05/TMEM/TMA implicit GEMM (bf16 -> kind::f16, fp32 -> kind::tf32), fp32 accumulate.
- * bias: fp32[Cout] or NULL; residual: NULL or a tensor addressed exactly like `out`. */
+ * bias: fp32[Cout] or NULL; residual: NULL or a tensor addressed exactly like `out` (same dtype, strides, os_lo).
+ * `residual` MAY alias `out` (in-place accumulation): every thread reads the residual of exactly the elements it
+ * stores, before it stores them. */
 int s3d_conv_igemm(const S3dConvParams* p, const void* in, const void* w, const float* bias,
                    const void* residual, void* out, void* stream);
 /* Same contract, plain fp32 SIMT FMA loop (exact-fp32 validation mode; in/out dtype free). */
@@ -153,9 +163,11 @@ int s3d_tap_gather_soft_argmin(const float* taps, float* disp, float* cost_out, 
 int s3d_cls_soft_argmin(const void* x, const void* w_taps, float* disp, int N, int D, int h, int w, int C,
                         float sign, void* stream);
 /* Fused correlation + soft-argmax; the [2B,D,h,w] cost is never materialised.
+ * feat: [2B,1,h,w,C] with C the PADDED channel count (row pitch); cost = (1/c_real) * sum_c ref*tgt over the real
+ * channels (padded channels must be zero; c_real = 0 means C).
  * disp: fp32 [2B,h,w]; cost_out may be NULL (debug: fp32 [2B,D,h,w]). */
 int s3d_corr_soft_argmin(const void* feat, float* disp, float* cost_out, int B, int h, int w,
-                         int C, int D, int dtype, void* stream);
+                         int C, int c_real, int D, int dtype, void* stream);
 /* disp_q fp32 [N,h,w] (1/4-res units) -> fp32 [N,H,W] = bilinear(scale*disp_q), align_corners=False. */
 int s3d_upsample_disp(const float* disp_q, float* disp, int N, int h, int w, int H, int W,
                       float scale, void* stream);

@@ -26,7 +26,7 @@ static void nn_dir(const float* q, const float* r, float* dist, int32_t* idx, in
       if (d < best) { best = d; bi = j; }
     }
     dist[i] = best;
-    idx[i] = bi;
+    idx[i] = bi == INT32_MAX ? 0 : bi;   /* nothing compared less (all NaN / +inf): a valid index */
   }
 }
 

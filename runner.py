@@ -29,6 +29,46 @@ def get_args():
     return p.parse_args()
 
 
+def flatten_checkpoint(ckpt, prefixes=()):
+    """-> flat {key: tensor}.  Accepts a plain state_dict, {'model' | 'state_dict': sd}, or a checkpoint holding one
+    state_dict PER SUB-NETWORK ({'dispnet': sd, 'decoder_state_dict': sd, ...}: the sub-dict's name, minus a
+    '_state_dict' suffix, becomes the key prefix); DataParallel 'module.' prefixes are stripped at every level.
+    (The upstream checkpoint layout is not on disk -- README.md:35-36 only names the files -- so nothing here maps
+    upstream LAYER names; a mismatch is reported key by key instead of a bare strict-load failure.)"""
+    flat = {}
+    for k, v in ckpt.items():
+        name = k[len('module.'):] if k.startswith('module.') else k
+        if torch.is_tensor(v):
+            flat['.'.join(prefixes + (name,))] = v
+        elif isinstance(v, dict) and v and all(isinstance(kk, str) for kk in v):
+            if name in ('model', 'state_dict') and not prefixes:
+                flat.update(flatten_checkpoint(v))
+            elif any(torch.is_tensor(t) or isinstance(t, dict) for t in v.values()) and 'optim' not in name and 'solver' not in name:
+                sub = name[:-len('_state_dict')] if name.endswith('_state_dict') else name
+                flat.update(flatten_checkpoint(v, prefixes + (sub,)))
+    return {k.replace('.module.', '.'): v for k, v in flat.items()}
+
+
+def load_checkpoint(model, path):
+    ckpt = torch.load(path, map_location='cpu')
+    if not isinstance(ckpt, dict):
+        sys.exit('--weights: %s does not hold a state_dict' % path)
+    sd = flatten_checkpoint(ckpt)
+    own = model.state_dict()
+    missing = sorted(k for k in own if k not in sd)
+    unexpected = sorted(k for k in sd if k not in own)
+    shape = sorted(k for k in own if k in sd and tuple(own[k].shape) != tuple(sd[k].shape))
+    if missing or unexpected or shape:
+        def head(keys):
+            return ', '.join(keys[:8]) + (' ... (+%d)' % (len(keys) - 8) if len(keys) > 8 else '')
+        sys.exit('--weights: %s does not match %s (this build defines its own [SPEC] layer names, DESIGN.md section 3; '
+                 'upstream .pth files need a key map that cannot be written without the upstream source).\n'
+                 '  missing    (%d): %s\n  unexpected (%d): %s\n  shape      (%d): %s'
+                 % (path, type(model).__name__, len(missing), head(missing), len(unexpected), head(unexpected),
+                    len(shape), head(shape)))
+    model.load_state_dict(sd)
+
+
 def main():
     args = get_args()
     from config import cfg
@@ -50,8 +90,7 @@ def main():
     n = args.n_samples or bs * world
     model = models.build_model(args.model, cfg, seed=None if args.weights else cfg.CONST.SEED)
     if args.weights:
-        sd = torch.load(args.weights, map_location='cpu')
-        model.load_state_dict(sd.get('model', sd) if isinstance(sd, dict) and 'model' in sd else sd)
+        load_checkpoint(model, args.weights)
     model.cuda().pack()
     if args.model == 'Stereo2Voxel':
         res = T.iou_summary(T.test_voxel(cfg, model, n, bs, rank, world).cpu(), cfg.TEST.VOXEL_THRESH)

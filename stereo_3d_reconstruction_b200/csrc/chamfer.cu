@@ -71,7 +71,7 @@ chamfer_nn_kernel(const float* __restrict__ q_xyz, const float* __restrict__ r_x
     }
     if (s == 0 && q0 + k < nq) {
       dist[(int64_t)b * nq + q0 + k] = best[k];
-      idx[(int64_t)b * nq + q0 + k] = bi[k];
+      idx[(int64_t)b * nq + q0 + k] = bi[k] == 0x7fffffff ? 0 : bi[k];     // nothing compared less (all NaN / +inf): index 0, never out of range
     }
   }
 }

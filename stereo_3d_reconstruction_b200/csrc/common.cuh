@@ -31,6 +31,20 @@ void set_error(const char* fmt, ...);
 
 int num_sms();   // SM count of the current device (cached)
 
+// A/B switches of the launchers.  Read ONCE from the S3D_* environment variables (first use), never per launch;
+// s3d_set_knob() overrides them at run time (tests, A/B scripts).  All default to 0 = the shipped path.
+struct Knobs {
+  int no_scatter;             // S3D_NO_SCATTER: 3x3x3 layers take the generic per-tap engine instead of conv_scatter
+  int scatter_tps3;           // S3D_SCATTER_TPS3: 3-tap weight stages where 9-tap ones are the default
+  int scatter_no_pair;        // S3D_SCATTER_NO_PAIR: single-CTA kernels instead of cta_group::2 pairs
+  int scatter_ring;           // S3D_SCATTER_RING=n: force the plane ring depth (0 = automatic)
+  int scatter_res_transpose;  // S3D_SCATTER_RES_TRANSPOSE: coalesced residual group loads + second shuffle transpose
+  int scatter_no_transpose;   // S3D_SCATTER_NO_TRANSPOSE: per-pixel stores instead of the transposed epilogue
+  int scatter_generic;        // S3D_SCATTER_GENERIC: all-in-one kernel instead of the lean per-shape ones
+  int no_corr_tc;             // S3D_NO_CORR_TC: SIMT correlation kernel even where the tensor-core one applies
+};
+Knobs& knobs();
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
@@ -42,9 +56,14 @@ template <typename T> __device__ __forceinline__ T from_f32(float v);
 template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
 template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 
+// NaN-propagating max / min (FMNMX.NAN, one instruction like fmaxf): fmaxf(NaN, 0) is 0, which would scrub a NaN
+// accumulator (corrupt checkpoint, inf - inf) out of every tensor-core layer while PyTorch and the fp32 engine keep it.
+__device__ __forceinline__ float fmax_nan(float a, float b) { float d; asm("max.NaN.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b)); return d; }
+__device__ __forceinline__ float fmin_nan(float a, float b) { float d; asm("min.NaN.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b)); return d; }
+
 __device__ __forceinline__ float apply_act(float v, int act, float a) {
   switch (act) {
-    case S3D_ACT_RELU:    return fmaxf(v, 0.f);
+    case S3D_ACT_RELU:    return fmax_nan(v, 0.f);
     case S3D_ACT_LEAKY:   return v > 0.f ? v : v * a;
     case S3D_ACT_SIGMOID: return 1.f / (1.f + expf(-v));
     case S3D_ACT_TANH:    return a * tanhf(v);

@@ -92,7 +92,7 @@ conv_first_kernel(const void* __restrict__ img_, const float* __restrict__ disp,
       TOut* o = out + (((int64_t)n * oH + oy) * oW + ox + px) * CO;
       if (act <= S3D_ACT_LEAKY) {
 #pragma unroll
-        for (int c = 0; c < CO; ++c) acc[px][c] = fmaxf(acc[px][c], 0.f) + slope * fminf(acc[px][c], 0.f);
+        for (int c = 0; c < CO; ++c) acc[px][c] = fmax_nan(acc[px][c], 0.f) + slope * fmin_nan(acc[px][c], 0.f);
       } else {
 #pragma unroll
         for (int c = 0; c < CO; ++c) acc[px][c] = apply_act(acc[px][c], act, act_param);

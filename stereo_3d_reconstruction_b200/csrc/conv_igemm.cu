@@ -299,30 +299,20 @@ int conv_igemm_launch(const S3dConvParams* p, const void* in, const void* w, con
 }  // namespace s3d
 
 namespace s3d {
-bool conv_halo_eligible(const S3dConvParams* p);
-int conv_halo_launch(const S3dConvParams* p, const void* in, const void* w, const float* bias, const void* residual,
-                     void* out, cudaStream_t stream);
 bool conv_scatter_eligible(const S3dConvParams* p);
 int conv_scatter_launch(const S3dConvParams* p, const void* in, const float* bias, const void* residual, void* out,
                         cudaStream_t stream);
 }
 
-// Dispatch: stride-1 3x3x3 layers with Cout <= 64 and host-packed weight rotations go to the plane-scatter kernel
-// (conv_scatter.cu; S3D_NO_SCATTER=1 disables it), stride-1 3x3 / 3x3x3 layers with 128-byte rows go to the halo-reuse kernel (conv_halo.cu),
-// everything else to the generic per-tap kernel.  S3D_NO_HALO=1 forces the generic kernel (A/B testing).
+// Dispatch: stride-1 3x3x3 layers with Cout <= 64 and host-packed weight rotations (w_nstack) go to the plane-scatter
+// kernel (conv_scatter.cu; the knob `no_scatter` disables it), everything else to the generic per-tap kernel.
 extern "C" int s3d_conv_igemm(const S3dConvParams* p, const void* in, const void* w, const float* bias,
                               const void* residual, void* out, void* stream) {
   if (!p || !in || !w || !out) { s3d::set_error("s3d_conv_igemm: null argument"); return S3D_ERR_INVALID; }
-  static const bool no_halo = getenv("S3D_NO_HALO") != nullptr;
-  if (!no_halo && s3d::conv_scatter_eligible(p)) {
+  if (s3d::conv_scatter_eligible(p)) {
     const int rc = s3d::conv_igemm_validate(p, in, w);
     if (rc != S3D_OK) return rc;
     return s3d::conv_scatter_launch(p, in, bias, residual, out, static_cast<cudaStream_t>(stream));
-  }
-  if (!no_halo && s3d::conv_halo_eligible(p)) {
-    const int rc = s3d::conv_igemm_validate(p, in, w);
-    if (rc != S3D_OK) return rc;
-    return s3d::conv_halo_launch(p, in, w, bias, residual, out, static_cast<cudaStream_t>(stream));
   }
   return s3d::conv_igemm_launch(p, in, w, bias, residual, out, static_cast<cudaStream_t>(stream));
 }

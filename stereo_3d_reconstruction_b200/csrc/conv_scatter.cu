@@ -8,7 +8,7 @@ using namespace scatter;
 // rotations present.
 bool conv_scatter_eligible(const S3dConvParams* p) {
   const int esz = p->in_dtype == S3D_DTYPE_F32 ? 4 : 2;
-  if (!p->w_nstack || getenv("S3D_NO_SCATTER") != nullptr) return false;
+  if (!p->w_nstack || knobs().no_scatter) return false;
   if (p->n_classes != 1 || p->sx != 1 || p->sy != 1 || p->sz != 1 || p->ntaps != 27) return false;
   if (p->omx != 1 || p->omy != 1 || p->omz != 1 || p->osC != 1 || p->proj_w) return false;
   if (p->oD != p->iD || p->oH != p->iH || p->oW != p->iW) return false;
@@ -36,7 +36,7 @@ int conv_scatter_launch(const S3dConvParams* p_in, const void* in, const float* 
   a.slot_bytes = a.nchunks * a.chunk_stride;
   a.cp = p.Cout;
   a.tps = spec_tps(a.row_bytes, a.cp);
-  if (getenv("S3D_SCATTER_TPS3") != nullptr && a.tps == 9) a.tps = 3;
+  if (knobs().scatter_tps3 && a.tps == 9) a.tps = 3;
   a.cols_x = ceil_div(p.oW, kTX);  a.cols_y = ceil_div(p.oH, kTY);
   const int64_t total = (int64_t)p.N * a.cols_x * a.cols_y;
   S3D_CHECK_ARG(total > 0 && total < (1ll << 31), "scatter: column count out of range");
@@ -45,7 +45,7 @@ int conv_scatter_launch(const S3dConvParams* p_in, const void* in, const float* 
   // HALF of the weight rows in shared memory.  That halves the B-operand reads and the weight TMA writes per SM -- the
   // single-CTA kernel saturates the shared-memory pipe (A 4 KB + B 6 KB per 96-cycle MMA, plus the TMA fills).
   int grid = num_sms();
-  a.pair = ((3 * a.cp / 2) % 8 == 0 && total >= 2 && grid >= 2 && getenv("S3D_SCATTER_NO_PAIR") == nullptr) ? 1 : 0;
+  a.pair = ((3 * a.cp / 2) % 8 == 0 && total >= 2 && grid >= 2 && !knobs().scatter_no_pair) ? 1 : 0;
   if (a.pair) {
     if ((int64_t)grid > total) grid = (int)((total + 1) / 2 * 2);
     grid -= grid % 2;
@@ -61,7 +61,7 @@ int conv_scatter_launch(const S3dConvParams* p_in, const void* in, const float* 
   if (ring > kMaxRing) ring = kMaxRing;
   if (ring < 2) ring = 2;
   if (a.row_bytes == 128 && ring > (a.pair && a.nchunks == 1 ? 3 : 2)) ring = a.pair && a.nchunks == 1 ? 3 : 2;
-  if (const char* e = getenv("S3D_SCATTER_RING")) { const int r = atoi(e); if (r >= 2 && r <= kMaxRing) ring = r; }
+  if (const int r = knobs().scatter_ring) { if (r >= 2 && r <= kMaxRing) ring = r; }
   a.ring = ring;
   a.w_stages = (budget - a.ring * a.slot_bytes) / a.w_bytes;
   if (a.w_stages > kMaxW) a.w_stages = kMaxW;
@@ -70,7 +70,7 @@ int conv_scatter_launch(const S3dConvParams* p_in, const void* in, const float* 
   // residual: each thread reads its own pixel's 128 bytes directly (measured 2.58 vs 2.71 ms on the residual layer against
   // coalesced group loads + a second shuffle transpose -- with CTA pairs the L1 data pipe has room for the scattered reads;
   // staging the residual tiles in shared memory by TMA was tried too: 2.66 vs 2.55 ms, it costs three weight stages)
-  a.res_direct = getenv("S3D_SCATTER_RES_TRANSPOSE") == nullptr;
+  a.res_direct = !knobs().scatter_res_transpose;
   {
     const int oesz = p.out_dtype == S3D_DTYPE_BF16 ? 2 : 4;
     const bool simple_act = p.act == S3D_ACT_NONE || p.act == S3D_ACT_RELU || p.act == S3D_ACT_LEAKY;
@@ -78,7 +78,7 @@ int conv_scatter_launch(const S3dConvParams* p_in, const void* in, const float* 
     auto dense16 = [&](int64_t st) { return (st * oesz) % 16 == 0; };
     a.fast_store = simple_act && bias != nullptr && p.cout_store == p.Cout && aligned(out) && aligned(residual) &&
                    dense16(p.osW) && dense16(p.osH) && dense16(p.osD) && dense16(p.osN) && p.osW < (1ll << 24) &&
-                   getenv("S3D_SCATTER_NO_TRANSPOSE") == nullptr;
+                   !knobs().scatter_no_transpose;
   }
 
   const CUtensorMapSwizzle sw = a.row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
@@ -96,7 +96,7 @@ int conv_scatter_launch(const S3dConvParams* p_in, const void* in, const float* 
                        : (tf32 ? conv_scatter_kernel<true, false> : conv_scatter_kernel<false, false>);
   // the network's own layer shapes (bf16, CTA pairs, coalesced epilogue) each have a lean kernel
   if (a.pair && !tf32 && a.nchunks == 1 && p.out_dtype == S3D_DTYPE_BF16 && a.fast_store && a.tps == spec_tps(a.row_bytes, a.cp) &&
-      getenv("S3D_SCATTER_GENERIC") == nullptr) {
+      !knobs().scatter_generic) {
     const bool relu = p.act == S3D_ACT_RELU;        // anything else: slope formula
     if (KernFn k = spec_kernel(a.row_bytes, a.cp, residual != nullptr, relu)) kern = k;
   }

@@ -361,7 +361,7 @@ __device__ __forceinline__ void sc_fast_store(const ScEpi& e, int64_t grp_off, i
       }
     }
 #pragma unroll
-    for (int i = 0; i < 16; ++i) f[i] = kAct == 0 ? fmaxf(f[i], 0.f) : (kAct == 1 ? f[i] : fmaxf(f[i], 0.f) + e.slope * fminf(f[i], 0.f));
+    for (int i = 0; i < 16; ++i) f[i] = kAct == 0 ? fmax_nan(f[i], 0.f) : (kAct == 1 ? f[i] : fmax_nan(f[i], 0.f) + e.slope * fmin_nan(f[i], 0.f));
     if (sizeof(TOut) == 2) {
 #pragma unroll
       for (int h = 0; h < 2; ++h) {

@@ -309,7 +309,7 @@ extern "C" int s3d_conv_concat_volume(const S3dConvParams* p_in, const void* fea
   S3D_CHECK_ARG(total > 0 && total < (1ll << 31), "conv_concat_volume: column count out of range");
   a.total_cols = (int)total;
   int grid = num_sms();
-  a.pair = ((3 * a.cp / 2) % 8 == 0 && total >= 2 && grid >= 2 && getenv("S3D_SCATTER_NO_PAIR") == nullptr) ? 1 : 0;
+  a.pair = ((3 * a.cp / 2) % 8 == 0 && total >= 2 && grid >= 2 && !knobs().scatter_no_pair) ? 1 : 0;
   if (a.pair) {
     if ((int64_t)grid > total) grid = (int)((total + 1) / 2 * 2);
     grid -= grid % 2;

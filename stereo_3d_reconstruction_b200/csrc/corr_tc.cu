@@ -193,10 +193,10 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap map_f, const __grid_constant_
 }  // namespace
 
 bool corr_tc_eligible(int w, int C, int D, int dtype) {
-  return dtype == S3D_DTYPE_BF16 && w <= kWP && (C * 2) % 32 == 0 && D >= 1 && getenv("S3D_NO_CORR_TC") == nullptr;
+  return dtype == S3D_DTYPE_BF16 && w <= kWP && (C * 2) % 32 == 0 && D >= 1 && !knobs().no_corr_tc;
 }
 
-int corr_tc_launch(const void* feat, float* disp, int B, int h, int w, int C, int D, cudaStream_t stream) {
+int corr_tc_launch(const void* feat, float* disp, int B, int h, int w, int C, int D, float inv_c, cudaStream_t stream) {
   CorrArgs a;
   memset(&a, 0, sizeof(a));
   a.disp = disp;  a.B = B;  a.h = h;  a.w = w;  a.C = C;  a.D = D;
@@ -212,7 +212,7 @@ int corr_tc_launch(const void* feat, float* disp, int B, int h, int w, int C, in
   const int64_t total = (int64_t)2 * B * a.tiles_per_img;
   S3D_CHECK_ARG(total > 0 && total < (1ll << 31), "corr_tc: tile count out of range");
   a.total_tiles = (int)total;
-  a.inv_c = 1.f / (float)C;
+  a.inv_c = inv_c;
   a.idesc = ptx::make_instr_desc(1, kM, kM);
   const CUtensorMapSwizzle sw = a.row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                               : a.row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;

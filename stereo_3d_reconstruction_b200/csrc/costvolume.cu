@@ -144,7 +144,7 @@ constexpr int kDG = 8;   // d per thread
 template <typename T, bool kLeftRef>
 __device__ __forceinline__ void corr_row(const T* __restrict__ ref_g, const T* __restrict__ tgt_g,
                                          float* __restrict__ disp_row, float* __restrict__ cost_row,
-                                         int64_t cost_plane, int w, int C, int D, float* smem) {
+                                         int64_t cost_plane, int w, int C, int D, float inv_c, float* smem) {
   const int WP = ((w + 3) & ~3);
   const int rs = WP + 4;                       // ref row stride (floats); +4 spreads banks
   const int ts = WP + D + 12 + 4;              // tgt row stride: zero pad D + window slack
@@ -167,7 +167,6 @@ __device__ __forceinline__ void corr_row(const T* __restrict__ ref_g, const T* _
   const int groups_per_pass = blockDim.x / ndg;
   const int dgi = threadIdx.x % ndg;
   const int d0 = dgi * kDG;
-  const float inv_c = 1.f / (float)C;
   for (int xg0 = 0; xg0 < nxg; xg0 += groups_per_pass) {
     const int xg = xg0 + threadIdx.x / ndg;
     const bool active = xg < nxg;
@@ -224,7 +223,7 @@ __device__ __forceinline__ void corr_row(const T* __restrict__ ref_g, const T* _
 template <typename T>
 __global__ void __launch_bounds__(256)
 corr_soft_argmin_kernel(const T* __restrict__ feat, float* __restrict__ disp, float* __restrict__ cost_out,
-                        int B, int h, int w, int C, int D) {
+                        int B, int h, int w, int C, int D, float inv_c) {
   extern __shared__ float smem_f[];
   const int n = blockIdx.x / h, y = blockIdx.x % h;
   const bool left_ref = n < B;
@@ -234,8 +233,8 @@ corr_soft_argmin_kernel(const T* __restrict__ feat, float* __restrict__ disp, fl
   float* disp_row = disp + ((int64_t)n * h + y) * w;
   const int64_t plane = (int64_t)h * w;
   float* cost_row = cost_out ? cost_out + (int64_t)n * D * plane + (int64_t)y * w : nullptr;
-  if (left_ref) corr_row<T, true>(ref_g, tgt_g, disp_row, cost_row, plane, w, C, D, smem_f);
-  else          corr_row<T, false>(ref_g, tgt_g, disp_row, cost_row, plane, w, C, D, smem_f);
+  if (left_ref) corr_row<T, true>(ref_g, tgt_g, disp_row, cost_row, plane, w, C, D, inv_c, smem_f);
+  else          corr_row<T, false>(ref_g, tgt_g, disp_row, cost_row, plane, w, C, D, inv_c, smem_f);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -267,7 +266,7 @@ using namespace s3d;
 
 namespace s3d {
 bool corr_tc_eligible(int w, int C, int D, int dtype);
-int corr_tc_launch(const void* feat, float* disp, int B, int h, int w, int C, int D, cudaStream_t stream);
+int corr_tc_launch(const void* feat, float* disp, int B, int h, int w, int C, int D, float inv_c, cudaStream_t stream);
 }
 
 extern "C" int s3d_cost_volume_concat(const void* feat, void* vol, int B, int h, int w, int C, int D, int dtype,
@@ -297,14 +296,17 @@ extern "C" int s3d_soft_argmin(const float* cost, float* disp, int N, int D, int
   return S3D_OK;
 }
 
-extern "C" int s3d_corr_soft_argmin(const void* feat, float* disp, float* cost_out, int B, int h, int w, int C, int D,
-                                    int dtype, void* stream) {
+extern "C" int s3d_corr_soft_argmin(const void* feat, float* disp, float* cost_out, int B, int h, int w, int C, int c_real,
+                                    int D, int dtype, void* stream) {
   if (!feat || !disp) { set_error("corr_soft_argmin: null argument"); return S3D_ERR_INVALID; }
   S3D_CHECK_ARG(dtype == S3D_DTYPE_F32 || dtype == S3D_DTYPE_BF16, "corr_soft_argmin: bad dtype");
   S3D_CHECK_ARG(B > 0 && h > 0 && w > 0 && C > 0 && D > 0, "corr_soft_argmin: bad shape");
+  S3D_CHECK_ARG(c_real >= 0 && c_real <= C, "corr_soft_argmin: c_real must be in [0, C] (0 = C)");
+  // the mean runs over the REAL feature channels; the padded ones are zero and only widen the rows
+  const float inv_c = 1.f / (float)(c_real > 0 ? c_real : C);
   // bf16 features, rows of up to 64 pixels, no debug cost output: Gram-matrix kernel on the tensor cores (corr_tc.cu)
   if (!cost_out && corr_tc_eligible(w, C, D, dtype))
-    return corr_tc_launch(feat, disp, B, h, w, C, D, static_cast<cudaStream_t>(stream));
+    return corr_tc_launch(feat, disp, B, h, w, C, D, inv_c, static_cast<cudaStream_t>(stream));
   S3D_CHECK_ARG(D >= 8 && D <= 128 && (D & (D - 1)) == 0, "corr_soft_argmin (SIMT path): D must be a power of two in [8,128]");
   const int WP = (w + 3) & ~3;
   const size_t smem = (size_t)C * ((WP + 4) + (WP + D + 16)) * sizeof(float);
@@ -318,11 +320,11 @@ extern "C" int s3d_corr_soft_argmin(const void* feat, float* disp, float* cost_o
   if (dtype == S3D_DTYPE_BF16) {
     S3D_CUDA(cudaFuncSetAttribute(corr_soft_argmin_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     corr_soft_argmin_kernel<__nv_bfloat16><<<2 * B * h, threads, smem, st>>>(
-        static_cast<const __nv_bfloat16*>(feat), disp, cost_out, B, h, w, C, D);
+        static_cast<const __nv_bfloat16*>(feat), disp, cost_out, B, h, w, C, D, inv_c);
   } else {
     S3D_CUDA(cudaFuncSetAttribute(corr_soft_argmin_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     corr_soft_argmin_kernel<float><<<2 * B * h, threads, smem, st>>>(
-        static_cast<const float*>(feat), disp, cost_out, B, h, w, C, D);
+        static_cast<const float*>(feat), disp, cost_out, B, h, w, C, D, inv_c);
   }
   S3D_LAUNCH_CHECK();
   return S3D_OK;

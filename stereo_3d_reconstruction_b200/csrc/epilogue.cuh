@@ -71,11 +71,13 @@ __device__ __forceinline__ void epilogue_store16(const EpiParams& e, int64_t off
     }
   }
   // ---- activation
-  if (e.act <= S3D_ACT_LEAKY) {
-    const float slope = e.act == S3D_ACT_NONE ? 1.f : (e.act == S3D_ACT_LEAKY ? e.act_param : 0.f);
+  if (e.act == S3D_ACT_RELU) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f) + slope * fminf(f[i], 0.f);
-  } else {
+    for (int i = 0; i < 16; ++i) f[i] = fmax_nan(f[i], 0.f);
+  } else if (e.act == S3D_ACT_LEAKY) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) f[i] = fmax_nan(f[i], 0.f) + e.act_param * fmin_nan(f[i], 0.f);
+  } else if (e.act != S3D_ACT_NONE) {
 #pragma unroll
     for (int i = 0; i < 16; ++i)
       if (cg + i < e.cout_store) f[i] = apply_act_slow(f[i], e.act, e.act_param);

@@ -2,6 +2,8 @@
 // context-aware fusion epilogue fused with the IoU statistics (rows X, F, M).  All bandwidth-bound
 // elementwise / small-reduction kernels.
 #include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
 #include "common.cuh"
 
 namespace s3d {
@@ -20,6 +22,31 @@ int num_sms() {
   if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
     n = 148;
   return n;
+}
+
+namespace {
+struct KnobName { const char* name; const char* env; int Knobs::*field; };
+const KnobName kKnobNames[] = {
+    {"no_scatter", "S3D_NO_SCATTER", &Knobs::no_scatter},
+    {"scatter_tps3", "S3D_SCATTER_TPS3", &Knobs::scatter_tps3},
+    {"scatter_no_pair", "S3D_SCATTER_NO_PAIR", &Knobs::scatter_no_pair},
+    {"scatter_ring", "S3D_SCATTER_RING", &Knobs::scatter_ring},
+    {"scatter_res_transpose", "S3D_SCATTER_RES_TRANSPOSE", &Knobs::scatter_res_transpose},
+    {"scatter_no_transpose", "S3D_SCATTER_NO_TRANSPOSE", &Knobs::scatter_no_transpose},
+    {"scatter_generic", "S3D_SCATTER_GENERIC", &Knobs::scatter_generic},
+    {"no_corr_tc", "S3D_NO_CORR_TC", &Knobs::no_corr_tc},
+};
+}  // namespace
+
+Knobs& knobs() {
+  static Knobs k = [] {
+    Knobs v;
+    memset(&v, 0, sizeof(v));
+    for (const KnobName& n : kKnobNames)
+      if (const char* e = getenv(n.env)) { const int x = atoi(e); v.*(n.field) = x != 0 ? x : 1; }   // "S3D_X=" or "=yes" -> 1
+    return v;
+  }();
+  return k;
 }
 
 namespace {
@@ -169,6 +196,21 @@ using namespace s3d;
 
 extern "C" const char* s3d_version(void) { return "s3d_b200 0.1 (sm_100a)"; }
 extern "C" const char* s3d_last_error(void) { return g_err; }
+
+extern "C" int s3d_set_knob(const char* name, int value) {
+  if (!name) { set_error("s3d_set_knob: null name"); return S3D_ERR_INVALID; }
+  for (const KnobName& n : kKnobNames)
+    if (strcmp(name, n.name) == 0) { knobs().*(n.field) = value; return S3D_OK; }
+  set_error("s3d_set_knob: unknown knob '%s'", name);
+  return S3D_ERR_INVALID;
+}
+extern "C" int s3d_get_knob(const char* name) {
+  if (name)
+    for (const KnobName& n : kKnobNames)
+      if (strcmp(name, n.name) == 0) return knobs().*(n.field);
+  set_error("s3d_get_knob: unknown knob");
+  return S3D_ERR_INVALID;
+}
 
 extern "C" int s3d_device_check(int dev) {
   cudaDeviceProp prop;

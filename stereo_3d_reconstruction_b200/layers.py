@@ -93,28 +93,12 @@ class PackedConv:
         self.bias = bp.to(device)
         self.taps = taps
         self.ksize, self.pad = tuple(ksize), tuple(pad)
-        # stride-1 3x3x3 layers with Cout <= 64: pre-stack the weights for the z-stacked UMMA tile
-        # (two output planes x 64 channels = M 128), see csrc/conv_halo.cu and include/s3d.h
-        self.weight_zs = None
+        # stride-1 3x3x3 layers with Cout <= 64: the three kz slices stacked on the output side in four rotations for
+        # the plane-scatter kernel (csrc/conv_scatter.cuh, include/s3d.h w_nstack)
         self.weight_ns = None
         if tuple(ksize) == (3, 3, 3) and tuple(pad) == (1, 1, 1) and tuple(stride) == (1, 1, 1) and \
                 self.n_classes == 1 and self.cout_pad <= 64:
-            zs = torch.zeros(38, 128, self.cin_pad, dtype=torch.float32)
             w3 = wp.view(3, 9, self.cout_pad, self.cin_pad)
-            z4 = zs[:36].view(4, 9, 128, self.cin_pad)
-            for sv in range(4):
-                if sv <= 2:
-                    z4[sv, :, :self.cout_pad] = w3[sv]
-                if sv >= 1:
-                    z4[sv, :, 64:64 + self.cout_pad] = w3[sv - 1]
-            # row blocks 36 / 37: identity onto output plane z / z+1, so a residual tensor (same channel count as
-            # the input) can be added by the tensor core as one more "tap"
-            self.zs_ident = self.cin_pad == self.cout_pad
-            if self.zs_ident:
-                eye = torch.eye(self.cout_pad)
-                zs[36, :self.cout_pad] = eye
-                zs[37, 64:64 + self.cout_pad] = eye
-            self.weight_zs = zs.to(torch_dtype(dtype_code)).to(device).contiguous()
             self.weight_ns = self.pack_nstack(w3).to(torch_dtype(dtype_code)).to(device).contiguous()
         self.bn = _choose_bn(self.cout_pad)
         self.proj = None                 # optional fused 1x1 projection: (fp32[16] device tensor, channel, act)
@@ -279,8 +263,6 @@ class PackedConv:
         p.act, p.act_param = self.act, self.act_param
         p.tw, p.th, p.td, p.tn = _choose_tile(N, oD, oH, oW, self.stride[2], self.stride[1], self.stride[0])
         p.bn = self.bn
-        p.w_zstack = self.weight_zs.data_ptr() if self.weight_zs is not None else None
-        p.w_zstack_ident = 1 if (self.weight_zs is not None and self.zs_ident) else 0
         p.w_nstack = self.weight_ns.data_ptr() if self.weight_ns is not None else None
         if self.proj is not None:
             p.proj_w, p.proj_channel, p.proj_act = self.proj[0].data_ptr(), self.proj[1], self.proj[2]
@@ -304,8 +286,7 @@ class PackedConv:
             out = torch.empty((N, oD * m[0], oH * m[1], oW * m[2], self.cout_pad), dtype=odt, device=x.device)
         code = _lib.DTYPE_BF16 if out.dtype == torch.bfloat16 else _lib.DTYPE_F32
         if self.vol is not None and engine == 'igemm' and iD == 1 and self.proj is None and \
-                (out_view is None or len(out_view[1]) == 4) and os.environ.get('S3D_NO_VOL2D') is None and \
-                os.environ.get('S3D_NO_SCATTER') is None:
+                (out_view is None or len(out_view[1]) == 4) and not _lib.KNOBS['no_vol2d'] and not _lib.KNOBS['no_scatter']:
             return self._call_as_volume(x, out, residual, cout_store, out_view)
         if out_view is None:
             assert out.is_contiguous() and out.dim() == 5

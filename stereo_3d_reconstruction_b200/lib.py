@@ -34,8 +34,6 @@ class S3dConvParams(ctypes.Structure):
         ('act', ctypes.c_int32), ('act_param', ctypes.c_float),
         ('tw', ctypes.c_int32), ('th', ctypes.c_int32), ('td', ctypes.c_int32), ('tn', ctypes.c_int32),
         ('bn', ctypes.c_int32),
-        ('w_zstack', ctypes.c_void_p),
-        ('w_zstack_ident', ctypes.c_int32),
         ('proj_w', ctypes.c_void_p), ('proj_channel', ctypes.c_int32), ('proj_act', ctypes.c_int32),
         ('w_nstack', ctypes.c_void_p),
     ]
@@ -49,6 +47,8 @@ SIGNATURES = {
     's3d_version': ([], ctypes.c_char_p),
     's3d_last_error': ([], ctypes.c_char_p),
     's3d_device_check': ([_i], _i),
+    's3d_set_knob': ([ctypes.c_char_p, _i], _i),
+    's3d_get_knob': ([ctypes.c_char_p], _i),
     's3d_conv_igemm': (_CONV_SIG, _i),
     's3d_conv_direct': (_CONV_SIG, _i),
     's3d_pack_image': ([_vp, _vp, _f, _vp, _i, _i, _i, _i, _i, _vp], _i),
@@ -59,7 +59,7 @@ SIGNATURES = {
     's3d_soft_argmin': ([_vp, _vp, _i, _i, _i, _i, _f, _vp], _i),
     's3d_tap_gather_soft_argmin': ([_vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp], _i),
     's3d_cls_soft_argmin': ([_vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp], _i),
-    's3d_corr_soft_argmin': ([_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp], _i),
+    's3d_corr_soft_argmin': ([_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp], _i),
     's3d_upsample_disp': ([_vp, _vp, _i, _i, _i, _i, _i, _f, _vp], _i),
     's3d_latent_to_vox': ([_vp, _vp, _i, _i, _i, _i, _i, _i, _vp], _i),
     's3d_avg_pool': ([_vp, _vp, _i, _i, _i, _i, _i, _i, _vp], _i),
@@ -98,6 +98,27 @@ def check(rc, what):
     if rc != 0:
         msg = load().s3d_last_error().decode('utf-8', 'replace')
         raise S3dError('%s failed (rc=%d): %s' % (what, rc, msg))
+
+
+# ---- A/B knobs ---------------------------------------------------------------------------------------------------
+# Read ONCE (here, at import) from the S3D_* environment variables, never on the forward path.  The host-side ones live
+# in this dict; the launcher-side ones live in the library (include/s3d.h, s3d_set_knob).  set_knob() changes either
+# at run time (tests, A/B scripts) -- a model picks host-side knobs up at its next pack().
+HOST_KNOBS = ('no_vol2d', 'no_concat_fuse', 'no_cls_fused', 'no_conv_first', 'no_d2s')
+LIB_KNOBS = ('no_scatter', 'scatter_tps3', 'scatter_no_pair', 'scatter_ring', 'scatter_res_transpose',
+             'scatter_no_transpose', 'scatter_generic', 'no_corr_tc')
+KNOBS = {k: int(os.environ.get('S3D_' + k.upper()) is not None) for k in HOST_KNOBS}
+KNOBS['no_scatter'] = int(os.environ.get('S3D_NO_SCATTER') is not None)        # both sides look at this one
+
+
+def set_knob(name, value):
+    value = int(value)
+    if name in LIB_KNOBS:
+        check(load().s3d_set_knob(name.encode(), value), 's3d_set_knob')
+    elif name not in HOST_KNOBS:
+        raise KeyError('unknown knob %r' % name)
+    if name in KNOBS:
+        KNOBS[name] = value
 
 
 _launches = 0

@@ -167,6 +167,25 @@ class _StereoBase(nn.Module):
         self._packed = None
         self._ws = {}
         self._graphs = {}
+        self._packed_prec = None
+        # the nn layers are parameter containers: anything that changes them (load_state_dict, .to / .cuda / .half,
+        # init_synthetic_weights writes in place and calls eval()) must drop the folded copies, workspaces and graphs
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module._invalidate())
+
+    def _invalidate(self):
+        self._packed = None
+        self._ws = {}
+        self._graphs = {}
+
+    def _apply(self, fn, *args, **kwargs):
+        r = super()._apply(fn, *args, **kwargs)
+        self._invalidate()
+        return r
+
+    def train(self, mode=True):
+        # init_synthetic_weights() / a user's model.eval() after editing parameters in place: re-pack on the next forward
+        self._invalidate()
+        return super().train(mode)
 
     # ---- packing ---------------------------------------------------------------------------
     @property
@@ -181,6 +200,10 @@ class _StereoBase(nn.Module):
 
     def pack(self):
         """Fold BN + re-lay weights for the conv engine.  Call after load_state_dict / .cuda()."""
+        cfgn = self.cfg.NETWORK
+        if cfgn.DEC_CHANNELS[0] % 16 or cfgn.REC_CHANNELS[-1] % 16:
+            # latent_to_vox writes [.., C*L*L/8] densely; dec0 reads it with its padded channel pitch
+            raise ValueError('NETWORK.DEC_CHANNELS[0] and NETWORK.REC_CHANNELS[-1] must be multiples of 16')
         dev = next(self.parameters()).device
         if dev.type != 'cuda':
             raise _lib.S3dError('Stereo2Voxel/Stereo2Point run on CUDA only (no CPU fallback); call .cuda() first')
@@ -207,6 +230,7 @@ class _StereoBase(nn.Module):
             # every conv as three TF32 passes over split operands (layers.py::SplitConv): fp32 accuracy on the tensor cores
             P = {k: SplitConv(v) for k, v in P.items()}
         self._packed = P
+        self._packed_prec = self.precision
         self._ws = {}
         self._graphs = {}
         return self
@@ -247,7 +271,7 @@ class _StereoBase(nn.Module):
         p5, p0 = self._packed['enc5'], self._packed.get('dres0a')
         fuse_volume = (cfg.NETWORK.COST_VOLUME == 'concat' and self.precision in ('bf16', 'tf32') and p5.cout_pad == C and
                        isinstance(p0, PackedConv) and p0.weight_ns is not None and C * x.element_size() in (32, 64) and
-                       os.environ.get('S3D_NO_CONCAT_FUSE') is None and os.environ.get('S3D_NO_SCATTER') is None)
+                       not _lib.KNOBS['no_concat_fuse'] and not _lib.KNOBS['no_scatter'])
         if fuse_volume:
             # features go into rows with D zero pixels on both sides: the fused cost-volume + dres0a kernel reads the shifted
             # target view of every disparity plane straight out of them (csrc/conv_scatter_concat.cu), no volume is written
@@ -270,8 +294,7 @@ class _StereoBase(nn.Module):
             a = self._conv('dres1b', y, residual=a, out=self._bufo('a3', 'dres1b', y))
             c = self._conv('cls_a', a, out=self._bufo('a0', 'cls_a', a))
             S = self._packed['cls_b'].cout_pad                      # 27 taps padded to 32 planes
-            if c.dtype == torch.bfloat16 and c.shape[-1] in (16, 32, 64) and S == 32 and \
-                    os.environ.get('S3D_NO_CLS_FUSED') is None:
+            if c.dtype == torch.bfloat16 and c.shape[-1] in (16, 32, 64) and S == 32 and not _lib.KNOBS['no_cls_fused']:
                 # classifier + soft-argmin in one pass over the volume (csrc/cls_fused.cu)
                 ops.cls_soft_argmin(c, self._packed['cls_b'].weight, -1.0, out=disp_q)
             else:
@@ -279,7 +302,7 @@ class _StereoBase(nn.Module):
                 self._conv('cls_b', c, out=taps, out_view=(0, (D * h * S * w, h * S * w, S * w, 1, w)), cout_store=S)
                 ops.tap_gather_soft_argmin(taps, -1.0, out=disp_q)
         else:
-            ops.corr_soft_argmin(feat, B, D, out=disp_q)
+            ops.corr_soft_argmin(feat, B, D, out=disp_q, c_real=C)       # mean over the REAL channels (feat is padded)
         disp = ops.upsample_disp(disp_q, H, W, 4.0, out=self._buf('disp', (2 * B, H, W), torch.float32))
         return disp, disp_q
 
@@ -308,7 +331,7 @@ class _StereoBase(nn.Module):
         pc = self._packed[layer]
         dt = torch_dtype(self._dtype_code())
         if pc.ksize == (1, 3, 3) and pc.stride == (1, 2, 2) and pc.pad == (0, 1, 1) and pc.cout_pad in (16, 32, 64) and \
-                os.environ.get('S3D_NO_CONV_FIRST') is None:
+                not _lib.KNOBS['no_conv_first']:
             oH, oW = (H - 1) // 2 + 1, (W - 1) // 2 + 1
             out = self._buf(out_name, (2 * B, 1, oH, oW, pc.cout_pad), dt)
             ops.conv_first(left, pc, None if disp is None else disp[:B], scale, out=out[:B])
@@ -339,7 +362,7 @@ class _StereoBase(nn.Module):
         return g(left, right, gt)
 
     def _check_inputs(self, left, right):
-        if self._packed is None:
+        if self._packed is None or self._packed_prec != self.precision:
             self.pack()
         if not (left.is_cuda and right.is_cuda):
             raise _lib.S3dError('inputs must be CUDA tensors (no CPU fallback)')
@@ -376,7 +399,7 @@ class Stereo2Voxel(_StereoBase):
         esz = 2 if dc == A.DTYPE_BF16 else 4
         seq = self.decoder.layers[nl - 1]
         if last.cout == 8 and last.cin_pad * esz in (32, 64, 128) and self.precision != 'fp32' and \
-                os.environ.get('S3D_NO_D2S') is None:
+                not _lib.KNOBS['no_d2s']:
             P['dec%d' % (nl - 1)] = PackedConv.from_deconv_k4s2p1_blocked(seq[0], seq[1], A.ACT_RELU, dc, dev)
             pw = torch.zeros(8, dtype=torch.float32)
             pw[:] = w.detach().float().cpu().view(-1)[:8]

@@ -194,8 +194,9 @@ def cls_soft_argmin(x, w_taps, sign=-1.0, out=None):
     return out
 
 
-def corr_soft_argmin(feat, B, D, out=None, want_cost=False):
-    """feat [2B,1,h,w,C] -> disp fp32 [2B,h,w] (fused correlation + soft-argmax)."""
+def corr_soft_argmin(feat, B, D, out=None, want_cost=False, c_real=None):
+    """feat [2B,1,h,w,C] -> disp fp32 [2B,h,w] (fused correlation + soft-argmax).  c_real: number of REAL feature
+    channels when C is a padded pitch (the correlation is a mean over the real channels; padded ones are zero)."""
     _chk(feat, out)
     n2, one, h, w, C = feat.shape
     assert n2 == 2 * B and one == 1
@@ -203,7 +204,7 @@ def corr_soft_argmin(feat, B, D, out=None, want_cost=False):
         out = torch.empty((2 * B, h, w), dtype=torch.float32, device=feat.device)
     cost = torch.empty((2 * B, D, h, w), dtype=torch.float32, device=feat.device) if want_cost else None
     rc = _lib.load().s3d_corr_soft_argmin(feat.data_ptr(), out.data_ptr(), cost.data_ptr() if want_cost else None,
-                                          B, h, w, C, D, _code(feat), _stream())
+                                          B, h, w, C, int(c_real or 0), D, _code(feat), _stream())
     _lib.check(rc, 's3d_corr_soft_argmin')
     _lib.count_launch()
     return (out, cost) if want_cost else out

@@ -20,3 +20,18 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if 'gpu' in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture
+def knobs():
+    """A/B switches (lib.set_knob) for the duration of one test; everything is reset afterwards."""
+    from stereo_3d_reconstruction_b200 import lib
+    touched = []
+
+    def set_(name, value):
+        touched.append(name)
+        lib.set_knob(name, value)
+
+    yield set_
+    for name in touched:
+        lib.set_knob(name, 0)

@@ -1,6 +1,7 @@
-"""BASELINE.json's full sizes, checked through size-independent properties (the CPU oracle is too slow there):
-structure of the concat volume, invariances of soft-argmin, batch-composition invariance and determinism of the
-whole forward, exactness of the integer IoU counts."""
+"""BASELINE.json's full sizes and LARGE batches, checked through size-independent properties: structure of the concat
+volume, invariances of soft-argmin, batch-composition invariance and determinism of the whole forward, exactness of the
+integer IoU counts.  (Value parity with the CPU oracle at the default configuration itself is
+tests/test_gpu_baseline_configs.py; these tests cover what a 2-pair oracle run cannot: B = 16..128, micro-batching.)"""
 import pytest
 import torch
 

@@ -64,6 +64,24 @@ def test_stereo2point_matches_oracle(prec):
     assert (p.cpu() - rp).abs().max().item() <= (1e-4 if prec == 'fp32' else 3e-2)
 
 
+@pytest.mark.parametrize('prec', ['fp32', 'bf16'])
+def test_corr_with_feature_channels_not_a_multiple_of_16(prec):
+    """FEAT_CHANNELS = 24 is stored padded to 32: the correlation is still a mean over the 24 REAL channels."""
+    cfg = small_cfg(NETWORK__PRECISION=prec, NETWORK__COST_VOLUME='corr', NETWORK__FEAT_CHANNELS=24)
+    oracle = O.make_model('Stereo2Voxel', cfg, seed=2)
+    model = M.build_model('Stereo2Voxel', cfg)
+    model.load_state_dict(oracle.state_dict())
+    model.cuda().pack()
+    left, right = _pair(cfg, 2)
+    with torch.no_grad():
+        rdl, rdr, rvox = oracle(left, right)
+        dl, dr, vox = model(left.cuda(), right.cuda())
+    td, tv = TOLS[prec]
+    assert (dl.cpu() - rdl).abs().max().item() <= td * rdl.abs().max().item()
+    assert (dr.cpu() - rdr).abs().max().item() <= td * rdl.abs().max().item()
+    assert (vox.cpu() - rvox).abs().max().item() <= tv
+
+
 def test_uint8_inputs_match_float_inputs():
     """Decoded 8-bit HWC images take the same path as their float NCHW equivalent (x/255), bit for bit."""
     cfg = small_cfg(NETWORK__PRECISION='bf16')

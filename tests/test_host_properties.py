@@ -1,5 +1,6 @@
 """Property tests (hypothesis) of the host logic: tile chooser, sharding, and PackedConv tap tables vs
 torch.nn.functional on random small shapes (CPU emulation of the S3dConvParams contract)."""
+import pytest
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -53,21 +54,60 @@ def test_deconv_packing_matches_torch(cin, cout, D, H, W, seed):
     torch.testing.assert_close(out[..., :cout], to_cl(dc(x)), rtol=1e-4, atol=1e-5)
 
 
-def test_zstack_weights_layout():
-    """weight_zs[sv*9+kyx] rows 0..63 = W[kz=sv], rows 64..127 = W[kz=sv-1], zeros out of range (conv_halo.cu)."""
+def test_nstack_weights_layout():
+    """weight_ns[r*9+kyx] block s = W[kz = (r+1-s) mod 3] (rotation 3 = rotation 0 with block 2 zeroed): include/s3d.h."""
     torch.manual_seed(0)
     conv = nn.Conv3d(16, 24, 3, 1, 1, bias=False)
     pc = PackedConv.from_conv(conv, None, lib.ACT_NONE, lib.DTYPE_F32, 'cpu')
-    assert pc.weight_zs.shape[0] == 38 and not pc.zs_ident and pc.weight_zs[36:].abs().sum() == 0      # Cin != Cout: no identity blocks
-    zs = pc.weight_zs[:36].view(4, 9, 128, pc.cin_pad)
-    w = pc.weight.view(3, 9, pc.cout_pad, pc.cin_pad)
-    for sv in range(4):
-        top = w[sv] if sv <= 2 else torch.zeros_like(w[0])
-        bot = w[sv - 1] if sv >= 1 else torch.zeros_like(w[0])
-        assert torch.equal(zs[sv, :, :pc.cout_pad], top) and torch.equal(zs[sv, :, 64:64 + pc.cout_pad], bot)
-        assert zs[sv, :, pc.cout_pad:64].abs().sum() == 0 and zs[sv, :, 64 + pc.cout_pad:].abs().sum() == 0
-    pc2 = PackedConv.from_conv(nn.Conv3d(32, 32, 3, 1, 1), None, lib.ACT_NONE, lib.DTYPE_F32, 'cpu')
-    assert pc2.zs_ident and torch.equal(pc2.weight_zs[36, :32], torch.eye(32)) and torch.equal(pc2.weight_zs[37, 64:96], torch.eye(32))
-    assert pc2.weight_zs[36, 32:].abs().sum() == 0 and pc2.weight_zs[37, :64].abs().sum() == 0
+    co = pc.cout_pad
+    ns = pc.weight_ns.view(4, 9, 3, co, pc.cin_pad)
+    w = pc.weight.view(3, 9, co, pc.cin_pad)
+    for r in range(4):
+        for s_ in range(3):
+            want = torch.zeros_like(w[0]) if (r == 3 and s_ == 2) else w[((r % 3) + 1 - s_) % 3]
+            assert torch.equal(ns[r, :, s_], want)
     conv2 = nn.Conv3d(16, 128, 3, 1, 1)
-    assert PackedConv.from_conv(conv2, None, lib.ACT_NONE, lib.DTYPE_F32, 'cpu').weight_zs is None
+    assert PackedConv.from_conv(conv2, None, lib.ACT_NONE, lib.DTYPE_F32, 'cpu').weight_ns is None
+
+
+def test_model_repacks_when_its_parameters_change():
+    """load_state_dict / .to() / init_synthetic_weights drop the folded weights, workspaces and graphs."""
+    from stereo_3d_reconstruction_b200 import models
+    from tests.common import small_cfg
+    m = models.build_model('Stereo2Voxel', small_cfg(), seed=0)
+    m._packed, m._ws, m._graphs = {'stale': 1}, {'x': 1}, {'g': 1}
+    m.load_state_dict(m.state_dict())
+    assert m._packed is None and not m._ws and not m._graphs
+    m._packed = {'stale': 1}
+    m.float()
+    assert m._packed is None
+    m._packed = {'stale': 1}
+    models.init_synthetic_weights(m, 1)
+    assert m._packed is None
+    c = small_cfg(NETWORK__DEC_CHANNELS=[24, 32, 16, 16, 8])
+    with pytest.raises(ValueError):
+        models.build_model('Stereo2Voxel', c, seed=0).pack()
+
+
+def test_runner_flattens_checkpoints(tmp_path):
+    """runner.py --weights: DataParallel prefixes, {'model': sd}, one state_dict per sub-network; clear error otherwise."""
+    import runner
+    from stereo_3d_reconstruction_b200 import models
+    from tests.common import small_cfg
+    m = models.build_model('Stereo2Voxel', small_cfg(), seed=0)
+    sd = m.state_dict()
+    ck = {'epoch_idx': 3}
+    for sub in ('dispnet', 'rgbd_encoder', 'decoder', 'merger'):
+        ck[sub + '_state_dict'] = {'module.' + k[len(sub) + 1:]: v for k, v in sd.items() if k.startswith(sub + '.')}
+    assert set(runner.flatten_checkpoint(ck)) == set(sd)
+    assert set(runner.flatten_checkpoint({'model': {'module.' + k: v for k, v in sd.items()}})) == set(sd)
+    path = tmp_path / 'w.pth'
+    torch.save(ck, path)
+    runner.load_checkpoint(m, str(path))
+    bad = dict(sd)
+    bad.pop(next(iter(bad)))
+    bad['encoder.upstream_name.weight'] = torch.zeros(1)
+    torch.save(bad, path)
+    with pytest.raises(SystemExit) as e:
+        runner.load_checkpoint(m, str(path))
+    assert 'missing' in str(e.value) and 'unexpected' in str(e.value)
