@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('S3D_LIB_PATH') or os.path.join(_HERE, 'libs3d_b200.so')   # env override: A/B-testing builds
 
 S3D_MAX_TAPS = 64
-DTYPE_F32, DTYPE_BF16 = 0, 1
+DTYPE_F32, DTYPE_BF16, DTYPE_BF16X2 = 0, 1, 2
 ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_SIGMOID, ACT_TANH = 0, 1, 2, 3, 4
 
 
@@ -28,6 +28,7 @@ class S3dConvParams(ctypes.Structure):
         ('dx', ctypes.c_int8 * S3D_MAX_TAPS),
         ('osN', ctypes.c_int64), ('osD', ctypes.c_int64), ('osH', ctypes.c_int64), ('osW', ctypes.c_int64),
         ('osC', ctypes.c_int64),
+        ('os_lo', ctypes.c_int64),
         ('omz', ctypes.c_int32), ('omy', ctypes.c_int32), ('omx', ctypes.c_int32),
         ('cout_store', ctypes.c_int32),
         ('in_dtype', ctypes.c_int32), ('out_dtype', ctypes.c_int32),

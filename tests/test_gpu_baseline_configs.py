@@ -145,8 +145,9 @@ def test_aggregation_layer_at_bench_shape(res):
     scale = ref.abs().max().item()
     err = (got - ref).abs()
     assert err.max().item() <= 4e-3 * scale
-    # against the fp32 value rounded the way the kernel stores it: only the accumulation order is left
-    assert (got - _bf16(ref)).abs().max().item() <= 2e-3 * scale
+    # against the fp32 value rounded the way the kernel stores it only the accumulation order is left: at most ONE
+    # bf16 ulp (a value on a rounding boundary; ulp <= 2^-7 of the value), and that for a small minority of outputs
+    assert (got - _bf16(ref)).abs().max().item() <= scale * 2.0 ** -7
     assert (got == _bf16(ref)).float().mean().item() > 0.98
 
 
