@@ -33,7 +33,7 @@ def parse():
     p.add_argument('--warmup', type=int, default=3)
     p.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     p.add_argument('--batch', type=int, default=None, help='pairs per GPU per step (default cfg.CONST.BATCH_SIZE = 64)')
-    p.add_argument('--precision', default='bf16', choices=['bf16', 'tf32', 'tf32x3', 'fp32'])
+    p.add_argument('--precision', default='bf16', choices=['bf16', 'bf16x3', 'tf32', 'tf32x3', 'fp32'])
     p.add_argument('--no-cpu-baseline', action='store_true')
     return p.parse_args()
 

@@ -76,7 +76,9 @@ __C.NETWORK.DEC_CHANNELS = [2048, 512, 128, 32, 8]    # 2^3 -> 32^3 transposed-c
 __C.NETWORK.MERGER_CHANNELS = [9, 16, 8, 4, 2, 1]     # context-aware fusion scorer
 __C.NETWORK.LEAKY_VALUE = 0.2
 __C.NETWORK.POINT_FC = 2048            # Stereo2Point hidden width
-__C.NETWORK.PRECISION = 'bf16'         # 'bf16' | 'tf32' (fp32 storage, TF32 tensor cores) | 'tf32x3' (3 split TF32 passes, fp32 accuracy) | 'fp32' (SIMT, exact)
+# 'bf16' | 'bf16x3' (bf16 hi/lo pairs, 3 MMAs per product: fp32 accuracy at a third of the bf16 rate) | 'tf32' (fp32
+# storage, TF32 tensor cores) | 'tf32x3' (3 split TF32 passes through HBM, fp32 accuracy) | 'fp32' (SIMT, exact)
+__C.NETWORK.PRECISION = 'bf16'
 
 #
 # Test  [SPEC]

@@ -132,7 +132,8 @@ int s3d_pack_image_u8(const uint8_t* img, const float* disp, float disp_scale, f
  * raw image -- img fp32 NCHW [B,3,H,W] (img_u8 = 0) or uint8 HWC [B,H,W,3] scaled by 1/255 (img_u8 = 1), plus for
  * cin = 4 the channel disp[B,H,W] * disp_scale -- to channels-last [B,1,oH,oW,cout_pad] (oH = (H-1)/2+1) of `dtype`.
  * w: the layer's packed weights [9][cout_pad][cin_pad] of `dtype` (only ci < cin is read); bias fp32[cout_pad] or NULL.
- * Same arithmetic as s3d_pack_image + s3d_conv_igemm (inputs/weights rounded to `dtype`, fp32 accumulate). */
+ * Same arithmetic as s3d_pack_image + s3d_conv_igemm (inputs/weights rounded to `dtype`, fp32 accumulate).
+ * dtype BF16X2: w is [9][cout_pad][hi(cin_pad) | lo(cin_pad)], the image is not rounded, out is [.., hi | lo]. */
 int s3d_conv_first(const void* img, int img_u8, const float* disp, float disp_scale, const void* w, const float* bias,
                    void* out, int B, int H, int W, int cin, int cin_pad, int cout_pad, int dtype, int act,
                    float act_param, void* stream);
@@ -145,7 +146,8 @@ int s3d_conv_first(const void* img, int img_u8, const float* disp, float disp_sc
 int s3d_conv_concat_volume(const S3dConvParams* p, const void* feat, int feat_pitch, int feat_pad, const float* bias,
                            void* out, void* stream);
 /* feat: [2B,1,h,w,C] (left maps first, then right).  vol: [2B,D,h,w,2C]; entries [0,B) are
- * left-referenced (target sampled at x-d), [B,2B) right-referenced (target at x+d). */
+ * left-referenced (target sampled at x-d), [B,2B) right-referenced (target at x+d).
+ * dtype BF16X2: feat [.., hi(C) | lo(C)] -> vol [.., hi(2C) | lo(2C)] (C logical channels). */
 int s3d_cost_volume_concat(const void* feat, void* vol, int B, int h, int w, int C, int D,
                            int dtype, void* stream);
 /* cost: fp32 [N,D,h,w] -> disp fp32 [N,h,w] = sum_d d*softmax_d(sign*cost).  sign=-1: soft-argmin. */
@@ -174,7 +176,8 @@ int s3d_upsample_disp(const float* disp_q, float* disp, int N, int h, int w, int
 
 /* --- decoder glue (rows X, D, F, M) ---------------------------------------------------- */
 /* adaptive average pool [N,1,H,W,C] -> [N,1,L,L,C], then the NCHW .view(N,C*L*L/8,2,2,2)
- * re-indexing of the oracle, written channels-last as [N,2,2,2,C*L*L/8]. */
+ * re-indexing of the oracle, written channels-last as [N,2,2,2,C*L*L/8].
+ * (This and the next two accept dtype BF16X2: split tensors in and out, C / 64 / Cpad = LOGICAL channels.) */
 int s3d_latent_to_vox(const void* x, void* out, int N, int H, int W, int C, int L, int dtype,
                       void* stream);
 /* Generic adaptive average pool, channels-last [N,1,H,W,C] -> [N,1,L,L,C]. */
@@ -190,12 +193,17 @@ int s3d_depth_to_space(const void* in, void* out, const float* proj_w, int proj_
  * in TF32), lo = x - hi (exact).  conv(x, w) ~= conv(hi, w_hi) + conv(lo, w_hi) + conv(hi, w_lo) on kind::tf32 tensor
  * cores with fp32 accumulation reproduces fp32 to ~1e-6 relative.  n (elements) must be a multiple of 4. */
 int s3d_split_tf32(const float* x, float* hi, float* lo, int64_t n, void* stream);
+/* fp32 [npix, C] <-> split bf16 pairs [npix, hi(C) | lo(C)] (S3D_DTYPE_BF16X2): hi = bf16(x), lo = bf16(x - hi);
+ * unsplit returns hi + lo.  Hand-off between 'bf16x3' tensors and the kernels that take fp32. */
+int s3d_split_bf16(const float* x, void* out, int64_t npix, int C, void* stream);
+int s3d_unsplit_bf16(const void* x, float* out, int64_t npix, int C, void* stream);
 /* Context-aware fusion epilogue + IoU.  score, vol: [V*B, 32^3] planes with element strides
  * score_stride / vol_stride (view-major); fused[b,v] = clamp(sum_v softmax_v(score)*vol, 0, 1).
- * gt (uint8 [B,32^3]) and iou (int64 [B,T,2] = intersection, union) may be NULL. */
+ * gt (uint8 [B,32^3]) and iou (int64 [B,T,2] = intersection, union) may be NULL.
+ * dtype BF16X2: score_lo / vol_lo are the element offsets from a value's hi part to its lo part (0 for other dtypes). */
 int s3d_fuse_views(const void* score, int64_t score_stride, const void* vol, int64_t vol_stride,
                    int dtype, float* fused, int B, int V, int nvox, const uint8_t* gt,
-                   const float* thresholds, int T, long long* iou, void* stream);
+                   const float* thresholds, int T, long long* iou, int64_t score_lo, int64_t vol_lo, void* stream);
 
 /* --- Chamfer distance (row C; replaces extensions/chamfer_dist, README.md:62-65) ------- */
 /* xyz1 fp32 [B,N,3], xyz2 fp32 [B,M,3] -> dist1 fp32 [B,N], idx1 int32 [B,N] (nearest in

@@ -23,7 +23,7 @@ def get_args():
     p.add_argument('--test', action='store_true', help='run the test (inference) path')
     p.add_argument('--weights', default=None, help='checkpoint (.pth) with a state_dict or {"model": state_dict}')
     p.add_argument('--model', default='Stereo2Voxel', choices=['Stereo2Voxel', 'Stereo2Point'])
-    p.add_argument('--precision', default=None, choices=['bf16', 'tf32', 'tf32x3', 'fp32'])
+    p.add_argument('--precision', default=None, choices=['bf16', 'bf16x3', 'tf32', 'tf32x3', 'fp32'])
     p.add_argument('--batch-size', type=int, default=None)
     p.add_argument('--n-samples', type=int, default=None, help='synthetic test-set size (default: one batch per rank)')
     return p.parse_args()

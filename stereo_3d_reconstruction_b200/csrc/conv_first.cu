@@ -20,7 +20,9 @@ __device__ __forceinline__ void ffma2(float& d0, float& d1, float x, float w0, f
   asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(rd));
 }
 
-template <int CO, int CIN, typename TW, typename TOut, bool kU8>
+// kSplit (S3D_DTYPE_BF16X2, 'bf16x3' precision): weights are [hi(cin_pad) | lo(cin_pad)] bf16 rows (summed back to fp32 here),
+// the input is NOT rounded, and the output is written as [hi(CO) | lo(CO)] bf16 per pixel.
+template <int CO, int CIN, typename TW, typename TOut, bool kU8, bool kSplit = false>
 __global__ void __launch_bounds__(128)
 conv_first_kernel(const void* __restrict__ img_, const float* __restrict__ disp, float disp_scale, float img_scale,
                   const TW* __restrict__ w, int cin_pad, const float* __restrict__ bias, TOut* __restrict__ out,
@@ -30,7 +32,8 @@ conv_first_kernel(const void* __restrict__ img_, const float* __restrict__ disp,
   __shared__ __align__(16) float bs[CO];
   for (int i = threadIdx.x; i < 9 * CIN * CO; i += blockDim.x) {
     const int co = i % CO, ci = (i / CO) % CIN, t = i / (CO * CIN);
-    ws[i] = to_f32(w[((int64_t)t * CO + co) * cin_pad + ci]);
+    if (kSplit) ws[i] = to_f32(w[((int64_t)t * CO + co) * 2 * cin_pad + ci]) + to_f32(w[((int64_t)t * CO + co) * 2 * cin_pad + cin_pad + ci]);
+    else        ws[i] = to_f32(w[((int64_t)t * CO + co) * cin_pad + ci]);
   }
   for (int i = threadIdx.x; i < CO; i += blockDim.x) bs[i] = bias ? bias[i] : 0.f;
   __syncthreads();
@@ -65,8 +68,10 @@ conv_first_kernel(const void* __restrict__ img_, const float* __restrict__ disp,
           for (int ci = 0; ci < 3; ++ci) v[cx][ci] = in ? __ldg(ip + ci * (int64_t)H * W) : 0.f;
         }
         if (CIN > 3) v[cx][3] = in ? __ldg(disp + ((int64_t)n * H + iy) * W + ix) * disp_scale : 0.f;
+        if (!kSplit) {
 #pragma unroll
-        for (int ci = 0; ci < CIN; ++ci) v[cx][ci] = to_f32(from_f32<TW>(v[cx][ci]));   // rounding of the staged copy it replaces
+          for (int ci = 0; ci < CIN; ++ci) v[cx][ci] = to_f32(from_f32<TW>(v[cx][ci]));   // rounding of the staged copy it replaces
+        }
       }
 #pragma unroll
       for (int kx = 0; kx < 3; ++kx) {
@@ -89,7 +94,7 @@ conv_first_kernel(const void* __restrict__ img_, const float* __restrict__ disp,
 #pragma unroll
     for (int px = 0; px < 2; ++px) {
       if (ox + px >= oW) break;
-      TOut* o = out + (((int64_t)n * oH + oy) * oW + ox + px) * CO;
+      TOut* o = out + (((int64_t)n * oH + oy) * oW + ox + px) * (kSplit ? 2 * CO : CO);
       if (act <= S3D_ACT_LEAKY) {
 #pragma unroll
         for (int c = 0; c < CO; ++c) acc[px][c] = fmax_nan(acc[px][c], 0.f) + slope * fmin_nan(acc[px][c], 0.f);
@@ -97,7 +102,21 @@ conv_first_kernel(const void* __restrict__ img_, const float* __restrict__ disp,
 #pragma unroll
         for (int c = 0; c < CO; ++c) acc[px][c] = apply_act(acc[px][c], act, act_param);
       }
-      if (sizeof(TOut) == 2) {
+      if (kSplit) {
+#pragma unroll
+        for (int c8 = 0; c8 < CO / 8; ++c8) {
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const __nv_bfloat162 h = __floats2bfloat162_rn(acc[px][8 * c8 + 2 * i], acc[px][8 * c8 + 2 * i + 1]);
+            const float2 hf = __bfloat1622float2(h);
+            const __nv_bfloat162 l = __floats2bfloat162_rn(acc[px][8 * c8 + 2 * i] - hf.x, acc[px][8 * c8 + 2 * i + 1] - hf.y);
+            hi[i] = *reinterpret_cast<const uint32_t*>(&h);  lo[i] = *reinterpret_cast<const uint32_t*>(&l);
+          }
+          reinterpret_cast<uint4*>(o)[c8] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          reinterpret_cast<uint4*>(o + CO)[c8] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+      } else if (sizeof(TOut) == 2) {
 #pragma unroll
         for (int c8 = 0; c8 < CO / 8; ++c8) {
           uint4 pk;
@@ -115,7 +134,7 @@ conv_first_kernel(const void* __restrict__ img_, const float* __restrict__ disp,
   }
 }
 
-template <int CO, typename TW, typename TOut>
+template <int CO, typename TW, typename TOut, bool kSplit = false>
 int launch_first(const void* img, int img_u8, const float* disp, float disp_scale, float img_scale, const void* w, int cin_pad,
                  const float* bias, void* out, int B, int H, int W, int oH, int oW, int cin, int act, float act_param,
                  cudaStream_t st) {
@@ -124,7 +143,7 @@ int launch_first(const void* img, int img_u8, const float* disp, float disp_scal
   const int64_t cap = (int64_t)num_sms() * 16;
   if (blocks > cap) blocks = cap;
 #define S3D_FIRST_LAUNCH(CIN, U8)                                                                                          \
-  conv_first_kernel<CO, CIN, TW, TOut, U8><<<(int)blocks, 128, 0, st>>>(img, disp, disp_scale, img_scale, static_cast<const TW*>(w), \
+  conv_first_kernel<CO, CIN, TW, TOut, U8, kSplit><<<(int)blocks, 128, 0, st>>>(img, disp, disp_scale, img_scale, static_cast<const TW*>(w), \
       cin_pad, bias, static_cast<TOut*>(out), B, H, W, oH, oW, act, act_param)
   if (cin == 3) { if (img_u8) S3D_FIRST_LAUNCH(3, true); else S3D_FIRST_LAUNCH(3, false); }
   else          { if (img_u8) S3D_FIRST_LAUNCH(4, true); else S3D_FIRST_LAUNCH(4, false); }
@@ -151,12 +170,15 @@ extern "C" int s3d_conv_first(const void* img, int img_u8, const float* disp, fl
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const float img_scale = 1.0f / 255.0f;
 #define S3D_FIRST(CO)                                                                                                    \
-  (dtype == S3D_DTYPE_BF16                                                                                               \
+  (dtype == S3D_DTYPE_BF16X2                                                                                             \
+       ? launch_first<CO, __nv_bfloat16, __nv_bfloat16, true>(img, img_u8, disp, disp_scale, img_scale, w, cin_pad, bias, out, B, \
+                                                              H, W, oH, oW, cin, act, act_param, st)                     \
+   : dtype == S3D_DTYPE_BF16                                                                                               \
        ? launch_first<CO, __nv_bfloat16, __nv_bfloat16>(img, img_u8, disp, disp_scale, img_scale, w, cin_pad, bias, out, B, H, W, \
                                                         oH, oW, cin, act, act_param, st)                                 \
        : launch_first<CO, float, float>(img, img_u8, disp, disp_scale, img_scale, w, cin_pad, bias, out, B, H, W, oH, oW, cin,    \
                                         act, act_param, st))
-  if (dtype != S3D_DTYPE_BF16 && dtype != S3D_DTYPE_F32) { set_error("conv_first: bad dtype"); return S3D_ERR_INVALID; }
+  if (dtype != S3D_DTYPE_BF16 && dtype != S3D_DTYPE_F32 && dtype != S3D_DTYPE_BF16X2) { set_error("conv_first: bad dtype"); return S3D_ERR_INVALID; }
   if (cout_pad == 16) return S3D_FIRST(16);
   if (cout_pad == 32) return S3D_FIRST(32);
   return S3D_FIRST(64);

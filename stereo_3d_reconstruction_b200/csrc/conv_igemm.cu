@@ -46,6 +46,7 @@ struct KernelArgs {
   int kc;            // channels per K chunk
   int row_bytes;     // kc * elem size: 32 / 64 / 128
   int n_kchunks;     // Cin / kc
+  int npass;         // 1, or 3 for split (BF16X2) operands: (x_hi, w_hi), (x_lo, w_hi), (x_hi, w_lo) per tap and K chunk
   int stages;
   int a_bytes, b_bytes, stage_bytes;   // smem footprint (b_bytes rounded up to 1024)
   int tx_bytes;                        // bytes the two TMA boxes actually deliver per stage
@@ -113,7 +114,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   ptx::tc_fence_after();
   const uint32_t tmem_base = ctrl.tmem_base;
 
-  const int ksteps = a.p.ntaps * a.n_kchunks;
+  const int ksteps = a.p.ntaps * a.npass * a.n_kchunks;
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -125,14 +126,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         for (int tap = 0; tap < a.p.ntaps; ++tap) {
           const int ti = t.cls * a.p.ntaps + tap;
           const int cx = xin + a.p.dx[ti], cy = yin + a.p.dy[ti], cz = zin + a.p.dz[ti];
-          for (int kc = 0; kc < a.n_kchunks; ++kc) {
-            ptx::mbar_wait(&ctrl.empty[stage], phase ^ 1);
-            uint8_t* sa = smem + stage * a.stage_bytes;
-            uint8_t* sb = sa + a.a_bytes;
-            ptx::mbar_arrive_expect_tx(&ctrl.full[stage], a.tx_bytes);
-            ptx::tma_load_5d(sa, &map_a, &ctrl.full[stage], kc * a.kc, cx, cy, cz, t.n0);
-            ptx::tma_load_3d(sb, &map_b, &ctrl.full[stage], kc * a.kc, t.nt * a.p.bn, ti);
-            if (++stage == a.stages) { stage = 0; phase ^= 1; }
+          // split operands: the lo halves sit Cin channels after the hi halves, in the activations and in the weights
+          for (int pass = 0; pass < a.npass; ++pass) {
+            const int ca = pass == 1 ? a.p.Cin : 0, cb = pass == 2 ? a.p.Cin : 0;
+            for (int kc = 0; kc < a.n_kchunks; ++kc) {
+              ptx::mbar_wait(&ctrl.empty[stage], phase ^ 1);
+              uint8_t* sa = smem + stage * a.stage_bytes;
+              uint8_t* sb = sa + a.a_bytes;
+              ptx::mbar_arrive_expect_tx(&ctrl.full[stage], a.tx_bytes);
+              ptx::tma_load_5d(sa, &map_a, &ctrl.full[stage], ca + kc * a.kc, cx, cy, cz, t.n0);
+              ptx::tma_load_3d(sb, &map_b, &ctrl.full[stage], cb + kc * a.kc, t.nt * a.p.bn, ti);
+              if (++stage == a.stages) { stage = 0; phase ^= 1; }
+            }
           }
         }
       }
@@ -180,7 +185,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const int dzr = (r >> (a.lw + a.lh)) & (a.p.td - 1);
     const int dnr = r >> (a.lw + a.lh + a.ld);
     const EpiParams epi = {a.bias, a.residual, a.out, a.p.cout_store, a.p.out_dtype == S3D_DTYPE_BF16, a.p.act,
-                           a.p.act_param, a.p.osC, a.p.proj_w, a.p.proj_channel, a.p.proj_act};
+                           a.p.act_param, a.p.osC, a.p.proj_w, a.p.proj_channel, a.p.proj_act,
+                           a.p.os_lo ? a.p.os_lo : (int64_t)a.p.Cout};
+    const bool split_out = a.p.out_dtype == S3D_DTYPE_BF16X2;
     int buf = 0;  uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(a, tile);
@@ -197,7 +204,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         uint32_t v[16];
         ptx::tmem_ld16(taddr + c0, v);
         ptx::tmem_ld_wait();
-        if (valid) epilogue_store16(epi, off, c_base + c0, v);
+        if (valid) {
+          if (split_out) epilogue_store16_split(epi, off, c_base + c0, v);
+          else epilogue_store16(epi, off, c_base + c0, v);
+        }
       }
       ptx::tc_fence_before();
       ptx::mbar_arrive(&ctrl.acc_empty[buf]);
@@ -221,8 +231,10 @@ bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
 int conv_igemm_validate(const S3dConvParams* p, const void* in, const void* w) {
   const int esz = p->in_dtype == S3D_DTYPE_F32 ? 4 : 2;
-  S3D_CHECK_ARG(p->in_dtype == S3D_DTYPE_F32 || p->in_dtype == S3D_DTYPE_BF16, "igemm: bad in_dtype");
-  S3D_CHECK_ARG(p->out_dtype == S3D_DTYPE_F32 || p->out_dtype == S3D_DTYPE_BF16, "igemm: bad out_dtype");
+  S3D_CHECK_ARG(p->in_dtype == S3D_DTYPE_F32 || p->in_dtype == S3D_DTYPE_BF16 || p->in_dtype == S3D_DTYPE_BF16X2, "igemm: bad in_dtype");
+  S3D_CHECK_ARG(p->out_dtype == S3D_DTYPE_F32 || p->out_dtype == S3D_DTYPE_BF16 || p->out_dtype == S3D_DTYPE_BF16X2, "igemm: bad out_dtype");
+  S3D_CHECK_ARG(p->out_dtype != S3D_DTYPE_BF16X2 || (p->osC == 1 && !p->proj_w && p->os_lo >= 0),
+                "igemm: a split (BF16X2) output is channels-last, without a fused projection");
   S3D_CHECK_ARG(p->Cin > 0 && (p->Cin * esz) % 32 == 0, "igemm: Cin*elem must be a multiple of 32 B (Cin=%d)", p->Cin);
   S3D_CHECK_ARG(p->bn >= 16 && p->bn <= 256 && p->bn % 16 == 0 && p->Cout % p->bn == 0,
                 "igemm: bn=%d must be a multiple of 16 <= 256 dividing Cout=%d", p->bn, p->Cout);
@@ -252,6 +264,9 @@ int conv_igemm_launch(const S3dConvParams* p, const void* in, const void* w, con
   a.row_bytes = cin_bytes % 128 == 0 ? 128 : (cin_bytes % 64 == 0 ? 64 : 32);
   a.kc = a.row_bytes / esz;
   a.n_kchunks = p->Cin / a.kc;
+  const bool split = p->in_dtype == S3D_DTYPE_BF16X2;
+  a.npass = split ? 3 : 1;
+  const int cin_phys = split ? 2 * p->Cin : p->Cin;        // [hi(Cin) | lo(Cin)] rows, activations and weights alike
   a.a_bytes = kTileM * a.row_bytes;
   a.b_bytes = ((p->bn * a.row_bytes + 1023) / 1024) * 1024;
   a.tx_bytes = a.a_bytes + p->bn * a.row_bytes;
@@ -259,7 +274,6 @@ int conv_igemm_launch(const S3dConvParams* p, const void* in, const void* w, con
   const int smem_budget = 200 * 1024;
   a.stages = smem_budget / a.stage_bytes;
   if (a.stages > kMaxStages) a.stages = kMaxStages;
-  const int ksteps = p->ntaps * a.n_kchunks;
   if (a.stages < 2) a.stages = 2;
   a.tiles_x = ceil_div(p->oW, p->tw);  a.tiles_y = ceil_div(p->oH, p->th);
   a.tiles_z = ceil_div(p->oD, p->td);  a.tiles_n = ceil_div(p->N, p->tn);
@@ -269,7 +283,6 @@ int conv_igemm_launch(const S3dConvParams* p, const void* in, const void* w, con
   a.total_tiles = (int)total;
   a.lw = ilog2(p->tw);  a.lh = ilog2(p->th);  a.ld = ilog2(p->td);
   a.idesc = ptx::make_instr_desc(tf32 ? 2 : 1, kTileM, p->bn);
-  (void)ksteps;
 
   const CUtensorMapSwizzle sw = a.row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                               : a.row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
@@ -279,9 +292,9 @@ int conv_igemm_launch(const S3dConvParams* p, const void* in, const void* w, con
                          (cuuint32_t)(p->td * p->sz), (cuuint32_t)p->tn};
     cuuint32_t estr[5] = {1, (cuuint32_t)p->sx, (cuuint32_t)p->sy, (cuuint32_t)p->sz, 1};
     S3D_CHECK_ARG(box[1] <= 256 && box[2] <= 256 && box[3] <= 256 && box[4] <= 256, "igemm: TMA box too large");
-    int rc = encode_act_map(&map_a, in, esz, tf32, p->Cin, p->iW, p->iH, p->iD, p->N, box, estr, sw);
+    int rc = encode_act_map(&map_a, in, esz, tf32, cin_phys, p->iW, p->iH, p->iD, p->N, box, estr, sw);
     if (rc != S3D_OK) return rc;
-    rc = encode_weight_map(&map_b, w, esz, tf32, p->Cin, p->Cout, p->ntaps * p->n_classes, a.kc, p->bn, sw);
+    rc = encode_weight_map(&map_b, w, esz, tf32, cin_phys, p->Cout, p->ntaps * p->n_classes, a.kc, p->bn, sw);
     if (rc != S3D_OK) return rc;
   }
 

@@ -8,13 +8,19 @@ using namespace scatter;
 // rotations present.
 bool conv_scatter_eligible(const S3dConvParams* p) {
   const int esz = p->in_dtype == S3D_DTYPE_F32 ? 4 : 2;
+  const bool split = p->in_dtype == S3D_DTYPE_BF16X2;
   if (!p->w_nstack || knobs().no_scatter) return false;
+  // split operands: [hi | lo] rows of 64 / 128 / 256 bytes, split output, transposed stores (Cout a power of two)
+  if (split && (p->out_dtype != S3D_DTYPE_BF16X2 || p->Cin > 64 || (p->Cout != 16 && p->Cout != 32 && p->Cout != 64) ||
+                p->cout_store != p->Cout)) return false;
+  if (!split && p->out_dtype == S3D_DTYPE_BF16X2) return false;
   if (p->n_classes != 1 || p->sx != 1 || p->sy != 1 || p->sz != 1 || p->ntaps != 27) return false;
   if (p->omx != 1 || p->omy != 1 || p->omz != 1 || p->osC != 1 || p->proj_w) return false;
   if (p->oD != p->iD || p->oH != p->iH || p->oW != p->iW) return false;
   for (int t = 0; t < 27; ++t)
     if (p->dz[t] != t / 9 - 1 || p->dy[t] != (t % 9) / 3 - 1 || p->dx[t] != t % 3 - 1) return false;
-  const int cin_bytes = p->Cin * esz;
+  const int cin_bytes = (split ? 2 : 1) * p->Cin * esz;
+  if (split && cin_bytes == 32) return false;
   if (cin_bytes != 32 && cin_bytes != 64 && cin_bytes != 128 && cin_bytes != 256) return false;
   if (p->Cout > 64 || p->Cout % 16 != 0) return false;
   return true;
@@ -24,14 +30,18 @@ int conv_scatter_launch(const S3dConvParams* p_in, const void* in, const float* 
                         cudaStream_t stream) {
   const S3dConvParams& p = *p_in;
   const bool tf32 = p.in_dtype == S3D_DTYPE_F32;
+  const bool split = p.in_dtype == S3D_DTYPE_BF16X2;
   const int esz = tf32 ? 4 : 2;
+  const int cin_phys = split ? 2 * p.Cin : p.Cin;            // channels of a physical pixel row ([hi | lo] when split)
   S3D_CHECK_ARG(p.cout_store >= 1 && p.cout_store <= p.Cout, "scatter: cout_store");
   ScArgs a;
   memset(&a, 0, sizeof(a));
   a.p = p;  a.bias = bias;  a.residual = residual;  a.out = out;
-  a.nchunks = p.Cin * esz == 256 ? 2 : 1;
-  a.row_bytes = p.Cin * esz / a.nchunks;
-  a.kc = p.Cin / a.nchunks;
+  a.split = split ? 1 : 0;
+  a.os_lo = p.os_lo ? p.os_lo : (int64_t)p.Cout;
+  a.nchunks = cin_phys * esz == 256 ? 2 : 1;
+  a.row_bytes = cin_phys * esz / a.nchunks;
+  a.kc = cin_phys / a.nchunks;
   a.chunk_stride = (kPlaneRows * a.row_bytes + 1023) / 1024 * 1024;
   a.slot_bytes = a.nchunks * a.chunk_stride;
   a.cp = p.Cout;
@@ -72,13 +82,18 @@ int conv_scatter_launch(const S3dConvParams* p_in, const void* in, const float* 
   // staging the residual tiles in shared memory by TMA was tried too: 2.66 vs 2.55 ms, it costs three weight stages)
   a.res_direct = !knobs().scatter_res_transpose;
   {
-    const int oesz = p.out_dtype == S3D_DTYPE_BF16 ? 2 : 4;
+    const int oesz = p.out_dtype == S3D_DTYPE_F32 ? 4 : 2;
     const bool simple_act = p.act == S3D_ACT_NONE || p.act == S3D_ACT_RELU || p.act == S3D_ACT_LEAKY;
     auto aligned = [&](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
     auto dense16 = [&](int64_t st) { return (st * oesz) % 16 == 0; };
     a.fast_store = simple_act && bias != nullptr && p.cout_store == p.Cout && aligned(out) && aligned(residual) &&
                    dense16(p.osW) && dense16(p.osH) && dense16(p.osD) && dense16(p.osN) && p.osW < (1ll << 24) &&
-                   !knobs().scatter_no_transpose;
+                   (split || !knobs().scatter_no_transpose);
+    if (split) {
+      S3D_CHECK_ARG(a.fast_store && dense16(a.os_lo) && a.os_lo >= p.Cout,
+                    "scatter (split operands): needs a bias, a none / ReLU / LeakyReLU activation and 16-byte aligned out / residual / strides");
+      a.res_direct = 1;
+    }
   }
 
   const CUtensorMapSwizzle sw = a.row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
@@ -86,16 +101,20 @@ int conv_scatter_launch(const S3dConvParams* p_in, const void* in, const float* 
   CUtensorMap map_x, map_w;
   cuuint32_t box[5] = {(cuuint32_t)a.kc, kHX, kHY, 1, 1};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  int rc = encode_act_map(&map_x, in, esz, tf32, p.Cin, p.iW, p.iH, p.iD, p.N, box, estr, sw);
+  int rc = encode_act_map(&map_x, in, esz, tf32, cin_phys, p.iW, p.iH, p.iD, p.N, box, estr, sw);
   if (rc != S3D_OK) return rc;
-  rc = encode_weight_map(&map_w, p.w_nstack, esz, tf32, p.Cin, 3 * a.cp, 36, a.kc, w_rows, sw, a.tps);
+  rc = encode_weight_map(&map_w, p.w_nstack, esz, tf32, cin_phys, 3 * a.cp, 36, a.kc, w_rows, sw, a.tps);
   if (rc != S3D_OK) return rc;
 
   const int smem_bytes = a.ring * a.slot_bytes + a.w_stages * a.w_bytes + 1024;
   KernFn kern = a.pair ? (tf32 ? conv_scatter_kernel<true, true> : conv_scatter_kernel<false, true>)
                        : (tf32 ? conv_scatter_kernel<true, false> : conv_scatter_kernel<false, false>);
+  if (split) {
+    const bool lean = a.pair && a.tps == spec_tps(a.row_bytes, a.cp) && !knobs().scatter_generic;
+    kern = split_kernel(lean, a.pair != 0, cin_phys * esz, a.cp, residual != nullptr, p.act == S3D_ACT_RELU);
+  }
   // the network's own layer shapes (bf16, CTA pairs, coalesced epilogue) each have a lean kernel
-  if (a.pair && !tf32 && a.nchunks == 1 && p.out_dtype == S3D_DTYPE_BF16 && a.fast_store && a.tps == spec_tps(a.row_bytes, a.cp) &&
+  else if (a.pair && !tf32 && a.nchunks == 1 && p.out_dtype == S3D_DTYPE_BF16 && a.fast_store && a.tps == spec_tps(a.row_bytes, a.cp) &&
       !knobs().scatter_generic) {
     const bool relu = p.act == S3D_ACT_RELU;        // anything else: slope formula
     if (KernFn k = spec_kernel(a.row_bytes, a.cp, residual != nullptr, relu)) kern = k;

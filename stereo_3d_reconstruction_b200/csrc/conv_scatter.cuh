@@ -74,6 +74,12 @@ struct ScArgs {
   uint32_t idesc;
   int fast_store;     // epilogue may use the transposed (coalesced) store path
   int res_direct;
+  // Split (BF16X2, 'bf16x3' precision) operands: rows are [hi(Cin) | lo(Cin)] bf16, weights [hi | lo] likewise, and every tap
+  // issues (x_hi, w_hi), (x_lo, w_hi), (x_hi, w_lo) into the same accumulator.  64 / 128-byte physical rows are ONE K chunk
+  // (the lo half starts row_bytes / 2 into the swizzle atom); 256-byte rows are two chunks as in the fp32 case, with one
+  // weight stage per (tap, hi | lo weights).  The output is split as well: lo parts os_lo elements after the hi parts.
+  int split;
+  int64_t os_lo;
 };
 
 struct ScCtrl {
@@ -203,24 +209,58 @@ __device__ __forceinline__ void sc_commit(uint32_t bar) {
   else       ptx::tc_commit_u32(bar);
 }
 
-template <bool kTF32, int TPS, int kPer, bool kPair, int NK>
+template <bool kTF32, bool kPair>
+__device__ __forceinline__ void sc_mma(uint32_t d_tmem, uint64_t ad, uint64_t bd, uint32_t idesc, uint32_t acc) {
+  if (kPair) { if (kTF32) ptx::mma_tf32_2sm(d_tmem, ad, bd, idesc, acc); else ptx::mma_bf16_2sm(d_tmem, ad, bd, idesc, acc); }
+  else       { if (kTF32) ptx::mma_tf32(d_tmem, ad, bd, idesc, acc);     else ptx::mma_bf16(d_tmem, ad, bd, idesc, acc); }
+}
+
+// kPer = MMAs (of 32 K bytes) per operand HALF in split mode, per chunk otherwise.
+template <bool kTF32, int TPS, int kPer, bool kPair, int NK, bool kSplit>
 __device__ __forceinline__ void sc_issue_group(const ScIssue& z, uint32_t d_tmem, uint64_t xdesc, uint64_t wdesc, int g,
                                                uint32_t first) {
 #pragma unroll
   for (int tt = 0; tt < TPS; ++tt) {
     const int kyx = NK == 2 ? g / 2 : g * TPS + tt;
-    const uint32_t xoff = ((kyx / 3) * kHX + (kyx % 3)) * z.rb16 + (NK == 2 ? (g & 1) * z.chunk_step : 0u);
+    const uint32_t xrow = ((kyx / 3) * kHX + (kyx % 3)) * z.rb16;
+    if constexpr (!kSplit) {
+      const uint32_t xoff = xrow + (NK == 2 ? (g & 1) * z.chunk_step : 0u);
 #pragma unroll
-    for (int k = 0; k < kPer; ++k) {
-      const uint32_t acc = (g == 0 && tt == 0 && k == 0) ? first : 1u;
-      const uint64_t ad = xdesc + xoff + 2 * k, bd = wdesc + tt * z.tap_step + 2 * k;
-      if (kPair) { if (kTF32) ptx::mma_tf32_2sm(d_tmem, ad, bd, z.idesc, acc); else ptx::mma_bf16_2sm(d_tmem, ad, bd, z.idesc, acc); }
-      else       { if (kTF32) ptx::mma_tf32(d_tmem, ad, bd, z.idesc, acc);     else ptx::mma_bf16(d_tmem, ad, bd, z.idesc, acc); }
+      for (int k = 0; k < kPer; ++k) {
+        const uint32_t acc = (g == 0 && tt == 0 && k == 0) ? first : 1u;
+        sc_mma<kTF32, kPair>(d_tmem, xdesc + xoff + 2 * k, wdesc + tt * z.tap_step + 2 * k, z.idesc, acc);
+      }
+    } else if constexpr (NK == 2) {
+      // 256-byte rows: chunk 0 = hi, chunk 1 = lo; stage g = (tap g / 2, hi weights | lo weights)
+      if ((g & 1) == 0) {
+#pragma unroll
+        for (int k = 0; k < kPer; ++k)               // x_hi * w_hi
+          sc_mma<kTF32, kPair>(d_tmem, xdesc + xrow + 2 * k, wdesc + 2 * k, z.idesc, (g == 0 && k == 0) ? first : 1u);
+#pragma unroll
+        for (int k = 0; k < kPer; ++k)               // x_lo * w_hi
+          sc_mma<kTF32, kPair>(d_tmem, xdesc + xrow + z.chunk_step + 2 * k, wdesc + 2 * k, z.idesc, 1u);
+      } else {
+#pragma unroll
+        for (int k = 0; k < kPer; ++k)               // x_hi * w_lo
+          sc_mma<kTF32, kPair>(d_tmem, xdesc + xrow + 2 * k, wdesc + 2 * k, z.idesc, 1u);
+      }
+    } else {
+      // one physical chunk [hi | lo]: the lo half starts kPer MMA steps (32 bytes each) into the row
+      const uint64_t wd = wdesc + tt * z.tap_step;
+#pragma unroll
+      for (int k = 0; k < kPer; ++k)                 // x_hi * w_hi
+        sc_mma<kTF32, kPair>(d_tmem, xdesc + xrow + 2 * k, wd + 2 * k, z.idesc, (g == 0 && tt == 0 && k == 0) ? first : 1u);
+#pragma unroll
+      for (int k = 0; k < kPer; ++k)                 // x_lo * w_hi
+        sc_mma<kTF32, kPair>(d_tmem, xdesc + xrow + 2 * (kPer + k), wd + 2 * k, z.idesc, 1u);
+#pragma unroll
+      for (int k = 0; k < kPer; ++k)                 // x_hi * w_lo
+        sc_mma<kTF32, kPair>(d_tmem, xdesc + xrow + 2 * k, wd + 2 * (kPer + k), z.idesc, 1u);
     }
   }
 }
 
-template <bool kTF32, int TPS, int kPer, bool kPair, int NK = 1>
+template <bool kTF32, int TPS, int kPer, bool kPair, int NK = 1, bool kSplit = false>
 __device__ __forceinline__ void sc_issue(const ScIssue& z) {
   constexpr int G = 9 * NK / TPS;
   int ws = 0;  uint32_t wphase = 0;
@@ -244,7 +284,7 @@ __device__ __forceinline__ void sc_issue(const ScIssue& z) {
           ptx::tc_fence_after();
           const uint64_t wd = z.w_hi | (w_lo0 + ws * w_lo_step);
           if (ptx::elect_one()) {
-            sc_issue_group<kTF32, TPS, kPer, kPair, NK>(z, d0, xd0, wd, g, first);
+            sc_issue_group<kTF32, TPS, kPer, kPair, NK, kSplit>(z, d0, xd0, wd, g, first);
             if (g == G - 1) sc_commit<kPair>(z.bar_af);
           }
           __syncwarp();
@@ -253,7 +293,7 @@ __device__ __forceinline__ void sc_issue(const ScIssue& z) {
           if (g == 1) { ptx::mbar_wait_u32(z.bar_ae + 8, aphase ^ 1); ptx::tc_fence_after(); }
           const uint64_t wd = z.w_hi | (w_lo0 + ws_prev * w_lo_step);
           if (ptx::elect_one()) {
-            sc_issue_group<kTF32, TPS, kPer, kPair, NK>(z, d1, xd1, wd, g - 1, first);
+            sc_issue_group<kTF32, TPS, kPer, kPair, NK, kSplit>(z, d1, xd1, wd, g - 1, first);
             sc_commit<kPair>(z.bar_we + 8 * ws_prev);
             if (g == G) { sc_commit<kPair>(z.bar_af + 8); sc_commit<kPair>(z.bar_pe + 8 * pw); }
           }
@@ -483,6 +523,148 @@ __device__ __forceinline__ void sc_epilogue_dispatch(const ScArgs& a, ScCtrl& ct
   }
 }
 
+// ---- split (BF16X2) epilogue -------------------------------------------------------------------------------------------
+// Output and residual are [hi(CP) | lo(CP)] bf16 per pixel (lo parts os_lo elements after the hi parts).  The value is
+// finished in fp32 (bias, residual = hi + lo, activation), written back over the accumulator registers, and stored as
+// two transposed (coalesced) passes: hi = bf16(v), then lo = bf16(v - hi).  With three MMA passes per tap the tensor core
+// spends 3x longer on a plane than in the bf16 kernel, so this epilogue has slack the bf16 one does not.
+template <int NCH>
+__device__ __forceinline__ void sc_res_load_split(const ScEpi& e, int64_t os_lo, int64_t grp_off, int lane, uint32_t okmask,
+                                                  uint4 (&rh)[NCH], uint4 (&rl)[NCH]) {
+  const int own = (lane & 7) & (NCH - 1);              // this lane's pixel inside its transpose group
+  const __nv_bfloat16* rs = reinterpret_cast<const __nv_bfloat16*>(e.residual) + grp_off + (int64_t)own * e.osW;
+  const bool ok = (okmask >> own) & 1u;
+#pragma unroll
+  for (int k = 0; k < NCH; ++k) {
+    rh[k] = ok ? __ldg(reinterpret_cast<const uint4*>(rs) + k) : make_uint4(0, 0, 0, 0);
+    rl[k] = ok ? __ldg(reinterpret_cast<const uint4*>(rs + os_lo) + k) : make_uint4(0, 0, 0, 0);
+  }
+}
+
+template <int CP, bool kRes, int kAct>
+__device__ __forceinline__ void sc_split_store(const ScEpi& e, int64_t os_lo, int64_t grp_off, int lane, uint32_t okmask,
+                                               uint32_t (&v)[CP / 16][16], const uint4 (&rh)[CP / 8], const uint4 (&rl)[CP / 8]) {
+  constexpr int NCH = CP / 8;                           // 16-byte chunks of one half of a pixel
+  // pass 0: v <- act(v + bias (+ residual)) as fp32 bits
+#pragma unroll
+  for (int jg = 0; jg < CP / 16; ++jg) {
+    const float4* b4 = reinterpret_cast<const float4*>(e.bias + 16 * jg);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 b = __ldg(b4 + i);
+      float f0 = __uint_as_float(v[jg][4 * i]) + b.x, f1 = __uint_as_float(v[jg][4 * i + 1]) + b.y;
+      float f2 = __uint_as_float(v[jg][4 * i + 2]) + b.z, f3 = __uint_as_float(v[jg][4 * i + 3]) + b.w;
+      if (kRes) {
+        // channels 16 jg + 4 i .. + 3 = halves (2 i) % 4, (2 i + 1) % 4 of chunk 2 jg + i / 2
+        const __nv_bfloat162* ph = reinterpret_cast<const __nv_bfloat162*>(&rh[2 * jg + (i >> 1)]) + 2 * (i & 1);
+        const __nv_bfloat162* pl = reinterpret_cast<const __nv_bfloat162*>(&rl[2 * jg + (i >> 1)]) + 2 * (i & 1);
+        const float2 h0 = __bfloat1622float2(ph[0]), h1 = __bfloat1622float2(ph[1]);
+        const float2 l0 = __bfloat1622float2(pl[0]), l1 = __bfloat1622float2(pl[1]);
+        f0 += h0.x + l0.x;  f1 += h0.y + l0.y;  f2 += h1.x + l1.x;  f3 += h1.y + l1.y;
+      }
+      if (kAct == 0) { f0 = fmax_nan(f0, 0.f); f1 = fmax_nan(f1, 0.f); f2 = fmax_nan(f2, 0.f); f3 = fmax_nan(f3, 0.f); }
+      else if (kAct == 2) {
+        f0 = fmax_nan(f0, 0.f) + e.slope * fmin_nan(f0, 0.f);  f1 = fmax_nan(f1, 0.f) + e.slope * fmin_nan(f1, 0.f);
+        f2 = fmax_nan(f2, 0.f) + e.slope * fmin_nan(f2, 0.f);  f3 = fmax_nan(f3, 0.f) + e.slope * fmin_nan(f3, 0.f);
+      }
+      v[jg][4 * i] = __float_as_uint(f0);      v[jg][4 * i + 1] = __float_as_uint(f1);
+      v[jg][4 * i + 2] = __float_as_uint(f2);  v[jg][4 * i + 3] = __float_as_uint(f3);
+    }
+  }
+  const int j = lane & (NCH - 1);
+  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(e.out) + grp_off + j * 8;
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {               // 0: hi parts, 1: lo parts
+    uint4 c[NCH];
+#pragma unroll
+    for (int jg = 0; jg < CP / 16; ++jg) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint32_t hi, lo;
+          split_bf16x2(__uint_as_float(v[jg][8 * h + 2 * i]), __uint_as_float(v[jg][8 * h + 2 * i + 1]), hi, lo);
+          w[i] = half == 0 ? hi : lo;
+        }
+        c[2 * jg + h] = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+    }
+    chunk_transpose<NCH>(c, lane);
+    __nv_bfloat16* oh = o + (half == 0 ? (int64_t)0 : os_lo);
+#pragma unroll
+    for (int k = 0; k < NCH; ++k)
+      if ((okmask >> k) & 1u) *reinterpret_cast<uint4*>(oh + k * e.osW) = c[k];
+  }
+}
+
+template <int CP, int kSRes = -1, int kSAct = -1>
+__device__ __forceinline__ void sc_epilogue_split(const ScArgs& a, ScCtrl& ctrl, uint32_t tmem_base, int warp, int lane) {
+  constexpr int NCH = CP / 8;
+  const int t = (warp - 4) >> 2, q = warp & 3;
+  const ScEpi fe = {a.bias, a.residual, a.out,
+                    a.p.act == S3D_ACT_NONE ? 1.f : (a.p.act == S3D_ACT_LEAKY ? a.p.act_param : 0.f), (int)a.p.osW, 1};
+  const int64_t os_lo = a.os_lo;
+  const uint32_t bar_af = ptx::smem_u32(&ctrl.acc_full[t]), bar_ae = ptx::smem_u32(&ctrl.acc_empty[t]);
+  const uint32_t tbase = tmem_base + t * kTileCols + (static_cast<uint32_t>(q * 32) << 16);
+  const int yl = t * kTileY + q * 4 + (lane >> 3), xl = lane & 7;
+  const int D = a.p.oD;
+  const int xb = xl & ~(NCH - 1);
+  uint32_t aphase = 0;
+  const int ncols = cta_cols(a);
+  for (int ci = 0; ci < ncols; ++ci) {
+    const Col c = decode_col(a, blockIdx.x + ci * gridDim.x);
+    const bool rowok = c.y0 + yl < a.p.oH && c.n < a.p.N;
+    const int64_t row_off = (int64_t)c.n * a.p.osN + (int64_t)(c.y0 + yl) * a.p.osH + (int64_t)c.x0 * a.p.osW;
+    const int64_t grp_off = row_off + (int64_t)xb * a.p.osW;
+    uint32_t okmask = 0;
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) okmask |= (rowok && c.x0 + xb + k < a.p.oW) ? (1u << k) : 0u;
+    int slot = 0, z = 0;
+    for (int p = 0; p < D; ++p) {
+      const int ndrain = (p >= 1 ? 1 : 0) + (p == D - 1 ? 1 : 0);
+      uint4 rh[NCH], rl[NCH];
+      if (a.residual && ndrain) sc_res_load_split<NCH>(fe, os_lo, grp_off + (int64_t)z * a.p.osD, lane, okmask, rh, rl);
+      ptx::mbar_wait_u32(bar_af, aphase);
+      ptx::tc_fence_after();
+      if (ndrain == 0) {
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) { if (a.pair) ptx::mbar_arrive_cluster_u32(bar_ae, 0); else ptx::mbar_arrive_u32(bar_ae); }
+      }
+      for (int i = 0; i < ndrain; ++i) {
+        uint32_t v[CP / 16][16];
+        const uint32_t taddr = tbase + slot * CP;
+#pragma unroll
+        for (int j = 0; j < CP / 16; ++j) ptx::tmem_ld16(taddr + 16 * j, v[j]);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < CP / 16; ++j) ptx::tmem_st16_zero(taddr + 16 * j);
+        ptx::tmem_st_wait();
+        if (i == ndrain - 1) {
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) { if (a.pair) ptx::mbar_arrive_cluster_u32(bar_ae, 0); else ptx::mbar_arrive_u32(bar_ae); }
+        }
+        const int64_t zo = (int64_t)z * a.p.osD;
+        if (i == 1 && a.residual) sc_res_load_split<NCH>(fe, os_lo, grp_off + zo, lane, okmask, rh, rl);
+        if constexpr (kSRes >= 0) {
+          sc_split_store<CP, kSRes != 0, kSAct>(fe, os_lo, grp_off + zo, lane, okmask, v, rh, rl);
+        } else if (fe.slope == 0.f) {
+          if (a.residual) sc_split_store<CP, true, 0>(fe, os_lo, grp_off + zo, lane, okmask, v, rh, rl);
+          else            sc_split_store<CP, false, 0>(fe, os_lo, grp_off + zo, lane, okmask, v, rh, rl);
+        } else {
+          if (a.residual) sc_split_store<CP, true, 2>(fe, os_lo, grp_off + zo, lane, okmask, v, rh, rl);
+          else            sc_split_store<CP, false, 2>(fe, os_lo, grp_off + zo, lane, okmask, v, rh, rl);
+        }
+        ++z;
+        if (++slot == 3) slot = 0;
+      }
+      aphase ^= 1;
+    }
+  }
+}
+
 // Taps per weight stage.  Narrow layers take all 9 in-plane taps in one stage when that fits 28 KB: a tile's accumulator
 // hand-back hides behind the OTHER tile's current stage, and a stage of 3 one-MMA taps (~180 cycles) is too short for
 // it (fusion scorer: 0.148 -> 0.100 ms per layer).
@@ -494,7 +676,8 @@ __host__ __device__ constexpr int spec_tps(int rb, int cp) {
 // Every variant of producer / issuer / epilogue is inlined into the kernel, and the kernel is sensitive to its own code
 // size (measured: two more epilogue variants in the all-in-one kernel cost 4 % of the whole forward), so the layer
 // shapes of the network each get a kernel that contains only their own code.  RB == 0: all-in-one, run-time dispatch.
-template <bool kTF32, bool kPair, int RB = 0, int CP = 0, int kSRes = -1, int kSAct = -1>
+// kSplit: BF16X2 operands and output (see ScArgs::split).  RB is then the PHYSICAL row (64 / 128 bytes: one chunk; 256: two).
+template <bool kTF32, bool kPair, int RB = 0, int CP = 0, int kSRes = -1, int kSAct = -1, bool kSplit = false>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_scatter_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                     const __grid_constant__ ScArgs a) {
@@ -525,7 +708,8 @@ conv_scatter_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
 
   if (warp == 0) {
     const uint32_t planes_u32 = ptx::smem_u32(smem), w_u32 = ptx::smem_u32(smem_w);
-    if constexpr (RB == 128) sc_produce<1, kPair>(a, ctrl, planes_u32, w_u32, &map_x, &map_w);
+    if constexpr (RB == 256) sc_produce<1, kPair, 2>(a, ctrl, planes_u32, w_u32, &map_x, &map_w);
+    else if constexpr (RB == 128) sc_produce<1, kPair>(a, ctrl, planes_u32, w_u32, &map_x, &map_w);
     else if constexpr (RB != 0) sc_produce<spec_tps(RB, CP), kPair>(a, ctrl, planes_u32, w_u32, &map_x, &map_w);
     else if (a.nchunks == 2) sc_produce<1, kPair, 2>(a, ctrl, planes_u32, w_u32, &map_x, &map_w);
     else if (a.tps == 1) sc_produce<1, kPair>(a, ctrl, planes_u32, w_u32, &map_x, &map_w);
@@ -539,7 +723,17 @@ conv_scatter_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                         desc_hi(kHX * rb, rb), desc_hi(8 * rb, rb), a.slot_bytes, a.w_bytes, a.w_stages, a.ring,
                         (uint32_t)(rb >> 4), (uint32_t)(((kPair ? 3 * a.cp / 2 : 3 * a.cp) * rb) >> 4), (uint32_t)((kTileY * kHX * rb) >> 4), (uint32_t)(a.chunk_stride >> 4), a.idesc,
                         a.p.iD, cta_cols(a)};
-    if constexpr (RB == 128) sc_issue<kTF32, 1, 4, kPair>(zi);
+    if constexpr (kSplit) {
+      // kPer counts the MMAs of one operand HALF here
+      if constexpr (RB == 256) sc_issue<false, 1, 4, kPair, 2, true>(zi);
+      else if constexpr (RB == 128) sc_issue<false, 1, 2, kPair, 1, true>(zi);
+      else if constexpr (RB == 64) sc_issue<false, spec_tps(RB, CP), 1, kPair, 1, true>(zi);
+      else if (a.nchunks == 2) sc_issue<false, 1, 4, kPair, 2, true>(zi);
+      else if (rb == 128) sc_issue<false, 1, 2, kPair, 1, true>(zi);
+      else if (a.tps == 9) sc_issue<false, 9, 1, kPair, 1, true>(zi);
+      else sc_issue<false, 3, 1, kPair, 1, true>(zi);
+    }
+    else if constexpr (RB == 128) sc_issue<kTF32, 1, 4, kPair>(zi);
     else if constexpr (RB == 64) sc_issue<kTF32, spec_tps(RB, CP), 2, kPair>(zi);
     else if constexpr (RB == 32) sc_issue<kTF32, spec_tps(RB, CP), 1, kPair>(zi);
     else if (a.nchunks == 2) sc_issue<kTF32, 1, 4, kPair, 2>(zi);
@@ -549,7 +743,13 @@ conv_scatter_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     else if (a.tps == 3) sc_issue<kTF32, 3, 1, kPair>(zi);
     else sc_issue<kTF32, 9, 1, kPair>(zi);
   } else if (warp >= 4) {
-    if constexpr (RB != 0) sc_epilogue<CP, __nv_bfloat16, true, kSRes, kSAct>(a, ctrl, tmem_base, warp, lane);
+    if constexpr (kSplit) {
+      if constexpr (RB != 0) sc_epilogue_split<CP, kSRes, kSAct>(a, ctrl, tmem_base, warp, lane);
+      else if (a.cp == 64) sc_epilogue_split<64>(a, ctrl, tmem_base, warp, lane);
+      else if (a.cp == 32) sc_epilogue_split<32>(a, ctrl, tmem_base, warp, lane);
+      else sc_epilogue_split<16>(a, ctrl, tmem_base, warp, lane);
+    }
+    else if constexpr (RB != 0) sc_epilogue<CP, __nv_bfloat16, true, kSRes, kSAct>(a, ctrl, tmem_base, warp, lane);
     else if (a.cp == 64) sc_epilogue_dispatch<64>(a, ctrl, tmem_base, warp, lane);
     else if (a.cp == 48) sc_epilogue_dispatch<48>(a, ctrl, tmem_base, warp, lane);
     else if (a.cp == 32) sc_epilogue_dispatch<32>(a, ctrl, tmem_base, warp, lane);
@@ -569,6 +769,9 @@ conv_scatter_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
 typedef void (*KernFn)(CUtensorMap, CUtensorMap, ScArgs);
 // conv_scatter_spec.cu: the lean kernel for this layer shape (bf16, CTA pairs, coalesced epilogue), or nullptr
 KernFn spec_kernel(int row_bytes, int cp, bool residual, bool relu);
+// conv_scatter_split.cu: kernels for split (BF16X2) operands -- lean per-shape ones (CTA pairs; phys_row_bytes = bytes of a
+// [hi | lo] pixel row) or, with lean = false, the all-in-one kernel for the given pairing
+KernFn split_kernel(bool lean, bool pair, int phys_row_bytes, int cp, bool residual, bool relu);
 
 }  // namespace scatter
 }  // namespace s3d

@@ -258,14 +258,9 @@ conv_scatter_concat_kernel(const __grid_constant__ CUtensorMap map_ref, const __
 
 static int encode5(CUtensorMap* m, const void* base, bool f32, const cuuint64_t dims[5], const cuuint64_t strides[4],
                    const cuuint32_t box[5], CUtensorMapSwizzle sw) {
-  EncodeTiledFn enc = get_encode_fn();
-  if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return S3D_ERR_CUDA; }
-  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = enc(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims,
-                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(concat view) failed: %d", (int)r); return S3D_ERR_CUDA; }
-  return S3D_OK;
+  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  return encode_tiled_cached(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, dims, strides, box,
+                             estr, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, "concat view");
 }
 
 }  // namespace scatter

@@ -50,6 +50,43 @@ concat_volume_kernel(const uint4* __restrict__ feat, uint4* __restrict__ vol, in
   }
 }
 
+// Split (BF16X2) features [.., hi(C) | lo(C)] -> split volume [.., hi(ref C, tgt C) | lo(ref C, tgt C)]: the hi halves and the
+// lo halves each form the plain concat volume, so a 2C-channel split layer reads it like any other split tensor.
+__global__ void __launch_bounds__(256)
+concat_volume_split_kernel(const uint4* __restrict__ feat, uint4* __restrict__ vol, int B, int h, int w,
+                           int vpp /* 16-B vectors per pixel of one HALF of a feature map */, int D) {
+  extern __shared__ uint4 srow[];          // [2][w * 2 vpp]: ref row, tgt row (physical pixels)
+  const int n = blockIdx.x / h, y = blockIdx.x % h;
+  const bool left_ref = n < B;
+  const int tgt_n = left_ref ? n + B : n - B;
+  const int rowv = w * 2 * vpp;
+  const uint4* ref_g = feat + ((int64_t)n * h + y) * rowv;
+  const uint4* tgt_g = feat + ((int64_t)tgt_n * h + y) * rowv;
+  for (int i = threadIdx.x; i < rowv; i += blockDim.x) {
+    srow[i] = __ldg(ref_g + i);
+    srow[rowv + i] = __ldg(tgt_g + i);
+  }
+  __syncthreads();
+  const int outv = 2 * rowv;               // vectors per (d, row) output line: 4 vpp per pixel
+  const uint4 zero = make_uint4(0, 0, 0, 0);
+  for (int d = 0; d < D; ++d) {
+    uint4* o = vol + (((int64_t)n * D + d) * h + y) * outv;
+    for (int i = threadIdx.x; i < outv; i += blockDim.x) {
+      const int x = i / (4 * vpp), j = i % (4 * vpp);
+      const int part = j / vpp, jj = j % vpp;          // part: 0 ref hi, 1 tgt hi, 2 ref lo, 3 tgt lo
+      const int half = part >> 1;
+      uint4 v;
+      if ((part & 1) == 0) {
+        v = srow[x * 2 * vpp + half * vpp + jj];
+      } else {
+        const int xs = left_ref ? x - d : x + d;
+        v = (xs >= 0 && xs < w) ? srow[rowv + xs * 2 * vpp + half * vpp + jj] : zero;
+      }
+      __stcs(o + i, v);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // standalone soft-argmin over a [N,D,h,w] fp32 cost
 // ------------------------------------------------------------------------------------------
@@ -272,13 +309,21 @@ int corr_tc_launch(const void* feat, float* disp, int B, int h, int w, int C, in
 extern "C" int s3d_cost_volume_concat(const void* feat, void* vol, int B, int h, int w, int C, int D, int dtype,
                                       void* stream) {
   if (!feat || !vol) { set_error("cost_volume_concat: null argument"); return S3D_ERR_INVALID; }
-  S3D_CHECK_ARG(dtype == S3D_DTYPE_F32 || dtype == S3D_DTYPE_BF16, "cost_volume_concat: bad dtype");
+  S3D_CHECK_ARG(dtype == S3D_DTYPE_F32 || dtype == S3D_DTYPE_BF16 || dtype == S3D_DTYPE_BF16X2, "cost_volume_concat: bad dtype");
   const int esz = dtype == S3D_DTYPE_F32 ? 4 : 2;
   S3D_CHECK_ARG(B > 0 && h > 0 && w > 0 && D > 0 && C > 0 && (C * esz) % 16 == 0,
                 "cost_volume_concat: C*elem must be a multiple of 16 B");
   const int vpp = C * esz / 16;
-  const size_t smem = (size_t)2 * w * vpp * sizeof(uint4);
+  const bool split = dtype == S3D_DTYPE_BF16X2;
+  const size_t smem = (size_t)(split ? 4 : 2) * w * vpp * sizeof(uint4);
   S3D_CHECK_ARG(smem <= 200 * 1024, "cost_volume_concat: row too large for shared memory");
+  if (split) {
+    S3D_CUDA(cudaFuncSetAttribute(concat_volume_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    concat_volume_split_kernel<<<2 * B * h, 256, smem, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const uint4*>(feat), static_cast<uint4*>(vol), B, h, w, vpp, D);
+    S3D_LAUNCH_CHECK();
+    return S3D_OK;
+  }
   S3D_CUDA(cudaFuncSetAttribute(concat_volume_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   concat_volume_kernel<<<2 * B * h, 256, smem, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const uint4*>(feat), static_cast<uint4*>(vol), B, h, w, vpp, D);

@@ -137,6 +137,41 @@ __global__ void pool_kernel(const T* __restrict__ x, T* __restrict__ out, int N,
   }
 }
 
+// Split (BF16X2) variant: x [N,H,W, hi(C) | lo(C)], the mean is taken over hi + lo in fp32 and written split again
+// ([N,L,L, hi(C) | lo(C)], or [N,2,2,2, hi(K) | lo(K)] with K = C*L*L/8 for to_vox).
+__global__ void pool_split_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, int N, int H, int W, int C,
+                                  int L, int to_vox) {
+  const int64_t total = (int64_t)N * L * L * C;
+  const int K = C * L * L / 8;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i;
+    const int c = (int)(r % C);  r /= C;
+    const int px = (int)(r % L);  r /= L;
+    const int py = (int)(r % L);  r /= L;
+    const int n = (int)r;
+    int ys, ye, xs, xe;
+    pool_bin(py, H, L, ys, ye);
+    pool_bin(px, W, L, xs, xe);
+    float acc = 0.f;
+    for (int yy = ys; yy < ye; ++yy)
+      for (int xx = xs; xx < xe; ++xx) {
+        const __nv_bfloat16* q = x + (((int64_t)n * H + yy) * W + xx) * 2 * C + c;
+        acc += __bfloat162float(q[0]) + __bfloat162float(q[C]);
+      }
+    acc /= (float)((ye - ys) * (xe - xs));
+    const __nv_bfloat16 hi = __float2bfloat16_rn(acc), lo = __float2bfloat16_rn(acc - __bfloat162float(hi));
+    if (to_vox) {
+      const int f = (c * L + py) * L + px;
+      const int k = f >> 3, cell = f & 7;
+      __nv_bfloat16* o = out + ((int64_t)n * 8 + cell) * 2 * K + k;
+      o[0] = hi;  o[K] = lo;
+    } else {
+      __nv_bfloat16* o = out + (i / C) * 2 * C + c;
+      o[0] = hi;  o[C] = lo;
+    }
+  }
+}
+
 constexpr int kMaxThresh = 8;
 struct Thresh { float t[kMaxThresh]; };
 
@@ -144,20 +179,22 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 fuse_views_kernel(const T* __restrict__ score, int64_t sstride, const T* __restrict__ vol, int64_t vstride,
                   float* __restrict__ fused, int B, int V, int nvox, const uint8_t* __restrict__ gt, Thresh th, int nT,
-                  unsigned long long* __restrict__ iou) {
+                  unsigned long long* __restrict__ iou, int64_t score_lo, int64_t vol_lo) {
+  // score_lo / vol_lo != 0: split (BF16X2) tensors, value = [e] + [e + lo offset]
+  auto ld = [](const T* p, int64_t lo) { return lo ? to_f32(p[0]) + to_f32(p[lo]) : to_f32(p[0]); };
   const int b = blockIdx.y;
   unsigned inter[kMaxThresh], uni[kMaxThresh];
 #pragma unroll
   for (int t = 0; t < kMaxThresh; ++t) { inter[t] = 0; uni[t] = 0; }
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nvox; i += gridDim.x * blockDim.x) {
     float m = -INFINITY;
-    for (int v = 0; v < V; ++v) m = fmaxf(m, to_f32(score[(((int64_t)v * B + b) * nvox + i) * sstride]));
+    for (int v = 0; v < V; ++v) m = fmaxf(m, ld(score + (((int64_t)v * B + b) * nvox + i) * sstride, score_lo));
     float s = 0.f, acc = 0.f;
     for (int v = 0; v < V; ++v) {
       const int64_t e = ((int64_t)v * B + b) * nvox + i;
-      const float w = expf(to_f32(score[e * sstride]) - m);
+      const float w = expf(ld(score + e * sstride, score_lo) - m);
       s += w;
-      acc += w * to_f32(vol[e * vstride]);
+      acc += w * ld(vol + e * vstride, vol_lo);
     }
     float f = acc / s;
     f = fminf(fmaxf(f, 0.f), 1.f);
@@ -314,13 +351,55 @@ __global__ void depth_to_space_kernel(const T* __restrict__ in, T* __restrict__ 
   }
 }
 
+// Split (BF16X2) variant: in [N,d,h,w, hi(64) | lo(64)] -> out [N,2d,2h,2w, hi(16) | lo(16)]; the projection is computed
+// from hi + lo in fp32 and stored split in channel 8.
+__global__ void depth_to_space_split_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out,
+                                            const float* __restrict__ proj_w, int proj_act, int N, int d, int h, int w) {
+  const int64_t total = (int64_t)N * d * h * w * 8;
+  float pw[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) pw[c] = proj_w ? __ldg(proj_w + c) : 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cls = (int)(i & 7);
+    int64_t r = i >> 3;
+    const int64_t pix = r;
+    const int x = (int)(r % w);  r /= w;
+    const int y = (int)(r % h);  r /= h;
+    const int z = (int)(r % d);  r /= d;
+    const int n = (int)r;
+    const __nv_bfloat16* ip = in + pix * 128 + cls * 8;
+    const uint4 rh = __ldg(reinterpret_cast<const uint4*>(ip)), rl = __ldg(reinterpret_cast<const uint4*>(ip + 64));
+    const __nv_bfloat162* ph = reinterpret_cast<const __nv_bfloat162*>(&rh);
+    const __nv_bfloat162* pl = reinterpret_cast<const __nv_bfloat162*>(&rl);
+    float pr = 0.f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float2 gh = __bfloat1622float2(ph[c]), gl = __bfloat1622float2(pl[c]);
+      pr = fmaf(gh.x + gl.x, pw[2 * c], pr);  pr = fmaf(gh.y + gl.y, pw[2 * c + 1], pr);
+    }
+    pr = proj_w ? apply_act(pr, proj_act, 1.f) : 0.f;
+    const __nv_bfloat16 prh = __float2bfloat16_rn(pr), prl = __float2bfloat16_rn(pr - __bfloat162float(prh));
+    const int oz = 2 * z + (cls >> 2), oy = 2 * y + ((cls >> 1) & 1), ox = 2 * x + (cls & 1);
+    __nv_bfloat16* op = out + ((((int64_t)n * 2 * d + oz) * 2 * h + oy) * 2 * w + ox) * 32;
+    uint4 zh = make_uint4(0, 0, 0, 0), zl = make_uint4(0, 0, 0, 0);
+    zh.x = (uint32_t)(*reinterpret_cast<const unsigned short*>(&prh));
+    zl.x = (uint32_t)(*reinterpret_cast<const unsigned short*>(&prl));
+    reinterpret_cast<uint4*>(op)[0] = rh;  reinterpret_cast<uint4*>(op)[1] = zh;      // hi: 8 features, projection, zeros
+    reinterpret_cast<uint4*>(op)[2] = rl;  reinterpret_cast<uint4*>(op)[3] = zl;      // lo
+  }
+}
+
 extern "C" int s3d_depth_to_space(const void* in, void* out, const float* proj_w, int proj_act, int N, int d, int h, int w,
                                   int Cpad, int dtype, void* stream) {
   if (!in || !out) { set_error("depth_to_space: null argument"); return S3D_ERR_INVALID; }
   S3D_CHECK_ARG(N > 0 && d > 0 && h > 0 && w > 0 && Cpad >= 8 && (Cpad == 8 || Cpad >= 9), "depth_to_space: bad shape");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int64_t total = (int64_t)N * d * h * w * 8;
-  if (dtype == S3D_DTYPE_BF16)
+  if (dtype == S3D_DTYPE_BF16X2) {
+    S3D_CHECK_ARG(Cpad == 16, "depth_to_space (split): Cpad must be 16");
+    depth_to_space_split_kernel<<<grid_for(total, 256), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(in),
+        static_cast<__nv_bfloat16*>(out), proj_w, proj_act, N, d, h, w);
+  } else if (dtype == S3D_DTYPE_BF16)
     depth_to_space_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(in),
         static_cast<__nv_bfloat16*>(out), proj_w, proj_act, N, d, h, w, Cpad);
   else if (dtype == S3D_DTYPE_F32)
@@ -356,13 +435,50 @@ extern "C" int s3d_split_tf32(const float* x, float* hi, float* lo, int64_t n, v
   return S3D_OK;
 }
 
+// Split (BF16X2) tensor [npix, hi(C) | lo(C)] <-> fp32 [npix, C] (hand-off to / from the kernels that take plain fp32).
+__global__ void unsplit_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, int64_t npix, int C) {
+  const int64_t total = npix * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t pix = i / C;  const int c = (int)(i % C);
+    const __nv_bfloat16* q = x + pix * 2 * C + c;
+    out[i] = __bfloat162float(q[0]) + __bfloat162float(q[C]);
+  }
+}
+__global__ void split_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int64_t npix, int C) {
+  const int64_t total = npix * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t pix = i / C;  const int c = (int)(i % C);
+    const float v = x[i];
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    __nv_bfloat16* q = out + pix * 2 * C + c;
+    q[0] = hi;  q[C] = __float2bfloat16_rn(v - __bfloat162float(hi));
+  }
+}
+
+extern "C" int s3d_split_bf16(const float* x, void* out, int64_t npix, int C, void* stream) {
+  if (!x || !out) { set_error("split_bf16: null argument"); return S3D_ERR_INVALID; }
+  S3D_CHECK_ARG(npix > 0 && C > 0, "split_bf16: bad shape");
+  split_kernel<<<grid_for(npix * C, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, static_cast<__nv_bfloat16*>(out), npix, C);
+  S3D_LAUNCH_CHECK();
+  return S3D_OK;
+}
+extern "C" int s3d_unsplit_bf16(const void* x, float* out, int64_t npix, int C, void* stream) {
+  if (!x || !out) { set_error("unsplit_bf16: null argument"); return S3D_ERR_INVALID; }
+  S3D_CHECK_ARG(npix > 0 && C > 0, "unsplit_bf16: bad shape");
+  unsplit_kernel<<<grid_for(npix * C, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(x), out, npix, C);
+  S3D_LAUNCH_CHECK();
+  return S3D_OK;
+}
+
 static int pool_launch(const void* x, void* out, int N, int H, int W, int C, int L, int dtype, int to_vox, void* stream) {
   if (!x || !out) { set_error("pool: null argument"); return S3D_ERR_INVALID; }
   S3D_CHECK_ARG(N > 0 && H > 0 && W > 0 && C > 0 && L > 0, "pool: bad shape");
   S3D_CHECK_ARG(!to_vox || (C * L * L) % 8 == 0, "latent_to_vox: C*L*L must be a multiple of 8");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int64_t total = (int64_t)N * L * L * C;
-  if (dtype == S3D_DTYPE_BF16)
+  if (dtype == S3D_DTYPE_BF16X2)
+    pool_split_kernel<<<grid_for(total, 256), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(out), N, H, W, C, L, to_vox);
+  else if (dtype == S3D_DTYPE_BF16)
     pool_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(out), N, H, W, C, L, to_vox);
   else if (dtype == S3D_DTYPE_F32)
     pool_kernel<float><<<grid_for(total, 256), 256, 0, st>>>(static_cast<const float*>(x), static_cast<float*>(out), N, H, W, C, L, to_vox);
@@ -380,7 +496,7 @@ extern "C" int s3d_avg_pool(const void* x, void* out, int N, int H, int W, int C
 
 extern "C" int s3d_fuse_views(const void* score, int64_t score_stride, const void* vol, int64_t vol_stride, int dtype,
                               float* fused, int B, int V, int nvox, const uint8_t* gt, const float* thresholds, int T,
-                              long long* iou, void* stream) {
+                              long long* iou, int64_t score_lo, int64_t vol_lo, void* stream) {
   if (!score || !vol || !fused) { set_error("fuse_views: null argument"); return S3D_ERR_INVALID; }
   S3D_CHECK_ARG(B > 0 && V > 0 && nvox > 0 && T >= 0 && T <= kMaxThresh, "fuse_views: bad shape (T<=8)");
   S3D_CHECK_ARG(!gt || (thresholds && iou), "fuse_views: gt needs thresholds and iou");
@@ -388,10 +504,12 @@ extern "C" int s3d_fuse_views(const void* score, int64_t score_stride, const voi
   for (int t = 0; t < kMaxThresh; ++t) th.t[t] = (gt && t < T) ? thresholds[t] : 2.f;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   dim3 grid(ceil_div(nvox, 256 * 4), B);
-  if (dtype == S3D_DTYPE_BF16)
-    fuse_views_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(score), score_stride, static_cast<const __nv_bfloat16*>(vol), vol_stride, fused, B, V, nvox, gt, th, T, reinterpret_cast<unsigned long long*>(iou));
+  S3D_CHECK_ARG(dtype == S3D_DTYPE_BF16X2 ? (score_lo > 0 && vol_lo > 0) : (score_lo == 0 && vol_lo == 0),
+                "fuse_views: score_lo / vol_lo are the lo-part offsets of split (BF16X2) tensors, 0 otherwise");
+  if (dtype == S3D_DTYPE_BF16 || dtype == S3D_DTYPE_BF16X2)
+    fuse_views_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(score), score_stride, static_cast<const __nv_bfloat16*>(vol), vol_stride, fused, B, V, nvox, gt, th, T, reinterpret_cast<unsigned long long*>(iou), score_lo, vol_lo);
   else if (dtype == S3D_DTYPE_F32)
-    fuse_views_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(score), score_stride, static_cast<const float*>(vol), vol_stride, fused, B, V, nvox, gt, th, T, reinterpret_cast<unsigned long long*>(iou));
+    fuse_views_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(score), score_stride, static_cast<const float*>(vol), vol_stride, fused, B, V, nvox, gt, th, T, reinterpret_cast<unsigned long long*>(iou), 0, 0);
   else { set_error("fuse_views: bad dtype"); return S3D_ERR_INVALID; }
   S3D_LAUNCH_CHECK();
   return S3D_OK;

@@ -26,7 +26,36 @@ def pad_to(c, m=PAD):
 
 
 def torch_dtype(code):
-    return torch.bfloat16 if code == _lib.DTYPE_BF16 else torch.float32
+    return torch.float32 if code == _lib.DTYPE_F32 else torch.bfloat16
+
+
+def is_split(code):
+    return code == _lib.DTYPE_BF16X2
+
+
+def cmult(code):
+    """Physical channels per logical channel: split (BF16X2) tensors are [hi(C) | lo(C)]."""
+    return 2 if code == _lib.DTYPE_BF16X2 else 1
+
+
+def to_storage(w, code):
+    """fp32 [..., C] -> the storage form of `code`: fp32, bf16, or the bf16 pair [hi(C) | lo(C)] with hi = bf16(w),
+    lo = bf16(w - hi) (include/s3d.h, S3D_DTYPE_BF16X2)."""
+    if code == _lib.DTYPE_F32:
+        return w.float()
+    hi = w.to(torch.bfloat16)
+    if code == _lib.DTYPE_BF16:
+        return hi
+    lo = (w.float() - hi.float()).to(torch.bfloat16)
+    return torch.cat([hi, lo], -1)
+
+
+def from_storage(t, code):
+    """Inverse of to_storage (fp32 values of a stored tensor)."""
+    if code != _lib.DTYPE_BF16X2:
+        return t.float()
+    c = t.shape[-1] // 2
+    return t[..., :c].float() + t[..., c:].float()
 
 
 def _fold_bn(w_out_first, bias, bn):
@@ -87,7 +116,7 @@ class PackedConv:
         self.dtype_code = dtype_code
         wp = torch.zeros(self.n_classes * self.ntaps, self.cout_pad, self.cin_pad, dtype=torch.float32)
         wp[:, :cout, :cin] = w_rows.cpu()
-        self.weight = wp.to(torch_dtype(dtype_code)).to(device).contiguous()
+        self.weight = to_storage(wp, dtype_code).to(device).contiguous()      # split: [rows, Cout_pad, hi(Cin_pad) | lo(Cin_pad)]
         bp = torch.zeros(self.cout_pad, dtype=torch.float32)
         bp[:cout] = bias.cpu()
         self.bias = bp.to(device)
@@ -99,7 +128,7 @@ class PackedConv:
         if tuple(ksize) == (3, 3, 3) and tuple(pad) == (1, 1, 1) and tuple(stride) == (1, 1, 1) and \
                 self.n_classes == 1 and self.cout_pad <= 64:
             w3 = wp.view(3, 9, self.cout_pad, self.cin_pad)
-            self.weight_ns = self.pack_nstack(w3).to(torch_dtype(dtype_code)).to(device).contiguous()
+            self.weight_ns = to_storage(self.pack_nstack(w3), dtype_code).to(device).contiguous()
         self.bn = _choose_bn(self.cout_pad)
         self.proj = None                 # optional fused 1x1 projection: (fp32[16] device tensor, channel, act)
         self._cache = {}
@@ -108,9 +137,11 @@ class PackedConv:
         # of a column without per-image pipeline bubbles) runs them; its zero N blocks are free while N <= 96 (an MMA
         # costs ~51 cycles for its A operand anyway).  `vol` is the 27-tap twin of this layer.
         self.vol = None
-        esz = 2 if dtype_code == _lib.DTYPE_BF16 else 4
+        row_bytes = self.cin_pad * (4 if dtype_code == _lib.DTYPE_F32 else 2) * cmult(dtype_code)
         if tuple(ksize) == (1, 3, 3) and tuple(pad) == (0, 1, 1) and tuple(stride) == (1, 1, 1) and \
-                self.n_classes == 1 and self.cout_pad <= 64 and self.cin_pad * esz in (32, 64, 128) and \
+                self.n_classes == 1 and self.cout_pad <= 64 and \
+                row_bytes in ((64, 128, 256) if is_split(dtype_code) else (32, 64, 128)) and \
+                (not is_split(dtype_code) or self.cout_pad in (16, 32, 64)) and \
                 [tuple(t) for t in taps[0]] == [(0, dy, dx) for dy in (-1, 0, 1) for dx in (-1, 0, 1)]:
             w27 = torch.zeros(27, cout, cin, dtype=torch.float32)
             w27[9:18] = w_rows.cpu()
@@ -239,8 +270,8 @@ class PackedConv:
             return iD, iH, iW
         return tuple((i + 2 * p - k) // s + 1 for i, k, p, s in zip((iD, iH, iW), self.ksize, self.pad, self.stride))
 
-    def params(self, N, iD, iH, iW, out_strides, out_dtype_code, cout_store=None):
-        key = (N, iD, iH, iW, tuple(out_strides), out_dtype_code, cout_store)
+    def params(self, N, iD, iH, iW, out_strides, out_dtype_code, cout_store=None, os_lo=0):
+        key = (N, iD, iH, iW, tuple(out_strides), out_dtype_code, cout_store, os_lo)
         p = self._cache.get(key)
         if p is not None:
             return p
@@ -257,6 +288,7 @@ class PackedConv:
                 i += 1
         p.osN, p.osD, p.osH, p.osW = out_strides[:4]
         p.osC = out_strides[4] if len(out_strides) > 4 else 1
+        p.os_lo = os_lo
         p.omz, p.omy, p.omx = self.out_mult
         p.cout_store = self.cout_pad if cout_store is None else cout_store
         p.in_dtype, p.out_dtype = self.dtype_code, out_dtype_code
@@ -270,12 +302,13 @@ class PackedConv:
         return p
 
     def __call__(self, x, out=None, residual=None, out_dtype=None, cout_store=None, out_view=None, engine='igemm'):
-        """x: channels-last [N,D,H,W,Cin_pad] contiguous CUDA tensor.
+        """x: channels-last [N,D,H,W,Cin_pad] contiguous CUDA tensor ([.., hi(Cin_pad) | lo(Cin_pad)] for a split layer).
 
         out: destination tensor (allocated if None) -- `out_view` optionally gives
         (data_ptr_offset_elems, (osN, osD, osH, osW[, osC])) to write into a channel slice of a wider buffer
-        or (osC != 1) a planar layout."""
-        assert x.is_cuda and x.is_contiguous() and x.dim() == 5 and x.shape[-1] == self.cin_pad, \
+        or (osC != 1) a planar layout.  A split (BF16X2) layer writes a split output unless `out` is fp32."""
+        cm = cmult(self.dtype_code)
+        assert x.is_cuda and x.is_contiguous() and x.dim() == 5 and x.shape[-1] == cm * self.cin_pad, \
             (tuple(x.shape), self.cin_pad)
         assert x.dtype == torch_dtype(self.dtype_code)
         N, iD, iH, iW, _ = x.shape
@@ -283,10 +316,14 @@ class PackedConv:
         m = self.out_mult
         odt = x.dtype if out_dtype is None else out_dtype
         if out is None:
-            out = torch.empty((N, oD * m[0], oH * m[1], oW * m[2], self.cout_pad), dtype=odt, device=x.device)
-        code = _lib.DTYPE_BF16 if out.dtype == torch.bfloat16 else _lib.DTYPE_F32
+            out = torch.empty((N, oD * m[0], oH * m[1], oW * m[2], self.cout_pad * (cm if odt == torch.bfloat16 else 1)),
+                              dtype=odt, device=x.device)
+        if out.dtype == torch.float32:
+            code = _lib.DTYPE_F32
+        else:
+            code = _lib.DTYPE_BF16X2 if is_split(self.dtype_code) else _lib.DTYPE_BF16
         if self.vol is not None and engine == 'igemm' and iD == 1 and self.proj is None and \
-                (out_view is None or len(out_view[1]) == 4) and not _lib.KNOBS['no_vol2d'] and not _lib.KNOBS['no_scatter']:
+                (out_view is None or len(out_view[1]) == 4) and (out.dtype == x.dtype or not is_split(self.dtype_code)) and not _lib.KNOBS['no_vol2d'] and not _lib.KNOBS['no_scatter']:
             return self._call_as_volume(x, out, residual, cout_store, out_view)
         if out_view is None:
             assert out.is_contiguous() and out.dim() == 5
@@ -296,9 +333,14 @@ class PackedConv:
             off = 0
             if cout_store is None:
                 cout_store = min(self.cout_pad, C)
+            if code == _lib.DTYPE_BF16X2:
+                assert C == 2 * self.cout_pad, 'split output: [.., hi(Cout_pad) | lo(Cout_pad)]'
+            os_lo = 0                                   # = Cout_pad
         else:
-            off, strides = out_view
-        p = self.params(N, iD, iH, iW, strides, code, cout_store)
+            off, strides = out_view[:2]
+            os_lo = out_view[2] if len(out_view) > 2 else 0
+            assert code != _lib.DTYPE_BF16X2 or os_lo > 0, 'a split output view needs its hi -> lo offset'
+        p = self.params(N, iD, iH, iW, strides, code, cout_store, os_lo)
         L = _lib.load()
         fn = L.s3d_conv_igemm if engine == 'igemm' else L.s3d_conv_direct
         esz = out.element_size()
@@ -327,10 +369,12 @@ class PackedConv:
             off = 0
             if cout_store is None:
                 cout_store = min(self.cout_pad, Co)
+            os_lo = self.cout_pad
         else:
-            off, (sN, _, sH, sW) = out_view
+            off, (sN, _, sH, sW) = out_view[:2]
+            os_lo = out_view[2] if len(out_view) > 2 else 0
         self.vol(x.view(G, Dv, H, W, C), out=out, residual=residual, cout_store=cout_store,
-                 out_view=(off, (Dv * sN, sN, sH, sW)))
+                 out_view=(off, (Dv * sN, sN, sH, sW), os_lo))
         return out
 
     def flops(self, N, iD, iH, iW):

@@ -66,7 +66,9 @@ SIGNATURES = {
     's3d_avg_pool': ([_vp, _vp, _i, _i, _i, _i, _i, _i, _vp], _i),
     's3d_depth_to_space': ([_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp], _i),
     's3d_split_tf32': ([_vp, _vp, _vp, _i64, _vp], _i),
-    's3d_fuse_views': ([_vp, _i64, _vp, _i64, _i, _vp, _i, _i, _i, _vp, ctypes.POINTER(_f), _i, _vp, _vp], _i),
+    's3d_split_bf16': ([_vp, _vp, _i64, _i, _vp], _i),
+    's3d_unsplit_bf16': ([_vp, _vp, _i64, _i, _vp], _i),
+    's3d_fuse_views': ([_vp, _i64, _vp, _i64, _i, _vp, _i, _i, _i, _vp, ctypes.POINTER(_f), _i, _vp, _i64, _i64, _vp], _i),
     's3d_chamfer_forward': ([_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp], _i),
 }
 

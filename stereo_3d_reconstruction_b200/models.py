@@ -18,9 +18,14 @@ import torch.nn as nn
 
 from . import lib as _lib
 from . import ops
-from .layers import PackedConv, SplitConv, pad_to, torch_dtype
+from .layers import PackedConv, SplitConv, pad_to, torch_dtype, cmult
 
 A = _lib  # activation / dtype codes
+
+# NETWORK.PRECISION.  'bf16x3': every activation and weight is a bf16 pair v = hi + lo and every tensor-core product runs as
+# hi*hi + lo*hi + hi*lo on kind::f16 MMAs into one fp32 accumulator (include/s3d.h, S3D_DTYPE_BF16X2): the FAST mode that
+# meets the north_star's 1e-3 fp32 tolerance.  'tf32x3' does the same with three kind::tf32 passes per layer through HBM.
+PRECISIONS = ('bf16', 'bf16x3', 'tf32', 'tf32x3', 'fp32')
 
 
 def _conv_bn2d(cin, cout, k, s, p):
@@ -193,7 +198,13 @@ class _StereoBase(nn.Module):
         return self.cfg.NETWORK.PRECISION
 
     def _dtype_code(self):
-        return A.DTYPE_BF16 if self.precision == 'bf16' else A.DTYPE_F32
+        if self.precision not in PRECISIONS:
+            raise ValueError('NETWORK.PRECISION must be one of %s, got %r' % (PRECISIONS, self.precision))
+        return {'bf16': A.DTYPE_BF16, 'bf16x3': A.DTYPE_BF16X2}.get(self.precision, A.DTYPE_F32)
+
+    @property
+    def _split(self):
+        return self.precision == 'bf16x3'
 
     def _engine(self):
         return 'direct' if self.precision == 'fp32' else 'igemm'
@@ -272,6 +283,7 @@ class _StereoBase(nn.Module):
         fuse_volume = (cfg.NETWORK.COST_VOLUME == 'concat' and self.precision in ('bf16', 'tf32') and p5.cout_pad == C and
                        isinstance(p0, PackedConv) and p0.weight_ns is not None and C * x.element_size() in (32, 64) and
                        not _lib.KNOBS['no_concat_fuse'] and not _lib.KNOBS['no_scatter'])
+        cm = cmult(self._dtype_code())                           # physical channels per logical channel (2 when split)
         if fuse_volume:
             # features go into rows with D zero pixels on both sides: the fused cost-volume + dres0a kernel reads the shifted
             # target view of every disparity plane straight out of them (csrc/conv_scatter_concat.cu), no volume is written
@@ -286,15 +298,15 @@ class _StereoBase(nn.Module):
             if fuse_volume:
                 a = ops.conv_concat_volume(p0, featp, B, D, pad, out=self._buf('a0', (2 * B, D, h, w, p0.cout_pad), dt))
             else:
-                assert feat.shape[-1] == C, 'FEAT_CHANNELS must be a multiple of 16'
-                vol = ops.cost_volume_concat(feat, B, D, out=self._buf('vol', (2 * B, D, h, w, 2 * C), dt))
+                assert feat.shape[-1] == cm * C, 'FEAT_CHANNELS must be a multiple of 16'
+                vol = ops.cost_volume_concat(feat, B, D, out=self._buf('vol', (2 * B, D, h, w, 2 * cm * C), dt), split=self._split)
                 a = self._conv('dres0a', vol, out=self._bufo('a0', 'dres0a', vol))
             a = self._conv('dres0b', a, out=self._bufo('a1', 'dres0b', a))
             y = self._conv('dres1a', a, out=self._bufo('a2', 'dres1a', a))
             a = self._conv('dres1b', y, residual=a, out=self._bufo('a3', 'dres1b', y))
             c = self._conv('cls_a', a, out=self._bufo('a0', 'cls_a', a))
             S = self._packed['cls_b'].cout_pad                      # 27 taps padded to 32 planes
-            if c.dtype == torch.bfloat16 and c.shape[-1] in (16, 32, 64) and S == 32 and not _lib.KNOBS['no_cls_fused']:
+            if self.precision == 'bf16' and c.shape[-1] in (16, 32, 64) and S == 32 and not _lib.KNOBS['no_cls_fused']:
                 # classifier + soft-argmin in one pass over the volume (csrc/cls_fused.cu)
                 ops.cls_soft_argmin(c, self._packed['cls_b'].weight, -1.0, out=disp_q)
             else:
@@ -302,6 +314,8 @@ class _StereoBase(nn.Module):
                 self._conv('cls_b', c, out=taps, out_view=(0, (D * h * S * w, h * S * w, S * w, 1, w)), cout_store=S)
                 ops.tap_gather_soft_argmin(taps, -1.0, out=disp_q)
         else:
+            if self._split:                                               # exact fp32 correlation on hi + lo
+                feat = ops.unsplit_bf16(feat, out=self._buf('feat32', feat.shape[:-1] + (feat.shape[-1] // 2,), torch.float32))
             ops.corr_soft_argmin(feat, B, D, out=disp_q, c_real=C)       # mean over the REAL channels (feat is padded)
         disp = ops.upsample_disp(disp_q, H, W, 4.0, out=self._buf('disp', (2 * B, H, W), torch.float32))
         return disp, disp_q
@@ -312,7 +326,7 @@ class _StereoBase(nn.Module):
         N, iD, iH, iW, _ = x.shape
         oD, oH, oW = pc.out_grid(iD, iH, iW)
         m = pc.out_mult
-        return self._buf(name, (N, oD * m[0], oH * m[1], oW * m[2], pc.cout_pad), x.dtype)
+        return self._buf(name, (N, oD * m[0], oH * m[1], oW * m[2], pc.cout_pad * cmult(pc.dtype_code)), x.dtype)
 
     def _latent(self, left, right, disp):
         """RGB-D encoder on both views -> [2B,1,h',w',C_last] (before pooling)."""
@@ -333,10 +347,12 @@ class _StereoBase(nn.Module):
         if pc.ksize == (1, 3, 3) and pc.stride == (1, 2, 2) and pc.pad == (0, 1, 1) and pc.cout_pad in (16, 32, 64) and \
                 not _lib.KNOBS['no_conv_first']:
             oH, oW = (H - 1) // 2 + 1, (W - 1) // 2 + 1
-            out = self._buf(out_name, (2 * B, 1, oH, oW, pc.cout_pad), dt)
+            out = self._buf(out_name, (2 * B, 1, oH, oW, pc.cout_pad * cmult(pc.dtype_code)), dt)
             ops.conv_first(left, pc, None if disp is None else disp[:B], scale, out=out[:B])
             ops.conv_first(right, pc, None if disp is None else disp[B:], scale, out=out[B:])
             return out
+        if self._split:
+            raise _lib.S3dError("'bf16x3' needs the direct first layer (3x3 stride-2 conv, <= 64 output channels)")
         x = self._buf(stage_name, (2 * B, 1, H, W, 16), dt)
         ops.pack_image(left, None if disp is None else disp[:B], scale, out=x[:B])
         ops.pack_image(right, None if disp is None else disp[B:], scale, out=x[B:])
@@ -396,15 +412,17 @@ class Stereo2Voxel(_StereoBase):
         # also applies the final 1x1x1 transposed conv + sigmoid (coarse volume -> channel 8)
         self._d2s = None
         self._fused_out = False
-        esz = 2 if dc == A.DTYPE_BF16 else 4
+        row_bytes = last.cin_pad * (4 if dc == A.DTYPE_F32 else 2) * cmult(dc)
         seq = self.decoder.layers[nl - 1]
-        if last.cout == 8 and last.cin_pad * esz in (32, 64, 128) and self.precision != 'fp32' and \
+        if last.cout == 8 and row_bytes in ((64, 128, 256) if self._split else (32, 64, 128)) and self.precision != 'fp32' and \
                 not _lib.KNOBS['no_d2s']:
             P['dec%d' % (nl - 1)] = PackedConv.from_deconv_k4s2p1_blocked(seq[0], seq[1], A.ACT_RELU, dc, dev)
             pw = torch.zeros(8, dtype=torch.float32)
             pw[:] = w.detach().float().cpu().view(-1)[:8]
             self._d2s = pw.to(dev)
             self._fused_out = True
+        elif self._split:
+            raise _lib.S3dError("'bf16x3' needs DEC_CHANNELS[-1] == 8 and DEC_CHANNELS[-2] in (16, 32, 64) (blocked last deconv)")
         elif last.cout_pad == 16 and last.cout < 16 and self.precision != 'tf32x3':     # (a projection epilogue cannot be split)
             self._fused_out = True
             # 1x1x1 transposed conv + sigmoid folded into the last deconv's epilogue: coarse volume -> channel `cout`
@@ -438,16 +456,19 @@ class Stereo2Voxel(_StereoBase):
         x = self._latent(left, right, disp)
         L = cfg.NETWORK.LATENT_HW
         k0 = cfg.NETWORK.DEC_CHANNELS[0]
-        assert x.shape[-1] * L * L == k0 * 8, 'REC_CHANNELS[-1]*LATENT_HW^2 must equal DEC_CHANNELS[0]*8'
-        x = ops.latent_to_vox(x, L, out=self._buf('lat', (2 * B, 2, 2, 2, pad_to(k0)), x.dtype, zero=True))
+        km = cmult(self._dtype_code())                             # physical channels per logical channel
+        assert x.shape[-1] // km * L * L == k0 * 8, 'REC_CHANNELS[-1]*LATENT_HW^2 must equal DEC_CHANNELS[0]*8'
+        x = ops.latent_to_vox(x, L, out=self._buf('lat', (2 * B, 2, 2, 2, km * pad_to(k0)), x.dtype, zero=True), split=self._split)
         nl = len(self.decoder.layers)
         for i in range(nl):
             x = self._conv('dec%d' % i, x, out=self._bufo('d%d' % i, 'dec%d' % i, x))
         if self._d2s is not None:
             # x is the blocked output [2B,16,16,16,8 classes x 8]: depth-to-space + coarse-volume projection
             n2, dd, hh, ww, _ = x.shape
-            x = ops.depth_to_space(x, 16, self._d2s, A.ACT_SIGMOID, out=self._buf('d2s', (n2, 2 * dd, 2 * hh, 2 * ww, 16), x.dtype))
+            x = ops.depth_to_space(x, 16, self._d2s, A.ACT_SIGMOID, split=self._split,
+                                   out=self._buf('d2s', (n2, 2 * dd, 2 * hh, 2 * ww, 16 * km), x.dtype))
         m_in = x                                                   # [2B,32,32,32,16]: ch 0-7 raw, 8 coarse volume, 9.. zero
+        split_lo = m_in.shape[-1] // 2 if self._split else 0       # split: [.., hi(16) | lo(16)]
         cm = m_in.shape[-1]
         craw = cfg.NETWORK.DEC_CHANNELS[-1]
         assert m_in.shape[1] == nv and cm > craw
@@ -468,7 +489,8 @@ class Stereo2Voxel(_StereoBase):
             iou.zero_()
             gt8 = gt.reshape(B, -1).to(torch.uint8).contiguous()
         ops.fuse_views(s, 0, s.shape[-1], m_in, craw, cm, B, 2, nv ** 3, gt=gt8,
-                       thresholds=list(cfg.TEST.VOXEL_THRESH) if gt is not None else None, iou=iou, out=fused)
+                       thresholds=list(cfg.TEST.VOXEL_THRESH) if gt is not None else None, iou=iou, out=fused,
+                       score_lo=s.shape[-1] // 2 if self._split else 0, vol_lo=split_lo)
         out = (disp[:B].unsqueeze(1), disp[B:].unsqueeze(1), fused.view(B, nv, nv, nv))
         return out + (iou,) if gt is not None else out
 
@@ -498,11 +520,16 @@ class Stereo2Point(_StereoBase):
         x = self._latent(left, right, disp)
         L = cfg.NETWORK.LATENT_HW
         if x.shape[2] != L or x.shape[3] != L:
-            x = ops.avg_pool(x, L, out=self._buf('pool', (2 * B, 1, L, L, x.shape[-1]), x.dtype))
+            x = ops.avg_pool(x, L, out=self._buf('pool', (2 * B, 1, L, L, x.shape[-1]), x.dtype), split=self._split)
         c = x.shape[-1]
         cat = self._buf('latcat', (B, 1, L, L, 2 * c), x.dtype)
-        cat[..., :c].copy_(x[:B])          # channel concat of the two views' latents (tiny copy)
-        cat[..., c:].copy_(x[B:])
+        if self._split:                    # [hi(left, right) | lo(left, right)]
+            h = c // 2
+            cat[..., :h].copy_(x[:B, ..., :h]);  cat[..., h:c].copy_(x[B:, ..., :h])
+            cat[..., c:c + h].copy_(x[:B, ..., h:]);  cat[..., c + h:].copy_(x[B:, ..., h:])
+        else:
+            cat[..., :c].copy_(x[:B])          # channel concat of the two views' latents (tiny copy)
+            cat[..., c:].copy_(x[B:])
         y = self._conv('pt_conv', cat, out=self._bufo('p0', 'pt_conv', cat))
         y = self._conv('pt_fc1', y, out=self._bufo('p1', 'pt_fc1', y))
         npts = cfg.CONST.N_POINTS

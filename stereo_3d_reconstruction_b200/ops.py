@@ -17,6 +17,14 @@ def _code(t):
     raise TypeError('unsupported dtype %s' % t.dtype)
 
 
+def _code_like(t, split):
+    """dtype code of an activation tensor; split=True: bf16 pairs [hi(C) | lo(C)] (include/s3d.h, S3D_DTYPE_BF16X2)."""
+    if split:
+        assert t.dtype == torch.bfloat16 and t.shape[-1] % 2 == 0
+        return _lib.DTYPE_BF16X2
+    return _code(t)
+
+
 def _chk(*ts):
     for t in ts:
         if t is None:
@@ -57,15 +65,17 @@ def pack_image(img, disp=None, disp_scale=1.0, cpad=16, dtype=torch.bfloat16, ou
     return out
 
 
-def cost_volume_concat(feat, B, D, C=None, out=None):
-    """feat [2B,1,h,w,C] -> vol [2B,D,h,w,2C]."""
+def cost_volume_concat(feat, B, D, C=None, out=None, split=False):
+    """feat [2B,1,h,w,C] -> vol [2B,D,h,w,2C].  split: feat [.., hi(C) | lo(C)] -> vol [.., hi(2C) | lo(2C)]."""
     _chk(feat, out)
     n2, one, h, w, Cf = feat.shape
     C = Cf if C is None else C
     assert n2 == 2 * B and one == 1 and C == Cf
     if out is None:
         out = torch.empty((2 * B, D, h, w, 2 * C), dtype=feat.dtype, device=feat.device)
-    rc = _lib.load().s3d_cost_volume_concat(feat.data_ptr(), out.data_ptr(), B, h, w, C, D, _code(feat), _stream())
+    assert out.shape == (2 * B, D, h, w, 2 * C) and out.dtype == feat.dtype
+    rc = _lib.load().s3d_cost_volume_concat(feat.data_ptr(), out.data_ptr(), B, h, w, C // 2 if split else C, D,
+                                            _code_like(feat, split), _stream())
     _lib.check(rc, 's3d_cost_volume_concat')
     _lib.count_launch()
     return out
@@ -111,19 +121,46 @@ def split_tf32(x, hi=None, lo=None):
     return hi, lo
 
 
-def depth_to_space(x, cpad=16, proj_w=None, proj_act=0, out=None):
+def split_bf16(x, out=None):
+    """fp32 [..., C] -> bf16 pairs [..., hi(C) | lo(C)] (include/s3d.h, S3D_DTYPE_BF16X2)."""
+    _chk(x, out)
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    C = x.shape[-1]
+    if out is None:
+        out = torch.empty(x.shape[:-1] + (2 * C,), dtype=torch.bfloat16, device=x.device)
+    rc = _lib.load().s3d_split_bf16(x.data_ptr(), out.data_ptr(), x.numel() // C, C, _stream())
+    _lib.check(rc, 's3d_split_bf16')
+    _lib.count_launch()
+    return out
+
+
+def unsplit_bf16(x, out=None):
+    """bf16 pairs [..., hi(C) | lo(C)] -> fp32 [..., C] = hi + lo."""
+    _chk(x, out)
+    assert x.dtype == torch.bfloat16 and x.is_contiguous() and x.shape[-1] % 2 == 0
+    C = x.shape[-1] // 2
+    if out is None:
+        out = torch.empty(x.shape[:-1] + (C,), dtype=torch.float32, device=x.device)
+    rc = _lib.load().s3d_unsplit_bf16(x.data_ptr(), out.data_ptr(), x.numel() // (2 * C), C, _stream())
+    _lib.check(rc, 's3d_unsplit_bf16')
+    _lib.count_launch()
+    return out
+
+
+def depth_to_space(x, cpad=16, proj_w=None, proj_act=0, out=None, split=False):
     """x [N,d,h,w,64] (channel = parity class * 8 + c, from PackedConv.from_deconv_k4s2p1_blocked) -> [N,2d,2h,2w,cpad];
     optional projection of the 8 features into channel 8 (include/s3d.h, s3d_depth_to_space)."""
     _chk(x, proj_w, out)
-    assert x.dim() == 5 and x.shape[-1] == 64 and x.is_contiguous()
+    m = 2 if split else 1                                       # split: [.., hi(64) | lo(64)] -> [.., hi(cpad) | lo(cpad)]
+    assert x.dim() == 5 and x.shape[-1] == 64 * m and x.is_contiguous()
     N, d, h, w, _ = x.shape
     if out is None:
-        out = torch.empty((N, 2 * d, 2 * h, 2 * w, cpad), dtype=x.dtype, device=x.device)
-    assert out.dtype == x.dtype and out.is_contiguous() and out.shape == (N, 2 * d, 2 * h, 2 * w, cpad)
+        out = torch.empty((N, 2 * d, 2 * h, 2 * w, cpad * m), dtype=x.dtype, device=x.device)
+    assert out.dtype == x.dtype and out.is_contiguous() and out.shape == (N, 2 * d, 2 * h, 2 * w, cpad * m)
     if proj_w is not None:
         assert proj_w.dtype == torch.float32 and proj_w.numel() >= 8
     rc = _lib.load().s3d_depth_to_space(x.data_ptr(), out.data_ptr(), proj_w.data_ptr() if proj_w is not None else None,
-                                        int(proj_act), N, d, h, w, cpad, _code(x), _stream())
+                                        int(proj_act), N, d, h, w, cpad, _code_like(x, split), _stream())
     _lib.check(rc, 's3d_depth_to_space')
     _lib.count_launch()
     return out
@@ -145,9 +182,10 @@ def conv_first(img, pc, disp=None, disp_scale=1.0, out=None):
     assert pc.cin == cin, (pc.cin, cin)
     oH, oW = (H - 1) // 2 + 1, (W - 1) // 2 + 1
     dt = pc.weight.dtype
+    co = pc.cout_pad * (2 if pc.dtype_code == _lib.DTYPE_BF16X2 else 1)      # split layer: [.., hi | lo]
     if out is None:
-        out = torch.empty((B, 1, oH, oW, pc.cout_pad), dtype=dt, device=img.device)
-    assert out.dtype == dt and out.is_contiguous() and out.shape[-1] == pc.cout_pad
+        out = torch.empty((B, 1, oH, oW, co), dtype=dt, device=img.device)
+    assert out.dtype == dt and out.is_contiguous() and out.shape[-1] == co
     rc = _lib.load().s3d_conv_first(img.data_ptr(), 1 if u8 else 0, disp.data_ptr() if disp is not None else None,
                                     float(disp_scale), pc.weight.data_ptr(), pc.bias.data_ptr(), out.data_ptr(), B, H, W, cin,
                                     pc.cin_pad, pc.cout_pad, pc.dtype_code, pc.act, pc.act_param, _stream())
@@ -222,33 +260,37 @@ def upsample_disp(disp_q, H, W, scale, out=None):
     return out
 
 
-def latent_to_vox(x, L, out=None):
-    """[N,1,H,W,C] -> pooled to LxL -> [N,2,2,2,C*L*L/8] (oracle's NCHW .view order)."""
+def latent_to_vox(x, L, out=None, split=False):
+    """[N,1,H,W,C] -> pooled to LxL -> [N,2,2,2,C*L*L/8] (oracle's NCHW .view order).  split: hi | lo pairs in and out."""
     _chk(x, out)
     N, one, H, W, C = x.shape
     if out is None:
         out = torch.empty((N, 2, 2, 2, C * L * L // 8), dtype=x.dtype, device=x.device)
-    rc = _lib.load().s3d_latent_to_vox(x.data_ptr(), out.data_ptr(), N, H, W, C, L, _code(x), _stream())
+    assert out.shape[-1] == C * L * L // 8, 'latent_to_vox writes K = C*L*L/8 channels densely'
+    rc = _lib.load().s3d_latent_to_vox(x.data_ptr(), out.data_ptr(), N, H, W, C // 2 if split else C, L,
+                                       _code_like(x, split), _stream())
     _lib.check(rc, 's3d_latent_to_vox')
     _lib.count_launch()
     return out
 
 
-def avg_pool(x, L, out=None):
+def avg_pool(x, L, out=None, split=False):
     _chk(x, out)
     N, one, H, W, C = x.shape
     if out is None:
         out = torch.empty((N, 1, L, L, C), dtype=x.dtype, device=x.device)
-    rc = _lib.load().s3d_avg_pool(x.data_ptr(), out.data_ptr(), N, H, W, C, L, _code(x), _stream())
+    rc = _lib.load().s3d_avg_pool(x.data_ptr(), out.data_ptr(), N, H, W, C // 2 if split else C, L, _code_like(x, split),
+                                  _stream())
     _lib.check(rc, 's3d_avg_pool')
     _lib.count_launch()
     return out
 
 
 def fuse_views(score, score_off, score_stride, vol, vol_off, vol_stride, B, V, nvox, gt=None, thresholds=None,
-               iou=None, out=None):
+               iou=None, out=None, score_lo=0, vol_lo=0):
     """Context-aware fusion epilogue (+ IoU counts).  score/vol: tensors holding [V*B, nvox] planes
-    at element offset *_off with element stride *_stride between voxels."""
+    at element offset *_off with element stride *_stride between voxels.  score_lo / vol_lo > 0: split (hi | lo) tensors,
+    the lo part of a value sits that many elements after its hi part."""
     _chk(score, vol, gt, iou, out)
     assert score.dtype == vol.dtype
     if out is None:
@@ -261,9 +303,10 @@ def fuse_views(score, score_off, score_stride, vol, vol_off, vol_stride, B, V, n
         th = (ctypes.c_float * T)(*[float(t) for t in thresholds])
     esz = score.element_size()
     rc = _lib.load().s3d_fuse_views(score.data_ptr() + score_off * esz, score_stride,
-                                    vol.data_ptr() + vol_off * esz, vol_stride, _code(score), out.data_ptr(), B, V,
+                                    vol.data_ptr() + vol_off * esz, vol_stride,
+                                    _lib.DTYPE_BF16X2 if score_lo else _code(score), out.data_ptr(), B, V,
                                     nvox, gt.data_ptr() if gt is not None else None, th, T,
-                                    iou.data_ptr() if iou is not None else None, _stream())
+                                    iou.data_ptr() if iou is not None else None, int(score_lo), int(vol_lo), _stream())
     _lib.check(rc, 's3d_fuse_views')
     _lib.count_launch()
     return out

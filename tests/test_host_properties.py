@@ -111,3 +111,22 @@ def test_runner_flattens_checkpoints(tmp_path):
     with pytest.raises(SystemExit) as e:
         runner.load_checkpoint(m, str(path))
     assert 'missing' in str(e.value) and 'unexpected' in str(e.value)
+
+
+def test_split_storage_and_packing():
+    """'bf16x3' storage (S3D_DTYPE_BF16X2): v = hi + lo to 2^-16; packed weights are [.., hi(Cin_pad) | lo(Cin_pad)]."""
+    from stereo_3d_reconstruction_b200.layers import to_storage, from_storage
+    torch.manual_seed(0)
+    x = torch.randn(4, 7, 24) * 5
+    s = to_storage(x, lib.DTYPE_BF16X2)
+    assert s.dtype == torch.bfloat16 and s.shape == (4, 7, 48)
+    assert torch.equal(s[..., :24], x.to(torch.bfloat16))
+    assert (from_storage(s, lib.DTYPE_BF16X2) - x).abs().max() <= 2.0 ** -16 * x.abs().max()
+    conv = nn.Conv3d(16, 24, 3, 1, 1, bias=False)
+    pc = PackedConv.from_conv(conv, None, lib.ACT_NONE, lib.DTYPE_BF16X2, 'cpu')
+    ref = PackedConv.from_conv(conv, None, lib.ACT_NONE, lib.DTYPE_F32, 'cpu')
+    assert pc.weight.shape == (27, pc.cout_pad, 2 * pc.cin_pad) and pc.weight_ns.shape == (36, 3 * pc.cout_pad, 2 * pc.cin_pad)
+    torch.testing.assert_close(from_storage(pc.weight, lib.DTYPE_BF16X2), ref.weight, rtol=2.0 ** -15, atol=1e-7)
+    torch.testing.assert_close(from_storage(pc.weight_ns, lib.DTYPE_BF16X2), ref.weight_ns, rtol=2.0 ** -15, atol=1e-7)
+    conv2 = nn.Conv2d(32, 32, 3, 1, 1)
+    assert PackedConv.from_conv(conv2, None, lib.ACT_RELU, lib.DTYPE_BF16X2, 'cpu').vol is not None     # 2-D layers as volumes
