@@ -11,7 +11,17 @@ N GPUs every rank runs its own batch of 64 (weak scaling: 64*N pairs per step = 
 N=8) and the per-shard IoU counts are summed with one NCCL all-reduce per step.
 
 Prints ONE JSON line (rank 0).  `value` = pairs/s with inputs resident in HBM; `e2e` = the same through
-the public nn.Module call with pinned HOST inputs (H2D inside the timed region, voxels + IoU read back).
+the public nn.Module call with pinned HOST inputs (decoded 8-bit HWC images -- the reference's inputs are PNG renders,
+README.md:73-74 -- H2D inside the timed region, voxels + IoU read back).
+
+The same line carries the other BASELINE configs as extra keys, each measured briefly in the same run (N = 1):
+  fp32_mode              configs[1] "fp32": the fast tensor-core mode that meets the 1e-3 tolerance ('bf16x3'), with its error
+  latency                B = 1 / 8 through the CUDA-graph replay
+  stereo2point_chamfer   configs[3]: Stereo2Point forward + chamfer_dist at B = 32, 2048 vs 16384 points
+  costvolume_sweep       configs[4]: D in {32,64,128} x C in {32,64} at 1/4 resolution, HBM fraction per point
+  gpu_stock_baseline     the oracle module on the SAME GPU through stock torch + cuDNN (the on-box bar)
+  peaks_measured         TF32 matmul and fp32 FMA issue peaks measured in this run
+and, at N > 1, `strong_512`: configs[2] as written (global batch 512 sharded over the N GPUs).  --no-extras skips them.
 """
 import argparse
 import json
@@ -35,6 +45,7 @@ def parse():
     p.add_argument('--batch', type=int, default=None, help='pairs per GPU per step (default cfg.CONST.BATCH_SIZE = 64)')
     p.add_argument('--precision', default='bf16', choices=['bf16', 'bf16x3', 'tf32', 'tf32x3', 'fp32'])
     p.add_argument('--no-cpu-baseline', action='store_true')
+    p.add_argument('--no-extras', action='store_true', help='only the headline measurement (no secondary configs)')
     return p.parse_args()
 
 
@@ -152,6 +163,229 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Secondary BASELINE configs, measured briefly on rank 0 at N = 1 and reported as extra keys of the same JSON line.
+# Every timing: >= 3 warm-ups, CUDA events on the launching stream, inputs larger than L2 or an explicit L2 flush.
+# ---------------------------------------------------------------------------------------------------------------------
+def _events_ms(fn, iters, warm=3, flush=None):
+    """Median ms of `fn` over `iters` single launches, each preceded by an L2 flush when `flush` is given."""
+    import torch
+    for _ in range(warm):
+        fn()
+    ts = []
+    for _ in range(iters):
+        if flush is not None:
+            flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def _loop_ms(fn, iters, warm=3):
+    """Mean ms per call of `iters` back-to-back calls (for steps that stream far more than L2 per call)."""
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def extra_fp32_mode(cfg0, B, dev, steps):
+    """configs[1] 'fp32': 'bf16x3' (bf16 hi/lo pairs, three MMAs per product) -- throughput at batch B and the error
+    against the CPU oracle on 1 pair of the same default config (tolerance the north_star states for fp32: 1e-3)."""
+    import torch
+    from oracle import models as O
+    from stereo_3d_reconstruction_b200 import models
+    from stereo_3d_reconstruction_b200.utils import synthetic
+    cfg = cfg0.clone()
+    cfg.NETWORK.PRECISION = 'bf16x3'
+    cfg.CONST.MICRO_BATCH = max(B, cfg.CONST.MICRO_BATCH)
+    H, W, D = cfg.CONST.IMG_H, cfg.CONST.IMG_W, cfg.NETWORK.MAX_DISP
+    model = models.build_model('Stereo2Voxel', cfg, seed=cfg.CONST.SEED).to(dev).pack()
+    sets = [tuple(t.to(dev) for t in synthetic.stereo_pair(B, H, W, 2 * D, seed=77 + i)[:2]) for i in range(2)]
+    it = [0]
+
+    def step():
+        l, r = sets[it[0] & 1]; it[0] += 1
+        model(l, r)
+    ms = _loop_ms(step, max(3, min(steps, 5)))
+    oracle = O.make_model('Stereo2Voxel', cfg, seed=cfg.CONST.SEED)
+    l1, r1, _ = synthetic.stereo_pair(1, H, W, 2 * D, seed=99)
+    with torch.no_grad():
+        rdl, rdr, rvox = oracle(l1, r1)
+        dl, dr, vox = model(l1.to(dev), r1.to(dev))
+    dmax = max(rdl.abs().max().item(), rdr.abs().max().item())
+    e_d = max((dl.cpu() - rdl).abs().max().item(), (dr.cpu() - rdr).abs().max().item()) / dmax
+    e_v = (vox.cpu() - rvox).abs().max().item()
+    del model
+    torch.cuda.empty_cache()
+    return {'precision': 'bf16x3', 'what': 'bf16 hi/lo operand pairs, hi*hi + lo*hi + hi*lo per product on kind::f16 MMAs, fp32 accumulate',
+            'value': B / ms * 1e3, 'unit': 'pairs/s', 'ms_per_step': ms, 'batch': B,
+            'disparity_rel_err_vs_oracle': e_d, 'occupancy_abs_err_vs_oracle': e_v, 'tolerance': 1e-3,
+            'within_tolerance': bool(e_d <= 1e-3 and e_v <= 1e-3)}
+
+
+def extra_latency(model, cfg, dev):
+    """Small-batch latency through the CUDA-graph replay (one graph launch per forward)."""
+    import torch
+    from stereo_3d_reconstruction_b200.utils import synthetic
+    out = {}
+    for b in (1, 8):
+        l, r, _ = synthetic.stereo_pair(b, cfg.CONST.IMG_H, cfg.CONST.IMG_W, 2 * cfg.NETWORK.MAX_DISP, seed=300 + b)
+        l, r = l.to(dev), r.to(dev)
+        with torch.no_grad():
+            ms = _loop_ms(lambda: model.graphed(l, r), 30, warm=5)
+        out['b%d_ms' % b] = ms
+        out['b%d_pairs_per_s' % b] = b / ms * 1e3
+    out['how'] = 'model.graphed(): CUDA-graph replay, inputs resident, bf16'
+    return out
+
+
+def extra_stereo2point(cfg0, dev, fma_peak):
+    """configs[3]: Stereo2Point forward + chamfer_dist, batch 32, 2048 predicted vs 16384 GT points."""
+    import torch
+    from stereo_3d_reconstruction_b200 import models, ops
+    from stereo_3d_reconstruction_b200.extensions.chamfer_dist import chamfer_per_sample
+    from stereo_3d_reconstruction_b200.utils import synthetic
+    cfg = cfg0.clone()
+    cfg.NETWORK.PRECISION = 'bf16'
+    B, N, M = 32, cfg.CONST.N_POINTS, cfg.CONST.N_GT_POINTS
+    model = models.build_model('Stereo2Point', cfg, seed=cfg.CONST.SEED).to(dev).pack()
+    sets = [tuple(t.to(dev) for t in synthetic.stereo_pair(B, cfg.CONST.IMG_H, cfg.CONST.IMG_W, 2 * cfg.NETWORK.MAX_DISP, seed=400 + i)[:2])
+            for i in range(4)]                                   # 4 x 2 x 25 MB of images > L2
+    gt = synthetic.point_clouds(B, 1, M, seed=3)[1].to(dev)
+    it = [0]
+
+    def step():
+        l, r = sets[it[0] % 4]; it[0] += 1
+        with torch.no_grad():
+            _, _, pts = model(l, r)
+            return chamfer_per_sample(pts.contiguous(), gt)
+    ms = _loop_ms(step, 8)
+    pts = torch.rand(B, N, 3, device=dev) - 0.5
+    flush = torch.empty(256 * 2 ** 20, dtype=torch.uint8, device=dev)
+    ms_ch = _events_ms(lambda: ops.chamfer_forward(pts, gt), 10, flush=flush)
+    pair_evals = 2.0 * B * N * M
+    instr = 11                                                    # 3 sub, 3 mul, 2 add, compare, 2 selects per pair (SASS of chamfer_nn_kernel)
+    res = {'value': B / ms * 1e3, 'unit': 'pairs/s', 'ms_per_step': ms, 'batch': B, 'n_pred': N, 'n_gt': M, 'precision': 'bf16',
+           'chamfer_ms': ms_ch, 'chamfer_pair_evals_per_s': pair_evals / ms_ch * 1e3, 'chamfer_instr_per_pair': instr,
+           'chamfer_bytes': B * (N + M) * 20}
+    if fma_peak:
+        res['chamfer_frac_of_measured_fp32_issue_peak'] = pair_evals * instr / (ms_ch / 1e3) / fma_peak
+    del model
+    torch.cuda.empty_cache()
+    return res
+
+
+def extra_costvolume_sweep(dev, hbm_gbs):
+    """configs[4]: cost-volume + soft-argmin sweep at 1/4 resolution (64x64), batch 64, bf16 features.  Algorithmic bytes
+    (SURVEY.md 8(d)): every unique input read once + every output written once."""
+    import torch
+    from stereo_3d_reconstruction_b200 import ops
+    B, h, w = 64, 64, 64
+    flush = torch.empty(256 * 2 ** 20, dtype=torch.uint8, device=dev)
+    pts = []
+    for C in (32, 64):
+        feat = torch.randn(2 * B, 1, h, w, C, device=dev).to(torch.bfloat16)
+        for D in (32, 64, 128):
+            rec = {'C': C, 'D': D}
+            vol = torch.empty(2 * B, D, h, w, 2 * C, device=dev, dtype=torch.bfloat16)
+            ms = _events_ms(lambda: ops.cost_volume_concat(feat, B, D, out=vol), 5, flush=flush)
+            by = 2 * B * C * h * w * 2 + vol.numel() * 2
+            rec.update(concat_ms=ms, concat_frac_hbm=by / ms / 1e6 / hbm_gbs)
+            del vol
+            disp = torch.empty(2 * B, h, w, device=dev)
+            ms = _events_ms(lambda: ops.corr_soft_argmin(feat, B, D, out=disp), 10, flush=flush)
+            by = 2 * B * C * h * w * 2 + 2 * B * h * w * 4
+            rec.update(corr_ms=ms, corr_frac_hbm=by / ms / 1e6 / hbm_gbs, corr_tensor_tflops=2.0 * 2 * B * C * w * h * w / ms / 1e9)
+            if C == 32:
+                cost = torch.randn(2 * B, D, h, w, device=dev)
+                ms = _events_ms(lambda: ops.soft_argmin(cost, -1.0, out=disp), 10, flush=flush)
+                by = cost.numel() * 4 + disp.numel() * 4
+                rec.update(softargmin_ms=ms, softargmin_frac_hbm=by / ms / 1e6 / hbm_gbs)
+                del cost
+            pts.append(rec)
+    return {'batch': B, 'hw': [h, w], 'dtype': 'bf16', 'peak_hbm_gbs': hbm_gbs, 'l2': 'flushed (256 MB write) before every launch',
+            'points': pts}
+
+
+def extra_gpu_stock_baseline(cfg0, B, dev):
+    """The oracle module (stock torch.nn -> cuDNN / cuBLAS) on the same GPU: the on-box bar of SURVEY.md 8(d).  Same
+    default config, batch B, inputs resident, CUDA events.  Not the product path (it is cuDNN) -- a baseline beside it."""
+    import torch
+    from oracle import models as O
+    from stereo_3d_reconstruction_b200.utils import synthetic
+    H, W, D = cfg0.CONST.IMG_H, cfg0.CONST.IMG_W, cfg0.NETWORK.MAX_DISP
+    oracle = O.make_model('Stereo2Voxel', cfg0, seed=cfg0.CONST.SEED).to(dev)
+    l, r, _ = synthetic.stereo_pair(B, H, W, 2 * D, seed=500)
+    l, r = l.to(dev), r.to(dev)
+    out = {'batch': B, 'what': 'oracle/models.py (torch.nn) through stock torch %s + cuDNN %s on this GPU' %
+           (torch.__version__, torch.backends.cudnn.version())}
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark)
+    torch.backends.cudnn.benchmark = True
+    try:
+        for name, tf32, ac in (('fp32', False, None), ('tf32', True, None), ('bf16_autocast', True, torch.bfloat16)):
+            torch.backends.cudnn.allow_tf32 = tf32
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            try:
+                def step():
+                    with torch.no_grad():
+                        if ac is None:
+                            oracle(l, r)
+                        else:
+                            with torch.autocast('cuda', dtype=ac):
+                                oracle(l, r)
+                ms = _loop_ms(step, 3, warm=3)
+                out[name] = {'value': B / ms * 1e3, 'unit': 'pairs/s', 'ms_per_step': ms}
+            except Exception as e:                      # e.g. an op without a bf16 kernel: report, do not fail the bench
+                out[name] = {'unavailable': '%s: %s' % (type(e).__name__, str(e)[:120])}
+            torch.cuda.empty_cache()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = old
+    del oracle
+    torch.cuda.empty_cache()
+    return out
+
+
+def extra_peaks(dev):
+    """TF32 matmul (cuBLAS, 8192^3) and fp32 FMA issue peaks, measured here the way MEASURED_PEAKS.json measures bf16."""
+    import ctypes
+    import torch
+    from stereo_3d_reconstruction_b200 import lib
+    out = {}
+    n = 8192
+    a = torch.randn(n, n, device=dev)
+    b = torch.randn(n, n, device=dev)
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        ms = _events_ms(lambda: torch.matmul(a, b), 10)
+        out['tf32_matmul_tflops'] = 2.0 * n ** 3 / ms / 1e9
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    del a, b
+    sink = torch.zeros(4, device=dev)
+    cnt = ctypes.c_int64(0)
+    L = lib.load()
+    st = torch.cuda.current_stream().cuda_stream
+    ms = _events_ms(lambda: lib.check(L.s3d_fma_probe(sink.data_ptr(), 4096, ctypes.byref(cnt), st), 's3d_fma_probe'), 10)
+    out['fp32_fma_per_s'] = cnt.value / (ms / 1e3)
+    out['fp32_fma_tflops'] = 2.0 * cnt.value / ms / 1e9
+    out['how'] = 'torch.matmul fp32 with allow_tf32 (8192^3, median of 10); s3d_fma_probe: 8 independent FFMA chains per thread, 8 CTAs x 256 threads per SM'
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -181,7 +415,11 @@ def run_ours(args):
     for i in range(n_sets):
         l, r, _ = synthetic.stereo_pair(B, H, W, 2 * D, seed=1000 * rank + i)
         g = synthetic.gt_volume(B, cfg.CONST.N_VOX, seed=5000 * rank + i)
-        host_sets.append((l.pin_memory(), r.pin_memory(), g.pin_memory()))
+        # the end-to-end path feeds DECODED 8-bit images, HWC (what a PNG loader hands over, README.md:73-74): 4x fewer H2D bytes
+        # than fp32 NCHW; the first layer reads them directly (csrc/conv_first.cu)
+        l8 = (l.clamp(0, 1) * 255).round().to(torch.uint8).permute(0, 2, 3, 1).contiguous()
+        r8 = (r.clamp(0, 1) * 255).round().to(torch.uint8).permute(0, 2, 3, 1).contiguous()
+        host_sets.append((l8.pin_memory(), r8.pin_memory(), g.pin_memory()))
         dev_sets.append((l.to(dev), r.to(dev), g.to(dev)))
     T = len(cfg.TEST.VOXEL_THRESH)
     stats = torch.zeros(2 * T + 1, dtype=torch.int64, device=dev)
@@ -207,7 +445,7 @@ def run_ours(args):
     out_stream = torch.cuda.Stream(device=dev)
     out_ready = [torch.cuda.Event() for _ in range(2)]
     out_done = [torch.cuda.Event() for _ in range(2)]
-    d_in = [(torch.empty((B, 3, H, W), dtype=torch.float32, device=dev), torch.empty((B, 3, H, W), dtype=torch.float32, device=dev),
+    d_in = [(torch.empty((B, H, W, 3), dtype=torch.uint8, device=dev), torch.empty((B, H, W, 3), dtype=torch.uint8, device=dev),
              torch.empty((B, nv, nv, nv), dtype=torch.uint8, device=dev)) for _ in range(2)]
     copy_stream = torch.cuda.Stream(device=dev)
     in_ready = [torch.cuda.Event() for _ in range(2)]
@@ -322,6 +560,28 @@ def run_ours(args):
     e2e_state['first_timed'] = warm_e2e
     ms_e2e = timed(step_e2e, args.steps, warm_e2e, e2e_finish)
 
+    # ---- configs[2] as written: global batch 512 sharded over the N GPUs (strong scaling; the headline above is weak) ----
+    strong = None
+    if world > 1 and not args.no_extras and 512 % world == 0:
+        per = 512 // world
+        sl, sr, _ = synthetic.stereo_pair(per, H, W, 2 * D, seed=7000 + rank)
+        sg = synthetic.gt_volume(per, cfg.CONST.N_VOX, seed=8000 + rank)
+        sl, sr, sg = sl.to(dev), sr.to(dev), sg.to(dev)
+        cfg.CONST.MICRO_BATCH = 64
+
+        def step_strong(i):
+            _, _, _, iou = model(sl, sr, sg)
+            stats[:T] = iou[:, :, 0].sum(0)
+            stats[T:2 * T] = iou[:, :, 1].sum(0)
+            stats[2 * T] = per
+            dist.all_reduce(stats)
+        k = max(2, args.steps // 3)
+        ms_s = timed(step_strong, k, 3)
+        strong = {'value': 512 * k / (ms_s / 1e3), 'unit': 'pairs/s', 'global_batch': 512, 'per_gpu': per, 'steps': k,
+                  'ms_per_step': ms_s / k, 'micro_batch': 64, 'scaling': 'strong',
+                  'note': 'BASELINE configs[2]: batch 512 sharded across %d GPUs, IoU stats reduced with one NCCL all-reduce per step' % world}
+        del sl, sr, sg
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -348,7 +608,8 @@ def run_ours(args):
                    'l2': 'inputs rotate over %d batches (%d MB > 126 MB L2); each step streams >10 GB of activations'
                          % (n_sets, n_sets * 2 * B * 3 * H * W * 4 // 2 ** 20)},
         'e2e': {'value': e2e, 'unit': 'pairs/s', 'ms_per_step': ms_e2e / args.steps,
-                'h2d_bytes_per_step': 2 * B * 3 * H * W * 4 + B * cfg.CONST.N_VOX ** 3,
+                'h2d_bytes_per_step': 2 * B * 3 * H * W + B * cfg.CONST.N_VOX ** 3,
+                'inputs': 'uint8 HWC [B,H,W,3] left/right + uint8 GT volume from pinned host memory (decoded-PNG layout)',
                 'd2h_bytes_per_step': B * cfg.CONST.N_VOX ** 3 * 4 + (2 * T + 1) * 8},
         'gpu_launches': launches * args.steps,          # kernels of this library launched inside the timed region
         'gpu_launches_per_step': launches,
@@ -360,9 +621,10 @@ def run_ours(args):
                      # power cap allows (ncu: 96.7 % tensor-pipe active) and draws less than cuBLAS, hence frac > 1 above
                      'peak_burst': pk['bf16_tflops'], 'frac_of_burst': achieved / pk['bf16_tflops'],
                      'ms_per_launch': dom, 'flops_per_launch': flops, 'share_of_step': dom * len(dom_layers) / (ms / args.steps),
-                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel at this exact shape,
-                     # from the round-1 `ncu --set full` capture (profiles/r1_ncu_summary.md); algorithmic bytes = 4.295e9
-                     'traffic': 4.2810e9 if (B == 64 and args.precision == 'bf16' and (H, W, D) == (256, 256, 32)) else None},
+                     # not measured in this run (needs ncu): one `ncu --set full` capture of this kernel at this shape read
+                     # dram__bytes_read.sum + dram__bytes_write.sum = 4.281e9 against 4.295e9 algorithmic bytes (profiles/r1_ncu_summary.md)
+                     'traffic': None, 'traffic_source': 'profiles/r1_ncu_summary.md (ncu capture, not live)',
+                     'algorithmic_bytes_per_launch': 2 * (2 * B) * D * h * w * pc.cin * 2},
         'roofline_hbm': None if not cls_t else {
             'bound': 'hbm', 'kernel': 'cls_fused_kernel (Cout=1 3x3x3 classifier + soft-argmin, one pass over the aggregated volume)',
             'achieved': cls_t[0][1] / (sum(t for t, _ in cls_t) / len(cls_t) / 1e3) / 1e9, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
@@ -371,11 +633,34 @@ def run_ours(args):
         'model_tflops_per_step': total_flops / 1e12,
         'model_tflops_achieved': total_flops / (ms / args.steps / 1e3) / 1e12,
     }
+    if strong is not None:
+        line['strong_512'] = strong
     if not args.no_cpu_baseline and world == 1:
         cores = os.cpu_count() or 1
         v, sec = cpu_oracle_run(cfg, 1, 5, 1, cores)
         line['cpu_baseline'] = {'value': v, 'unit': 'pairs/s', 'cores': cores, 'kind': 'port',
                                 'sample': 'batch 1 (BASELINE configs[0]), 5 forwards, fp32 torch.nn oracle on %d threads' % cores}
+    if world == 1 and not args.no_extras:
+        # the other BASELINE configs, each measured briefly (see the module docstring); a failure is reported, not fatal
+        def guarded(fn, *a):
+            try:
+                return fn(*a)
+            except Exception as e:
+                return {'failed': '%s: %s' % (type(e).__name__, str(e)[:200])}
+        base_cfg = cfg.clone()
+        base_cfg.NETWORK.PRECISION = 'bf16'
+        line['latency'] = guarded(extra_latency, model, cfg, dev) if args.precision == 'bf16' else None
+        del model
+        dev_sets.clear()
+        torch.cuda.empty_cache()
+        pm = guarded(extra_peaks, dev)
+        line['peaks_measured'] = pm
+        line['fp32_mode'] = guarded(extra_fp32_mode, base_cfg, B, dev, args.steps)
+        line['stereo2point_chamfer'] = guarded(extra_stereo2point, base_cfg, dev, pm.get('fp32_fma_per_s'))
+        line['costvolume_sweep'] = guarded(extra_costvolume_sweep, dev, pk['hbm_gbs'])
+        line['gpu_stock_baseline'] = guarded(extra_gpu_stock_baseline, base_cfg, B, dev)
+        if isinstance(line['gpu_stock_baseline'].get('bf16_autocast'), dict) and 'value' in line['gpu_stock_baseline']['bf16_autocast']:
+            line['gpu_stock_baseline']['ours_over_stock_bf16'] = value / line['gpu_stock_baseline']['bf16_autocast']['value']
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

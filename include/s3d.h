@@ -213,6 +213,11 @@ int s3d_fuse_views(const void* score, int64_t score_stride, const void* vol, int
 int s3d_chamfer_forward(const float* xyz1, const float* xyz2, float* dist1, int32_t* idx1,
                         float* dist2, int32_t* idx2, int B, int N, int M, void* stream);
 
+/* Measurement aid (bench.py): a launch of independent fp32 FMA chains that is bound by the FMA issue rate only;
+ * *fma_count (HOST) receives the number of thread-level FMAs the launch executes.  Timed with CUDA events it gives the
+ * MEASURED fp32 SIMT peak the Chamfer kernel's pair rate is quoted against.  sink: any device float. */
+int s3d_fma_probe(float* sink, int iters, int64_t* fma_count, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

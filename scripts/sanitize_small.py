@@ -1,0 +1,60 @@
+"""One small launch of each mbarrier / cluster-protocol kernel, for compute-sanitizer (racecheck / synccheck / memcheck):
+
+    compute-sanitizer --tool racecheck python scripts/sanitize_small.py scatter_pair
+
+usage: sanitize_small.py <case>      cases: scatter_pair scatter_single scatter_split concat cls_fused corr_tc igemm all"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import torch.nn as nn
+from stereo_3d_reconstruction_b200 import lib, ops
+from stereo_3d_reconstruction_b200.layers import PackedConv, to_storage
+
+case = sys.argv[1] if len(sys.argv) > 1 else 'all'
+torch.manual_seed(0)
+
+
+def conv3(cin, cout, code, act=lib.ACT_RELU):
+    return PackedConv.from_conv(nn.Conv3d(cin, cout, 3, 1, 1, bias=True), None, act, code, 'cuda')
+
+
+def run(name):
+    if name in ('scatter_pair', 'scatter_single'):
+        lib.set_knob('scatter_no_pair', int(name == 'scatter_single'))
+        pc = conv3(64, 64, lib.DTYPE_BF16, lib.ACT_NONE)
+        x = torch.randn(2, 4, 33, 9, 64, device='cuda').to(torch.bfloat16)
+        r = torch.randn(2, 4, 33, 9, 64, device='cuda').to(torch.bfloat16)
+        pc(x, residual=r)
+        lib.set_knob('scatter_no_pair', 0)
+    elif name == 'scatter_split':
+        pc = conv3(64, 64, lib.DTYPE_BF16X2)
+        x = to_storage(torch.randn(2, 4, 33, 9, 64), lib.DTYPE_BF16X2).cuda()
+        pc(x)
+        pc = conv3(16, 16, lib.DTYPE_BF16X2, lib.ACT_LEAKY)
+        x = to_storage(torch.randn(1, 3, 16, 16, 16), lib.DTYPE_BF16X2).cuda()
+        pc(x)
+    elif name == 'concat':
+        B, C, D, h, w = 1, 32, 4, 16, 16
+        pc = conv3(2 * C, 64, lib.DTYPE_BF16)
+        featp = torch.zeros(2 * B, 1, h, w + 2 * D, C, dtype=torch.bfloat16, device='cuda')
+        featp[:, :, :, D:D + w] = torch.randn(2 * B, 1, h, w, C, device='cuda').to(torch.bfloat16)
+        ops.conv_concat_volume(pc, featp, B, D, D)
+    elif name == 'cls_fused':
+        x = torch.randn(1, 4, 33, 9, 64, device='cuda').to(torch.bfloat16)
+        wt = torch.zeros(32, 64, dtype=torch.bfloat16, device='cuda')
+        wt[:27] = torch.randn(27, 64, device='cuda').to(torch.bfloat16) * 0.2
+        ops.cls_soft_argmin(x, wt, -1.0)
+    elif name == 'corr_tc':
+        f = torch.randn(2, 1, 5, 40, 32, device='cuda').to(torch.bfloat16)
+        ops.corr_soft_argmin(f, 1, 16)
+    elif name == 'igemm':
+        pc = PackedConv.from_conv(nn.Conv2d(32, 64, 3, 2, 1), None, lib.ACT_RELU, lib.DTYPE_BF16, 'cuda')
+        pc(torch.randn(2, 1, 19, 23, 32, device='cuda').to(torch.bfloat16))
+    else:
+        raise SystemExit('unknown case %s' % name)
+    torch.cuda.synchronize()
+    print('ran', name)
+
+
+for n in (['scatter_pair', 'scatter_single', 'scatter_split', 'concat', 'cls_fused', 'corr_tc', 'igemm'] if case == 'all' else [case]):
+    run(n)

@@ -76,6 +76,22 @@ chamfer_nn_kernel(const float* __restrict__ q_xyz, const float* __restrict__ r_x
   }
 }
 
+// fp32 issue-rate probe: every thread runs 8 independent FFMA chains, so the FMA pipe is the only limit.  bench.py times it
+// with CUDA events to get the MEASURED fp32 SIMT peak (instructions/s) that the Chamfer kernel's pair rate is quoted against.
+__global__ void __launch_bounds__(256) fma_probe_kernel(float* __restrict__ sink, int iters, float a, float b) {
+  float r[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) r[k] = (float)(threadIdx.x + k);
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r[k] = fmaf(r[k], a, b);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s += r[k];
+  if (s == 12345.678f) sink[0] = s;                    // never true in practice; keeps the chains alive
+}
+
 int launch_dir(const float* q, const float* r, float* dist, int32_t* idx, int B, int nq, int nr, cudaStream_t st) {
   // lanes per query group: enough threads to fill the chip (~2 waves of 2048 threads / SM)
   const int64_t want = (int64_t)num_sms() * 2048 * 2;
@@ -90,6 +106,17 @@ int launch_dir(const float* q, const float* r, float* dist, int32_t* idx, int B,
 
 }  // namespace
 }  // namespace s3d
+
+extern "C" int s3d_fma_probe(float* sink, int iters, int64_t* fma_count, void* stream) {
+  using namespace s3d;
+  if (!sink || !fma_count) { set_error("fma_probe: null argument"); return S3D_ERR_INVALID; }
+  S3D_CHECK_ARG(iters > 0, "fma_probe: iters");
+  const int blocks = num_sms() * 8;
+  fma_probe_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(sink, iters, 1.0000001f, 1e-7f);
+  S3D_LAUNCH_CHECK();
+  *fma_count = (int64_t)blocks * 256 * 8 * iters;       // thread-level FMAs executed by the launch
+  return S3D_OK;
+}
 
 extern "C" int s3d_chamfer_forward(const float* xyz1, const float* xyz2, float* dist1, int32_t* idx1, float* dist2,
                                    int32_t* idx2, int B, int N, int M, void* stream) {

@@ -5,17 +5,61 @@
 disk, so the class names below follow the same author's public GRNet extension from memory
 [RECALL] and are a convenience, not a verified API).
 
-No `setup.py install` step: the kernel ships inside libs3d_b200.so (s3d_chamfer_forward).
+The kernel ships inside libs3d_b200.so (s3d_chamfer_forward).  Two bindings reach it: the thin torch C++ extension
+`chamfer` built by /extensions/chamfer_dist/setup.py (the reference's build step, README.md:64-65) when it has been built,
+else the ctypes binding (ops.chamfer_forward).  Same kernel, same results; `backend()` says which one is in use.
 """
+import importlib.util
+import os
+import sys
+
 import torch
 
 from ... import ops
+
+_EXT_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))),
+                        'extensions', 'chamfer_dist')
+_ext = None
+
+
+def _load_ext():
+    """The compiled torch C++ shim (`chamfer`), from site-packages (setup.py install) or in-tree (build_ext --inplace)."""
+    global _ext
+    if _ext is None:
+        _ext = False
+        try:
+            import chamfer as _c                       # installed
+            _ext = _c
+        except ImportError:
+            if os.path.isdir(_EXT_DIR):
+                for f in sorted(os.listdir(_EXT_DIR)):
+                    if f.startswith('chamfer') and f.endswith('.so'):
+                        spec = importlib.util.spec_from_file_location('chamfer', os.path.join(_EXT_DIR, f))
+                        try:
+                            mod = importlib.util.module_from_spec(spec)
+                            spec.loader.exec_module(mod)
+                            sys.modules.setdefault('chamfer', mod)
+                            _ext = mod
+                        except (ImportError, OSError):
+                            _ext = False
+                        break
+    return _ext
+
+
+def backend():
+    return 'torch_extension' if _load_ext() else 'ctypes'
 
 
 class ChamferFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, xyz1, xyz2):
-        dist1, dist2, idx1, idx2 = ops.chamfer_forward(xyz1.contiguous().float(), xyz2.contiguous().float())
+        ext = _load_ext()
+        if ext and xyz1.is_cuda and xyz2.is_cuda:
+            from ... import lib as _lib
+            dist1, dist2, idx1, idx2 = ext.forward(xyz1.contiguous().float(), xyz2.contiguous().float())
+            _lib.count_launch(2)
+        else:
+            dist1, dist2, idx1, idx2 = ops.chamfer_forward(xyz1.contiguous().float(), xyz2.contiguous().float())
         ctx.mark_non_differentiable(dist1, dist2, idx1, idx2)
         return dist1, dist2, idx1, idx2
 

@@ -70,6 +70,7 @@ SIGNATURES = {
     's3d_unsplit_bf16': ([_vp, _vp, _i64, _i, _vp], _i),
     's3d_fuse_views': ([_vp, _i64, _vp, _i64, _i, _vp, _i, _i, _i, _vp, ctypes.POINTER(_f), _i, _vp, _i64, _i64, _vp], _i),
     's3d_chamfer_forward': ([_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp], _i),
+    's3d_fma_probe': ([_vp, _i, ctypes.POINTER(ctypes.c_int64), _vp], _i),
 }
 
 _lib = None

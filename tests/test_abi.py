@@ -55,6 +55,26 @@ def test_version_and_no_cpu_fallback():
             models.build_model('Stereo2Voxel', small_cfg(), seed=0).pack()
 
 
+def test_chamfer_extension_entry_point():
+    """The reference-shaped entry (README.md:62-65): top-level `extensions.chamfer_dist`, built by its setup.py as a thin
+    torch C++ extension over the C ABI (no kernel in it: it links libs3d_b200.so)."""
+    import subprocess
+    import torch
+    from extensions.chamfer_dist import ChamferDistance, backend
+    ext_dir = os.path.join(ROOT, 'extensions', 'chamfer_dist')
+    assert os.path.exists(os.path.join(ext_dir, 'setup.py'))
+    assert backend() == 'torch_extension', 'run __graft_entry__.build() (python setup.py build_ext --inplace)'
+    so = [f for f in os.listdir(ext_dir) if f.startswith('chamfer') and f.endswith('.so')][0]
+    needed = subprocess.check_output(['readelf', '-d', os.path.join(ext_dir, so)]).decode()
+    assert 'libs3d_b200.so' in needed                     # the shim links the C-ABI library
+    if not torch.cuda.is_available():
+        with pytest.raises((RuntimeError, lib.S3dError)):   # CPU tensors: loud failure, no CPU path
+            ChamferDistance()(torch.zeros(1, 4, 3), torch.zeros(1, 4, 3))
+    x = torch.zeros(1, 4, 3, requires_grad=True)
+    with pytest.raises(NotImplementedError):              # never silently gradient-less
+        ChamferDistance()(x, torch.zeros(1, 4, 3))
+
+
 def test_product_never_imports_oracle():
     pkg = os.path.join(ROOT, 'stereo_3d_reconstruction_b200')
     for dp, _, fs in os.walk(pkg):
