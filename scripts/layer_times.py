@@ -1,5 +1,5 @@
 """Per-kernel time breakdown of one Stereo2Voxel forward (CUDA events around every C-ABI call).
-usage: layer_times.py [batch] [precision]"""
+usage: layer_times.py [batch] [precision] [u8]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -12,6 +12,9 @@ cfg.NETWORK.PRECISION = sys.argv[2] if len(sys.argv) > 2 else 'bf16'
 cfg.CONST.MICRO_BATCH = max(B, 64)
 model = models.build_model('Stereo2Voxel', cfg, seed=0).cuda().pack()
 l, r, _ = synthetic.stereo_pair(B, cfg.CONST.IMG_H, cfg.CONST.IMG_W, 64, seed=0)
+if len(sys.argv) > 3 and sys.argv[3] == 'u8':          # decoded 8-bit HWC inputs (the e2e path)
+    l = (l.clamp(0, 1) * 255).round().to(torch.uint8).permute(0, 2, 3, 1).contiguous()
+    r = (r.clamp(0, 1) * 255).round().to(torch.uint8).permute(0, 2, 3, 1).contiguous()
 l, r = l.cuda(), r.cuda()
 gt = synthetic.gt_volume(B).cuda()
 for _ in range(2):

@@ -42,6 +42,7 @@ struct Knobs {
   int scatter_no_transpose;   // S3D_SCATTER_NO_TRANSPOSE: per-pixel stores instead of the transposed epilogue
   int scatter_generic;        // S3D_SCATTER_GENERIC: all-in-one kernel instead of the lean per-shape ones
   int no_corr_tc;             // S3D_NO_CORR_TC: SIMT correlation kernel even where the tensor-core one applies
+  int scatter_zsplit;         // S3D_SCATTER_ZSPLIT=n: force n z-chunks per column (-1: never split; 0 = automatic)
 };
 Knobs& knobs();
 

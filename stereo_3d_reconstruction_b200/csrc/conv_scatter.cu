@@ -48,8 +48,22 @@ int conv_scatter_launch(const S3dConvParams* p_in, const void* in, const float* 
   a.tps = spec_tps(a.row_bytes, a.cp);
   if (knobs().scatter_tps3 && a.tps == 9) a.tps = 3;
   a.cols_x = ceil_div(p.oW, kTX);  a.cols_y = ceil_div(p.oH, kTY);
-  const int64_t total = (int64_t)p.N * a.cols_x * a.cols_y;
+  int64_t total = (int64_t)p.N * a.cols_x * a.cols_y;
   S3D_CHECK_ARG(total > 0 && total < (1ll << 31), "scatter: column count out of range");
+  // z-split for small batches (conv_scatter.cuh, ScArgs::nz): as many chunks as fill the chip in ONE wave, each at least 4
+  // output planes deep (a chunk marches over 2 extra planes)
+  a.nz = 1;  a.zc = p.oD;  a.dl = p.oD;
+  {
+    const int sms = num_sms();
+    int nz = knobs().scatter_zsplit > 0 ? knobs().scatter_zsplit : (knobs().scatter_zsplit < 0 ? 1 : (int)(sms / total));
+    if (nz > p.oD / 4) nz = p.oD / 4;
+    if (nz > 1) {
+      a.zc = ceil_div(p.oD, nz);
+      a.nz = ceil_div(p.oD, a.zc);
+      a.dl = a.zc + 2;
+      if (a.nz > 1) total *= a.nz; else { a.nz = 1; a.zc = p.oD; a.dl = p.oD; }
+    }
+  }
   a.total_cols = (int)total;
   // CTA pairs (cta_group::2): the two SMs of a TPC run one M = 256 MMA, each on its own 128 pixels, and each keeps only
   // HALF of the weight rows in shared memory.  That halves the B-operand reads and the weight TMA writes per SM -- the

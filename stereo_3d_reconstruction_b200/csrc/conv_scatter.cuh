@@ -80,6 +80,11 @@ struct ScArgs {
   // weight stage per (tap, hi | lo weights).  The output is split as well: lo parts os_lo elements after the hi parts.
   int split;
   int64_t os_lo;
+  // z-split (small batches): with fewer columns than SMs a column of D planes is a serial chain on a fraction of the chip,
+  // so a column is cut into nz chunks of zc output planes.  A chunk marches over the zc + 2 input planes z0-1 .. z0+zc
+  // exactly like a whole column (planes outside the volume are TMA zero fill) and only STORES its own zc output planes:
+  // the first and last local output plane of a chunk are incomplete and dropped.  nz <= 1: no split (dl = D).
+  int nz, zc, dl;     // chunks per column, output planes per chunk, local planes marched per work item
 };
 
 struct ScCtrl {
@@ -89,10 +94,12 @@ struct ScCtrl {
   uint32_t tmem_base;
 };
 
-struct Col { int n, y0, x0; };
+struct Col { int n, y0, x0, zb; };             // zb: global z of local plane 0 (0, or z0 - 1 of a z-chunk)
 
 __device__ __forceinline__ Col decode_col(const ScArgs& a, int c) {
   Col r;
+  r.zb = 0;
+  if (a.nz > 1) { r.zb = (c % a.nz) * a.zc - 1;  c /= a.nz; }
   r.x0 = (c % a.cols_x) * kTX;  c /= a.cols_x;
   r.y0 = (c % a.cols_y) * kTY;  c /= a.cols_y;
   r.n = c;
@@ -118,7 +125,7 @@ __device__ __forceinline__ void sc_produce(const ScArgs& a, ScCtrl& ctrl, uint32
   constexpr int G = 9 * NK / TPS;
   const uint32_t bar_pf = ptx::smem_u32(&ctrl.plane_full[0]), bar_pe = ptx::smem_u32(&ctrl.plane_empty[0]);
   const uint32_t bar_wf = ptx::smem_u32(&ctrl.w_full[0]), bar_we = ptx::smem_u32(&ctrl.w_empty[0]);
-  const int D = a.p.iD, ring = a.ring, w_stages = a.w_stages, ncols = cta_cols(a);
+  const int D = a.dl, ring = a.ring, w_stages = a.w_stages, ncols = cta_cols(a);
   const int slot_bytes = a.slot_bytes, w_bytes = a.w_bytes, w_tx = a.w_tx;
   // pair mode: this CTA stages its own planes and ITS half of the weight rows; every load signals the leader's `full`
   // barrier, on which the leader's producer expects the bytes of both CTAs
@@ -141,12 +148,12 @@ __device__ __forceinline__ void sc_produce(const ScArgs& a, ScCtrl& ctrl, uint32
         if (leader) ptx::mbar_arrive_expect_tx_u32(bf, 2 * plane_tx);
 #pragma unroll
         for (int ch = 0; ch < NK; ++ch)
-          ptx::tma_load_5d_2sm_u32(planes_u32 + pslot * slot_bytes + ch * chunk_stride, map_x, bf, ch * kc, pc.x0 - 1, pc.y0 - 1, pj, pc.n);
+          ptx::tma_load_5d_2sm_u32(planes_u32 + pslot * slot_bytes + ch * chunk_stride, map_x, bf, ch * kc, pc.x0 - 1, pc.y0 - 1, pc.zb + pj, pc.n);
       } else {
         ptx::mbar_arrive_expect_tx_u32(bf, plane_tx);
 #pragma unroll
         for (int ch = 0; ch < NK; ++ch)
-          ptx::tma_load_5d_u32(planes_u32 + pslot * slot_bytes + ch * chunk_stride, map_x, bf, ch * kc, pc.x0 - 1, pc.y0 - 1, pj, pc.n);
+          ptx::tma_load_5d_u32(planes_u32 + pslot * slot_bytes + ch * chunk_stride, map_x, bf, ch * kc, pc.x0 - 1, pc.y0 - 1, pc.zb + pj, pc.n);
       }
     }
     __syncwarp();
@@ -447,7 +454,8 @@ __device__ __forceinline__ void sc_epilogue(const ScArgs& a, ScCtrl& ctrl, uint3
   const uint32_t bar_af = ptx::smem_u32(&ctrl.acc_full[t]), bar_ae = ptx::smem_u32(&ctrl.acc_empty[t]);
   const uint32_t tbase = tmem_base + t * kTileCols + (static_cast<uint32_t>(q * 32) << 16);
   const int yl = t * kTileY + q * 4 + (lane >> 3), xl = lane & 7;      // TMEM lane = 8 * row + x inside the tile
-  const int D = a.p.oD;
+  const int D = a.dl;                                 // local planes per work item (= oD unless z-split)
+  const int zs0 = a.nz > 1 ? 1 : 0, zs1 = a.nz > 1 ? a.zc + 1 : D;     // local output planes a work item stores
   const int xb = xl & ~(NCH - 1);                     // first pixel of this lane's transpose group
   uint32_t aphase = 0;
   const int ncols = cta_cols(a);
@@ -467,7 +475,9 @@ __device__ __forceinline__ void sc_epilogue(const ScArgs& a, ScCtrl& ctrl, uint3
       const int ndrain = (p >= 1 ? 1 : 0) + (p == D - 1 ? 1 : 0);
       uint4 r[NCH];
       if constexpr (kFast) {                          // residual of the plane about to be drained: in flight during the wait
-        if (a.residual && ndrain) sc_res_load<NCH, TOut>(fe, grp_off + (int64_t)z * a.p.osD, fe.osW, lane, okmask, r);
+        if (a.residual && ndrain)
+          sc_res_load<NCH, TOut>(fe, grp_off + (int64_t)(c.zb + z) * a.p.osD, fe.osW, lane,
+                                 (z >= zs0 && z < zs1 && c.zb + z < a.p.oD) ? okmask : 0u, r);
       }
       ptx::mbar_wait_u32(bar_af, aphase);
       ptx::tc_fence_after();
@@ -490,14 +500,16 @@ __device__ __forceinline__ void sc_epilogue(const ScArgs& a, ScCtrl& ctrl, uint3
           __syncwarp();
           if (lane == 0) { if (a.pair) ptx::mbar_arrive_cluster_u32(bar_ae, 0); else ptx::mbar_arrive_u32(bar_ae); }
         }
-        const int64_t zo = (int64_t)z * a.p.osD;
+        const int64_t zo = (int64_t)(c.zb + z) * a.p.osD;
+        const bool stz = z >= zs0 && z < zs1 && c.zb + z < a.p.oD;       // z-split: a chunk's border planes are not stored
+        const uint32_t om = stz ? okmask : 0u;
         if constexpr (kFast) {
           // (second drain of the last plane: its residual could not be prefetched)
-          if (i == 1 && a.residual) sc_res_load<NCH, TOut>(fe, grp_off + zo, fe.osW, lane, okmask, r);
-          if constexpr (kSRes >= 0) sc_fast_store<CP, TOut, kSRes != 0, kSAct>(fe, grp_off + zo, lane, okmask, v, r);
-          else sc_fast_plane<CP, TOut>(fe, grp_off + zo, lane, okmask, v, r);
+          if (i == 1 && a.residual) sc_res_load<NCH, TOut>(fe, grp_off + zo, fe.osW, lane, om, r);
+          if constexpr (kSRes >= 0) sc_fast_store<CP, TOut, kSRes != 0, kSAct>(fe, grp_off + zo, lane, om, v, r);
+          else sc_fast_plane<CP, TOut>(fe, grp_off + zo, lane, om, v, r);
         } else {
-          if (ok) {
+          if (ok && stz) {
 #pragma unroll
             for (int j = 0; j < CP / 16; ++j) epilogue_store16(ep, pix_off + zo, 16 * j, v[j]);
           }
@@ -608,7 +620,8 @@ __device__ __forceinline__ void sc_epilogue_split(const ScArgs& a, ScCtrl& ctrl,
   const uint32_t bar_af = ptx::smem_u32(&ctrl.acc_full[t]), bar_ae = ptx::smem_u32(&ctrl.acc_empty[t]);
   const uint32_t tbase = tmem_base + t * kTileCols + (static_cast<uint32_t>(q * 32) << 16);
   const int yl = t * kTileY + q * 4 + (lane >> 3), xl = lane & 7;
-  const int D = a.p.oD;
+  const int D = a.dl;
+  const int zs0 = a.nz > 1 ? 1 : 0, zs1 = a.nz > 1 ? a.zc + 1 : D;
   const int xb = xl & ~(NCH - 1);
   uint32_t aphase = 0;
   const int ncols = cta_cols(a);
@@ -624,7 +637,9 @@ __device__ __forceinline__ void sc_epilogue_split(const ScArgs& a, ScCtrl& ctrl,
     for (int p = 0; p < D; ++p) {
       const int ndrain = (p >= 1 ? 1 : 0) + (p == D - 1 ? 1 : 0);
       uint4 rh[NCH], rl[NCH];
-      if (a.residual && ndrain) sc_res_load_split<NCH>(fe, os_lo, grp_off + (int64_t)z * a.p.osD, lane, okmask, rh, rl);
+      if (a.residual && ndrain)
+        sc_res_load_split<NCH>(fe, os_lo, grp_off + (int64_t)(c.zb + z) * a.p.osD, lane,
+                               (z >= zs0 && z < zs1 && c.zb + z < a.p.oD) ? okmask : 0u, rh, rl);
       ptx::mbar_wait_u32(bar_af, aphase);
       ptx::tc_fence_after();
       if (ndrain == 0) {
@@ -646,16 +661,17 @@ __device__ __forceinline__ void sc_epilogue_split(const ScArgs& a, ScCtrl& ctrl,
           __syncwarp();
           if (lane == 0) { if (a.pair) ptx::mbar_arrive_cluster_u32(bar_ae, 0); else ptx::mbar_arrive_u32(bar_ae); }
         }
-        const int64_t zo = (int64_t)z * a.p.osD;
-        if (i == 1 && a.residual) sc_res_load_split<NCH>(fe, os_lo, grp_off + zo, lane, okmask, rh, rl);
+        const int64_t zo = (int64_t)(c.zb + z) * a.p.osD;
+        const uint32_t om = (z >= zs0 && z < zs1 && c.zb + z < a.p.oD) ? okmask : 0u;
+        if (i == 1 && a.residual) sc_res_load_split<NCH>(fe, os_lo, grp_off + zo, lane, om, rh, rl);
         if constexpr (kSRes >= 0) {
-          sc_split_store<CP, kSRes != 0, kSAct>(fe, os_lo, grp_off + zo, lane, okmask, v, rh, rl);
+          sc_split_store<CP, kSRes != 0, kSAct>(fe, os_lo, grp_off + zo, lane, om, v, rh, rl);
         } else if (fe.slope == 0.f) {
-          if (a.residual) sc_split_store<CP, true, 0>(fe, os_lo, grp_off + zo, lane, okmask, v, rh, rl);
-          else            sc_split_store<CP, false, 0>(fe, os_lo, grp_off + zo, lane, okmask, v, rh, rl);
+          if (a.residual) sc_split_store<CP, true, 0>(fe, os_lo, grp_off + zo, lane, om, v, rh, rl);
+          else            sc_split_store<CP, false, 0>(fe, os_lo, grp_off + zo, lane, om, v, rh, rl);
         } else {
-          if (a.residual) sc_split_store<CP, true, 2>(fe, os_lo, grp_off + zo, lane, okmask, v, rh, rl);
-          else            sc_split_store<CP, false, 2>(fe, os_lo, grp_off + zo, lane, okmask, v, rh, rl);
+          if (a.residual) sc_split_store<CP, true, 2>(fe, os_lo, grp_off + zo, lane, om, v, rh, rl);
+          else            sc_split_store<CP, false, 2>(fe, os_lo, grp_off + zo, lane, om, v, rh, rl);
         }
         ++z;
         if (++slot == 3) slot = 0;
@@ -722,7 +738,7 @@ conv_scatter_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                         ptx::smem_u32(&ctrl.w_empty[0]), ptx::smem_u32(&ctrl.acc_full[0]), ptx::smem_u32(&ctrl.acc_empty[0]),
                         desc_hi(kHX * rb, rb), desc_hi(8 * rb, rb), a.slot_bytes, a.w_bytes, a.w_stages, a.ring,
                         (uint32_t)(rb >> 4), (uint32_t)(((kPair ? 3 * a.cp / 2 : 3 * a.cp) * rb) >> 4), (uint32_t)((kTileY * kHX * rb) >> 4), (uint32_t)(a.chunk_stride >> 4), a.idesc,
-                        a.p.iD, cta_cols(a)};
+                        a.dl, cta_cols(a)};
     if constexpr (kSplit) {
       // kPer counts the MMAs of one operand HALF here
       if constexpr (RB == 256) sc_issue<false, 1, 4, kPair, 2, true>(zi);

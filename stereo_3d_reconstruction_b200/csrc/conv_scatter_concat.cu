@@ -299,6 +299,7 @@ extern "C" int s3d_conv_concat_volume(const S3dConvParams* p_in, const void* fea
   a.chunk_stride = (kPlaneRows * rb + 1023) / 1024 * 1024;
   a.slot_bytes = a.chunk_stride;                               // a slot holds ONE half (reference buffers / target ring)
   a.cp = p.Cout;  a.tps = 1;
+  a.nz = 1;  a.zc = D;  a.dl = D;                              // (no z-split here: small batches take the unfused path)
   a.cols_x = ceil_div(w, kTX);  a.cols_y = ceil_div(h, kTY);
   const int64_t total = (int64_t)p.N * a.cols_x * a.cols_y;
   S3D_CHECK_ARG(total > 0 && total < (1ll << 31), "conv_concat_volume: column count out of range");

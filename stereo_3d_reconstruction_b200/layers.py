@@ -88,13 +88,19 @@ def _choose_tile(N, oD, oH, oW, sx, sy, sz):
     return best[1]
 
 
-def _choose_bn(cout_pad):
-    if cout_pad <= 256:
-        return cout_pad
-    for bn in range(256, 15, -16):
-        if cout_pad % bn == 0:
+def _choose_bn(cout_pad, m_tiles=None, n_sms=148):
+    """GEMM N tile of the generic engine: the widest divisor of Cout (<= 256) -- unless that leaves most of the chip idle:
+    with few M tiles (small batches: dec0 at batch 1 is ONE 128-row tile x 8 classes streaming 134 MB of weights) the tile
+    is narrowed until there are about as many tiles as SMs, so that the weight stream is spread over all of them."""
+    divs = [bn for bn in range(min(256, cout_pad), 15, -16) if cout_pad % bn == 0]
+    if not divs:
+        raise ValueError('no N tile for Cout=%d' % cout_pad)
+    if m_tiles is None:
+        return divs[0]
+    for bn in divs:
+        if m_tiles * (cout_pad // bn) >= n_sms * 3 // 4:
             return bn
-    raise ValueError('no N tile for Cout=%d' % cout_pad)
+    return divs[-1]
 
 
 class PackedConv:
@@ -294,7 +300,8 @@ class PackedConv:
         p.in_dtype, p.out_dtype = self.dtype_code, out_dtype_code
         p.act, p.act_param = self.act, self.act_param
         p.tw, p.th, p.td, p.tn = _choose_tile(N, oD, oH, oW, self.stride[2], self.stride[1], self.stride[0])
-        p.bn = self.bn
+        m_tiles = self.n_classes * -(-oW // p.tw) * -(-oH // p.th) * -(-oD // p.td) * -(-N // p.tn)
+        p.bn = _choose_bn(self.cout_pad, m_tiles)
         p.w_nstack = self.weight_ns.data_ptr() if self.weight_ns is not None else None
         if self.proj is not None:
             p.proj_w, p.proj_channel, p.proj_act = self.proj[0].data_ptr(), self.proj[1], self.proj[2]

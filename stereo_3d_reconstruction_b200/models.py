@@ -282,7 +282,10 @@ class _StereoBase(nn.Module):
         p5, p0 = self._packed['enc5'], self._packed.get('dres0a')
         fuse_volume = (cfg.NETWORK.COST_VOLUME == 'concat' and self.precision in ('bf16', 'tf32') and p5.cout_pad == C and
                        isinstance(p0, PackedConv) and p0.weight_ns is not None and C * x.element_size() in (32, 64) and
-                       not _lib.KNOBS['no_concat_fuse'] and not _lib.KNOBS['no_scatter'])
+                       not _lib.KNOBS['no_concat_fuse'] and not _lib.KNOBS['no_scatter'] and
+                       # small batches: fewer columns than SMs -> unfused volume + the z-split plane-scatter kernel (a column of
+                       # D planes would be a serial chain on a fraction of the chip; csrc/conv_scatter.cuh, ScArgs::nz)
+                       2 * B * (-(-h // 32)) * (-(-w // 8)) > 74)
         cm = cmult(self._dtype_code())                           # physical channels per logical channel (2 when split)
         if fuse_volume:
             # features go into rows with D zero pixels on both sides: the fused cost-volume + dres0a kernel reads the shifted

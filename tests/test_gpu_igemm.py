@@ -237,3 +237,35 @@ def test_conv_concat_volume_fused_is_bit_identical(knobs, knob, prec, B, C, cout
         ref = to_cl(F.relu(conv(ref_vol)))
     err = (got.float().cpu()[..., :cout] - ref).abs().max().item()
     assert err <= TOL[prec] * (ref.abs().max().item() + 1e-6)
+
+
+@pytest.mark.parametrize('nz', [0, 2, 3, 5, 8])
+@pytest.mark.parametrize('prec,N,cin,cout,D,H,W,res', [
+    ('bf16', 1, 64, 64, 32, 64, 64, False),      # the aggregation layer at batch 1: 32 columns -> 4 chunks of 8 planes
+    ('bf16', 2, 64, 64, 13, 33, 9, True),        # ragged last chunk, residual
+    ('bf16', 2, 16, 16, 32, 32, 32, False),      # fusion scorer at batch 1
+    ('tf32', 1, 32, 32, 9, 20, 12, True),
+])
+def test_plane_scatter_z_split(knobs, nz, prec, N, cin, cout, D, H, W, res):
+    """Small batches: a column is cut into z-chunks that march over 2 extra planes and store only their own planes
+    (conv_scatter.cuh, ScArgs::nz).  nz = 0: the launcher's own choice; the result must equal the unsplit kernel's BIT FOR BIT
+    (same MMA sequence per output plane)."""
+    torch.manual_seed(11)
+    conv = _qmod(nn.Conv3d(cin, cout, 3, 1, 1, bias=True), prec)
+    x = _q(torch.randn(N, cin, D, H, W), prec)
+    dt = torch.bfloat16 if prec == 'bf16' else torch.float32
+    pc = PackedConv.from_conv(conv, None, lib.ACT_RELU, _code(prec), 'cuda')
+    kw = {}
+    with torch.no_grad():
+        ref = conv(x)
+    if res:
+        r = torch.randn(N, cout, D, H, W).to(dt).float()
+        ref = ref + r
+        kw['residual'] = pad_c(to_cl(r), pc.cout_pad).to(dt).cuda()
+    xc = pad_c(to_cl(x), pc.cin_pad).to(dt).cuda()
+    knobs('scatter_zsplit', -1)
+    whole = pc(xc, engine='igemm', **kw).clone()
+    knobs('scatter_zsplit', nz)
+    got = pc(xc, engine='igemm', **kw)
+    assert torch.equal(got, whole)
+    _check(pc, x, F.relu(ref), prec, cout, **kw)

@@ -110,6 +110,23 @@ def test_plane_scatter_split(knobs, knob, N, cin, cout, D, H, W, res, act):
     _check(pc, x, fn(ref), cout, **kw)
 
 
+@pytest.mark.parametrize('nz', [0, 3])
+def test_plane_scatter_split_z_split(knobs, nz):
+    """bf16x3 kernels with z-chunks (small batches): bit-identical to the unsplit march."""
+    torch.manual_seed(12)
+    conv = nn.Conv3d(64, 64, 3, 1, 1, bias=True)
+    x = torch.randn(1, 64, 16, 40, 24)
+    r = torch.randn(1, 64, 16, 40, 24)
+    pc = PackedConv.from_conv(conv, None, lib.ACT_NONE, X2, 'cuda')
+    xs, rs = _split(to_cl(x)).cuda(), _split(to_cl(r)).cuda()
+    knobs('scatter_zsplit', -1)
+    whole = pc(xs, residual=rs).clone()
+    knobs('scatter_zsplit', nz)
+    assert torch.equal(pc(xs, residual=rs), whole)
+    with torch.no_grad():
+        _check(pc, x, conv(x) + r, 64, residual=rs)
+
+
 def test_conv2d_as_volume_split():
     """stride-1 3x3 2-D layers run as volumes of images on the plane-scatter kernel (encoder layers 1, 3, 4, 5)."""
     torch.manual_seed(8)
