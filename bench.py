@@ -145,7 +145,7 @@ def run_reference(args):
         return
     from config import cfg
     cores = os.cpu_count() or 1
-    sample = 2
+    sample = 8
     value, sec = cpu_oracle_run(cfg, sample, max(1, args.steps), max(1, min(args.warmup, 2)), cores)
     B = args.batch or cfg.CONST.BATCH_SIZE
     line = {
