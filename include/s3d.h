@@ -145,6 +145,15 @@ int s3d_conv_first(const void* img, int img_u8, const float* disp, float disp_sc
  * (>= D-1 pixels on both sides) are ZERO; left images first.  Bit-identical to s3d_cost_volume_concat + s3d_conv_igemm. */
 int s3d_conv_concat_volume(const S3dConvParams* p, const void* feat, int feat_pitch, int feat_pad, const float* bias,
                            void* out, void* stream);
+/* The same layer in REFERENCE-ONCE form (bf16 only; Cout = 64, ReLU, dense output, CTA pairs).  The reference half of the
+ * concat volume is the same feature map on every disparity plane, so its contribution R = ref (*) sum_kz W[kz, :, ref ch]
+ * is computed once per column and added to every plane by the epilogue; the planes run the tensor cores on the TARGET half
+ * only (half the MMA work of the layer) and the two border planes get ref (*) -W[kz=0] / -W[kz=2] added.
+ * w_refonce: bf16 DEVICE tensor [3][9][Cout][C] = [sum_kz W[kz] | -W[kz=0] | -W[kz=2]] over the reference channels
+ * (in-plane tap order ky*3+kx).  Same result as s3d_conv_concat_volume up to bf16 rounding of the summed weights and
+ * the fp32 accumulation order (NOT bit-identical). */
+int s3d_conv_concat_volume_ro(const S3dConvParams* p, const void* feat, int feat_pitch, int feat_pad, const void* w_refonce,
+                              const float* bias, void* out, void* stream);
 /* feat: [2B,1,h,w,C] (left maps first, then right).  vol: [2B,D,h,w,2C]; entries [0,B) are
  * left-referenced (target sampled at x-d), [B,2B) right-referenced (target at x+d).
  * dtype BF16X2: feat [.., hi(C) | lo(C)] -> vol [.., hi(2C) | lo(2C)] (C logical channels). */

@@ -1,5 +1,5 @@
 """A few launches of ONE kernel at the bench shape, for `ncu --set full -k regex:...`.
-usage: prof_kernels.py <agg_bf16 | agg_bf16x3 | agg_res_bf16x3 | cls_fused | corr_tc | soft_argmin | chamfer | conv_first>"""
+usage: prof_kernels.py <agg_bf16 | concat | concat_ro | agg_bf16x3 | agg_res_bf16x3 | cls_fused | corr_tc | soft_argmin | chamfer | conv_first>"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -21,6 +21,14 @@ if what.startswith('agg'):
     out = torch.empty_like(x)
     for _ in range(3):
         pc(x, out=out, residual=r)
+elif what in ('concat', 'concat_ro'):
+    Cf = 32
+    pc = PackedConv.from_conv(nn.Conv3d(2 * Cf, C, 3, 1, 1, bias=True), None, lib.ACT_RELU, lib.DTYPE_BF16, 'cuda')
+    featp = torch.zeros(N, 1, h, w + 2 * D, Cf, dtype=torch.bfloat16, device='cuda')
+    featp[:, :, :, D:D + w] = torch.randn(N, 1, h, w, Cf, device='cuda').to(torch.bfloat16)
+    out = torch.empty(N, D, h, w, C, dtype=torch.bfloat16, device='cuda')
+    for _ in range(3):
+        ops.conv_concat_volume(pc, featp, N // 2, D, D, out=out, ref_once=what == 'concat_ro')
 elif what == 'cls_fused':
     x = torch.randn(N, D, h, w, C, device='cuda').to(torch.bfloat16)
     wt = torch.zeros(32, C, dtype=torch.bfloat16, device='cuda')

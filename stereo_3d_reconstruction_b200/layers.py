@@ -177,6 +177,21 @@ class PackedConv:
                 ns[r, :, s * co:(s + 1) * co] = w3[((r % 3) + 1 - s) % 3]
         return ns.view(36, 3 * co, ci)
 
+    def refonce_weights(self, C):
+        """Special weight sets of the reference-once concat kernel (include/s3d.h, s3d_conv_concat_volume_ro) for a 3x3x3 layer
+        over [ref(C) | tgt(C)] channels: [3, 9, Cout_pad, C] = [sum_kz W[kz] | -W[kz=0] | -W[kz=2]] on the reference channels."""
+        key = ('refonce', C)
+        if key not in self._cache:
+            assert self.ntaps == 27 and self.n_classes == 1 and self.cin_pad == 2 * C
+            w3 = self._ctor[0].view(3, 9, self.cout, self.cin)
+            ro = torch.zeros(3, 9, self.cout_pad, C, dtype=torch.float32)
+            cr = min(C, self.cin)
+            ro[0, :, :self.cout, :cr] = w3[:, :, :, :cr].sum(0)
+            ro[1, :, :self.cout, :cr] = -w3[0, :, :, :cr]
+            ro[2, :, :self.cout, :cr] = -w3[2, :, :, :cr]
+            self._cache[key] = to_storage(ro.view(27, self.cout_pad, C), self.dtype_code).to(self.weight.device).contiguous()
+        return self._cache[key]
+
     # ---- constructors ------------------------------------------------------------------
     @classmethod
     def from_conv(cls, conv, bn, act, dtype_code, device, act_param=0.0):

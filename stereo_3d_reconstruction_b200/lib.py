@@ -56,6 +56,7 @@ SIGNATURES = {
     's3d_pack_image_u8': ([_vp, _vp, _f, _f, _vp, _i, _i, _i, _i, _i, _vp], _i),
     's3d_conv_first': ([_vp, _i, _vp, _f, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp], _i),
     's3d_conv_concat_volume': ([ctypes.POINTER(S3dConvParams), _vp, _i, _i, _vp, _vp, _vp], _i),
+    's3d_conv_concat_volume_ro': ([ctypes.POINTER(S3dConvParams), _vp, _i, _i, _vp, _vp, _vp, _vp], _i),
     's3d_cost_volume_concat': ([_vp, _vp, _i, _i, _i, _i, _i, _i, _vp], _i),
     's3d_soft_argmin': ([_vp, _vp, _i, _i, _i, _i, _f, _vp], _i),
     's3d_tap_gather_soft_argmin': ([_vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp], _i),
@@ -108,7 +109,7 @@ def check(rc, what):
 # Read ONCE (here, at import) from the S3D_* environment variables, never on the forward path.  The host-side ones live
 # in this dict; the launcher-side ones live in the library (include/s3d.h, s3d_set_knob).  set_knob() changes either
 # at run time (tests, A/B scripts) -- a model picks host-side knobs up at its next pack().
-HOST_KNOBS = ('no_vol2d', 'no_concat_fuse', 'no_cls_fused', 'no_conv_first', 'no_d2s')
+HOST_KNOBS = ('no_vol2d', 'no_concat_fuse', 'no_cls_fused', 'no_conv_first', 'no_d2s', 'no_ref_once')
 LIB_KNOBS = ('no_scatter', 'scatter_tps3', 'scatter_no_pair', 'scatter_ring', 'scatter_res_transpose',
              'scatter_no_transpose', 'scatter_generic', 'no_corr_tc', 'scatter_zsplit')
 KNOBS = {k: int(os.environ.get('S3D_' + k.upper()) is not None) for k in HOST_KNOBS}

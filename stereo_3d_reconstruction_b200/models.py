@@ -299,7 +299,12 @@ class _StereoBase(nn.Module):
         disp_q = self._buf('disp_q', (2 * B, h, w), torch.float32)
         if cfg.NETWORK.COST_VOLUME == 'concat':
             if fuse_volume:
-                a = ops.conv_concat_volume(p0, featp, B, D, pad, out=self._buf('a0', (2 * B, D, h, w, p0.cout_pad), dt))
+                # bf16: reference-once form -- the d-independent reference half is convolved once per column, the planes run
+                # on the target half only (half the tensor-core work of this layer; csrc/conv_scatter_concat.cu)
+                ro = (self.precision == 'bf16' and p0.cout_pad == 64 and p0.act == _lib.ACT_RELU and
+                      not _lib.KNOBS['no_ref_once'])
+                a = ops.conv_concat_volume(p0, featp, B, D, pad, out=self._buf('a0', (2 * B, D, h, w, p0.cout_pad), dt),
+                                           ref_once=ro)
             else:
                 assert feat.shape[-1] == cm * C, 'FEAT_CHANNELS must be a multiple of 16'
                 vol = ops.cost_volume_concat(feat, B, D, out=self._buf('vol', (2 * B, D, h, w, 2 * cm * C), dt), split=self._split)

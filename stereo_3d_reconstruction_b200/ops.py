@@ -194,10 +194,11 @@ def conv_first(img, pc, disp=None, disp_scale=1.0, out=None):
     return out
 
 
-def conv_concat_volume(pc, featp, B, D, pad, out=None):
+def conv_concat_volume(pc, featp, B, D, pad, out=None, ref_once=False):
     """Concat cost volume + the 3x3x3 conv `pc` (PackedConv over 2C channels) in one kernel, the volume never written.
     featp: [2B,1,h,pitch,C] feature maps stored with `pad` >= D-1 ZERO pixels on both sides of every row (real pixels in
-    columns pad .. pitch-pad-1), left images first.  -> [2B,D,h,w,cout_pad].  include/s3d.h, s3d_conv_concat_volume."""
+    columns pad .. pitch-pad-1), left images first.  -> [2B,D,h,w,cout_pad].  include/s3d.h, s3d_conv_concat_volume.
+    ref_once: the reference-once form (s3d_conv_concat_volume_ro: half the tensor-core work, not bit-identical)."""
     import ctypes
     _chk(featp, out)
     n2, one, h, pitch, C = featp.shape
@@ -209,9 +210,14 @@ def conv_concat_volume(pc, featp, B, D, pad, out=None):
     assert out.is_contiguous() and out.shape == (2 * B, D, h, w, pc.cout_pad)
     Co = pc.cout_pad
     p = pc.params(2 * B, D, h, w, (D * h * w * Co, h * w * Co, w * Co, Co), _code(out), Co)
-    rc = _lib.load().s3d_conv_concat_volume(ctypes.byref(p), featp.data_ptr(), pitch, pad, pc.bias.data_ptr(), out.data_ptr(),
-                                            _stream())
-    _lib.check(rc, 's3d_conv_concat_volume')
+    if ref_once:
+        rc = _lib.load().s3d_conv_concat_volume_ro(ctypes.byref(p), featp.data_ptr(), pitch, pad, pc.refonce_weights(C).data_ptr(),
+                                                   pc.bias.data_ptr(), out.data_ptr(), _stream())
+        _lib.check(rc, 's3d_conv_concat_volume_ro')
+    else:
+        rc = _lib.load().s3d_conv_concat_volume(ctypes.byref(p), featp.data_ptr(), pitch, pad, pc.bias.data_ptr(), out.data_ptr(),
+                                                _stream())
+        _lib.check(rc, 's3d_conv_concat_volume')
     _lib.count_launch()
     return out
 

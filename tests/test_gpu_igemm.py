@@ -239,6 +239,50 @@ def test_conv_concat_volume_fused_is_bit_identical(knobs, knob, prec, B, C, cout
     assert err <= TOL[prec] * (ref.abs().max().item() + 1e-6)
 
 
+@pytest.mark.parametrize('B,C,D,h,w', [
+    (2, 32, 8, 16, 16),        # the network's shape (64-byte halves)
+    (3, 32, 32, 40, 64),       # D = 32 planes, two patch rows, several columns per CTA
+    (1, 16, 5, 9, 13),         # ragged patches, 32-byte halves
+    (2, 32, 1, 8, 8),          # one plane: both border corrections land on it
+    (2, 32, 2, 8, 8),          # two planes: out[0] and out[D-1] are neighbours
+    (1, 32, 12, 8, 8),         # more disparities than pixels in a row
+    (80, 32, 4, 8, 8),         # 160 columns on 148 SMs: some CTAs walk two columns (R rewritten per column), phantom column
+])
+def test_conv_concat_volume_ref_once(B, C, D, h, w):
+    """Reference-once form of the fused cost volume + first aggregation layer (s3d_conv_concat_volume_ro): same result as the
+    volume + conv3d on bf16-rounded operands within the bf16 engine tolerance, and as the bit-exact fused kernel to the
+    same bound (the summed reference weights are rounded to bf16 once: not bit-identical by design)."""
+    from stereo_3d_reconstruction_b200 import ops
+    from oracle import models as O
+    cout = 64
+    torch.manual_seed(11)
+    conv = _qmod(nn.Conv3d(2 * C, cout, 3, 1, 1, bias=True), 'bf16')
+    pc = PackedConv.from_conv(conv, None, lib.ACT_RELU, _code('bf16'), 'cuda')
+    f = _q(torch.randn(2 * B, C, h, w), 'bf16')
+    feat = to_cl(f).to(torch.bfloat16).cuda()
+    pad, P = D, w + 2 * D
+    featp = torch.zeros(2 * B, 1, h, P, C, dtype=torch.bfloat16, device='cuda')
+    featp[:, :, :, pad:pad + w] = feat
+    got = ops.conv_concat_volume(pc, featp, B, D, pad, ref_once=True)
+    exact = ops.conv_concat_volume(pc, featp, B, D, pad)
+    torch.cuda.synchronize()
+    assert got.shape == exact.shape
+    scale = exact.float().abs().max().item() + 1e-6
+    # two bf16 roundings of the output apart at most, plus the rounding of the summed weights
+    assert (got.float() - exact.float()).abs().max().item() <= 2 * TOL['bf16'] * scale
+    fr = feat.float().cpu()[:, 0].permute(0, 3, 1, 2)
+    ref_vol = torch.cat([O.build_concat_volume(fr[:B], fr[B:], D, -1), O.build_concat_volume(fr[B:], fr[:B], D, +1)], 0)
+    with torch.no_grad():
+        ref = to_cl(F.relu(conv(ref_vol)))
+    err = (got.float().cpu()[..., :cout] - ref).abs().max().item()
+    # the summed reference weights are rounded to bf16 once more than in the reference: allow twice the engine's bound
+    assert err <= 2 * TOL['bf16'] * (ref.abs().max().item() + 1e-6)
+    # every plane on its own (a wrong border correction would hide behind the max over the whole volume otherwise)
+    for z in sorted({0, 1, D // 2, D - 2, D - 1} & set(range(D))):
+        ez = (got.float().cpu()[:, z, ..., :cout] - ref[:, z]).abs().max().item()
+        assert ez <= 2 * TOL['bf16'] * (ref[:, z].abs().max().item() + 1e-6), (z, ez)
+
+
 @pytest.mark.parametrize('nz', [0, 2, 3, 5, 8])
 @pytest.mark.parametrize('prec,N,cin,cout,D,H,W,res', [
     ('bf16', 1, 64, 64, 32, 64, 64, False),      # the aggregation layer at batch 1: 32 columns -> 4 chunks of 8 planes
