@@ -43,6 +43,9 @@ struct Knobs {
   int scatter_generic;        // S3D_SCATTER_GENERIC: all-in-one kernel instead of the lean per-shape ones
   int no_corr_tc;             // S3D_NO_CORR_TC: SIMT correlation kernel even where the tensor-core one applies
   int scatter_zsplit;         // S3D_SCATTER_ZSPLIT=n: force n z-chunks per column (-1: never split; 0 = automatic)
+  int igemm_ts1;              // S3D_IGEMM_TS1: one tap per pipeline stage in the generic engine (conv_igemm.cu)
+  int igemm_one_cta;          // S3D_IGEMM_ONE_CTA: one CTA per SM in the generic engine even where two fit
+  int scatter_no_rm;          // S3D_SCATTER_NO_RM: residual added by the epilogue threads instead of an identity tap on the tensor core
 };
 Knobs& knobs();
 

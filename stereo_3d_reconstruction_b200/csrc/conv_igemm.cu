@@ -35,8 +35,9 @@ namespace {
 constexpr int kThreads = 256;
 constexpr int kTileM = 128;
 constexpr int kMaxStages = 8;
-constexpr int kTmemCols = 512;
-constexpr int kAccStride = 256;   // TMEM columns per accumulator buffer
+// TMEM: two accumulator buffers.  N tiles <= 128 take 2 x 128 columns and half of the shared memory, so that TWO CTAs share an
+// SM: a pipeline stage is a chain of barrier round trips (~400-800 cycles, scripts/tma_rate.cu) that one CTA cannot hide for
+// the small-K stride-2 / transposed layers; a second resident CTA overlaps its chain with the first one's.
 
 struct KernelArgs {
   S3dConvParams p;
@@ -48,13 +49,16 @@ struct KernelArgs {
   int n_kchunks;     // Cin / kc
   int npass;         // 1, or 3 for split (BF16X2) operands: (x_hi, w_hi), (x_lo, w_hi), (x_hi, w_lo) per tap and K chunk
   int stages;
-  int a_bytes, b_bytes, stage_bytes;   // smem footprint (b_bytes rounded up to 1024)
+  int ts;            // taps per pipeline stage (divides ntaps): TS activation boxes + ONE weight box of TS taps
+  int b_tap_bytes;   // bytes between the taps of a stage's weight box (bn * row_bytes)
+  int a_bytes, b_bytes, stage_bytes;   // smem footprint: a_bytes per tap, b_bytes per stage (rounded up to 1024)
   int tx_bytes;                        // bytes the two TMA boxes actually deliver per stage
   int tiles_x, tiles_y, tiles_z, tiles_n;   // M tiling
   int n_ntiles;                             // Cout / bn
   int total_tiles;                          // n_classes * M tiles * N tiles
   int lw, lh, ld;                           // log2 of tw, th, td
   uint32_t idesc;
+  int tmem_cols, acc_stride;                // TMEM columns allocated (256 or 512) and per accumulator buffer
 };
 
 struct SharedCtrl {
@@ -82,7 +86,7 @@ __device__ __forceinline__ TileCoord decode_tile(const KernelArgs& a, int tile) 
 }
 
 template <bool kTF32>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 2)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                   const __grid_constant__ KernelArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -108,36 +112,51 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     }
     ptx::fence_barrier_init();
   }
-  if (warp == 2) ptx::tmem_alloc(&ctrl.tmem_base, kTmemCols);
+  if (warp == 2) ptx::tmem_alloc(&ctrl.tmem_base, a.tmem_cols);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = ctrl.tmem_base;
 
-  const int ksteps = a.p.ntaps * a.npass * a.n_kchunks;
+  // A pipeline stage costs ~400-800 cycles of barrier round trips (wait empty -> expect_tx -> TMA -> wait full -> MMA ->
+  // commit; scripts/tma_rate.cu measures 420 cycles per iteration of the bare producer loop) however little it carries, so a
+  // stage holds TS taps: with one tap per stage the stride-2 / transposed layers ran the tensor pipe at 8-10 %.
+  const int ksteps = (a.p.ntaps / a.ts) * a.npass * a.n_kchunks;
 
   if (warp == 0) {
     // ================= TMA producer =================
-    if (lane == 0) {
-      int stage = 0;  uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
-        const TileCoord t = decode_tile(a, tile);
-        const int xin = t.x0 * a.p.sx, yin = t.y0 * a.p.sy, zin = t.z0 * a.p.sz;
-        for (int tap = 0; tap < a.p.ntaps; ++tap) {
-          const int ti = t.cls * a.p.ntaps + tap;
-          const int cx = xin + a.p.dx[ti], cy = yin + a.p.dy[ti], cz = zin + a.p.dz[ti];
-          // split operands: the lo halves sit Cin channels after the hi halves, in the activations and in the weights
-          for (int pass = 0; pass < a.npass; ++pass) {
-            const int ca = pass == 1 ? a.p.Cin : 0, cb = pass == 2 ? a.p.Cin : 0;
-            for (int kc = 0; kc < a.n_kchunks; ++kc) {
-              ptx::mbar_wait(&ctrl.empty[stage], phase ^ 1);
-              uint8_t* sa = smem + stage * a.stage_bytes;
-              uint8_t* sb = sa + a.a_bytes;
-              ptx::mbar_arrive_expect_tx(&ctrl.full[stage], a.tx_bytes);
-              ptx::tma_load_5d(sa, &map_a, &ctrl.full[stage], ca + kc * a.kc, cx, cy, cz, t.n0);
-              ptx::tma_load_3d(sb, &map_b, &ctrl.full[stage], cb + kc * a.kc, t.nt * a.p.bn, ti);
-              if (++stage == a.stages) { stage = 0; phase ^= 1; }
+    // Warp-uniform control flow, TMA issue under elect_one only.  (The first version ran the whole loop under `lane == 0`:
+    // the compiler then moves every TMA operand to uniform registers through R2UR + an ELECT / BRA.U.ANY waterfall, ~110
+    // dependent instructions = ~800 cycles per stage, and the issuer starved on `full` -- ncu: 8 % tensor pipe on enc2.)
+    int stage = 0;  uint32_t phase = 0;
+    const uint32_t full0 = ptx::smem_u32(&ctrl.full[0]), empty0 = ptx::smem_u32(&ctrl.empty[0]);
+    const uint32_t smem_u = ptx::smem_u32(smem);
+    const int stages = a.stages, stage_bytes = a.stage_bytes, a_bytes = a.a_bytes, tx_bytes = a.tx_bytes;
+    const int ntaps = a.p.ntaps, npass = a.npass, n_kchunks = a.n_kchunks, kcw = a.kc, Cin = a.p.Cin, bn = a.p.bn, ts = a.ts;
+    const int sb_off = ts * a_bytes;
+    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(a, tile);
+      const int xin = t.x0 * a.p.sx, yin = t.y0 * a.p.sy, zin = t.z0 * a.p.sz;
+      const int brow = t.nt * bn;
+      // K order: chunk -> pass -> tap, whatever TS is (TS depends on the N tile, which depends on the batch size: the
+      // accumulation order, and so every output bit, must not)
+      for (int kc = 0; kc < n_kchunks; ++kc) {
+        // split operands: the lo halves sit Cin channels after the hi halves, in the activations and in the weights
+        for (int pass = 0; pass < npass; ++pass) {
+          const int ca = (pass == 1 ? Cin : 0) + kc * kcw, cb = (pass == 2 ? Cin : 0) + kc * kcw;
+          for (int tap = 0; tap < ntaps; tap += ts) {
+            const int ti = t.cls * ntaps + tap;
+            ptx::mbar_wait_u32(empty0 + 8 * stage, phase ^ 1);
+            if (ptx::elect_one()) {
+              const uint32_t sa = smem_u + stage * stage_bytes, bf = full0 + 8 * stage;
+              ptx::mbar_arrive_expect_tx_u32(bf, tx_bytes);
+              for (int j = 0; j < ts; ++j)
+                ptx::tma_load_5d_u32(sa + j * a_bytes, &map_a, bf, ca, xin + a.p.dx[ti + j], yin + a.p.dy[ti + j],
+                                     zin + a.p.dz[ti + j], t.n0);
+              ptx::tma_load_3d_u32(sa + sb_off, &map_b, bf, cb, brow, ti);
             }
+            __syncwarp();
+            if (++stage == stages) { stage = 0; phase ^= 1; }
           }
         }
       }
@@ -154,18 +173,21 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
       ptx::mbar_wait(&ctrl.acc_empty[buf], acc_phase ^ 1);
       ptx::tc_fence_after();
-      const uint32_t d_tmem = tmem_base + buf * kAccStride;
+      const uint32_t d_tmem = tmem_base + buf * a.acc_stride;
       for (int ks = 0; ks < ksteps; ++ks) {
         ptx::mbar_wait(&ctrl.full[stage], phase);
         ptx::tc_fence_after();
         const uint32_t sa = smem_u + stage * a.stage_bytes;
         const uint64_t adesc = desc_hi | ((sa >> 4) | (1u << 16));
-        const uint64_t bdesc = desc_hi | (((sa + a.a_bytes) >> 4) | (1u << 16));
+        const uint64_t bdesc = desc_hi | (((sa + a.ts * a.a_bytes) >> 4) | (1u << 16));
         if (ptx::elect_one()) {
-          for (int k = 0; k < mma_per_stage; ++k) {
-            // advance 32 B along K inside the swizzle atom: +2 in the (addr >> 4) field
-            if (kTF32) ptx::mma_tf32(d_tmem, adesc + 2 * k, bdesc + 2 * k, a.idesc, (ks | k) != 0);
-            else       ptx::mma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, a.idesc, (ks | k) != 0);
+          for (int j = 0; j < a.ts; ++j) {
+            const uint64_t ad = adesc + j * (a.a_bytes >> 4), bd = bdesc + j * (a.b_tap_bytes >> 4);
+            for (int k = 0; k < mma_per_stage; ++k) {
+              // advance 32 B along K inside the swizzle atom: +2 in the (addr >> 4) field
+              if (kTF32) ptx::mma_tf32(d_tmem, ad + 2 * k, bd + 2 * k, a.idesc, (ks | j | k) != 0);
+              else       ptx::mma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, a.idesc, (ks | j | k) != 0);
+            }
           }
           ptx::tc_commit(&ctrl.empty[stage]);          // frees the smem slot when the MMAs retire
         }
@@ -198,7 +220,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                           (int64_t)(y * a.p.omy + ooy) * a.p.osH + (int64_t)(x * a.p.omx + oox) * a.p.osW;
       ptx::mbar_wait(&ctrl.acc_full[buf], acc_phase);
       ptx::tc_fence_after();
-      const uint32_t taddr = tmem_base + buf * kAccStride + (static_cast<uint32_t>(q * 32) << 16);
+      const uint32_t taddr = tmem_base + buf * a.acc_stride + (static_cast<uint32_t>(q * 32) << 16);
       const int c_base = t.nt * a.p.bn;
       for (int c0 = 0; c0 < a.p.bn; c0 += 16) {
         uint32_t v[16];
@@ -219,7 +241,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   __syncthreads();
   if (warp == 2) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, kTmemCols);
+    ptx::tmem_dealloc(tmem_base, a.tmem_cols);
   }
 }
 
@@ -267,11 +289,21 @@ int conv_igemm_launch(const S3dConvParams* p, const void* in, const void* w, con
   const bool split = p->in_dtype == S3D_DTYPE_BF16X2;
   a.npass = split ? 3 : 1;
   const int cin_phys = split ? 2 * p->Cin : p->Cin;        // [hi(Cin) | lo(Cin)] rows, activations and weights alike
-  a.a_bytes = kTileM * a.row_bytes;
-  a.b_bytes = ((p->bn * a.row_bytes + 1023) / 1024) * 1024;
-  a.tx_bytes = a.a_bytes + p->bn * a.row_bytes;
-  a.stage_bytes = a.a_bytes + a.b_bytes;          // a_bytes is a multiple of 1024 (4096..16384)
-  const int smem_budget = 200 * 1024;
+  a.a_bytes = kTileM * a.row_bytes;               // a multiple of 1024 (4096..16384)
+  a.b_tap_bytes = p->bn * a.row_bytes;            // bn % 16 == 0: a multiple of the swizzle atom (8 rows)
+  const bool two_ctas = p->bn <= 128 && !knobs().igemm_one_cta;
+  a.tmem_cols = two_ctas ? 256 : 512;  a.acc_stride = a.tmem_cols / 2;
+  const int smem_budget = two_ctas ? 104 * 1024 : 200 * 1024;
+  // taps per stage: as many as keep >= 4 stages of <= 48 KB in flight (a knob forces one tap per stage for A/B runs)
+  a.ts = 1;
+  for (int ts : {4, 3, 2}) {
+    if (knobs().igemm_ts1 || p->ntaps % ts != 0) continue;
+    const int sbytes = ts * a.a_bytes + ((ts * a.b_tap_bytes + 1023) / 1024) * 1024;
+    if (sbytes <= 48 * 1024 && smem_budget / sbytes >= (two_ctas ? 3 : 4)) { a.ts = ts; break; }
+  }
+  a.b_bytes = ((a.ts * a.b_tap_bytes + 1023) / 1024) * 1024;
+  a.tx_bytes = a.ts * (a.a_bytes + a.b_tap_bytes);
+  a.stage_bytes = a.ts * a.a_bytes + a.b_bytes;
   a.stages = smem_budget / a.stage_bytes;
   if (a.stages > kMaxStages) a.stages = kMaxStages;
   if (a.stages < 2) a.stages = 2;
@@ -294,7 +326,7 @@ int conv_igemm_launch(const S3dConvParams* p, const void* in, const void* w, con
     S3D_CHECK_ARG(box[1] <= 256 && box[2] <= 256 && box[3] <= 256 && box[4] <= 256, "igemm: TMA box too large");
     int rc = encode_act_map(&map_a, in, esz, tf32, cin_phys, p->iW, p->iH, p->iD, p->N, box, estr, sw);
     if (rc != S3D_OK) return rc;
-    rc = encode_weight_map(&map_b, w, esz, tf32, cin_phys, p->Cout, p->ntaps * p->n_classes, a.kc, p->bn, sw);
+    rc = encode_weight_map(&map_b, w, esz, tf32, cin_phys, p->Cout, p->ntaps * p->n_classes, a.kc, p->bn, sw, a.ts);
     if (rc != S3D_OK) return rc;
   }
 
@@ -302,7 +334,7 @@ int conv_igemm_launch(const S3dConvParams* p, const void* in, const void* w, con
   auto kern = tf32 ? conv_igemm_kernel<true> : conv_igemm_kernel<false>;
   // set on every launch: the attribute is per device and a process may use several (the call is a cheap host-side update)
   S3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-  int grid = num_sms();
+  int grid = (two_ctas ? 2 : 1) * num_sms();
   if (grid > a.total_tiles) grid = a.total_tiles;
   kern<<<grid, kThreads, smem_bytes, stream>>>(map_a, map_b, a);
   S3D_LAUNCH_CHECK();

@@ -120,6 +120,37 @@ int conv_scatter_launch(const S3dConvParams* p_in, const void* in, const float* 
   rc = encode_weight_map(&map_w, p.w_nstack, esz, tf32, cin_phys, 3 * a.cp, 36, a.kc, w_rows, sw, a.tps);
   if (rc != S3D_OK) return rc;
 
+  // the 64 -> 64 bf16 residual layers: residual staged by TMA and added as an identity tap on the tensor core
+  // (conv_scatter_rm.cu); the residual must be a dense channels-last tensor of the output's shape
+  const bool rm = residual != nullptr && a.pair && !tf32 && !split && a.nchunks == 1 && a.row_bytes == 128 && a.cp == 64 &&
+                  p.out_dtype == S3D_DTYPE_BF16 && a.fast_store && a.tps == 1 && (p.act == S3D_ACT_RELU || p.act == S3D_ACT_NONE) &&
+                  p.osW == 64 && p.osH == (int64_t)p.oW * 64 && p.osD == (int64_t)p.oH * p.osH && p.osN == (int64_t)p.oD * p.osD &&
+                  !knobs().scatter_no_rm && !knobs().scatter_generic;
+  if (rm) {
+    const int extra = kResBytes + 32 * 128;
+    a.w_stages = (budget - a.ring * a.slot_bytes - extra) / a.w_bytes;
+    if (a.w_stages > kMaxW) a.w_stages = kMaxW;
+    S3D_CHECK_ARG(a.w_stages >= 3, "scatter: not enough shared memory for the residual stage");
+    CUtensorMap map_r;
+    cuuint32_t rbox[5] = {64, kTX, kTY, 1, 1};
+    rc = encode_act_map(&map_r, residual, 2, false, 64, p.oW, p.oH, p.oD, p.N, rbox, estr, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc != S3D_OK) return rc;
+    a.residual = nullptr;                                     // the epilogue is the plain one
+    const int smem_rm = a.ring * a.slot_bytes + a.w_stages * a.w_bytes + extra + 1024;
+    KernFnR kr = rm_kernel(p.act == S3D_ACT_RELU);
+    S3D_CUDA(cudaFuncSetAttribute(kr, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_rm));
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);  cfg.blockDim = dim3(kThreads);  cfg.dynamicSmemBytes = smem_rm;  cfg.stream = stream;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2;  attr.val.clusterDim.y = 1;  attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;  cfg.numAttrs = 1;
+    S3D_CUDA(cudaLaunchKernelEx(&cfg, kr, map_x, map_w, map_r, a));
+    S3D_LAUNCH_CHECK();
+    return S3D_OK;
+  }
+
   const int smem_bytes = a.ring * a.slot_bytes + a.w_stages * a.w_bytes + 1024;
   KernFn kern = a.pair ? (tf32 ? conv_scatter_kernel<true, true> : conv_scatter_kernel<false, true>)
                        : (tf32 ? conv_scatter_kernel<true, false> : conv_scatter_kernel<false, false>);

@@ -91,8 +91,21 @@ struct ScCtrl {
   uint64_t plane_full[kMaxRing], plane_empty[kMaxRing];
   uint64_t w_full[kMaxW], w_empty[kMaxW];
   uint64_t acc_full[2], acc_empty[2];
+  uint64_t res_full, res_empty;                  // residual-by-MMA kernels (conv_scatter_rm.cu): one staged residual plane
   uint32_t tmem_base;
 };
+
+// Residual through the tensor core (conv_scatter_rm.cu): the residual plane of the 32x8 patch (256 pixels x 128 bytes, no halo)
+// is staged by TMA and added to the accumulators as one more "tap" whose weight matrix is the identity.
+struct ScRes {
+  const CUtensorMap* map_r;
+  uint32_t res_u32;        // staged residual plane: [tile][128 pixels][128 B], 128B swizzle
+  uint32_t ident_u32;      // identity rows of this CTA: [Cout / 2 (pair)][128 B], 128B swizzle
+  uint32_t bar_rf, bar_re;
+  uint32_t idesc_r;        // N = Cout
+  int cp;
+};
+constexpr int kResBytes = 256 * 128;
 
 struct Col { int n, y0, x0, zb; };             // zb: global z of local plane 0 (0, or z0 - 1 of a z-chunk)
 
@@ -119,9 +132,9 @@ __device__ __forceinline__ uint64_t desc_hi(uint32_t sbo, int row_bytes) {
 __device__ __forceinline__ uint32_t desc_lo(uint32_t addr) { return ((addr & 0x3FFFF) >> 4) | (1u << 16); }
 
 // ---- TMA producer: warp-uniform, incremental ring counters, TMA issue under small elect_one regions -----------------
-template <int TPS, bool kPair, int NK = 1>       // NK = 2: 256-byte rows as two 128-byte K chunks, one weight stage per (tap, chunk)
+template <int TPS, bool kPair, int NK = 1, bool kRM = false>       // NK = 2: 256-byte rows as two 128-byte K chunks, one weight stage per (tap, chunk)
 __device__ __forceinline__ void sc_produce(const ScArgs& a, ScCtrl& ctrl, uint32_t planes_u32, uint32_t w_u32,
-                                           const CUtensorMap* map_x, const CUtensorMap* map_w) {
+                                           const CUtensorMap* map_x, const CUtensorMap* map_w, const ScRes* rs = nullptr) {
   constexpr int G = 9 * NK / TPS;
   const uint32_t bar_pf = ptx::smem_u32(&ctrl.plane_full[0]), bar_pe = ptx::smem_u32(&ctrl.plane_empty[0]);
   const uint32_t bar_wf = ptx::smem_u32(&ctrl.w_full[0]), bar_we = ptx::smem_u32(&ctrl.w_empty[0]);
@@ -166,8 +179,29 @@ __device__ __forceinline__ void sc_produce(const ScArgs& a, ScCtrl& ctrl, uint32
     return true;
   };
   int gp = 0;                                    // global index of the current plane
+  [[maybe_unused]] uint32_t rphase = 0;
+  // Residual of output plane p (kRM): one staged plane, added by the issuer in the MIDDLE of plane p's taps.  The load for
+  // plane p + 1 goes out after plane p's weight stages: the weight ring (< 9 stages) keeps this warp less than a plane ahead
+  // of the issuer, so plane p's residual MMAs have retired (or are about to) and the wait is short, and the data arrives
+  // most of a plane before it is needed.
+  [[maybe_unused]] auto load_res = [&](const Col& rc, int p) {
+    ptx::mbar_wait_u32(rs->bar_re, rphase ^ 1);
+    if (ptx::elect_one()) {
+      if (kPair) {
+        if (leader) ptx::mbar_arrive_expect_tx_u32(rs->bar_rf, 2 * kResBytes);
+        ptx::tma_load_5d_2sm_u32(rs->res_u32, rs->map_r, rs->bar_rf, 0, rc.x0, rc.y0, rc.zb + p, rc.n);
+      } else {
+        ptx::mbar_arrive_expect_tx_u32(rs->bar_rf, kResBytes);
+        ptx::tma_load_5d_u32(rs->res_u32, rs->map_r, rs->bar_rf, 0, rc.x0, rc.y0, rc.zb + p, rc.n);
+      }
+    }
+    __syncwarp();
+    rphase ^= 1;
+  };
   for (int ci = 0; ci < ncols; ++ci) {
     int rot = 3;                                 // weight rotation: 3 for p = 0, then p % 3
+    [[maybe_unused]] const Col rc = decode_col(a, blockIdx.x + ci * gridDim.x);
+    if constexpr (kRM) load_res(rc, 0);
     for (int p = 0; p < D; ++p, ++gp) {
       while (issued <= gp) issue_plane(true);
       const int ahead = gp + ring;               // planes that may be in flight while plane gp is being read
@@ -190,6 +224,7 @@ __device__ __forceinline__ void sc_produce(const ScArgs& a, ScCtrl& ctrl, uint32
         __syncwarp();
         if (++ws == w_stages) { ws = 0; wphase ^= 1; }
       }
+      if constexpr (kRM) { if (p + 1 < D) load_res(rc, p + 1); }       // one plane ahead (see load_res)
       rot = (p == 0) ? 1 : (rot == 2 ? 0 : rot + 1);
     }
   }
@@ -267,12 +302,27 @@ __device__ __forceinline__ void sc_issue_group(const ScIssue& z, uint32_t d_tmem
   }
 }
 
-template <bool kTF32, int TPS, int kPer, bool kPair, int NK = 1, bool kSplit = false>
-__device__ __forceinline__ void sc_issue(const ScIssue& z) {
+// The residual plane as one more tap with identity weights: K = Cout channels = CP / 16 MMAs of N = CP into the slot of the
+// plane's own output (kz = 1 block: slot p % 3).
+template <bool kPair, int CP>
+__device__ __forceinline__ void sc_res_mma(const ScRes& rs, uint32_t d_tmem, uint64_t adesc, uint64_t idd) {
+#pragma unroll
+  for (int k = 0; k < CP / 16; ++k) sc_mma<false, kPair>(d_tmem, adesc + 2 * k, idd + 2 * k, rs.idesc_r, 1u);
+}
+
+template <bool kTF32, int TPS, int kPer, bool kPair, int NK = 1, bool kSplit = false, bool kRM = false>
+__device__ __forceinline__ void sc_issue(const ScIssue& z, const ScRes* rs = nullptr) {
   constexpr int G = 9 * NK / TPS;
   int ws = 0;  uint32_t wphase = 0;
   int pw = 0;  uint32_t pwphase = 0;
   uint32_t aphase = 0;
+  [[maybe_unused]] uint32_t rphase = 0;
+  [[maybe_unused]] uint64_t rdesc = 0, idd = 0;
+  if constexpr (kRM) {
+    const uint64_t hi = desc_hi(8 * 128, 128);
+    rdesc = hi | desc_lo(rs->res_u32);
+    idd = hi | desc_lo(rs->ident_u32);
+  }
   const uint32_t w_lo0 = desc_lo(z.w_u32), w_lo_step = z.w_bytes >> 4;
   const uint32_t x_lo0 = desc_lo(z.planes_u32), x_lo_step = z.slot_bytes >> 4;
   const uint32_t d0 = z.tmem_base, d1 = z.tmem_base + kTileCols;
@@ -290,8 +340,10 @@ __device__ __forceinline__ void sc_issue(const ScIssue& z) {
           if (g == 0) ptx::mbar_wait_u32(z.bar_ae, aphase ^ 1);
           ptx::tc_fence_after();
           const uint64_t wd = z.w_hi | (w_lo0 + ws * w_lo_step);
+          if constexpr (kRM) { if (g == G / 2) { ptx::mbar_wait_u32(rs->bar_rf, rphase); ptx::tc_fence_after(); } }
           if (ptx::elect_one()) {
             sc_issue_group<kTF32, TPS, kPer, kPair, NK, kSplit>(z, d0, xd0, wd, g, first);
+            if constexpr (kRM) { if (g == G / 2) sc_res_mma<kPair, 64>(*rs, d0 + (uint32_t)(p % 3) * rs->cp, rdesc, idd); }
             if (g == G - 1) sc_commit<kPair>(z.bar_af);
           }
           __syncwarp();
@@ -302,6 +354,12 @@ __device__ __forceinline__ void sc_issue(const ScIssue& z) {
           if (ptx::elect_one()) {
             sc_issue_group<kTF32, TPS, kPer, kPair, NK, kSplit>(z, d1, xd1, wd, g - 1, first);
             sc_commit<kPair>(z.bar_we + 8 * ws_prev);
+            if constexpr (kRM) {
+              if (g == G / 2 + 1) {                // tile 1's pixels are the second 16 KB of the staged residual plane
+                sc_res_mma<kPair, 64>(*rs, d1 + (uint32_t)(p % 3) * rs->cp, rdesc + (128 * 128 >> 4), idd);
+                sc_commit<kPair>(rs->bar_re);
+              }
+            }
             if (g == G) { sc_commit<kPair>(z.bar_af + 8); sc_commit<kPair>(z.bar_pe + 8 * pw); }
           }
           __syncwarp();
@@ -312,6 +370,7 @@ __device__ __forceinline__ void sc_issue(const ScIssue& z) {
         }
       }
       aphase ^= 1;
+      if constexpr (kRM) rphase ^= 1;
       if (++pw == z.ring) { pw = 0; pwphase ^= 1; }
     }
   }
@@ -788,6 +847,9 @@ KernFn spec_kernel(int row_bytes, int cp, bool residual, bool relu);
 // conv_scatter_split.cu: kernels for split (BF16X2) operands -- lean per-shape ones (CTA pairs; phys_row_bytes = bytes of a
 // [hi | lo] pixel row) or, with lean = false, the all-in-one kernel for the given pairing
 KernFn split_kernel(bool lean, bool pair, int phys_row_bytes, int cp, bool residual, bool relu);
+// conv_scatter_rm.cu: the 64 -> 64 bf16 layer with its residual added on the tensor core (CTA pairs, no activation / ReLU)
+typedef void (*KernFnR)(CUtensorMap, CUtensorMap, CUtensorMap, ScArgs);
+KernFnR rm_kernel(bool relu);
 
 }  // namespace scatter
 }  // namespace s3d

@@ -36,6 +36,9 @@ const KnobName kKnobNames[] = {
     {"scatter_generic", "S3D_SCATTER_GENERIC", &Knobs::scatter_generic},
     {"no_corr_tc", "S3D_NO_CORR_TC", &Knobs::no_corr_tc},
     {"scatter_zsplit", "S3D_SCATTER_ZSPLIT", &Knobs::scatter_zsplit},
+    {"scatter_no_rm", "S3D_SCATTER_NO_RM", &Knobs::scatter_no_rm},
+    {"igemm_ts1", "S3D_IGEMM_TS1", &Knobs::igemm_ts1},
+    {"igemm_one_cta", "S3D_IGEMM_ONE_CTA", &Knobs::igemm_one_cta},
 };
 }  // namespace
 

@@ -56,10 +56,13 @@ def _code(prec):
     return lib.DTYPE_BF16 if prec == 'bf16' else lib.DTYPE_F32
 
 
+@pytest.mark.parametrize('ts1', [0, 1])
 @pytest.mark.parametrize('prec', ['bf16', 'tf32'])
 @pytest.mark.parametrize('cin,cout,H,W,stride', [(3, 32, 32, 32, 2), (32, 64, 35, 35, 1), (64, 64, 16, 16, 1),
                                                  (16, 32, 37, 41, 2), (128, 256, 9, 9, 2), (256, 320, 8, 8, 1)])
-def test_conv2d(prec, cin, cout, H, W, stride):
+def test_conv2d(knobs, ts1, prec, cin, cout, H, W, stride):
+    """Generic engine, several taps per pipeline stage (default) and one (knob igemm_ts1)."""
+    knobs('igemm_ts1', ts1)
     torch.manual_seed(0)
     conv = _qmod(nn.Conv2d(cin, cout, 3, stride, 1), prec)
     x = _q(torch.randn(3, cin, H, W), prec)
@@ -79,9 +82,11 @@ def test_conv3d(prec, cin, cout, D, H, W):
         _check(pc, x, F.leaky_relu(conv(x), 0.2), prec, cout)
 
 
+@pytest.mark.parametrize('ts1', [0, 1])
 @pytest.mark.parametrize('prec', ['bf16', 'tf32'])
-@pytest.mark.parametrize('cin,cout,S,N', [(64, 32, 2, 5), (32, 8, 8, 2), (128, 64, 4, 3)])
-def test_deconv(prec, cin, cout, S, N):
+@pytest.mark.parametrize('cin,cout,S,N', [(64, 32, 2, 5), (32, 8, 8, 2), (128, 64, 4, 3), (512, 128, 4, 2)])
+def test_deconv(knobs, ts1, prec, cin, cout, S, N):
+    knobs('igemm_ts1', ts1)
     torch.manual_seed(2)
     dc = _qmod(nn.ConvTranspose3d(cin, cout, 4, 2, 1, bias=False), prec)
     x = _q(torch.randn(N, cin, S, S, S), prec)
@@ -160,9 +165,11 @@ def test_igemm_rejects_bad_shapes():
 
 
 @pytest.mark.parametrize('knob', [None, 'scatter_no_pair', 'scatter_generic', 'scatter_no_transpose',
-                                  'scatter_res_transpose', 'scatter_tps3', 'no_scatter'])
+                                  'scatter_res_transpose', 'scatter_tps3', 'no_scatter', 'scatter_no_rm'])
 @pytest.mark.parametrize('prec,N,cin,cout,D,H,W,res,act', [
     ('bf16', 1, 64, 64, 1, 8, 8, False, 'relu'),        # one column, one plane (no CTA pair possible)
+    ('bf16', 3, 64, 64, 9, 40, 20, True, 'relu'),       # residual by identity-tap MMA (conv_scatter_rm.cu) + ReLU, ragged patches
+    ('bf16', 40, 64, 64, 4, 32, 16, True, 'none'),      # 160 columns on 148 SMs: two columns per CTA, a phantom column
     ('bf16', 1, 64, 64, 2, 33, 9, True, 'none'),        # ragged patches in y and x, residual, 2 planes
     ('bf16', 3, 64, 48, 3, 40, 20, False, 'relu'),      # 48 channels: 6 chunks per pixel, non-transposed epilogue
     ('bf16', 2, 16, 16, 7, 32, 32, False, 'leaky'),     # fusion-scorer shape (32-byte rows, 9-tap stages)
