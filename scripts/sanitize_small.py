@@ -2,7 +2,7 @@
 
     compute-sanitizer --tool racecheck python scripts/sanitize_small.py scatter_pair
 
-usage: sanitize_small.py <case>      cases: scatter_pair scatter_single scatter_split concat cls_fused corr_tc igemm all"""
+usage: sanitize_small.py <case>      cases: scatter_pair scatter_single scatter_rm scatter_split concat concat_ro cls_fused corr_tc igemm all"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -19,13 +19,16 @@ def conv3(cin, cout, code, act=lib.ACT_RELU):
 
 
 def run(name):
-    if name in ('scatter_pair', 'scatter_single'):
+    if name in ('scatter_pair', 'scatter_single', 'scatter_rm'):
+        # scatter_pair: residual read by the epilogue threads (knob scatter_no_rm); scatter_rm: residual as an identity tap
         lib.set_knob('scatter_no_pair', int(name == 'scatter_single'))
+        lib.set_knob('scatter_no_rm', int(name == 'scatter_pair'))
         pc = conv3(64, 64, lib.DTYPE_BF16, lib.ACT_NONE)
         x = torch.randn(2, 4, 33, 9, 64, device='cuda').to(torch.bfloat16)
         r = torch.randn(2, 4, 33, 9, 64, device='cuda').to(torch.bfloat16)
         pc(x, residual=r)
         lib.set_knob('scatter_no_pair', 0)
+        lib.set_knob('scatter_no_rm', 0)
     elif name == 'scatter_split':
         pc = conv3(64, 64, lib.DTYPE_BF16X2)
         x = to_storage(torch.randn(2, 4, 33, 9, 64), lib.DTYPE_BF16X2).cuda()
@@ -33,12 +36,12 @@ def run(name):
         pc = conv3(16, 16, lib.DTYPE_BF16X2, lib.ACT_LEAKY)
         x = to_storage(torch.randn(1, 3, 16, 16, 16), lib.DTYPE_BF16X2).cuda()
         pc(x)
-    elif name == 'concat':
+    elif name in ('concat', 'concat_ro'):
         B, C, D, h, w = 1, 32, 4, 16, 16
         pc = conv3(2 * C, 64, lib.DTYPE_BF16)
         featp = torch.zeros(2 * B, 1, h, w + 2 * D, C, dtype=torch.bfloat16, device='cuda')
         featp[:, :, :, D:D + w] = torch.randn(2 * B, 1, h, w, C, device='cuda').to(torch.bfloat16)
-        ops.conv_concat_volume(pc, featp, B, D, D)
+        ops.conv_concat_volume(pc, featp, B, D, D, ref_once=name == 'concat_ro')
     elif name == 'cls_fused':
         x = torch.randn(1, 4, 33, 9, 64, device='cuda').to(torch.bfloat16)
         wt = torch.zeros(32, 64, dtype=torch.bfloat16, device='cuda')
@@ -56,5 +59,5 @@ def run(name):
     print('ran', name)
 
 
-for n in (['scatter_pair', 'scatter_single', 'scatter_split', 'concat', 'cls_fused', 'corr_tc', 'igemm'] if case == 'all' else [case]):
+for n in (['scatter_pair', 'scatter_single', 'scatter_rm', 'scatter_split', 'concat', 'concat_ro', 'cls_fused', 'corr_tc', 'igemm'] if case == 'all' else [case]):
     run(n)
