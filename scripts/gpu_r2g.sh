@@ -1,6 +1,8 @@
 #!/bin/bash
 O=gpurun_out/r2g; mkdir -p $O
-timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -5 > $O/pytest_all.log; tail -5 $O/pytest_all.log
-timeout 200 python scripts/layer_times.py 64 bf16 > $O/layers_2cta.txt 2>&1; grep "enc2\|rec\|dec\|forward" $O/layers_2cta.txt
-S3D_IGEMM_ONE_CTA=1 timeout 200 python scripts/layer_times.py 64 bf16 > $O/layers_1cta.txt 2>&1; grep "enc2\|rec\|dec\|forward" $O/layers_1cta.txt
-S3D_IGEMM_ONE_CTA=1 S3D_IGEMM_TS1=1 timeout 200 python scripts/layer_times.py 64 bf16 > $O/layers_1cta_ts1.txt 2>&1; grep "enc2\|rec\|dec\|forward" $O/layers_1cta_ts1.txt
+timeout 900 python bench.py --steps 10 --warmup 3 > $O/bench_full.json 2> $O/bench_full.err; tail -3 $O/bench_full.err; python -c "
+import json; d=json.load(open('$O/bench_full.json'))
+print(d['value'], d['ms_per_step'], d['e2e']['value'], d['gpu_launches_per_step'])
+print(json.dumps(d['roofline'], indent=0)[:1200])
+print(d['roofline_hbm'])
+print(d.get('fp32_mode')); print(d.get('latency')); print(d.get('stereo2point_chamfer'))"
