@@ -173,6 +173,15 @@ int s3d_tap_gather_soft_argmin(const float* taps, float* disp, float* cost_out, 
  * (rows 27..31 zero) -- the weight tensor of the pointwise layer above; disp: fp32 [N,h,w]. */
 int s3d_cls_soft_argmin(const void* x, const void* w_taps, float* disp, int N, int D, int h, int w, int C,
                         float sign, void* stream);
+/* Last aggregation layer + classifier + soft-argmin WITHOUT the layer's output volume (csrc/conv_scatter_cls.cu): `p` is the
+ * bf16 stride-1 3x3x3 64 -> 64 ReLU layer (w_nstack set) over in [N,D,h,w,64]; its output Y is projected on the 27 classifier
+ * taps w_taps (bf16 [32][64], as for s3d_cls_soft_argmin) on the tensor core, scattered into per-CTA partial cost planes in
+ * `workspace` (s3d_conv_cls_workspace_bytes(N, D, h, w) bytes, fp32) and a second kernel adds the partial sums in a fixed order
+ * and runs the soft-argmin: disp fp32 [N,h,w].  Same arithmetic as s3d_conv_igemm + s3d_cls_soft_argmin (Y rounded to bf16 as
+ * the stored tensor would be) up to the fp32 summation order of the 27 taps.  Needs N * ceil(h/32) * ceil(w/8) >= 2. */
+int64_t s3d_conv_cls_workspace_bytes(int N, int D, int h, int w);
+int s3d_conv_cls_soft_argmin(const S3dConvParams* p, const void* in, const float* bias, const void* w_taps, void* workspace,
+                             float* disp, float sign, void* stream);
 /* Fused correlation + soft-argmax; the [2B,D,h,w] cost is never materialised.
  * feat: [2B,1,h,w,C] with C the PADDED channel count (row pitch); cost = (1/c_real) * sum_c ref*tgt over the real
  * channels (padded channels must be zero; c_real = 0 means C).

@@ -28,7 +28,7 @@ print('%-78s %5s %10s %7s' % ('kernel', 'count', 'total ms', 'share'))
 for n, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     print('%-78s %5d %10.3f %6.1f%%' % (n[:78], c, t, 100 * t / tot))
 print('%-78s %5d %10.3f' % ('TOTAL (%d forwards of %d launches)' % (nf, per), len(win), tot))
-a = [t for n, t in win if re.search(r'conv_scatter_kernel<0, 1, (128|256), 64|conv_scatter_concat', n) and t > 1.0]   # (the 2-D encoder layers share the kernel)
+a = [t for n, t in win if re.search(r'conv_scatter_kernel<0, 1, (128|256), 64|conv_scatter_concat|conv_scatter_rm', n) and t > 1.0]   # (the 2-D encoder layers share the kernel)
 if a:
     print('\n# aggregation layers (fused volume + dres0a, dres0b, dres1a, dres1b, cls_a): %d launches, mean %.3f ms, %.1f%% of the window'
           % (len(a), sum(a) / len(a), 100 * sum(a) / tot))

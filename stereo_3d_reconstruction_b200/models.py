@@ -312,8 +312,19 @@ class _StereoBase(nn.Module):
             a = self._conv('dres0b', a, out=self._bufo('a1', 'dres0b', a))
             y = self._conv('dres1a', a, out=self._bufo('a2', 'dres1a', a))
             a = self._conv('dres1b', y, residual=a, out=self._bufo('a3', 'dres1b', y))
-            c = self._conv('cls_a', a, out=self._bufo('a0', 'cls_a', a))
             S = self._packed['cls_b'].cout_pad                      # 27 taps padded to 32 planes
+            pa = self._packed['cls_a']
+            if (self.precision == 'bf16' and isinstance(pa, PackedConv) and pa.weight_ns is not None and pa.cin_pad == 64 and
+                    pa.cout_pad == 64 and pa.act == _lib.ACT_RELU and S == 32 and a.shape[-1] == 64 and
+                    2 * B * (-(-h // 32)) * (-(-w // 8)) > 74 and
+                    not _lib.KNOBS['no_cls_chain'] and not _lib.KNOBS['no_cls_fused'] and not _lib.KNOBS['no_scatter']):
+                # cls_a + classifier + soft-argmin in one march, cls_a's 2.1 GB output never written (csrc/conv_scatter_cls.cu)
+                nb = ops.conv_cls_workspace_bytes(2 * B, D, h, w)
+                ops.conv_cls_soft_argmin(pa, a, self._packed['cls_b'].weight, -1.0, out=disp_q,
+                                         workspace=self._buf('cls_ws', (nb,), torch.uint8))
+                disp = ops.upsample_disp(disp_q, H, W, 4.0, out=self._buf('disp', (2 * B, H, W), torch.float32))
+                return disp, disp_q
+            c = self._conv('cls_a', a, out=self._bufo('a0', 'cls_a', a))
             if self.precision == 'bf16' and c.shape[-1] in (16, 32, 64) and S == 32 and not _lib.KNOBS['no_cls_fused']:
                 # classifier + soft-argmin in one pass over the volume (csrc/cls_fused.cu)
                 ops.cls_soft_argmin(c, self._packed['cls_b'].weight, -1.0, out=disp_q)

@@ -238,6 +238,34 @@ def cls_soft_argmin(x, w_taps, sign=-1.0, out=None):
     return out
 
 
+def conv_cls_workspace_bytes(N, D, h, w):
+    return int(_lib.load().s3d_conv_cls_workspace_bytes(N, D, h, w))
+
+
+def conv_cls_soft_argmin(pc, x, w_taps, sign=-1.0, out=None, workspace=None):
+    """The last aggregation layer `pc` (PackedConv, bf16 3x3x3 64 -> 64 + ReLU) over x [N,D,h,w,64], the Cout = 1 classifier
+    (w_taps bf16 [32,64]) and the soft-argmin, the layer's output volume never written (include/s3d.h,
+    s3d_conv_cls_soft_argmin; csrc/conv_scatter_cls.cu).  workspace: >= conv_cls_workspace_bytes(N, D, h, w) bytes.
+    -> disp fp32 [N,h,w]."""
+    import ctypes
+    _chk(x, w_taps, out, workspace)
+    assert x.dtype == torch.bfloat16 and w_taps.dtype == torch.bfloat16 and x.dim() == 5 and x.is_contiguous()
+    N, D, h, w, C = x.shape
+    assert C == 64 and pc.cin_pad == 64 and pc.cout_pad == 64 and w_taps.numel() == 32 * 64 and w_taps.is_contiguous()
+    need = conv_cls_workspace_bytes(N, D, h, w)
+    if workspace is None:
+        workspace = torch.empty(need, dtype=torch.uint8, device=x.device)
+    assert workspace.is_contiguous() and workspace.numel() * workspace.element_size() >= need
+    if out is None:
+        out = torch.empty((N, h, w), dtype=torch.float32, device=x.device)
+    p = pc.params(N, D, h, w, (D * h * w * 64, h * w * 64, w * 64, 64), _lib.DTYPE_BF16, 64)
+    rc = _lib.load().s3d_conv_cls_soft_argmin(ctypes.byref(p), x.data_ptr(), pc.bias.data_ptr(), w_taps.data_ptr(),
+                                              workspace.data_ptr(), out.data_ptr(), float(sign), _stream())
+    _lib.check(rc, 's3d_conv_cls_soft_argmin')
+    _lib.count_launch(2)
+    return out
+
+
 def corr_soft_argmin(feat, B, D, out=None, want_cost=False, c_real=None):
     """feat [2B,1,h,w,C] -> disp fp32 [2B,h,w] (fused correlation + soft-argmax).  c_real: number of REAL feature
     channels when C is a padded pitch (the correlation is a mean over the real channels; padded ones are zero)."""

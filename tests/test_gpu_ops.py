@@ -59,6 +59,47 @@ def test_cls_soft_argmin_fused_equals_cout1_conv(N, C, D, h, w):
     torch.testing.assert_close(got, two, rtol=1e-4, atol=1e-4 * max(D, 1))
 
 
+@pytest.mark.parametrize('N,D,h,w', [
+    (2, 8, 32, 16),       # 4 columns: patch borders in x, one CTA pair per two columns
+    (1, 5, 40, 21),       # ragged patches: pixels outside the image must enter the classifier as zeros
+    (2, 1, 8, 8),         # a single plane
+    (2, 2, 33, 9),        # two planes, one-pixel ragged edges
+    (3, 32, 64, 64),      # the network's volume shape, 48 columns
+    (20, 4, 64, 64),      # 320 columns on 148 SMs: several columns per CTA, phantom columns in the last round
+])
+def test_conv_cls_chain_equals_conv_then_classifier(N, D, h, w):
+    """conv_scatter_cls.cu: cls_a (3x3x3 64 -> 64 + ReLU) + Cout = 1 classifier + soft-argmin in one march (the layer's output never
+    written) == the plane-scatter conv followed by the one-pass classifier on its STORED bf16 output (same rounding of Y; only the
+    fp32 summation order of the 27 taps differs), and == Conv3d -> ReLU -> bf16 -> Conv3d(64,1) -> soft-argmin in torch."""
+    import torch.nn as nn
+    from stereo_3d_reconstruction_b200 import lib
+    from stereo_3d_reconstruction_b200.layers import PackedConv
+    g = torch.Generator().manual_seed(17)
+    conv = nn.Conv3d(64, 64, 3, 1, 1, bias=True)
+    with torch.no_grad():
+        conv.weight.copy_((torch.randn(conv.weight.shape, generator=g) * 0.04).to(torch.bfloat16).float())
+        conv.bias.copy_(torch.randn(64, generator=g) * 0.1)
+    pc = PackedConv.from_conv(conv, None, lib.ACT_RELU, lib.DTYPE_BF16, 'cuda')
+    x = torch.randn(N, 64, D, h, w, generator=g).to(torch.bfloat16)
+    wt = (torch.randn(1, 64, 3, 3, 3, generator=g) * 0.3).to(torch.bfloat16)
+    w_taps = torch.zeros(32, 64, dtype=torch.bfloat16)
+    w_taps[:27] = wt[0].reshape(64, 27).t()
+    xc = x.permute(0, 2, 3, 4, 1).contiguous().cuda()
+    got = ops.conv_cls_soft_argmin(pc, xc, w_taps.cuda(), -1.0)
+    y = pc(xc, engine='igemm')                                               # the stored bf16 volume
+    two = ops.cls_soft_argmin(y, w_taps.cuda(), -1.0)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(got, two, rtol=2e-4, atol=2e-4 * max(D, 1))
+    with torch.no_grad():
+        yr = F.relu(conv(x.float())).to(torch.bfloat16).float()
+        ref = O.soft_argmin(F.conv3d(yr, wt.float(), padding=1).squeeze(1))
+    # Y itself carries the conv engine's bf16 rounding (one ulp flips against torch's fp32 accumulation order): looser than above
+    torch.testing.assert_close(got.cpu(), ref, rtol=5e-3, atol=5e-3 * max(D, 1))
+    # deterministic: no atomics, fixed summation order
+    again = ops.conv_cls_soft_argmin(pc, xc, w_taps.cuda(), -1.0)
+    assert torch.equal(got, again)
+
+
 @pytest.mark.parametrize('dtype,tol', [(torch.float32, 1e-3), (torch.bfloat16, 1e-3)])
 @pytest.mark.parametrize('B,C,h,w,D', [(2, 32, 8, 64, 32), (1, 16, 5, 21, 8), (1, 64, 3, 35, 64), (1, 32, 2, 40, 128)])
 def test_corr_soft_argmin(dtype, tol, B, C, h, w, D):
