@@ -1,6 +1,8 @@
 #!/bin/bash
 O=gpurun_out/r2g; mkdir -p $O
-for rep in 1 2 3; do
-for k in NONE S3D_NO_CLS_CHAIN; do env $k=1 timeout 400 python bench.py --steps 30 --warmup 5 --no-extras --no-cpu-baseline > $O/bench_$k.json 2> $O/bench_$k.err; python -c "
-import json; d=json.load(open('$O/bench_$k.json')); print('$k', round(d['value'],1), round(d['ms_per_step'],3), round(d['e2e']['value'],1), round(d['roofline']['ms_per_launch'],3), d['roofline']['other_aggregation_ms'], d['roofline_hbm'] and round(d['roofline_hbm']['ms_per_launch'],3))"; done; done
-nvidia-smi --query-gpu=power.draw,power.limit,clocks.sm,temperature.gpu --format=csv
+timeout 900 python bench.py --steps 10 --warmup 3 > $O/bench_full.json 2> $O/bench_full.err; tail -3 $O/bench_full.err; python -c "
+import json; d=json.load(open('$O/bench_full.json'))
+print(d['value'], d['ms_per_step'], d['e2e']['value'], d['gpu_launches_per_step'])
+print(json.dumps(d['roofline'], indent=0)[:1500])
+print(d['roofline_hbm'])
+print(d.get('fp32_mode')); print(d.get('latency')); print(d.get('gpu_stock_baseline'))"
