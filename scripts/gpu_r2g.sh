@@ -1,8 +1,5 @@
 #!/bin/bash
 O=gpurun_out/r2g; mkdir -p $O
-timeout 900 python bench.py --steps 10 --warmup 3 > $O/bench_full.json 2> $O/bench_full.err; tail -3 $O/bench_full.err; python -c "
-import json; d=json.load(open('$O/bench_full.json'))
-print(d['value'], d['ms_per_step'], d['e2e']['value'], d['gpu_launches_per_step'])
-print(json.dumps(d['roofline'], indent=0)[:1500])
-print(d['roofline_hbm'])
-print(d.get('fp32_mode')); print(d.get('latency')); print(d.get('gpu_stock_baseline'))"
+timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -5 > $O/pytest_all.log; tail -5 $O/pytest_all.log
+timeout 200 python scripts/layer_times.py 64 bf16 > $O/layers_two.txt 2>&1; grep "mrg\|forward" $O/layers_two.txt
+S3D_SCATTER_ONE_CTA=1 timeout 200 python scripts/layer_times.py 64 bf16 > $O/layers_one.txt 2>&1; grep "mrg\|forward" $O/layers_one.txt

@@ -45,6 +45,7 @@ struct Knobs {
   int scatter_zsplit;         // S3D_SCATTER_ZSPLIT=n: force n z-chunks per column (-1: never split; 0 = automatic)
   int igemm_ts1;              // S3D_IGEMM_TS1: one tap per pipeline stage in the generic engine (conv_igemm.cu)
   int igemm_one_cta;          // S3D_IGEMM_ONE_CTA: one CTA per SM in the generic engine even where two fit
+  int scatter_one_cta;        // S3D_SCATTER_ONE_CTA: one CTA per SM for the narrow plane-scatter layers too
   int scatter_no_rm;          // S3D_SCATTER_NO_RM: residual added by the epilogue threads instead of an identity tap on the tensor core
 };
 Knobs& knobs();

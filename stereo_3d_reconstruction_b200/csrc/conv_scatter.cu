@@ -70,6 +70,11 @@ int conv_scatter_launch(const S3dConvParams* p_in, const void* in, const float* 
   // single-CTA kernel saturates the shared-memory pipe (A 4 KB + B 6 KB per 96-cycle MMA, plus the TMA fills).
   int grid = num_sms();
   a.pair = ((3 * a.cp / 2) % 8 == 0 && total >= 2 && grid >= 2 && !knobs().scatter_no_pair) ? 1 : 0;
+  // narrow lean shapes: two CTAs per SM (conv_scatter.cuh, kTwo) when there is work for both
+  const bool two = a.pair && !tf32 && !split && a.nchunks == 1 && p.out_dtype == S3D_DTYPE_BF16 && residual == nullptr &&
+                   spec_kernel(a.row_bytes, a.cp, false, p.act == S3D_ACT_RELU, true) != nullptr && total > grid &&
+                   !knobs().scatter_generic && !knobs().scatter_one_cta && !knobs().scatter_tps3 && !knobs().scatter_ring;
+  if (two) grid *= 2;
   if (a.pair) {
     if ((int64_t)grid > total) grid = (int)((total + 1) / 2 * 2);
     grid -= grid % 2;
@@ -78,7 +83,7 @@ int conv_scatter_launch(const S3dConvParams* p_in, const void* in, const float* 
   const int w_rows = a.pair ? 3 * a.cp / 2 : 3 * a.cp;          // weight rows staged per CTA
   a.w_tx = a.tps * w_rows * a.row_bytes;
   a.w_bytes = (a.w_tx + 1023) / 1024 * 1024;
-  const int budget = 227 * 1024 - 1024 - 512;                 // dynamic shared memory minus alignment slack and ScCtrl
+  const int budget = two ? 110 * 1024 : 227 * 1024 - 1024 - 512;   // dynamic shared memory minus alignment slack and ScCtrl
   // big planes: 2 slots and the rest for weight stages (weight latency is what stalls); small planes: a deeper ring
   // (a plane is then consumed faster than its TMA round trip), keeping at least 4 weight stages
   int ring = (budget - 4 * a.w_bytes) / a.slot_bytes;
@@ -162,7 +167,8 @@ int conv_scatter_launch(const S3dConvParams* p_in, const void* in, const float* 
   else if (a.pair && !tf32 && a.nchunks == 1 && p.out_dtype == S3D_DTYPE_BF16 && a.fast_store && a.tps == spec_tps(a.row_bytes, a.cp) &&
       !knobs().scatter_generic) {
     const bool relu = p.act == S3D_ACT_RELU;        // anything else: slope formula
-    if (KernFn k = spec_kernel(a.row_bytes, a.cp, residual != nullptr, relu)) kern = k;
+    if (KernFn k = spec_kernel(a.row_bytes, a.cp, residual != nullptr, relu, two && a.fast_store)) kern = k;
+    else if (two) { set_error("scatter: the two-CTA kernel needs the coalesced store path"); return S3D_ERR_INVALID; }
   }
   S3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   if (a.pair) {

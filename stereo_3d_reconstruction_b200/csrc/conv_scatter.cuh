@@ -310,7 +310,7 @@ __device__ __forceinline__ void sc_res_mma(const ScRes& rs, uint32_t d_tmem, uin
   for (int k = 0; k < CP / 16; ++k) sc_mma<false, kPair>(d_tmem, adesc + 2 * k, idd + 2 * k, rs.idesc_r, 1u);
 }
 
-template <bool kTF32, int TPS, int kPer, bool kPair, int NK = 1, bool kSplit = false, bool kRM = false>
+template <bool kTF32, int TPS, int kPer, bool kPair, int NK = 1, bool kSplit = false, bool kRM = false, int kTP = kTileCols>
 __device__ __forceinline__ void sc_issue(const ScIssue& z, const ScRes* rs = nullptr) {
   constexpr int G = 9 * NK / TPS;
   int ws = 0;  uint32_t wphase = 0;
@@ -325,7 +325,7 @@ __device__ __forceinline__ void sc_issue(const ScIssue& z, const ScRes* rs = nul
   }
   const uint32_t w_lo0 = desc_lo(z.w_u32), w_lo_step = z.w_bytes >> 4;
   const uint32_t x_lo0 = desc_lo(z.planes_u32), x_lo_step = z.slot_bytes >> 4;
-  const uint32_t d0 = z.tmem_base, d1 = z.tmem_base + kTileCols;
+  const uint32_t d0 = z.tmem_base, d1 = z.tmem_base + kTP;
   for (int ci = 0; ci < z.ncols; ++ci) {
     for (int p = 0; p < z.D; ++p) {
       ptx::mbar_wait_u32(z.bar_pf + 8 * pw, pwphase);
@@ -503,7 +503,7 @@ __device__ __forceinline__ void sc_fast_plane(const ScEpi& e, int64_t grp_off, i
 
 // kFast: transposed stores (needs a power-of-two chunk count per pixel).  kSRes / kSAct >= 0: residual / activation fixed at
 // compile time (the specialised kernels below), -1: decided at run time.
-template <int CP, typename TOut, bool kFast, int kSRes = -1, int kSAct = -1>
+template <int CP, typename TOut, bool kFast, int kSRes = -1, int kSAct = -1, int kTP = kTileCols>
 __device__ __forceinline__ void sc_epilogue(const ScArgs& a, ScCtrl& ctrl, uint32_t tmem_base, int warp, int lane) {
   constexpr int NCH = kFast ? CP * (int)sizeof(TOut) / 16 : 1;     // 16-byte chunks per pixel
   const int t = (warp - 4) >> 2, q = warp & 3;
@@ -511,7 +511,7 @@ __device__ __forceinline__ void sc_epilogue(const ScArgs& a, ScCtrl& ctrl, uint3
   const ScEpi fe = {a.bias, a.residual, a.out,
                     a.p.act == S3D_ACT_NONE ? 1.f : (a.p.act == S3D_ACT_LEAKY ? a.p.act_param : 0.f), (int)a.p.osW, a.res_direct};
   const uint32_t bar_af = ptx::smem_u32(&ctrl.acc_full[t]), bar_ae = ptx::smem_u32(&ctrl.acc_empty[t]);
-  const uint32_t tbase = tmem_base + t * kTileCols + (static_cast<uint32_t>(q * 32) << 16);
+  const uint32_t tbase = tmem_base + t * kTP + (static_cast<uint32_t>(q * 32) << 16);
   const int yl = t * kTileY + q * 4 + (lane >> 3), xl = lane & 7;      // TMEM lane = 8 * row + x inside the tile
   const int D = a.dl;                                 // local planes per work item (= oD unless z-split)
   const int zs0 = a.nz > 1 ? 1 : 0, zs1 = a.nz > 1 ? a.zc + 1 : D;     // local output planes a work item stores
@@ -752,8 +752,11 @@ __host__ __device__ constexpr int spec_tps(int rb, int cp) {
 // size (measured: two more epilogue variants in the all-in-one kernel cost 4 % of the whole forward), so the layer
 // shapes of the network each get a kernel that contains only their own code.  RB == 0: all-in-one, run-time dispatch.
 // kSplit: BF16X2 operands and output (see ScArgs::split).  RB is then the PHYSICAL row (64 / 128 bytes: one chunk; 256: two).
-template <bool kTF32, bool kPair, int RB = 0, int CP = 0, int kSRes = -1, int kSAct = -1, bool kSplit = false>
-__global__ void __launch_bounds__(kThreads, 1)
+// kTwo: a narrow layer shape (3 * CP <= 128 accumulator columns per tile) that leaves room for TWO CTAs per SM -- half the
+// TMEM columns (tile pitch 128), half the shared memory, <= 85 registers.  Its planes are too short (9 one-MMA taps per tile)
+// to hide the accumulator hand-back behind the other tile; a second resident CTA fills the bubbles (fusion scorer layers).
+template <bool kTF32, bool kPair, int RB = 0, int CP = 0, int kSRes = -1, int kSAct = -1, bool kSplit = false, bool kTwo = false>
+__global__ void __launch_bounds__(kThreads, kTwo ? 2 : 1)
 conv_scatter_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                     const __grid_constant__ ScArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -774,7 +777,8 @@ conv_scatter_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     for (int b = 0; b < 2; ++b) { ptx::mbar_init(&ctrl.acc_full[b], 1); ptx::mbar_init(&ctrl.acc_empty[b], kPair ? 8 : 4); }
     ptx::fence_barrier_init();
   }
-  if (warp == 2) { if (kPair) ptx::tmem_alloc_2sm(&ctrl.tmem_base, kTmemCols); else ptx::tmem_alloc(&ctrl.tmem_base, kTmemCols); }
+  constexpr int kTP = kTwo ? 128 : kTileCols;
+  if (warp == 2) { if (kPair) ptx::tmem_alloc_2sm(&ctrl.tmem_base, 2 * kTP); else ptx::tmem_alloc(&ctrl.tmem_base, 2 * kTP); }
   ptx::tc_fence_before();
   __syncthreads();
   if (kPair) ptx::cluster_sync_all();              // the peer's barriers exist before anything is signalled at them
@@ -810,7 +814,7 @@ conv_scatter_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     }
     else if constexpr (RB == 128) sc_issue<kTF32, 1, 4, kPair>(zi);
     else if constexpr (RB == 64) sc_issue<kTF32, spec_tps(RB, CP), 2, kPair>(zi);
-    else if constexpr (RB == 32) sc_issue<kTF32, spec_tps(RB, CP), 1, kPair>(zi);
+    else if constexpr (RB == 32) sc_issue<kTF32, spec_tps(RB, CP), 1, kPair, 1, false, false, kTP>(zi);
     else if (a.nchunks == 2) sc_issue<kTF32, 1, 4, kPair, 2>(zi);
     else if (rb == 128) sc_issue<kTF32, 1, 4, kPair>(zi);
     else if (rb == 64 && a.tps == 9) sc_issue<kTF32, 9, 2, kPair>(zi);
@@ -824,7 +828,7 @@ conv_scatter_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
       else if (a.cp == 32) sc_epilogue_split<32>(a, ctrl, tmem_base, warp, lane);
       else sc_epilogue_split<16>(a, ctrl, tmem_base, warp, lane);
     }
-    else if constexpr (RB != 0) sc_epilogue<CP, __nv_bfloat16, true, kSRes, kSAct>(a, ctrl, tmem_base, warp, lane);
+    else if constexpr (RB != 0) sc_epilogue<CP, __nv_bfloat16, true, kSRes, kSAct, kTP>(a, ctrl, tmem_base, warp, lane);
     else if (a.cp == 64) sc_epilogue_dispatch<64>(a, ctrl, tmem_base, warp, lane);
     else if (a.cp == 48) sc_epilogue_dispatch<48>(a, ctrl, tmem_base, warp, lane);
     else if (a.cp == 32) sc_epilogue_dispatch<32>(a, ctrl, tmem_base, warp, lane);
@@ -836,14 +840,14 @@ conv_scatter_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
   if (kPair) ptx::cluster_sync_all();              // no CTA leaves while its peer may still signal its barriers
   if (warp == 2) {
     ptx::tc_fence_after();
-    if (kPair) ptx::tmem_dealloc_2sm(tmem_base, kTmemCols); else ptx::tmem_dealloc(tmem_base, kTmemCols);
+    if (kPair) ptx::tmem_dealloc_2sm(tmem_base, 2 * kTP); else ptx::tmem_dealloc(tmem_base, 2 * kTP);
   }
 }
 
 
 typedef void (*KernFn)(CUtensorMap, CUtensorMap, ScArgs);
 // conv_scatter_spec.cu: the lean kernel for this layer shape (bf16, CTA pairs, coalesced epilogue), or nullptr
-KernFn spec_kernel(int row_bytes, int cp, bool residual, bool relu);
+KernFn spec_kernel(int row_bytes, int cp, bool residual, bool relu, bool two_ctas = false);
 // conv_scatter_split.cu: kernels for split (BF16X2) operands -- lean per-shape ones (CTA pairs; phys_row_bytes = bytes of a
 // [hi | lo] pixel row) or, with lean = false, the all-in-one kernel for the given pairing
 KernFn split_kernel(bool lean, bool pair, int phys_row_bytes, int cp, bool residual, bool relu);

@@ -5,7 +5,8 @@
 namespace s3d {
 namespace scatter {
 
-KernFn spec_kernel(int rb, int cp, bool res, bool relu) {
+KernFn spec_kernel(int rb, int cp, bool res, bool relu, bool two) {
+  if (two) return (rb == 32 && cp == 16 && !res && !relu) ? conv_scatter_kernel<false, true, 32, 16, 0, 2, false, true> : nullptr;
   if (rb == 128 && cp == 64 && !res && relu)  return conv_scatter_kernel<false, true, 128, 64, 0, 0>;   // aggregation
   if (rb == 128 && cp == 64 && res && !relu)  return conv_scatter_kernel<false, true, 128, 64, 1, 2>;   // residual layers
   if (rb == 32 && cp == 16 && !res && !relu)  return conv_scatter_kernel<false, true, 32, 16, 0, 2>;    // fusion scorer

@@ -165,7 +165,7 @@ def test_igemm_rejects_bad_shapes():
 
 
 @pytest.mark.parametrize('knob', [None, 'scatter_no_pair', 'scatter_generic', 'scatter_no_transpose',
-                                  'scatter_res_transpose', 'scatter_tps3', 'no_scatter', 'scatter_no_rm'])
+                                  'scatter_res_transpose', 'scatter_tps3', 'no_scatter', 'scatter_no_rm', 'scatter_one_cta'])
 @pytest.mark.parametrize('prec,N,cin,cout,D,H,W,res,act', [
     ('bf16', 1, 64, 64, 1, 8, 8, False, 'relu'),        # one column, one plane (no CTA pair possible)
     ('bf16', 3, 64, 64, 9, 40, 20, True, 'relu'),       # residual by identity-tap MMA (conv_scatter_rm.cu) + ReLU, ragged patches
@@ -173,6 +173,7 @@ def test_igemm_rejects_bad_shapes():
     ('bf16', 1, 64, 64, 2, 33, 9, True, 'none'),        # ragged patches in y and x, residual, 2 planes
     ('bf16', 3, 64, 48, 3, 40, 20, False, 'relu'),      # 48 channels: 6 chunks per pixel, non-transposed epilogue
     ('bf16', 2, 16, 16, 7, 32, 32, False, 'leaky'),     # fusion-scorer shape (32-byte rows, 9-tap stages)
+    ('bf16', 40, 16, 16, 5, 32, 32, False, 'leaky'),    # the same with 160 columns: two CTAs per SM (kTwo), phantom columns
     ('bf16', 1, 32, 32, 4, 70, 70, True, 'relu'),       # 64-byte rows, odd number of columns
     ('bf16', 5, 64, 64, 6, 16, 24, True, 'none'),       # the residual layer's kernel
     ('bf16', 2, 64, 32, 5, 24, 16, False, 'none'),
