@@ -1,5 +1,5 @@
 #!/bin/bash
 O=gpurun_out/r2g; mkdir -p $O
-timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -5 > $O/pytest_all.log; tail -5 $O/pytest_all.log
-timeout 200 python scripts/layer_times.py 64 bf16 > $O/layers_two.txt 2>&1; grep "mrg\|forward" $O/layers_two.txt
-S3D_SCATTER_ONE_CTA=1 timeout 200 python scripts/layer_times.py 64 bf16 > $O/layers_one.txt 2>&1; grep "mrg\|forward" $O/layers_one.txt
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:conv_scatter_cls -s 2 -c 1 -o $O/cls_chain -f python scripts/prof_kernels.py cls_chain > $O/ncu_chain.log 2>&1; tail -1 $O/ncu_chain.log
+timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"conv_scatter_cls|partials_soft" --csv python scripts/prof_kernels.py cls_chain 2>&1 | grep -i "gpu__time" | tail -6
+timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"conv_scatter_kernel" --csv python scripts/prof_kernels.py agg_bf16 2>&1 | grep -i "gpu__time" | tail -3

@@ -1,5 +1,5 @@
 """A few launches of ONE kernel at the bench shape, for `ncu --set full -k regex:...`.
-usage: prof_kernels.py <agg_bf16 | concat | concat_ro | agg_bf16x3 | agg_res_bf16x3 | cls_fused | corr_tc | soft_argmin | chamfer | conv_first>"""
+usage: prof_kernels.py <agg_bf16 | concat | concat_ro | cls_chain | agg_bf16x3 | agg_res_bf16x3 | cls_fused | corr_tc | soft_argmin | chamfer | conv_first>"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -29,6 +29,14 @@ elif what in ('concat', 'concat_ro'):
     out = torch.empty(N, D, h, w, C, dtype=torch.bfloat16, device='cuda')
     for _ in range(3):
         ops.conv_concat_volume(pc, featp, N // 2, D, D, out=out, ref_once=what == 'concat_ro')
+elif what == 'cls_chain':
+    pc = PackedConv.from_conv(nn.Conv3d(C, C, 3, 1, 1, bias=True), None, lib.ACT_RELU, lib.DTYPE_BF16, 'cuda')
+    x = torch.randn(N, D, h, w, C, device='cuda').to(torch.bfloat16)
+    wt = torch.zeros(32, C, dtype=torch.bfloat16, device='cuda')
+    wt[:27] = (torch.randn(27, C, device='cuda') * 0.2).to(torch.bfloat16)
+    ws = torch.empty(ops.conv_cls_workspace_bytes(N, D, h, w), dtype=torch.uint8, device='cuda')
+    for _ in range(3):
+        ops.conv_cls_soft_argmin(pc, x, wt, -1.0, workspace=ws)
 elif what == 'cls_fused':
     x = torch.randn(N, D, h, w, C, device='cuda').to(torch.bfloat16)
     wt = torch.zeros(32, C, dtype=torch.bfloat16, device='cuda')
