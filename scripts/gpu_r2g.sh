@@ -1,9 +1,4 @@
 #!/bin/bash
 O=gpurun_out/r2g; mkdir -p $O
-python - <<'PY'
-import json, torch, bench
-pk = bench.peaks()
-r = bench.extra_costvolume_sweep(torch.device('cuda:0'), pk['hbm_gbs'])
-for p in r['points']:
-    print({k: (round(v, 3) if isinstance(v, float) else v) for k, v in p.items()})
-PY
+timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -5 > $O/pytest_all.log; tail -5 $O/pytest_all.log
+timeout 300 python scripts/layer_times.py 64 bf16x3 > $O/layers_x3b.txt 2>&1; grep "concat\|dres0a\|enc5\|forward" $O/layers_x3b.txt

@@ -280,8 +280,12 @@ class _StereoBase(nn.Module):
         h, w = x.shape[2], x.shape[3]
         C = cfg.NETWORK.FEAT_CHANNELS
         p5, p0 = self._packed['enc5'], self._packed.get('dres0a')
-        fuse_volume = (cfg.NETWORK.COST_VOLUME == 'concat' and self.precision in ('bf16', 'tf32') and p5.cout_pad == C and
-                       isinstance(p0, PackedConv) and p0.weight_ns is not None and C * x.element_size() in (32, 64) and
+        # 'bf16x3' (split operands): the reference-once kernel only (C = 32 feature channels, 64-wide first layer)
+        ro_split = (self._split and C == 32 and isinstance(p0, PackedConv) and p0.cout_pad == 64 and p0.act == _lib.ACT_RELU and
+                    not _lib.KNOBS['no_ref_once'])
+        fuse_volume = (cfg.NETWORK.COST_VOLUME == 'concat' and (self.precision in ('bf16', 'tf32') or ro_split) and p5.cout_pad == C and
+                       isinstance(p0, PackedConv) and p0.weight_ns is not None and
+                       (ro_split or C * x.element_size() in (32, 64)) and
                        not _lib.KNOBS['no_concat_fuse'] and not _lib.KNOBS['no_scatter'] and
                        # small batches: fewer columns than SMs -> unfused volume + the z-split plane-scatter kernel (a column of
                        # D planes would be a serial chain on a fraction of the chip; csrc/conv_scatter.cuh, ScArgs::nz)
@@ -291,8 +295,10 @@ class _StereoBase(nn.Module):
             # features go into rows with D zero pixels on both sides: the fused cost-volume + dres0a kernel reads the shifted
             # target view of every disparity plane straight out of them (csrc/conv_scatter_concat.cu), no volume is written
             pad, P = D, w + 2 * D
-            featp = self._buf('featp', (2 * B, 1, h, P, C), dt, zero=True)
-            self._conv('enc5', x, out=featp, out_view=(pad * C, (h * P * C, h * P * C, P * C, C)), cout_store=C)
+            Cp = cm * C                                              # physical channels of a feature row ([hi | lo] when split)
+            featp = self._buf('featp', (2 * B, 1, h, P, Cp), dt, zero=True)
+            self._conv('enc5', x, out=featp, out_view=(pad * Cp, (h * P * Cp, h * P * Cp, P * Cp, Cp), C if self._split else 0),
+                       cout_store=C)
             feat = None
         else:
             feat = self._conv('enc5', x, out=self._bufo('e5', 'enc5', x))
@@ -301,9 +307,9 @@ class _StereoBase(nn.Module):
             if fuse_volume:
                 # bf16: reference-once form -- the d-independent reference half is convolved once per column, the planes run
                 # on the target half only (half the tensor-core work of this layer; csrc/conv_scatter_concat.cu)
-                ro = (self.precision == 'bf16' and p0.cout_pad == 64 and p0.act == _lib.ACT_RELU and
-                      not _lib.KNOBS['no_ref_once'])
-                a = ops.conv_concat_volume(p0, featp, B, D, pad, out=self._buf('a0', (2 * B, D, h, w, p0.cout_pad), dt),
+                ro = ro_split or (self.precision == 'bf16' and p0.cout_pad == 64 and p0.act == _lib.ACT_RELU and
+                                  not _lib.KNOBS['no_ref_once'])
+                a = ops.conv_concat_volume(p0, featp, B, D, pad, out=self._buf('a0', (2 * B, D, h, w, cm * p0.cout_pad), dt),
                                            ref_once=ro)
             else:
                 assert feat.shape[-1] == cm * C, 'FEAT_CHANNELS must be a multiple of 16'

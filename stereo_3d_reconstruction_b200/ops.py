@@ -200,16 +200,21 @@ def conv_concat_volume(pc, featp, B, D, pad, out=None, ref_once=False):
     columns pad .. pitch-pad-1), left images first.  -> [2B,D,h,w,cout_pad].  include/s3d.h, s3d_conv_concat_volume.
     ref_once: the reference-once form (s3d_conv_concat_volume_ro: half the tensor-core work, not bit-identical)."""
     import ctypes
+    from .layers import is_split
     _chk(featp, out)
+    split = is_split(pc.dtype_code)              # 'bf16x3': featp / out rows are [hi(C) | lo(C)] bf16 pairs, reference-once form only
+    cm = 2 if split else 1
     n2, one, h, pitch, C = featp.shape
+    C //= cm
     assert n2 == 2 * B and one == 1 and featp.is_contiguous() and pc.cin_pad == 2 * C and pad >= D - 1
+    assert not split or ref_once, 'split (BF16X2) operands: reference-once form only'
     w = pitch - 2 * pad
     assert w > 0
+    Co = cm * pc.cout_pad
     if out is None:
-        out = torch.empty((2 * B, D, h, w, pc.cout_pad), dtype=featp.dtype, device=featp.device)
-    assert out.is_contiguous() and out.shape == (2 * B, D, h, w, pc.cout_pad)
-    Co = pc.cout_pad
-    p = pc.params(2 * B, D, h, w, (D * h * w * Co, h * w * Co, w * Co, Co), _code(out), Co)
+        out = torch.empty((2 * B, D, h, w, Co), dtype=featp.dtype, device=featp.device)
+    assert out.is_contiguous() and out.shape == (2 * B, D, h, w, Co)
+    p = pc.params(2 * B, D, h, w, (D * h * w * Co, h * w * Co, w * Co, Co), _code_like(out, split), pc.cout_pad)
     if ref_once:
         rc = _lib.load().s3d_conv_concat_volume_ro(ctypes.byref(p), featp.data_ptr(), pitch, pad, pc.refonce_weights(C).data_ptr(),
                                                    pc.bias.data_ptr(), out.data_ptr(), _stream())

@@ -244,3 +244,36 @@ def test_odd_input_sizes_bf16x3(H, W, B):
     assert (dl.cpu() - rdl).abs().max().item() <= 5e-4 * rdl.abs().max().item()
     assert (vox.cpu() - rvox).abs().max().item() <= 5e-4
     assert torch.equal(iou.cpu(), O.iou_counts(vox.cpu(), gt, cfg.TEST.VOXEL_THRESH))
+
+
+@pytest.mark.parametrize('B,D,h,w', [
+    (2, 8, 16, 16),        # the network's shape, 8 columns
+    (3, 32, 40, 64),       # D = 32 planes, two patch rows, 96 columns
+    (1, 5, 9, 13),         # ragged patches
+    (2, 1, 8, 8),          # one plane: both border corrections land on it
+    (2, 2, 8, 8),          # two planes
+    (80, 4, 8, 8),         # 160 columns on 148 SMs: two columns per CTA, phantom column
+])
+def test_conv_concat_volume_ref_once_split(B, D, h, w):
+    """Reference-once cost volume + first aggregation layer on split (BF16X2) operands (conv_scatter_concat_ros_kernel) against
+    Conv3d + ReLU over the oracle's concat volume on UNROUNDED fp32 features, plane by plane: 1e-4 of the output's max."""
+    C, cout = 32, 64
+    torch.manual_seed(21)
+    conv = nn.Conv3d(2 * C, cout, 3, 1, 1, bias=True)
+    pc = PackedConv.from_conv(conv, None, lib.ACT_RELU, X2, 'cuda')
+    f = torch.randn(2 * B, C, h, w)
+    feat = _split(to_cl(f)).cuda()                                      # [2B,1,h,w, hi(C) | lo(C)]
+    pad, P = D, w + 2 * D
+    featp = torch.zeros(2 * B, 1, h, P, 2 * C, dtype=torch.bfloat16, device='cuda')
+    featp[:, :, :, pad:pad + w] = feat
+    got = ops.conv_concat_volume(pc, featp, B, D, pad, ref_once=True)
+    torch.cuda.synchronize()
+    assert got.shape == (2 * B, D, h, w, 2 * cout)
+    got = _unsplit(got)
+    ref_vol = torch.cat([O.build_concat_volume(f[:B], f[B:], D, -1), O.build_concat_volume(f[B:], f[:B], D, +1)], 0)
+    with torch.no_grad():
+        ref = to_cl(F.relu(conv(ref_vol)))
+    scale = ref.abs().max().item() + 1e-6
+    for z in range(D):
+        ez = (got[:, z] - ref[:, z]).abs().max().item()
+        assert ez <= TOL * scale, (z, ez, scale)
