@@ -299,7 +299,7 @@ int conv_igemm_launch(const S3dConvParams* p, const void* in, const void* w, con
   for (int ts : {4, 3, 2}) {
     if (knobs().igemm_ts1 || p->ntaps % ts != 0) continue;
     const int sbytes = ts * a.a_bytes + ((ts * a.b_tap_bytes + 1023) / 1024) * 1024;
-    if (sbytes <= 48 * 1024 && smem_budget / sbytes >= (two_ctas ? 3 : 4)) { a.ts = ts; break; }
+    if (sbytes <= 48 * 1024 && smem_budget / sbytes >= (two_ctas ? 2 : 4)) { a.ts = ts; break; }
   }
   a.b_bytes = ((a.ts * a.b_tap_bytes + 1023) / 1024) * 1024;
   a.tx_bytes = a.ts * (a.a_bytes + a.b_tap_bytes);

@@ -230,3 +230,144 @@ def test_tf32x3_three_pass_algebra_reaches_fp32_accuracy():
     e3 = (three[..., :16] - ref).abs().max().item() / scale
     assert 1e-5 < e1 < 5e-3, e1                                     # single-pass TF32: ~1e-3
     assert e3 < 5e-6, e3                                            # three passes: fp32-level
+
+
+def test_reference_once_algebra_matches_the_concat_conv():
+    """csrc/conv_scatter_concat.cu, reference-once form, restated on the host with the weights PackedConv.refonce_weights packs:
+    out[z] = bias + R + conv over the TARGET half only, R = ref (*) sum_kz W[kz] computed once, plus ref (*) (-W[kz=0]) on plane 0 and
+    ref (*) (-W[kz=2]) on plane D-1 -- equal to the 3x3x3 conv over the whole concat volume (fp32 here: exact up to summation order)."""
+    from oracle import models as O
+    g = torch.Generator().manual_seed(12)
+    B, C, h, w, cout = 1, 4, 5, 7, 6
+    for D in (1, 2, 5):
+        conv = nn.Conv3d(2 * C, cout, 3, 1, 1, bias=True)
+        pc = PackedConv.from_conv(conv, None, lib.ACT_NONE, lib.DTYPE_F32, 'cpu')
+        ro = pc.refonce_weights(pc.cin_pad // 2).float()              # [27, cout_pad, C_pad]: sum_kz W | -W[kz=0] | -W[kz=2]
+        Cp = pc.cin_pad // 2
+        assert ro.shape == (27, pc.cout_pad, Cp)
+        fL, fR = torch.randn(B, C, h, w, generator=g), torch.randn(B, C, h, w, generator=g)
+        vol = O.build_concat_volume(fL, fR, D, -1)                    # [B, 2C, D, h, w]: ref = left, target = right at x - d
+        with torch.no_grad():
+            want = conv(vol)
+        # this test's C is not a multiple of 16: the packed layer pads the channel axis, ref channels first
+        # (the product only ever uses C * elem in {32, 64} bytes)
+        def conv2d(x_nchw, w27):                                      # 3x3 2-D conv with taps [9, cout_pad, Cp]
+            wk = w27[:, :cout, :x_nchw.shape[1]].reshape(3, 3, cout, -1).permute(2, 3, 0, 1)
+            return F.conv2d(x_nchw, wk, padding=1)
+        if pc.cin_pad == 2 * C:
+            R = conv2d(fL, ro[0:9])
+            c0 = conv2d(fL, ro[9:18])
+            cL = conv2d(fL, ro[18:27])
+            wt = conv.weight[:, C:].detach()                          # target-channel weights
+            tgt = F.conv3d(vol[:, C:], wt, padding=1)
+            got = tgt + R.unsqueeze(2) + conv.bias.view(1, -1, 1, 1, 1)
+            got[:, :, 0] += c0
+            got[:, :, D - 1] += cL
+            torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-5)
+        else:
+            # padded layout (cin_pad > 2C): only check the packing rule itself
+            w3 = conv.weight.detach().permute(2, 3, 4, 0, 1).reshape(3, 9, cout, 2 * C)
+            torch.testing.assert_close(ro[0:9, :cout, :C], w3[:, :, :, :C].sum(0))
+            torch.testing.assert_close(ro[9:18, :cout, :C], -w3[0, :, :, :C])
+            torch.testing.assert_close(ro[18:27, :cout, :C], -w3[2, :, :, :C])
+
+
+def test_reference_once_algebra_with_16_channel_features():
+    """The same with a channel count the kernel takes (C = 16: cin_pad == 2C), through the packed weights end to end."""
+    from oracle import models as O
+    g = torch.Generator().manual_seed(13)
+    B, C, h, w, cout, D = 1, 16, 4, 6, 5, 3
+    conv = nn.Conv3d(2 * C, cout, 3, 1, 1, bias=True)
+    pc = PackedConv.from_conv(conv, None, lib.ACT_NONE, lib.DTYPE_F32, 'cpu')
+    assert pc.cin_pad == 2 * C
+    ro = pc.refonce_weights(C).float()
+    fL, fR = torch.randn(B, C, h, w, generator=g), torch.randn(B, C, h, w, generator=g)
+    vol = O.build_concat_volume(fL, fR, D, -1)
+    k2 = lambda w27: w27[:, :cout].reshape(3, 3, cout, C).permute(2, 3, 0, 1)
+    with torch.no_grad():
+        want = conv(vol)
+        got = F.conv3d(vol[:, C:], conv.weight[:, C:], padding=1) + F.conv2d(fL, k2(ro[0:9]), padding=1).unsqueeze(2) + \
+            conv.bias.view(1, -1, 1, 1, 1)
+        got[:, :, 0] += F.conv2d(fL, k2(ro[9:18]), padding=1)
+        got[:, :, D - 1] += F.conv2d(fL, k2(ro[18:27]), padding=1)
+    torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-5)
+
+
+def test_scatter_form_classifier_with_per_patch_partial_sums():
+    """csrc/conv_scatter_cls.cu restated on the host: the Cout = 1 3x3x3 classifier over Y in SCATTER form -- every pixel of a 32x8
+    patch projects its channels on the 27 taps, every cell of the patch plus its halo ring (34 x 10) gathers the taps of its
+    in-patch neighbours into three running cost planes, finished planes are stored as the patch's PARTIAL sums, and a second pass
+    adds, per pixel, the partial sums of the (<= 4) patches whose ring covers it -- equals conv3d(Y, Wb)."""
+    g = torch.Generator().manual_seed(14)
+    N, C, D, h, w = 1, 3, 4, 37, 19                                   # ragged: 2 x 3 patches of 32 x 8
+    TY, TX = 32, 8
+    cy, cx = -(-h // TY), -(-w // TX)
+    Y = torch.randn(N, C, D, h, w, generator=g)
+    Wb = torch.randn(1, C, 3, 3, 3, generator=g)
+    want = F.conv3d(Y, Wb, padding=1)[:, 0]                            # [N, D, h, w]
+    taps = Wb[0].reshape(C, 27)                                        # tap index (kz * 3 + ky) * 3 + kx
+    partials = torch.zeros(N, cy, cx, D, TY + 2, TX + 2)
+    for n in range(N):
+        for py in range(cy):
+            for px in range(cx):
+                run = torch.zeros(3, TY + 2, TX + 2)                   # cost planes z-1, z, z+1 of this patch (+ ring)
+                for z in range(D):
+                    # projections of the patch's pixels; pixels outside the image enter as zeros
+                    P = torch.zeros(TY, TX, 27)
+                    ys, xs = min(TY, h - py * TY), min(TX, w - px * TX)
+                    P[:ys, :xs] = torch.einsum('cyx,ct->yxt', Y[n, :, z, py * TY:py * TY + ys, px * TX:px * TX + xs], taps)
+                    # cell (yc, xc) in [-1, 32] x [-1, 8] gathers pixel (yc + ky - 1, xc + kx - 1) when it is inside the patch
+                    a = torch.zeros(3, TY + 2, TX + 2)                 # through kz = 2, 1, 0 -> planes z-1, z, z+1
+                    for ky in range(3):
+                        for kx in range(3):
+                            for kz in range(3):
+                                # pixels [0, TY) x [0, TX) land on cells pixel - (ky - 1, kx - 1), stored with the +1 ring offset
+                                a[2 - kz, 2 - ky:2 - ky + TY, 2 - kx:2 - kx + TX] += P[:, :, (kz * 3 + ky) * 3 + kx]
+                    run += a
+                    if z >= 1:
+                        partials[n, py, px, z - 1] = run[0]
+                    run = torch.stack([run[1], run[2], torch.zeros(TY + 2, TX + 2)])
+                partials[n, py, px, D - 1] = run[0]
+    got = torch.zeros(N, D, h, w)
+    for n in range(N):
+        for y in range(h):
+            for x in range(w):
+                py, px, yi, xi = y // TY, x // TX, y % TY, x % TX
+                dyn = -1 if yi == 0 else (1 if yi == TY - 1 else 0)
+                dxn = -1 if xi == 0 else (1 if xi == TX - 1 else 0)
+                hy = dyn != 0 and 0 <= py + dyn < cy
+                hx = dxn != 0 and 0 <= px + dxn < cx
+                c = partials[n, py, px, :, yi + 1, xi + 1].clone()
+                yn = (-1 if dyn > 0 else TY) + 1                       # the pixel in the neighbour's ring coordinates
+                xn = (-1 if dxn > 0 else TX) + 1
+                if hx:
+                    c += partials[n, py, px + dxn, :, yi + 1, xn]
+                if hy:
+                    c += partials[n, py + dyn, px, :, yn, xi + 1]
+                if hx and hy:
+                    c += partials[n, py + dyn, px + dxn, :, yn, xn]
+                got[n, :, y, x] = c
+    torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-4)
+
+
+def test_residual_as_identity_tap():
+    """csrc/conv_scatter_rm.cu: the residual enters the accumulator as one more tap whose weight matrix is the identity; in the
+    swizzled shared-memory operand layout row r (output channel) holds its 1.0 at 16-byte chunk (ci / 8) ^ (r % 8)."""
+    CP = 64
+    for rank in (0, 1):
+        tile = torch.zeros(CP // 2 * 128, dtype=torch.uint8)           # this CTA's 32 rows x 128 bytes
+        for lane in range(32):
+            r, ci = lane, rank * (CP // 2) + lane
+            off = (r >> 3) * 1024 + (r & 7) * 128 + (((ci >> 3) ^ (r & 7)) << 4) + (ci & 7) * 2
+            tile[off + 1] = 0x3F                                       # bf16 1.0 = 0x3F80, little endian
+            tile[off] = 0x80
+        # undo the 128B swizzle and read the rows back
+        rows = torch.zeros(CP // 2, CP)
+        for r in range(CP // 2):
+            for chunk in range(8):
+                phys = (r >> 3) * 1024 + (r & 7) * 128 + ((chunk ^ (r & 7)) << 4)
+                for e in range(8):
+                    lo, hi = int(tile[phys + 2 * e]), int(tile[phys + 2 * e + 1])
+                    rows[r, chunk * 8 + e] = 1.0 if (hi, lo) == (0x3F, 0x80) else 0.0
+        want = torch.eye(CP)[rank * (CP // 2):(rank + 1) * (CP // 2)]
+        assert torch.equal(rows, want)
