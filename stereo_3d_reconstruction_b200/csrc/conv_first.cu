@@ -158,6 +158,13 @@ int launch_first(const void* img, int img_u8, const float* disp, float disp_scal
 }  // namespace
 }  // namespace s3d
 
+namespace s3d {
+bool conv_first_tc_eligible(int cout_pad, int dtype, int act);
+int conv_first_tc_launch(const void* img, int img_u8, const float* disp, float disp_scale, float img_scale, const void* w,
+                         int cin_pad, const float* bias, void* out, int B, int H, int W, int oH, int oW, int cin, int act,
+                         float act_param, cudaStream_t st);
+}
+
 extern "C" int s3d_conv_first(const void* img, int img_u8, const float* disp, float disp_scale, const void* w, const float* bias,
                               void* out, int B, int H, int W, int cin, int cin_pad, int cout_pad, int dtype, int act,
                               float act_param, void* stream) {
@@ -172,6 +179,9 @@ extern "C" int s3d_conv_first(const void* img, int img_u8, const float* disp, fl
   const int oH = (H - 1) / 2 + 1, oW = (W - 1) / 2 + 1;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const float img_scale = 1.0f / 255.0f;
+  // bf16, 32 output channels: im2col rows built by the threads + tcgen05 MMAs (conv_first_tc.cu)
+  if (conv_first_tc_eligible(cout_pad, dtype, act))
+    return conv_first_tc_launch(img, img_u8, disp, disp_scale, img_scale, w, cin_pad, bias, out, B, H, W, oH, oW, cin, act, act_param, st);
 #define S3D_FIRST(CO)                                                                                                    \
   (dtype == S3D_DTYPE_BF16X2                                                                                             \
        ? launch_first<CO, __nv_bfloat16, __nv_bfloat16, true>(img, img_u8, disp, disp_scale, img_scale, w, cin_pad, bias, out, B, \

@@ -38,6 +38,7 @@ const KnobName kKnobNames[] = {
     {"scatter_zsplit", "S3D_SCATTER_ZSPLIT", &Knobs::scatter_zsplit},
     {"scatter_no_rm", "S3D_SCATTER_NO_RM", &Knobs::scatter_no_rm},
     {"igemm_ts1", "S3D_IGEMM_TS1", &Knobs::igemm_ts1},
+    {"no_conv_first_tc", "S3D_NO_CONV_FIRST_TC", &Knobs::no_conv_first_tc},
     {"scatter_one_cta", "S3D_SCATTER_ONE_CTA", &Knobs::scatter_one_cta},
     {"igemm_one_cta", "S3D_IGEMM_ONE_CTA", &Knobs::igemm_one_cta},
 };

@@ -192,11 +192,15 @@ def test_pack_image_u8(dtype):
     assert got[..., 4:].abs().max() == 0
 
 
+@pytest.mark.parametrize('simt', [0, 1])
 @pytest.mark.parametrize('dtype_code,dtype,tol', [(lib.DTYPE_F32, torch.float32, 1e-5), (lib.DTYPE_BF16, torch.bfloat16, 2e-2)])
 @pytest.mark.parametrize('with_disp,u8,H,W,cout', [(False, False, 16, 20, 32), (True, False, 9, 11, 16), (False, True, 12, 12, 64),
-                                                    (True, True, 7, 5, 32)])
-def test_conv_first_direct_from_raw_image(dtype_code, dtype, tol, with_disp, u8, H, W, cout):
-    """conv_first.cu == Conv2d(3|4, cout, 3, stride 2, pad 1) + bias + ReLU on the raw image (fp32 NCHW or uint8 HWC)."""
+                                                    (True, True, 7, 5, 32), (False, True, 131, 70, 32), (True, False, 70, 131, 32)])
+def test_conv_first_direct_from_raw_image(knobs, simt, dtype_code, dtype, tol, with_disp, u8, H, W, cout):
+    """conv_first.cu (SIMT) / conv_first_tc.cu (bf16, 32 channels: im2col rows built by the threads + tcgen05; knob
+    no_conv_first_tc selects the SIMT kernel) == Conv2d(3|4, cout, 3, stride 2, pad 1) + bias + ReLU on the raw image (fp32 NCHW or
+    uint8 HWC)."""
+    knobs('no_conv_first_tc', simt)
     g = torch.Generator().manual_seed(21)
     cin = 4 if with_disp else 3
     conv = nn.Conv2d(cin, cout, 3, 2, 1)
