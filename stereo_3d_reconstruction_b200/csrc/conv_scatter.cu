@@ -70,8 +70,19 @@ int conv_scatter_launch(const S3dConvParams* p_in, const void* in, const float* 
   // single-CTA kernel saturates the shared-memory pipe (A 4 KB + B 6 KB per 96-cycle MMA, plus the TMA fills).
   int grid = num_sms();
   a.pair = ((3 * a.cp / 2) % 8 == 0 && total >= 2 && grid >= 2 && !knobs().scatter_no_pair) ? 1 : 0;
+  // coalesced (transposed) store path: needed by every lean kernel
+  bool fast_ok;
+  {
+    const int oesz = p.out_dtype == S3D_DTYPE_F32 ? 4 : 2;
+    const bool simple_act = p.act == S3D_ACT_NONE || p.act == S3D_ACT_RELU || p.act == S3D_ACT_LEAKY;
+    auto aligned = [&](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    auto dense16 = [&](int64_t st) { return (st * oesz) % 16 == 0; };
+    fast_ok = simple_act && bias != nullptr && p.cout_store == p.Cout && aligned(out) && aligned(residual) &&
+              dense16(p.osW) && dense16(p.osH) && dense16(p.osD) && dense16(p.osN) && p.osW < (1ll << 24) &&
+              (split || !knobs().scatter_no_transpose);
+  }
   // narrow lean shapes: two CTAs per SM (conv_scatter.cuh, kTwo) when there is work for both
-  const bool two = a.pair && !tf32 && !split && a.nchunks == 1 && p.out_dtype == S3D_DTYPE_BF16 && residual == nullptr &&
+  const bool two = fast_ok && a.pair && !tf32 && !split && a.nchunks == 1 && p.out_dtype == S3D_DTYPE_BF16 && residual == nullptr &&
                    spec_kernel(a.row_bytes, a.cp, false, p.act == S3D_ACT_RELU, true) != nullptr && total > grid &&
                    !knobs().scatter_generic && !knobs().scatter_one_cta && !knobs().scatter_tps3 && !knobs().scatter_ring;
   if (two) grid *= 2;
@@ -101,13 +112,8 @@ int conv_scatter_launch(const S3dConvParams* p_in, const void* in, const float* 
   // staging the residual tiles in shared memory by TMA was tried too: 2.66 vs 2.55 ms, it costs three weight stages)
   a.res_direct = !knobs().scatter_res_transpose;
   {
-    const int oesz = p.out_dtype == S3D_DTYPE_F32 ? 4 : 2;
-    const bool simple_act = p.act == S3D_ACT_NONE || p.act == S3D_ACT_RELU || p.act == S3D_ACT_LEAKY;
-    auto aligned = [&](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
-    auto dense16 = [&](int64_t st) { return (st * oesz) % 16 == 0; };
-    a.fast_store = simple_act && bias != nullptr && p.cout_store == p.Cout && aligned(out) && aligned(residual) &&
-                   dense16(p.osW) && dense16(p.osH) && dense16(p.osD) && dense16(p.osN) && p.osW < (1ll << 24) &&
-                   (split || !knobs().scatter_no_transpose);
+    auto dense16 = [&](int64_t st) { return (st * 2) % 16 == 0; };
+    a.fast_store = fast_ok;
     if (split) {
       S3D_CHECK_ARG(a.fast_store && dense16(a.os_lo) && a.os_lo >= p.Cout,
                     "scatter (split operands): needs a bias, a none / ReLU / LeakyReLU activation and 16-byte aligned out / residual / strides");

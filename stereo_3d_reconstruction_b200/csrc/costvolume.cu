@@ -338,6 +338,33 @@ __global__ void upsample_disp_kernel(const float* __restrict__ q, float* __restr
   }
 }
 
+// The same, four consecutive outputs per thread (one 16-byte store), 32-bit index arithmetic: the scalar kernel spends its time
+// in 64-bit divisions (0.051 ms for 33.5 MB at B = 64, 8x its HBM time).  Same formula per output, bit-identical results.
+__global__ void __launch_bounds__(256)
+upsample_disp_v4_kernel(const float* __restrict__ q, float4* __restrict__ out, uint32_t total4, int h, int w, int H, int W4,
+                        float ry, float rx, float scale) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total4) return;
+  const uint32_t X4 = i % (uint32_t)W4, row = i / (uint32_t)W4;
+  const uint32_t Y = row % (uint32_t)H, n = row / (uint32_t)H;
+  float sy = ((float)Y + 0.5f) * ry - 0.5f;  if (sy < 0.f) sy = 0.f;
+  const int y0 = (int)sy, y1 = y0 + (y0 < h - 1 ? 1 : 0);
+  const float ly = sy - (float)y0, hy = 1.f - ly;
+  const float* p0 = q + ((int64_t)n * h + y0) * w;
+  const float* p1 = q + ((int64_t)n * h + y1) * w;
+  float r[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int X = 4 * (int)X4 + k;
+    float sx = ((float)X + 0.5f) * rx - 0.5f;  if (sx < 0.f) sx = 0.f;
+    const int x0 = (int)sx, x1 = x0 + (x0 < w - 1 ? 1 : 0);
+    const float lx = sx - (float)x0, hx = 1.f - lx;
+    const float v = hy * (hx * __ldg(p0 + x0) + lx * __ldg(p0 + x1)) + ly * (hx * __ldg(p1 + x0) + lx * __ldg(p1 + x1));
+    r[k] = v * scale;
+  }
+  out[i] = make_float4(r[0], r[1], r[2], r[3]);
+}
+
 }  // namespace
 }  // namespace s3d
 
@@ -428,6 +455,13 @@ extern "C" int s3d_upsample_disp(const float* disp_q, float* disp, int N, int h,
   if (!disp_q || !disp) { set_error("upsample_disp: null argument"); return S3D_ERR_INVALID; }
   S3D_CHECK_ARG(N > 0 && h > 0 && w > 0 && H > 0 && W > 0, "upsample_disp: bad shape");
   const int64_t total = (int64_t)N * H * W;
+  if (W % 4 == 0 && total / 4 < (1ll << 31) && (reinterpret_cast<uintptr_t>(disp) & 15) == 0) {
+    const uint32_t total4 = (uint32_t)(total / 4);
+    upsample_disp_v4_kernel<<<(total4 + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        disp_q, reinterpret_cast<float4*>(disp), total4, h, w, H, W / 4, (float)h / (float)H, (float)w / (float)W, scale);
+    S3D_LAUNCH_CHECK();
+    return S3D_OK;
+  }
   int64_t blocks = ceil_div64(total, 256);
   if (blocks > (int64_t)num_sms() * 16) blocks = (int64_t)num_sms() * 16;
   upsample_disp_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(disp_q, disp, N, h, w, H, W, scale);
