@@ -37,12 +37,15 @@ HAVE = getattr(M, 'PRECISIONS', ('bf16', 'tf32', 'tf32x3', 'fp32'))
 MEASURED = {}           # printed at the end of the module (pytest -s) and usable by scripts/parity_report.py
 
 
-@pytest.fixture(scope='module')
-def voxel_case():
+# B = 2: 64 columns per aggregation layer, fewer than half the SMs -> the small-batch paths (materialised volume, z-split columns,
+# separate classifier kernel).  B = 3: 96 columns -> the paths of the benchmark (reference-once first layer, residual on the tensor
+# core, last layer + classifier chain; for 'bf16x3' the split reference-once kernel).
+@pytest.fixture(scope='module', params=[2, 3], ids=['B2-small-batch-paths', 'B3-batched-paths'])
+def voxel_case(request):
     cfg = default_cfg.clone()
     torch.set_num_threads(max(1, torch.get_num_threads()))
     oracle = O.make_model('Stereo2Voxel', cfg, seed=0)
-    B = 2
+    B = request.param
     left, right, _ = synthetic.stereo_pair(B, cfg.CONST.IMG_H, cfg.CONST.IMG_W, 2 * cfg.NETWORK.MAX_DISP, seed=11)
     gt = synthetic.gt_volume(B, seed=12)
     with torch.no_grad():
@@ -68,8 +71,9 @@ def test_default_stereo2voxel_matches_oracle(voxel_case, prec):
     dmax = max(rdl.abs().max().item(), rdr.abs().max().item())
     e_d = max((dl - rdl).abs().max().item(), (dr - rdr).abs().max().item()) / dmax
     e_v = (vox - rvox).abs().max().item()
-    MEASURED['stereo2voxel/' + prec] = (e_d, e_v, (vox - rvox).abs().mean().item())
-    assert dl.shape == (2, 1, 256, 256) and vox.shape == (2, 32, 32, 32)
+    B = left.shape[0]
+    MEASURED['stereo2voxel/%s/B%d' % (prec, B)] = (e_d, e_v, (vox - rvox).abs().mean().item())
+    assert dl.shape == (B, 1, 256, 256) and vox.shape == (B, 32, 32, 32)
     assert rdl.std() > 1.0 and rvox.std() > 0.05                               # a non-degenerate target
     assert e_d <= td, ('disparity', prec, e_d)
     assert e_v <= tv, ('occupancy', prec, e_v)
