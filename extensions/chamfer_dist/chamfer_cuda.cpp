@@ -3,7 +3,7 @@
 // upstream Stereo2Point branch and is not on disk, so the module surface below -- `chamfer.forward(xyz1, xyz2)` returning
 // (dist1, dist2, idx1, idx2) -- follows the same author's public GRNet extension from memory [RECALL]).
 //
-// No kernel lives here: the shim validates the tensors, allocates the outputs with torch, and calls s3d_chamfer_forward
+// No kernel lives here: the shim validates the tensors, allocates the outputs (and the workspace) with torch, and calls s3d_chamfer_forward_ws
 // (libs3d_b200.so, csrc/chamfer.cu) on the current CUDA stream.  There is no CPU path.
 #include <torch/extension.h>
 #include <c10/cuda/CUDAGuard.h>
@@ -25,10 +25,14 @@ static std::vector<torch::Tensor> chamfer_forward(torch::Tensor xyz1, torch::Ten
   auto i = xyz1.options().dtype(torch::kInt32);
   torch::Tensor dist1 = torch::empty({B, N}, f), dist2 = torch::empty({B, M}, f);
   torch::Tensor idx1 = torch::empty({B, N}, i), idx2 = torch::empty({B, M}, i);
-  const int rc = s3d_chamfer_forward(xyz1.data_ptr<float>(), xyz2.data_ptr<float>(), dist1.data_ptr<float>(), idx1.data_ptr<int32_t>(),
-                                     dist2.data_ptr<float>(), idx2.data_ptr<int32_t>(), (int)B, (int)N, (int)M,
-                                     c10::cuda::getCurrentCUDAStream().stream());
-  TORCH_CHECK(rc == S3D_OK, "s3d_chamfer_forward failed (rc=", rc, "): ", s3d_last_error());
+  // large problems: one pass for both directions, with a torch-owned workspace (0 bytes when the problem is small)
+  const int64_t ws_bytes = (B > 0 && N > 0 && M > 0) ? s3d_chamfer_workspace_bytes((int)B, (int)N, (int)M) : 0;
+  torch::Tensor ws = torch::empty({ws_bytes > 0 ? ws_bytes : 0}, xyz1.options().dtype(torch::kUInt8));
+  const int rc = s3d_chamfer_forward_ws(xyz1.data_ptr<float>(), xyz2.data_ptr<float>(), dist1.data_ptr<float>(), idx1.data_ptr<int32_t>(),
+                                        dist2.data_ptr<float>(), idx2.data_ptr<int32_t>(), (int)B, (int)N, (int)M,
+                                        ws_bytes > 0 ? ws.data_ptr() : nullptr, ws_bytes,
+                                        c10::cuda::getCurrentCUDAStream().stream());
+  TORCH_CHECK(rc == S3D_OK, "s3d_chamfer_forward_ws failed (rc=", rc, "): ", s3d_last_error());
   return {dist1, dist2, idx1, idx2};
 }
 

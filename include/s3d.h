@@ -99,7 +99,7 @@ const char* s3d_last_error(void);
 /* 0 if device `dev` is usable (compute capability 10.x), else a negative code. */
 int s3d_device_check(int dev);
 /* A/B switches of the launchers ("no_scatter", "scatter_no_pair", "scatter_generic", "scatter_tps3", "scatter_ring",
- * "scatter_res_transpose", "scatter_no_transpose", "no_corr_tc", "scatter_zsplit", "scatter_no_rm", "igemm_ts1", "igemm_one_cta", "scatter_one_cta", "no_conv_first_tc"; all 0 by default = the shipped path).  They are
+ * "scatter_res_transpose", "scatter_no_transpose", "no_corr_tc", "scatter_zsplit", "scatter_no_rm", "igemm_ts1", "igemm_one_cta", "scatter_one_cta", "no_conv_first_tc", "chamfer_sym"; all 0 by default = the shipped path).  They are
  * initialised ONCE from the environment variables S3D_<NAME> when the library is first used and are never read from
  * the environment on the launch path; s3d_set_knob overrides one at run time.  Process-wide, not thread-safe against
  * concurrent launches. */
@@ -230,6 +230,15 @@ int s3d_fuse_views(const void* score, int64_t score_stride, const void* vol, int
  * ties resolve to the lowest index. */
 int s3d_chamfer_forward(const float* xyz1, const float* xyz2, float* dist1, int32_t* idx1,
                         float* dist2, int32_t* idx2, int B, int N, int M, void* stream);
+/* The same forward with a caller-owned device workspace (8-byte aligned, s3d_chamfer_workspace_bytes(B, N, M) bytes; that
+ * is 0 when the problem is too small for it).  With the workspace every point pair is evaluated ONCE for both directions
+ * (d(i, j) is the same fp32 number either way round): row minima in registers, column minima merged through 64-bit
+ * atomicMin keys in the workspace, indices recovered by rescanning one 32- / 256-point chunk.  Results are bit-identical
+ * to s3d_chamfer_forward (which is this call with workspace = NULL: one search per direction). */
+int64_t s3d_chamfer_workspace_bytes(int B, int N, int M);
+int s3d_chamfer_forward_ws(const float* xyz1, const float* xyz2, float* dist1, int32_t* idx1,
+                           float* dist2, int32_t* idx2, int B, int N, int M, void* workspace,
+                           int64_t workspace_bytes, void* stream);
 
 /* Measurement aid (bench.py): a launch of independent fp32 FMA chains that is bound by the FMA issue rate only;
  * *fma_count (HOST) receives the number of thread-level FMAs the launch executes.  Timed with CUDA events it gives the

@@ -19,7 +19,8 @@ def build():
 def _load():
     global _lib
     if _lib is None:
-        if not os.path.exists(_SO):
+        src = os.path.join(_HERE, 'chamfer_ref.c')
+        if not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):      # never check against a stale build
             build()
         _lib = ctypes.CDLL(_SO)
         _lib.chamfer_ref.argtypes = [ctypes.c_void_p] * 6 + [ctypes.c_int] * 4

@@ -4,9 +4,11 @@
 // flop/B in fp32, beyond the fp32 ridge for D >= 32).  The correlation of one image row is a Gram
 // matrix, S = X_ref [w x C] . X_tgt^T [C x w], whose band S[x, x -/+ d] is the cost volume -- a dense
 // contraction, so it goes to tcgen05:
-//   tile      two image rows (y, y+1) of one volume n: M = 128 reference pixels (2 x 64, x padded to 64
+//   tile      two image rows (y, y+1) of one stereo pair: M = 128 reference pixels (2 x 64, x padded to 64
 //             by TMA zero fill), N = 128 target pixels of the same two rows, K = C.  One TMA box per
-//             operand and K chunk; the accumulator [128 x 128] fp32 lives in TMEM (two buffers).
+//             image and K chunk, loaded ONCE for both views: the left-reference accumulator is L . R^T, the
+//             right-reference one R . L^T (a second MMA with the operands exchanged).  Accumulators
+//             [128 x 128] fp32 live in TMEM (four buffers).
 //             Only the two 64 x 64 diagonal blocks are used (the off-diagonal blocks pair different
 //             image rows), and of those only the band -- the tensor pipe has ~50x headroom here.
 //   epilogue  thread = reference pixel (TMEM lane).  It reads the <= 64 target columns of its own row
@@ -39,7 +41,7 @@ struct CorrArgs {
   int op_bytes;        // bytes of one operand tile per chunk: 128 * row_bytes
   int stage_bytes;     // 2 * op_bytes
   int stages;
-  int tiles_per_img, total_tiles;
+  int tiles_per_img, pair_tiles;   // pair tile = (stereo pair, two image rows): one load, two accumulators (left / right reference)
   float inv_c;
   uint32_t idesc;
 };
@@ -49,6 +51,10 @@ struct CorrCtrl {
   uint64_t acc_full[kGroups], acc_empty[kGroups];
   uint32_t tmem_base;
 };
+
+// MUFU.EX2 as one instruction (exp2f() wraps it in range tests and two scalings for denormal results, which a softmax
+// weight does not need): <= 2 ulp, results below 2^-126 flush to zero.
+__device__ __forceinline__ float ex2_approx(float x) { float r;  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));  return r; }
 
 __global__ void __launch_bounds__(kThreads, 1)
 corr_tc_kernel(const __grid_constant__ CUtensorMap map_f, const __grid_constant__ CorrArgs a) {
@@ -72,15 +78,17 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap map_f, const __grid_constant_
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0;  uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
-        const int n = tile / a.tiles_per_img, y0 = (tile % a.tiles_per_img) * kRows;
-        const int nt = n < a.B ? n + a.B : n - a.B;          // the other view is the target
+      // a pair tile (stereo pair b, rows y0, y0+1) loads the LEFT and the RIGHT feature rows once; both views' accumulators
+      // are built from that one stage (S_right = S_left^T, formed by a second MMA with the operands exchanged): half the
+      // TMA rows per disparity map -- the loads, at ~2-4 cycles per 64-byte row, were what the epilogue warps waited for
+      for (int pt = blockIdx.x; pt < a.pair_tiles; pt += gridDim.x) {
+        const int n = pt / a.tiles_per_img, y0 = (pt % a.tiles_per_img) * kRows;
         for (int ch = 0; ch < a.nchunks; ++ch) {
           ptx::mbar_wait(&ctrl.empty[stage], phase ^ 1);
           uint8_t* s = smem + stage * a.stage_bytes;
           ptx::mbar_arrive_expect_tx(&ctrl.full[stage], a.stage_bytes);
           ptx::tma_load_5d(s, &map_f, &ctrl.full[stage], ch * a.kc, 0, y0, 0, n);
-          ptx::tma_load_5d(s + a.op_bytes, &map_f, &ctrl.full[stage], ch * a.kc, 0, y0, 0, nt);
+          ptx::tma_load_5d(s + a.op_bytes, &map_f, &ctrl.full[stage], ch * a.kc, 0, y0, 0, n + a.B);
           if (++stage == a.stages) { stage = 0; phase ^= 1; }
         }
       }
@@ -91,26 +99,31 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap map_f, const __grid_constant_
     const int kper = a.row_bytes >> 5;
     const uint64_t hi = ptx::make_smem_desc(0, a.row_bytes) & 0xFFFFFFFF00000000ull;
     const uint32_t smem_u = ptx::smem_u32(smem);
-    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
-      ptx::mbar_wait(&ctrl.acc_empty[buf], acc_phase ^ 1);
-      ptx::tc_fence_after();
-      const uint32_t d_tmem = tmem_base + buf * kM;
-      for (int ch = 0; ch < a.nchunks; ++ch) {
-        ptx::mbar_wait(&ctrl.full[stage], phase);
+    for (int pt = blockIdx.x; pt < a.pair_tiles; pt += gridDim.x) {
+      int st = stage;  uint32_t ph = phase;
+      for (int view = 0; view < 2; ++view) {               // 0: left image is the reference (A = left rows), 1: right
+        ptx::mbar_wait(&ctrl.acc_empty[buf], acc_phase ^ 1);
         ptx::tc_fence_after();
-        const uint32_t sa = smem_u + stage * a.stage_bytes;
-        const uint64_t adesc = hi | ((sa >> 4) | (1u << 16));
-        const uint64_t bdesc = hi | (((sa + a.op_bytes) >> 4) | (1u << 16));
-        if (ptx::elect_one()) {
-          for (int k = 0; k < kper; ++k) ptx::mma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, a.idesc, (ch | k) != 0);
-          ptx::tc_commit(&ctrl.empty[stage]);
+        const uint32_t d_tmem = tmem_base + buf * kM;
+        st = stage;  ph = phase;
+        for (int ch = 0; ch < a.nchunks; ++ch) {
+          if (view == 0) { ptx::mbar_wait(&ctrl.full[st], ph);  ptx::tc_fence_after(); }
+          const uint32_t sa = smem_u + st * a.stage_bytes;
+          const uint64_t ldesc = hi | ((sa >> 4) | (1u << 16));
+          const uint64_t rdesc = hi | (((sa + a.op_bytes) >> 4) | (1u << 16));
+          if (ptx::elect_one()) {
+            for (int k = 0; k < kper; ++k)
+              ptx::mma_bf16(d_tmem, (view ? rdesc : ldesc) + 2 * k, (view ? ldesc : rdesc) + 2 * k, a.idesc, (ch | k) != 0);
+            if (view == 1) ptx::tc_commit(&ctrl.empty[st]);      // the stage is free once BOTH views have read it
+          }
+          __syncwarp();
+          if (++st == a.stages) { st = 0; ph ^= 1; }
         }
+        if (ptx::elect_one()) ptx::tc_commit(&ctrl.acc_full[buf]);
         __syncwarp();
-        if (++stage == a.stages) { stage = 0; phase ^= 1; }
+        if (++buf == kGroups) { buf = 0; acc_phase ^= 1; }
       }
-      if (ptx::elect_one()) ptx::tc_commit(&ctrl.acc_full[buf]);
-      __syncwarp();
-      if (++buf == kGroups) { buf = 0; acc_phase ^= 1; }
+      stage = st;  phase = ph;
     }
   } else if (warp >= 4) {
     const int q = warp & 3;
@@ -124,57 +137,65 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap map_f, const __grid_constant_
     // 16-column chunks so only one chunk is live in registers (<= 102 registers per thread at 640 threads).
     const int grp = (warp - 4) >> 2;
     const int buf = grp;  uint32_t acc_phase = 0;
+    // Per thread and view, the target columns inside the disparity window as a 64-bit mask (bit xt): the per-column test is
+    // then ONE instruction (LOP3 -> predicate).  out-of-image disparities keep cost 0 (oracle semantics): d in [dz0, D) with
+    //   left-ref : x - d < 0   <=>  d > x            right-ref: x + d >= w  <=>  d >= w - x
+    const int dz0_l = min(D, x + 1), dz0_r = min(D, max(0, w - x));
+    const uint64_t ones_l = dz0_l >= 64 ? ~0ull : ((1ull << dz0_l) - 1ull), ones_r = dz0_r >= 64 ? ~0ull : ((1ull << dz0_r) - 1ull);
+    const uint64_t win_l = ones_l << (x - dz0_l + 1);          // xt in [x - dz0 + 1, x]
+    const uint64_t win_r = ones_r << x;                        // xt in [x, x + dz0 - 1]   (x < 64; empty when dz0 = 0)
     int it = 0;
-    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
+    for (int pt = blockIdx.x; pt < a.pair_tiles; pt += gridDim.x)
+    for (int view = 0; view < 2; ++view, ++it) {
       if (it % kGroups != grp) continue;
-      const int n = tile / a.tiles_per_img, y = (tile % a.tiles_per_img) * kRows + rowblk;
-      const bool left_ref = n < a.B;
+      const bool left_ref = view == 0;
+      const int n = pt / a.tiles_per_img + (left_ref ? 0 : a.B), y = (pt % a.tiles_per_img) * kRows + rowblk;
       // target columns this warp needs: left-ref xt in [xw0-D+1, xw0+31], right-ref xt in [xw0, xw0+31+D-1]
       const int lo = left_ref ? max(0, xw0 - D + 1) : xw0;
       const int hi_ = left_ref ? xw0 + 31 : min(kWP - 1, xw0 + 31 + D - 1);
       const int c_lo = lo >> 4, c_hi = hi_ >> 4;          // 16-column chunks, warp-uniform
-      // out-of-image disparities keep cost 0 (oracle semantics): d in [dz0, D) where
-      //   left-ref : x - d < 0   <=>  d > x            right-ref: x + d >= w  <=>  d >= w - x
-      const int dz0 = left_ref ? min(D, x + 1) : min(D, max(0, w - x));
-      // base-2 exponent domain: v = S * log2(e)/C.  Columns outside this thread's disparity window become
-      // -inf (ex2 -> 0); the running max starts at a finite floor so no (-inf) - (-inf) can occur.
+      const int dz0 = left_ref ? dz0_l : dz0_r;
+      const uint64_t win = left_ref ? win_l : win_r;
+      // base-2 exponent domain: v = S * log2(e)/C.  The running max starts at a finite floor so no (-inf) - (-inf) can occur.
       float m = dz0 < D ? 0.f : -1e30f;
       float s = 0.f, tx = 0.f;                             // sum e, sum e * xt  (xt is a compile-time column index)
       ptx::mbar_wait(&ctrl.acc_full[buf], acc_phase);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + buf * kM + rowblk * kWP + (static_cast<uint32_t>(q * 32) << 16);
+      // All the columns this warp needs go to registers first and the accumulator buffer is handed back AT ONCE: the MMA of
+      // the group's next tile (4 tiles ahead) then runs under this tile's softmax instead of after it (ncu: the epilogue warps
+      // spent most of their time waiting on acc_full with the buffer held through the arithmetic).
+      uint32_t u[4][16];
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (c >= c_lo && c <= c_hi) ptx::tmem_ld16(taddr + c * 16, u[c]);
+      ptx::tmem_ld_wait();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&ctrl.acc_empty[buf]);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         if (c >= c_lo && c <= c_hi) {
-          uint32_t u[16];
-          ptx::tmem_ld16(taddr + c * 16, u);
-          ptx::tmem_ld_wait();
+          const uint32_t mb = (uint32_t)(win >> (16 * c));
+          // columns outside the window become -inf ONCE (they drop out of the max, and ex2(-inf * scale2 - m) = 0 needs no predicate)
           float v[16];
           float cm = -INFINITY;
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int xt = c * 16 + i;
-            const bool ok = left_ref ? (unsigned)(x - xt) < (unsigned)dz0 : (unsigned)(xt - x) < (unsigned)dz0;
-            v[i] = ok ? __uint_as_float(u[i]) * scale2 : -INFINITY;
-            cm = fmaxf(cm, v[i]);
-          }
-          const float mn = fmaxf(m, cm);
-          const float sc = exp2f(m - mn);
+          for (int i = 0; i < 16; ++i) { v[i] = (mb >> i) & 1u ? __uint_as_float(u[c][i]) : -INFINITY;  cm = fmaxf(cm, v[i]); }
+          const float mn = fmaxf(m, cm * scale2);          // scale2 > 0: max commutes with the scaling
+          const float sc = ex2_approx(m - mn);
           s *= sc;  tx *= sc;  m = mn;
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const float e = exp2f(v[i] - m);
+            const float e = ex2_approx(fmaf(v[i], scale2, -m));
             s += e;
             tx = fmaf(e, (float)(c * 16 + i), tx);
           }
         }
       }
-      ptx::tc_fence_before();
-      ptx::mbar_arrive(&ctrl.acc_empty[buf]);
       acc_phase ^= 1;
       float t = left_ref ? fmaf((float)x, s, -tx) : fmaf(-(float)x, s, tx);     // sum e * d
       if (dz0 < D) {                                       // (D - dz0) terms of cost 0 at d = dz0 .. D-1
-        const float e0 = exp2f(-m), cnt = (float)(D - dz0);
+        const float e0 = ex2_approx(-m), cnt = (float)(D - dz0);
         s += e0 * cnt;
         t += e0 * cnt * 0.5f * (float)(dz0 + D - 1);
       }
@@ -193,7 +214,7 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap map_f, const __grid_constant_
 }  // namespace
 
 bool corr_tc_eligible(int w, int C, int D, int dtype) {
-  return dtype == S3D_DTYPE_BF16 && w <= kWP && (C * 2) % 32 == 0 && D >= 1 && !knobs().no_corr_tc;
+  return dtype == S3D_DTYPE_BF16 && w <= kWP && (C * 2) % 32 == 0 && C <= 6 * 64 && D >= 1 && !knobs().no_corr_tc;
 }
 
 int corr_tc_launch(const void* feat, float* disp, int B, int h, int w, int C, int D, float inv_c, cudaStream_t stream) {
@@ -208,10 +229,11 @@ int corr_tc_launch(const void* feat, float* disp, int B, int h, int w, int C, in
   a.stage_bytes = 2 * a.op_bytes;
   a.stages = (200 * 1024) / a.stage_bytes;
   if (a.stages > kMaxStages) a.stages = kMaxStages;
+  S3D_CHECK_ARG(a.nchunks <= a.stages, "corr_tc: C = %d needs %d K chunks resident at once (at most %d)", C, a.nchunks, a.stages);
   a.tiles_per_img = ceil_div(h, kRows);
-  const int64_t total = (int64_t)2 * B * a.tiles_per_img;
-  S3D_CHECK_ARG(total > 0 && total < (1ll << 31), "corr_tc: tile count out of range");
-  a.total_tiles = (int)total;
+  const int64_t total = (int64_t)B * a.tiles_per_img;
+  S3D_CHECK_ARG(total > 0 && total < (1ll << 30), "corr_tc: tile count out of range");
+  a.pair_tiles = (int)total;
   a.inv_c = inv_c;
   a.idesc = ptx::make_instr_desc(1, kM, kM);
   const CUtensorMapSwizzle sw = a.row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
@@ -224,7 +246,7 @@ int corr_tc_launch(const void* feat, float* disp, int B, int h, int w, int C, in
   const int smem_bytes = a.stages * a.stage_bytes + 1024;
   S3D_CUDA(cudaFuncSetAttribute(corr_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   int grid = num_sms();
-  if (grid > a.total_tiles) grid = a.total_tiles;
+  if (grid > a.pair_tiles) grid = a.pair_tiles;
   corr_tc_kernel<<<grid, kThreads, smem_bytes, stream>>>(map_f, a);
   S3D_LAUNCH_CHECK();
   return S3D_OK;

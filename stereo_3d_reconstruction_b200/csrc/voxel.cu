@@ -41,6 +41,7 @@ const KnobName kKnobNames[] = {
     {"no_conv_first_tc", "S3D_NO_CONV_FIRST_TC", &Knobs::no_conv_first_tc},
     {"scatter_one_cta", "S3D_SCATTER_ONE_CTA", &Knobs::scatter_one_cta},
     {"igemm_one_cta", "S3D_IGEMM_ONE_CTA", &Knobs::igemm_one_cta},
+    {"chamfer_sym", "S3D_CHAMFER_SYM", &Knobs::chamfer_sym},
 };
 }  // namespace
 

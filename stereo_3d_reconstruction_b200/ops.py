@@ -351,8 +351,11 @@ def fuse_views(score, score_off, score_stride, vol, vol_off, vol_stride, B, V, n
     return out
 
 
-def chamfer_forward(xyz1, xyz2):
-    """xyz1 [B,N,3], xyz2 [B,M,3] fp32 -> dist1 [B,N], dist2 [B,M], idx1 [B,N], idx2 [B,M] (int32)."""
+def chamfer_forward(xyz1, xyz2, workspace=None):
+    """xyz1 [B,N,3], xyz2 [B,M,3] fp32 -> dist1 [B,N], dist2 [B,M], idx1 [B,N], idx2 [B,M] (int32).
+    Large problems take the symmetric one-pass kernel (s3d_chamfer_forward_ws: every pair evaluated once for both
+    directions), which needs a device workspace of s3d_chamfer_workspace_bytes(B, N, M) bytes; it is allocated here
+    unless the caller passes one (uint8 tensor)."""
     _chk(xyz1, xyz2)
     assert xyz1.dtype == torch.float32 and xyz2.dtype == torch.float32
     B, N, three = xyz1.shape
@@ -364,8 +367,13 @@ def chamfer_forward(xyz1, xyz2):
     dist2 = torch.empty((B, M), dtype=torch.float32, device=dev)
     idx1 = torch.empty((B, N), dtype=torch.int32, device=dev)
     idx2 = torch.empty((B, M), dtype=torch.int32, device=dev)
-    rc = _lib.load().s3d_chamfer_forward(xyz1.data_ptr(), xyz2.data_ptr(), dist1.data_ptr(), idx1.data_ptr(),
-                                         dist2.data_ptr(), idx2.data_ptr(), B, N, M, _stream())
-    _lib.check(rc, 's3d_chamfer_forward')
+    L = _lib.load()
+    need = int(L.s3d_chamfer_workspace_bytes(B, N, M)) if min(B, N, M) > 0 else 0
+    if need and (workspace is None or workspace.numel() * workspace.element_size() < need):
+        workspace = torch.empty(need, dtype=torch.uint8, device=dev)
+    rc = L.s3d_chamfer_forward_ws(xyz1.data_ptr(), xyz2.data_ptr(), dist1.data_ptr(), idx1.data_ptr(),
+                                  dist2.data_ptr(), idx2.data_ptr(), B, N, M,
+                                  workspace.data_ptr() if need else None, need, _stream())
+    _lib.check(rc, 's3d_chamfer_forward_ws')
     _lib.count_launch(2)
     return dist1, dist2, idx1, idx2

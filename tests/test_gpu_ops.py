@@ -131,6 +131,46 @@ def test_chamfer_bit_exact(B, N, M, dup):
     assert np.array_equal(d1.cpu().numpy(), rd1) and np.array_equal(d2.cpu().numpy(), rd2)          # bit-exact distances
 
 
+@pytest.mark.parametrize('B,N,M,dup', [(2, 300, 1000, True), (1, 1, 1, False), (3, 17, 5, True), (2, 2048, 4096, True),
+                                       (1, 1025, 1023, False), (2, 4100, 2500, True), (1, 257, 33, True), (4, 31, 513, False)])
+def test_chamfer_symmetric_one_pass_bit_exact(B, N, M, dup):
+    """The symmetric kernel (every pair evaluated once for both directions; packed fp32 ops, value-only minima, index by
+    chunk rescan, 64-bit atomicMin keys) forced at every size: bit-identical to the C oracle, whichever set is the larger,
+    with ragged tails, several shared-memory tiles of the streamed set (> 2048 points) and exact ties."""
+    a, b = synthetic.point_clouds(B, N, M, seed=7, duplicates=dup)
+    rd1, rd2, ri1, ri2 = OC.chamfer_c(a.numpy(), b.numpy())
+    lib.set_knob('chamfer_sym', 1)
+    try:
+        assert lib.load().s3d_chamfer_workspace_bytes(B, N, M) == 8 * B * min(N, M)
+        d1, d2, i1, i2 = ops.chamfer_forward(a.cuda(), b.cuda())
+    finally:
+        lib.set_knob('chamfer_sym', 0)
+    assert np.array_equal(i1.cpu().numpy(), ri1) and np.array_equal(i2.cpu().numpy(), ri2)
+    assert np.array_equal(d1.cpu().numpy(), rd1) and np.array_equal(d2.cpu().numpy(), rd2)
+
+
+def test_chamfer_symmetric_ties_and_non_finite():
+    """All points identical (every distance ties: index 0 everywhere), NaN points (never win; an all-NaN set leaves +inf /
+    index 0), coordinates whose squared distance overflows to +inf (never 'less than' the initial +inf: index 0)."""
+    lib.set_knob('chamfer_sym', 1)
+    try:
+        a = torch.zeros(2, 300, 3);  b = torch.zeros(2, 700, 3)
+        cases = [(a.clone(), b.clone())]
+        a2, b2 = synthetic.point_clouds(2, 300, 700, seed=9, duplicates=True)
+        a2[0, 5] = float('nan');  b2[1, 100:400] = float('nan');  cases.append((a2, b2))
+        a3, b3 = synthetic.point_clouds(1, 64, 600, seed=10)
+        a3[:] = float('nan');  cases.append((a3, b3))
+        a4, b4 = synthetic.point_clouds(1, 40, 300, seed=11)
+        a4[0, :20] = 3e19;  b4[0, :10] = -3e19;  cases.append((a4, b4))
+        for x, y in cases:
+            rd1, rd2, ri1, ri2 = OC.chamfer_c(x.numpy(), y.numpy())
+            d1, d2, i1, i2 = ops.chamfer_forward(x.cuda(), y.cuda())
+            assert np.array_equal(i1.cpu().numpy(), ri1) and np.array_equal(i2.cpu().numpy(), ri2)
+            assert np.array_equal(d1.cpu().numpy(), rd1, equal_nan=True) and np.array_equal(d2.cpu().numpy(), rd2, equal_nan=True)
+    finally:
+        lib.set_knob('chamfer_sym', 0)
+
+
 def test_chamfer_rejects_empty():
     with pytest.raises(lib.S3dError):
         ops.chamfer_forward(torch.zeros(1, 0, 3).cuda(), torch.zeros(1, 4, 3).cuda())
