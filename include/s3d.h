@@ -99,7 +99,7 @@ const char* s3d_last_error(void);
 /* 0 if device `dev` is usable (compute capability 10.x), else a negative code. */
 int s3d_device_check(int dev);
 /* A/B switches of the launchers ("no_scatter", "scatter_no_pair", "scatter_generic", "scatter_tps3", "scatter_ring",
- * "scatter_res_transpose", "scatter_no_transpose", "no_corr_tc", "scatter_zsplit", "scatter_no_rm", "igemm_ts1", "igemm_one_cta", "scatter_one_cta", "no_conv_first_tc", "chamfer_sym"; all 0 by default = the shipped path).  They are
+ * "scatter_res_transpose", "scatter_no_transpose", "no_corr_tc", "scatter_zsplit", "scatter_no_rm", "igemm_ts1", "igemm_one_cta", "scatter_one_cta", "no_conv_first_tc", "chamfer_sym", "chamfer_sym_r"; all 0 by default = the shipped path).  They are
  * initialised ONCE from the environment variables S3D_<NAME> when the library is first used and are never read from
  * the environment on the launch path; s3d_set_knob overrides one at run time.  Process-wide, not thread-safe against
  * concurrent launches. */

@@ -94,8 +94,7 @@ chamfer_nn_kernel(const float* __restrict__ q_xyz, const float* __restrict__ r_x
 }
 
 // ---- symmetric one-pass search ---------------------------------------------------------------------------------------
-constexpr int kSymR = 8;                 // resident points per lane
-constexpr int kSymBlock = 32 * kSymR;    // resident points per warp
+constexpr int kSymRMax = 8;              // resident points per lane (template parameter R: 8, or 4 for twice the warps)
 constexpr int kSymWarps = 2;             // warps per CTA (they share the staged tile of the streamed set)
 constexpr int kSymTile = 2048;           // streamed points per shared-memory tile
 constexpr int kSymChunk = 32;            // streamed points between two "which rows improved" checks
@@ -127,9 +126,12 @@ __device__ __forceinline__ float pair_dist(float ax, float ay, float az, float b
 
 // res_xyz [B, nr, 3]: resident set (rows), str_xyz [B, ns, 3]: streamed set (columns).  Writes the rows' results
 // (res_dist, res_idx) and merges the columns' (distance, block) keys into keys[B, ns] (pre-set to all ones).
+template <int kSymR>
 __global__ void __launch_bounds__(32 * kSymWarps)
 chamfer_sym_kernel(const float* __restrict__ res_xyz, const float* __restrict__ str_xyz, float* __restrict__ res_dist,
                    int32_t* __restrict__ res_idx, unsigned long long* __restrict__ keys, int nr, int ns, int ctas_per_batch, float one_arg) {
+  constexpr int kSymBlock = 32 * kSymR;  // resident points per warp
+  static_assert(kSymChunk == 32, "the cooperative rescan maps lane j to point j of a chunk");
   __shared__ __align__(16) float sx[kSymTile], sy[kSymTile], sz[kSymTile];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int b = blockIdx.x / ctas_per_batch;
@@ -273,7 +275,7 @@ chamfer_sym_kernel(const float* __restrict__ res_xyz, const float* __restrict__ 
 // One warp per streamed point: decode its key, rescan the 256 resident points of the winning block for the lowest index.
 __global__ void __launch_bounds__(256)
 chamfer_sym_finish_kernel(const float* __restrict__ res_xyz, const float* __restrict__ str_xyz, const unsigned long long* __restrict__ keys,
-                          float* __restrict__ str_dist, int32_t* __restrict__ str_idx, int nr, int ns, int64_t total) {
+                          float* __restrict__ str_dist, int32_t* __restrict__ str_idx, int nr, int ns, int64_t total, int kSymBlock) {
   const int lane = threadIdx.x & 31;
   const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);      // b * ns + s
   if (i >= total) return;
@@ -344,7 +346,7 @@ static bool sym_eligible(int B, int N, int M) {
   if (k < 0) return false;
   if (k > 0) return true;
   const int nr = N > M ? N : M;
-  return (int64_t)B * s3d::ceil_div(nr, s3d::kSymBlock) >= 2 * (int64_t)s3d::num_sms();
+  return (int64_t)B * s3d::ceil_div(nr, 32 * s3d::kSymRMax) >= 2 * (int64_t)s3d::num_sms();
 }
 
 extern "C" int64_t s3d_chamfer_workspace_bytes(int B, int N, int M) {
@@ -370,12 +372,18 @@ extern "C" int s3d_chamfer_forward_ws(const float* xyz1, const float* xyz2, floa
     const int nr = swap ? N : M, ns = swap ? M : N;
     unsigned long long* keys = static_cast<unsigned long long*>(workspace);
     S3D_CUDA(cudaMemsetAsync(keys, 0xff, (size_t)need, st));
-    const int ctas_per_batch = ceil_div(ceil_div(nr, kSymBlock), kSymWarps);
+    // 8 resident points per lane amortise the per-step column reduction best; with fewer than ~24 warps per SM at that size
+    // 4 per lane (twice the warps) hide the dependent-issue latency better
+    const int R = (knobs().chamfer_sym_r == 4 || knobs().chamfer_sym_r == 8) ? knobs().chamfer_sym_r
+                : ((int64_t)B * ceil_div(nr, 32 * 8) >= 24 * (int64_t)num_sms() ? 8 : 4);
+    const int blk = 32 * R;
+    const int ctas_per_batch = ceil_div(ceil_div(nr, blk), kSymWarps);
     S3D_CHECK_ARG((int64_t)B * ctas_per_batch < (1ll << 31), "chamfer: grid too large");
-    chamfer_sym_kernel<<<B * ctas_per_batch, 32 * kSymWarps, 0, st>>>(res, str, res_d, res_i, keys, nr, ns, ctas_per_batch, 1.0f);
+    if (R == 8) chamfer_sym_kernel<8><<<B * ctas_per_batch, 32 * kSymWarps, 0, st>>>(res, str, res_d, res_i, keys, nr, ns, ctas_per_batch, 1.0f);
+    else        chamfer_sym_kernel<4><<<B * ctas_per_batch, 32 * kSymWarps, 0, st>>>(res, str, res_d, res_i, keys, nr, ns, ctas_per_batch, 1.0f);
     S3D_LAUNCH_CHECK();
     const int64_t total = (int64_t)B * ns;
-    chamfer_sym_finish_kernel<<<(unsigned)ceil_div64(total, 8), 256, 0, st>>>(res, str, keys, str_d, str_i, nr, ns, total);
+    chamfer_sym_finish_kernel<<<(unsigned)ceil_div64(total, 8), 256, 0, st>>>(res, str, keys, str_d, str_i, nr, ns, total, blk);
     S3D_LAUNCH_CHECK();
     return S3D_OK;
   }

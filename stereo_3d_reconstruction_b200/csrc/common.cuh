@@ -48,6 +48,7 @@ struct Knobs {
   int scatter_one_cta;        // S3D_SCATTER_ONE_CTA: one CTA per SM for the narrow plane-scatter layers too
   int no_conv_first_tc;       // S3D_NO_CONV_FIRST_TC: SIMT first layers (conv_first.cu) instead of the tensor-core ones
   int chamfer_sym;            // S3D_CHAMFER_SYM: 1 = symmetric one-pass Chamfer kernel at every size (given a workspace), -1 = never (0: when it fills the chip)
+  int chamfer_sym_r;          // S3D_CHAMFER_SYM_R: resident points per lane of the symmetric Chamfer kernel, 4 or 8 (0: automatic)
   int scatter_no_rm;          // S3D_SCATTER_NO_RM: residual added by the epilogue threads instead of an identity tap on the tensor core
 };
 Knobs& knobs();

@@ -42,6 +42,7 @@ const KnobName kKnobNames[] = {
     {"scatter_one_cta", "S3D_SCATTER_ONE_CTA", &Knobs::scatter_one_cta},
     {"igemm_one_cta", "S3D_IGEMM_ONE_CTA", &Knobs::igemm_one_cta},
     {"chamfer_sym", "S3D_CHAMFER_SYM", &Knobs::chamfer_sym},
+    {"chamfer_sym_r", "S3D_CHAMFER_SYM_R", &Knobs::chamfer_sym_r},
 };
 }  // namespace
 
