@@ -752,6 +752,24 @@ def run_ours(args):
         line['fp32_mode'] = guarded(extra_fp32_mode, base_cfg, B, dev, args.steps)
         line['stereo2point_chamfer'] = guarded(extra_stereo2point, base_cfg, dev, pm.get('fp32_fma_per_s'))
         line['costvolume_sweep'] = guarded(extra_costvolume_sweep, dev, pk['hbm_gbs'])
+        # HBM roofline of the path's bandwidth-bound kernels.  The shipped bf16 forward has NO kernel left that reads or writes the
+        # cost volume (the build is fused into the first aggregation layer's TMA loads, the classifier + soft-argmin into the
+        # last one's accumulators), so the headline HBM figure is the stand-alone cost-volume build of configs[4] at the default
+        # point (C = 32, D = 32, batch 64), measured live above with L2 flushed; the soft-argmin kernel at the same point and the
+        # fused classifier of the A/B forward (in-step) are reported beside it.
+        sw = line['costvolume_sweep']
+        if isinstance(sw, dict) and sw.get('points'):
+            p0 = sw['points'][0]
+            by = 2 * sw['batch'] * p0['C'] * sw['hw'][0] * sw['hw'][1] * 2 * (1 + 2 * p0['D'])
+            line['roofline_hbm_cls_fused_ab'] = line['roofline_hbm']
+            line['roofline_hbm'] = {
+                'bound': 'hbm', 'kernel': 'concat_volume_kernel (cost-volume build, C=%d, D=%d, batch %d, %dx%d; stand-alone op of '
+                                          'configs[4] -- the forward fuses it away)' % (p0['C'], p0['D'], sw['batch'], sw['hw'][0], sw['hw'][1]),
+                'achieved': by / p0['concat_ms'] / 1e6, 'peak': pk['hbm_gbs'], 'unit': 'GB/s', 'frac': by / p0['concat_ms'] / 1e6 / pk['hbm_gbs'],
+                'ms_per_launch': p0['concat_ms'], 'bytes_per_launch': by,
+                'soft_argmin_frac_isolated_launch': p0.get('softargmin_frac_hbm'),
+                'soft_argmin_frac_back_to_back': p0.get('softargmin_stream_frac_hbm'),
+                'cls_fused_in_step_frac': (line['roofline_hbm_cls_fused_ab'] or {}).get('frac')}
         line['gpu_stock_baseline'] = guarded(extra_gpu_stock_baseline, base_cfg, B, dev)
         if isinstance(line['gpu_stock_baseline'].get('bf16_autocast'), dict) and 'value' in line['gpu_stock_baseline']['bf16_autocast']:
             line['gpu_stock_baseline']['ours_over_stock_bf16'] = value / line['gpu_stock_baseline']['bf16_autocast']['value']
