@@ -18,7 +18,9 @@ __global__ void __launch_bounds__(256) k(float* sink, int iters, float a, float 
       if (KIND == 1) r[c] = __fadd_rn(r[c], a);
       if (KIND == 2) r[c] = __fmul_rn(r[c], a);
       if (KIND == 3) asm volatile("min.f32 %0, %0, %1, %2;" : "+f"(r[c]) : "f"(a), "f"(b));
-      if (KIND >= 4) {
+      if (KIND == 7) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(r[c]));
+      if (KIND == 8) asm volatile("rcp.approx.ftz.f32 %0, %0;" : "+f"(r[c]));
+      if (KIND >= 4 && KIND <= 6) {
         u64 v;
         asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "f"(r[2 * c]), "f"(r[2 * c + 1]));
         if (KIND == 4) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(v) : "l"(pa), "l"(pb));
@@ -41,12 +43,13 @@ template <int KIND> void run(const char* name, float* sink, int sms) {
   cudaEventRecord(e1);  cudaEventSynchronize(e1);
   float ms;  cudaEventElapsedTime(&ms, e0, e1);
   const double instr = (double)blocks * 256 / 32 * 8.0 * iters;       // warp instructions
-  printf("%-8s %8.3f ms  %7.2f warp-instr/clk/SM at 1.9 GHz (%.3e warp-instr/s)\n", name, ms, instr / (ms * 1e-3) / sms / 1.9e9, instr / (ms * 1e-3));
+  printf("%-9s %8.3f ms  %7.2f warp-instr/clk/SM at 1.9 GHz (%.3e warp-instr/s)\n", name, ms, instr / (ms * 1e-3) / sms / 1.9e9, instr / (ms * 1e-3));
 }
 int main() {
   int sms;  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
   float* sink;  cudaMalloc(&sink, 4);
   run<0>("FFMA", sink, sms);  run<1>("FADD", sink, sms);  run<2>("FMUL", sink, sms);  run<3>("FMNMX3", sink, sms);
+  run<7>("MUFU.EX2", sink, sms);  run<8>("MUFU.RCP", sink, sms);
   run<4>("FFMA2", sink, sms);  run<5>("FADD2", sink, sms);  run<6>("FMUL2", sink, sms);
   return 0;
 }

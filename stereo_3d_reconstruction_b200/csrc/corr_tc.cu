@@ -33,6 +33,7 @@ constexpr int kRows = 2;           // image rows per tile
 constexpr int kM = kWP * kRows;    // 128
 constexpr int kMaxStages = 6;
 constexpr int kTmemCols = kGroups * kM;   // 512
+static_assert(kGroups == 4, "the epilogue maps group g to view g & 1 and pair tiles g >> 1, g >> 1 + 2, ...");
 
 struct CorrArgs {
   float* disp;
@@ -65,7 +66,7 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap map_f, const __grid_constant_
 
   if (warp == 0 && lane == 0) ptx::prefetch_tensormap(&map_f);
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < kMaxStages; ++s) { ptx::mbar_init(&ctrl.full[s], 1); ptx::mbar_init(&ctrl.empty[s], 1); }
+    for (int s = 0; s < kMaxStages; ++s) { ptx::mbar_init(&ctrl.full[s], 1); ptx::mbar_init(&ctrl.empty[s], 2); }
     for (int b = 0; b < kGroups; ++b) { ptx::mbar_init(&ctrl.acc_full[b], 1); ptx::mbar_init(&ctrl.acc_empty[b], 128); }
     ptx::fence_barrier_init();
   }
@@ -87,43 +88,42 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap map_f, const __grid_constant_
           ptx::mbar_wait(&ctrl.empty[stage], phase ^ 1);
           uint8_t* s = smem + stage * a.stage_bytes;
           ptx::mbar_arrive_expect_tx(&ctrl.full[stage], a.stage_bytes);
-          ptx::tma_load_5d(s, &map_f, &ctrl.full[stage], ch * a.kc, 0, y0, 0, n);
-          ptx::tma_load_5d(s + a.op_bytes, &map_f, &ctrl.full[stage], ch * a.kc, 0, y0, 0, n + a.B);
+          ptx::tma_load_5d(s, &map_f, &ctrl.full[stage], ch * a.kc, 0, y0, n, 0);    // ONE box: [view][row][x][c] = L tile, R tile
           if (++stage == a.stages) { stage = 0; phase ^= 1; }
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 || warp == 2) {
+    // TWO MMA issuers, one per view (warp 1: left image is the reference, A = left rows; warp 2: right).  An item is only
+    // 2-4 MMAs, but around them sit ~800 cycles of serial barrier waits, fences and commits (clock64 timeline,
+    // profiles/r2_corr_tc_timeline.txt): with one issuer that chain, 28 items long, WAS the kernel.  Both issuers wait on the
+    // same `full` barrier of a stage and both commit to its `empty` barrier (count 2).
+    const int view = warp - 1;
     int stage = 0;  uint32_t phase = 0;
-    int buf = 0;    uint32_t acc_phase = 0;
+    int buf = view;  uint32_t acc_phase = 0;               // items alternate views: view v uses accumulator buffers v, v + 2
     const int kper = a.row_bytes >> 5;
     const uint64_t hi = ptx::make_smem_desc(0, a.row_bytes) & 0xFFFFFFFF00000000ull;
     const uint32_t smem_u = ptx::smem_u32(smem);
     for (int pt = blockIdx.x; pt < a.pair_tiles; pt += gridDim.x) {
-      int st = stage;  uint32_t ph = phase;
-      for (int view = 0; view < 2; ++view) {               // 0: left image is the reference (A = left rows), 1: right
-        ptx::mbar_wait(&ctrl.acc_empty[buf], acc_phase ^ 1);
+      ptx::mbar_wait(&ctrl.acc_empty[buf], acc_phase ^ 1);
+      const uint32_t d_tmem = tmem_base + buf * kM;
+      for (int ch = 0; ch < a.nchunks; ++ch) {
+        ptx::mbar_wait(&ctrl.full[stage], phase);
         ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + buf * kM;
-        st = stage;  ph = phase;
-        for (int ch = 0; ch < a.nchunks; ++ch) {
-          if (view == 0) { ptx::mbar_wait(&ctrl.full[st], ph);  ptx::tc_fence_after(); }
-          const uint32_t sa = smem_u + st * a.stage_bytes;
-          const uint64_t ldesc = hi | ((sa >> 4) | (1u << 16));
-          const uint64_t rdesc = hi | (((sa + a.op_bytes) >> 4) | (1u << 16));
-          if (ptx::elect_one()) {
-            for (int k = 0; k < kper; ++k)
-              ptx::mma_bf16(d_tmem, (view ? rdesc : ldesc) + 2 * k, (view ? ldesc : rdesc) + 2 * k, a.idesc, (ch | k) != 0);
-            if (view == 1) ptx::tc_commit(&ctrl.empty[st]);      // the stage is free once BOTH views have read it
-          }
-          __syncwarp();
-          if (++st == a.stages) { st = 0; ph ^= 1; }
+        const uint32_t sa = smem_u + stage * a.stage_bytes;
+        const uint64_t ldesc = hi | ((sa >> 4) | (1u << 16));
+        const uint64_t rdesc = hi | (((sa + a.op_bytes) >> 4) | (1u << 16));
+        if (ptx::elect_one()) {
+          for (int k = 0; k < kper; ++k)
+            ptx::mma_bf16(d_tmem, (view ? rdesc : ldesc) + 2 * k, (view ? ldesc : rdesc) + 2 * k, a.idesc, (ch | k) != 0);
+          ptx::tc_commit(&ctrl.empty[stage]);              // the stage is free once BOTH views have read it
+          if (ch == a.nchunks - 1) ptx::tc_commit(&ctrl.acc_full[buf]);
         }
-        if (ptx::elect_one()) ptx::tc_commit(&ctrl.acc_full[buf]);
         __syncwarp();
-        if (++buf == kGroups) { buf = 0; acc_phase ^= 1; }
+        if (++stage == a.stages) { stage = 0; phase ^= 1; }
       }
-      stage = st;  phase = ph;
+      buf += 2;
+      if (buf >= kGroups) { buf = view; acc_phase ^= 1; }
     }
   } else if (warp >= 4) {
     const int q = warp & 3;
@@ -132,39 +132,40 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap map_f, const __grid_constant_
     const int xw0 = (q & 1) * 32;              // first x of the warp
     const int D = a.D, w = a.w;
     const float scale2 = a.inv_c * 1.4426950408889634f;     // 1/C * log2(e)
-    // kGroups epilogue groups take tiles round-robin (group g owns accumulator buffer g): several warps per
-    // scheduler hide the dependent-issue latency of the softmax arithmetic.  The softmax is ONLINE over
-    // 16-column chunks so only one chunk is live in registers (<= 102 registers per thread at 640 threads).
+    // kGroups epilogue groups take the (pair tile, view) items round-robin; item i uses accumulator buffer i % 4 = its group's.
+    // With 4 groups and 2 views a group always serves the SAME view (group g: view g & 1, pair tiles g >> 1, g >> 1 + 2, ...),
+    // so everything that depends on the view -- disparity window, chunk range, closed-form tail -- is computed once per thread.
+    // (The timeline in profiles/r2_corr_tc_timeline.txt showed ~1100 cycles of serial per-item index arithmetic and a chunk
+    // loop bound by one warp's dependent-issue latency; hence: loop-invariant setup, ONE max over all columns first, then
+    // 16-way independent ex2 + four partial sums per chunk instead of an online softmax.)
     const int grp = (warp - 4) >> 2;
     const int buf = grp;  uint32_t acc_phase = 0;
-    // Per thread and view, the target columns inside the disparity window as a 64-bit mask (bit xt): the per-column test is
-    // then ONE instruction (LOP3 -> predicate).  out-of-image disparities keep cost 0 (oracle semantics): d in [dz0, D) with
+    const bool left_ref = (grp & 1) == 0;
+    // target columns this warp needs: left-ref xt in [xw0-D+1, xw0+31], right-ref xt in [xw0, xw0+31+D-1]
+    const int lo = left_ref ? max(0, xw0 - D + 1) : xw0;
+    const int hi_ = left_ref ? xw0 + 31 : min(kWP - 1, xw0 + 31 + D - 1);
+    const int c_lo = lo >> 4, c_hi = hi_ >> 4;            // 16-column chunks, warp-uniform
+    // out-of-image disparities keep cost 0 (oracle semantics): d in [dz0, D) where
     //   left-ref : x - d < 0   <=>  d > x            right-ref: x + d >= w  <=>  d >= w - x
-    const int dz0_l = min(D, x + 1), dz0_r = min(D, max(0, w - x));
-    const uint64_t ones_l = dz0_l >= 64 ? ~0ull : ((1ull << dz0_l) - 1ull), ones_r = dz0_r >= 64 ? ~0ull : ((1ull << dz0_r) - 1ull);
-    const uint64_t win_l = ones_l << (x - dz0_l + 1);          // xt in [x - dz0 + 1, x]
-    const uint64_t win_r = ones_r << x;                        // xt in [x, x + dz0 - 1]   (x < 64; empty when dz0 = 0)
-    int it = 0;
-    for (int pt = blockIdx.x; pt < a.pair_tiles; pt += gridDim.x)
-    for (int view = 0; view < 2; ++view, ++it) {
-      if (it % kGroups != grp) continue;
-      const bool left_ref = view == 0;
-      const int n = pt / a.tiles_per_img + (left_ref ? 0 : a.B), y = (pt % a.tiles_per_img) * kRows + rowblk;
-      // target columns this warp needs: left-ref xt in [xw0-D+1, xw0+31], right-ref xt in [xw0, xw0+31+D-1]
-      const int lo = left_ref ? max(0, xw0 - D + 1) : xw0;
-      const int hi_ = left_ref ? xw0 + 31 : min(kWP - 1, xw0 + 31 + D - 1);
-      const int c_lo = lo >> 4, c_hi = hi_ >> 4;          // 16-column chunks, warp-uniform
-      const int dz0 = left_ref ? dz0_l : dz0_r;
-      const uint64_t win = left_ref ? win_l : win_r;
-      // base-2 exponent domain: v = S * log2(e)/C.  The running max starts at a finite floor so no (-inf) - (-inf) can occur.
-      float m = dz0 < D ? 0.f : -1e30f;
-      float s = 0.f, tx = 0.f;                             // sum e, sum e * xt  (xt is a compile-time column index)
+    const int dz0 = left_ref ? min(D, x + 1) : min(D, max(0, w - x));
+    // the target columns inside the window as a 64-bit mask (bit xt): left xt in [x - dz0 + 1, x], right xt in [x, x + dz0 - 1]
+    const uint64_t ones = dz0 >= 64 ? ~0ull : ((1ull << dz0) - 1ull);
+    const uint64_t win = left_ref ? ones << (x - dz0 + 1) : ones << x;
+    const float m0 = dz0 < D ? 0.f : -1e30f;               // the zero-cost tail takes part in the max; else a finite floor
+    const float tail_cnt = (float)(D - dz0), tail_d = 0.5f * (float)(dz0 + D - 1);
+    const float xs = left_ref ? (float)x : -(float)x, sgn = left_ref ? -1.f : 1.f;
+    const uint32_t taddr = tmem_base + buf * kM + rowblk * kWP + (static_cast<uint32_t>(q * 32) << 16);
+    // image / row of this group's first pair tile, advanced incrementally (no division in the loop)
+    const int step = 2 * (int)gridDim.x;
+    const int step_img = step / a.tiles_per_img, step_row = step % a.tiles_per_img;
+    int pt = blockIdx.x + (grp >> 1) * gridDim.x;
+    int img = pt / a.tiles_per_img, yt = pt % a.tiles_per_img;
+    for (; pt < a.pair_tiles; pt += step) {
+      const int n = img + (left_ref ? 0 : a.B), y = yt * kRows + rowblk;
       ptx::mbar_wait(&ctrl.acc_full[buf], acc_phase);
       ptx::tc_fence_after();
-      const uint32_t taddr = tmem_base + buf * kM + rowblk * kWP + (static_cast<uint32_t>(q * 32) << 16);
-      // All the columns this warp needs go to registers first and the accumulator buffer is handed back AT ONCE: the MMA of
-      // the group's next tile (4 tiles ahead) then runs under this tile's softmax instead of after it (ncu: the epilogue warps
-      // spent most of their time waiting on acc_full with the buffer held through the arithmetic).
+      // all the columns this warp needs go to registers and the accumulator buffer is handed back at once: the MMA of the
+      // group's next item then runs under this item's arithmetic
       uint32_t u[4][16];
 #pragma unroll
       for (int c = 0; c < 4; ++c)
@@ -172,34 +173,54 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap map_f, const __grid_constant_
       ptx::tmem_ld_wait();
       ptx::tc_fence_before();
       ptx::mbar_arrive(&ctrl.acc_empty[buf]);
+      acc_phase ^= 1;
+      // pass 1: columns outside the window become -inf (they drop out of the max, and ex2(-inf * scale2 - m) = 0); one max
+      float mx = -INFINITY;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         if (c >= c_lo && c <= c_hi) {
           const uint32_t mb = (uint32_t)(win >> (16 * c));
-          // columns outside the window become -inf ONCE (they drop out of the max, and ex2(-inf * scale2 - m) = 0 needs no predicate)
-          float v[16];
-          float cm = -INFINITY;
-#pragma unroll
-          for (int i = 0; i < 16; ++i) { v[i] = (mb >> i) & 1u ? __uint_as_float(u[c][i]) : -INFINITY;  cm = fmaxf(cm, v[i]); }
-          const float mn = fmaxf(m, cm * scale2);          // scale2 > 0: max commutes with the scaling
-          const float sc = ex2_approx(m - mn);
-          s *= sc;  tx *= sc;  m = mn;
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const float e = ex2_approx(fmaf(v[i], scale2, -m));
-            s += e;
-            tx = fmaf(e, (float)(c * 16 + i), tx);
+            const float v = (mb >> i) & 1u ? __uint_as_float(u[c][i]) : -INFINITY;
+            u[c][i] = __float_as_uint(v);
+            mx = fmaxf(mx, v);
           }
         }
       }
-      acc_phase ^= 1;
-      float t = left_ref ? fmaf((float)x, s, -tx) : fmaf(-(float)x, s, tx);     // sum e * d
-      if (dz0 < D) {                                       // (D - dz0) terms of cost 0 at d = dz0 .. D-1
-        const float e0 = ex2_approx(-m), cnt = (float)(D - dz0);
-        s += e0 * cnt;
-        t += e0 * cnt * 0.5f * (float)(dz0 + D - 1);
+      const float m = fmaxf(m0, mx * scale2);               // scale2 > 0: max commutes with the scaling
+      // pass 2: base-2 exponentials IN PLACE, the 16 MUFU.EX2 of a chunk issued back to back (volatile: ptxas otherwise sinks
+      // each one next to its consumer -- with 64 accumulator values live it has no spare registers to look ahead -- and the warp
+      // stalls on every MUFU result); chunk c's sums are taken while chunk c+1's exponentials are in flight
+      float s4[4] = {0.f, 0.f, 0.f, 0.f}, t4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int c = 0; c <= 4; ++c) {
+        if (c < 4 && c >= c_lo && c <= c_hi) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) u[c][i] = __float_as_uint(fmaf(__uint_as_float(u[c][i]), scale2, -m));
+#pragma unroll
+          for (int i = 0; i < 16; ++i) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+r"(u[c][i]));
+        }
+        if (c >= 1 && c - 1 >= c_lo && c - 1 <= c_hi) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float e = __uint_as_float(u[c - 1][i]);
+            s4[i & 3] += e;
+            t4[i & 3] = fmaf(e, (float)((c - 1) * 16 + i), t4[i & 3]);
+          }
+        }
       }
-      if (x < w && y < a.h) a.disp[((int64_t)n * a.h + y) * w + x] = t / s;
+      float s = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+      const float tx = (t4[0] + t4[1]) + (t4[2] + t4[3]);
+      float t = fmaf(xs, s, sgn * tx);                      // sum e * d  (d = x - xt for the left view, xt - x for the right)
+      if (dz0 < D) {                                        // (D - dz0) terms of cost 0 at d = dz0 .. D-1
+        const float e0 = ex2_approx(-m) * tail_cnt;
+        s += e0;
+        t = fmaf(e0, tail_d, t);
+      }
+      if (x < w && y < a.h) a.disp[((int64_t)n * a.h + y) * w + x] = __fdividef(t, s);
+      img += step_img;  yt += step_row;
+      if (yt >= a.tiles_per_img) { yt -= a.tiles_per_img;  ++img; }
     }
   }
 
@@ -239,9 +260,12 @@ int corr_tc_launch(const void* feat, float* disp, int B, int h, int w, int C, in
   const CUtensorMapSwizzle sw = a.row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                               : a.row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
   CUtensorMap map_f;
-  cuuint32_t box[5] = {(cuuint32_t)a.kc, kWP, kRows, 1, 1};
+  // feat [2B, h, w, C] seen as (C, w, h, pair, view): one box {kc, 64, 2 rows, 1, 2 views} fetches the left AND the right rows of
+  // a pair tile -- issuing a tiled TMA costs the producer thread ~390 cycles whatever its size (clock64 timeline), so the op
+  // count per CTA, not the bytes, set the pace of the loads
+  cuuint32_t box[5] = {(cuuint32_t)a.kc, kWP, kRows, 1, 2};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  int rc = encode_act_map(&map_f, feat, 2, false, C, w, h, 1, 2 * B, box, estr, sw);
+  int rc = encode_act_map(&map_f, feat, 2, false, C, w, h, B, 2, box, estr, sw);
   if (rc != S3D_OK) return rc;
   const int smem_bytes = a.stages * a.stage_bytes + 1024;
   S3D_CUDA(cudaFuncSetAttribute(corr_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
