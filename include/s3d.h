@@ -154,6 +154,17 @@ int s3d_conv_concat_volume(const S3dConvParams* p, const void* feat, int feat_pi
  * the fp32 accumulation order (NOT bit-identical). */
 int s3d_conv_concat_volume_ro(const S3dConvParams* p, const void* feat, int feat_pitch, int feat_pad, const void* w_refonce,
                               const float* bias, void* out, void* stream);
+/* The same layer in SHEARED form (bf16, Cout = 64, ReLU): in the coordinate u = x -/+ d the target half of the volume is
+ * the same feature map on every plane, so the layer is a few 2-D convolutions (maps, computed by s3d_conv_igemm from
+ * weight sets packed by the host: layers.py, PackedConv.gonce_convs) and this streaming pass, which adds
+ *   bias + Psum[y,x] + G[y,u]  (+ the dz = -1 / +1 maps on the two border planes, + the edge-column maps at x = w-1 / 0),
+ * applies the ReLU and writes out bf16 [2B,D,h,w,64] (left-referenced volumes first).  maps_l / maps_r: fp32
+ * [B,h,map_w = w+4,384] from the left / right images, channels [Psum | Pm | Pp | G | Hm | Hp], map column j <-> u = j-2;
+ * a volume takes its reference maps from its own image and its target maps from the other one.  edge_l / edge_r: fp32
+ * [B,h,D,192] = [Ge | Gem | Gep].  Not bit-identical to s3d_conv_concat_volume (weights summed before the bf16 rounding,
+ * different summation order). */
+int s3d_concat_gonce_assemble(const float* maps_l, const float* maps_r, const float* edge_l, const float* edge_r,
+                              const float* bias, void* out, int B, int D, int h, int w, int map_w, void* stream);
 /* feat: [2B,1,h,w,C] (left maps first, then right).  vol: [2B,D,h,w,2C]; entries [0,B) are
  * left-referenced (target sampled at x-d), [B,2B) right-referenced (target at x+d).
  * dtype BF16X2: feat [.., hi(C) | lo(C)] -> vol [.., hi(2C) | lo(2C)] (C logical channels). */

@@ -192,6 +192,74 @@ class PackedConv:
             self._cache[key] = to_storage(ro.view(27, self.cout_pad, C), self.dtype_code).to(self.weight.device).contiguous()
         return self._cache[key]
 
+    def gonce_convs(self, C, pad, w, D):
+        """The 2-D map convolutions of the SHEARED form of the concat cost volume + this 3x3x3 layer (bf16, include/s3d.h,
+        s3d_concat_gonce_assemble).  With u = x - d (left reference; x + d for the right one) the target half of the volume is
+        tgt[y, u] on EVERY disparity plane, so its contribution is a 2-D map G[a, y, u] = sum_{dz,dy,dx,c} W[a, C+c, dz, dy, dx]
+        tgt[c, y+dy, u+dx-dz] read at a position that slides with d, and the reference half is the same map P on every plane:
+            out[a, d, y, x] = relu(bias + P[y, x] + G[y, x -/+ d])        (+ border-plane and edge-column maps)
+        i.e. the layer is a handful of 2-D convolutions (1/14 of its MMAs) plus a streaming pass that writes the volume.
+        Returns {'left', 'right': map convs over the zero-margined feature rows of the left / right images
+        -> fp32 [B,1,h,w+4,384] = [Psum | -P(dz=-1) | -P(dz=+1) | G | -H(dz=-1) | -H(dz=+1)], map column j <-> u = j - 2;
+        'edge_left', 'edge_right': -> fp32 [B,1,h,D,192] = [Ge | +Ge(dz=-1) | +Ge(dz=+1)], the in-plane taps that reach
+        past the image edge (x' = w for the left-referenced volumes, -1 for the right-referenced ones): the volume is zero
+        there but the sheared map reads a real target pixel}.  Weights are summed in fp32 and rounded to bf16 ONCE (like the
+        reference-once kernel's sum over kz): same result as the fused layer up to that rounding and the summation order."""
+        key = ('gonce', C, pad, w, D)
+        if key in self._cache:
+            return self._cache[key]
+        assert self.ntaps == 27 and self.n_classes == 1 and self.cin == 2 * C and self.dtype_code == _lib.DTYPE_BF16
+        A = self.cout
+        Ap = self.cout_pad
+        W = self._ctor[0].view(3, 3, 3, A, 2 * C)                 # [kz, ky, kx, a, c]
+        Wl, Wr = W[..., :C], W[..., C:]
+        dev = self.weight.device
+        P = w + 2 * pad
+        assert pad >= 2 and pad + w - D + 2 <= 127, 'tap offsets are int8'
+        out = {}
+        es = (-2, -1, 0, 1, 2)
+        for name, sgn in (('left', 1), ('right', -1)):            # left images are the targets of the right-referenced volumes
+            rows = torch.zeros(15, 6 * Ap, C)
+            for iy in range(3):
+                for ie, e in enumerate(es):
+                    r = rows[iy * 5 + ie]
+                    if -1 <= e <= 1:                              # reference maps: plain 3x3, dx = e
+                        r[0 * Ap:0 * Ap + A] = Wl[:, iy, e + 1].sum(0)
+                        r[1 * Ap:1 * Ap + A] = -Wl[0, iy, e + 1]
+                        r[2 * Ap:2 * Ap + A] = -Wl[2, iy, e + 1]
+                    for kz in range(3):                           # target maps: tap (dz, dx) lands on e = dx + sgn * dz
+                        dx = e - sgn * (kz - 1)
+                        if -1 <= dx <= 1:
+                            r[3 * Ap:3 * Ap + A] += Wr[kz, iy, dx + 1]
+                            if kz == 0:
+                                r[4 * Ap:4 * Ap + A] -= Wr[kz, iy, dx + 1]
+                            if kz == 2:
+                                r[5 * Ap:5 * Ap + A] -= Wr[kz, iy, dx + 1]
+            taps = [[(0, dy, e + pad - 2) for dy in (-1, 0, 1) for e in es]]
+            out[name] = PackedConv(rows, torch.zeros(6 * Ap), taps, (1, 1, 1), (1, 1, 1), C, 6 * Ap, _lib.ACT_NONE, 0.0,
+                                   self.dtype_code, dev, ksize=(1, 3, P - (w + 4) + 1), pad=(0, 1, 0))
+            # edge column: left-referenced volumes (targets = RIGHT images, sgn = -1): x = w-1, dx = +1, u = w-1-d;
+            #              right-referenced volumes (targets = LEFT images, sgn = +1): x = 0, dx = -1, u = d
+            dxe = -1 if name == 'left' else 1
+            rows = torch.zeros(9, 3 * Ap, C)
+            for iy in range(3):
+                for kz in range(3):
+                    e = dxe + sgn * (kz - 1)                      # left images: e in {-2,-1,0}; right images: e in {0,1,2}
+                    ie = e + 2 if name == 'left' else e
+                    r = rows[iy * 3 + ie]
+                    r[0:A] -= Wr[kz, iy, dxe + 1]
+                    if kz == 0:
+                        r[Ap:Ap + A] += Wr[kz, iy, dxe + 1]
+                    if kz == 2:
+                        r[2 * Ap:2 * Ap + A] += Wr[kz, iy, dxe + 1]
+            # output column j <-> u = j (left images) / u = w - D + j (right images); strip tap ie reads u + ie - 2 / u + ie
+            off = (pad - 2) if name == 'left' else (pad + w - D)
+            taps = [[(0, dy, ie + off) for dy in (-1, 0, 1) for ie in range(3)]]
+            out['edge_' + name] = PackedConv(rows, torch.zeros(3 * Ap), taps, (1, 1, 1), (1, 1, 1), C, 3 * Ap, _lib.ACT_NONE, 0.0,
+                                             self.dtype_code, dev, ksize=(1, 3, P - D + 1), pad=(0, 1, 0))
+        self._cache[key] = out
+        return out
+
     # ---- constructors ------------------------------------------------------------------
     @classmethod
     def from_conv(cls, conv, bn, act, dtype_code, device, act_param=0.0):

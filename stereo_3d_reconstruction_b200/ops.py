@@ -227,6 +227,39 @@ def conv_concat_volume(pc, featp, B, D, pad, out=None, ref_once=False):
     return out
 
 
+def conv_concat_volume_sheared(pc, featp, B, D, pad, out=None, bufs=None):
+    """Concat cost volume + the 3x3x3 layer `pc` in SHEARED form (bf16, Cout 64, ReLU): four 2-D map convolutions on the
+    tensor cores (1/14 of the layer's MMAs) + one streaming pass that writes the volume (include/s3d.h,
+    s3d_concat_gonce_assemble; layers.py, PackedConv.gonce_convs).  featp as for conv_concat_volume.  bufs: optional dict of
+    persistent fp32 workspaces {'maps_l', 'maps_r': [B,1,h,w+4,384], 'edge_l', 'edge_r': [B,1,h,D,192]}."""
+    _chk(featp, out)
+    n2, one, h, pitch, C = featp.shape
+    assert n2 == 2 * B and one == 1 and featp.is_contiguous() and featp.dtype == torch.bfloat16
+    assert pc.cin_pad == 2 * C and pc.cout_pad == 64 and pc.act == _lib.ACT_RELU and pad >= D - 1 and D >= 2
+    w = pitch - 2 * pad
+    g = pc.gonce_convs(C, pad, w, D)
+    bufs = {} if bufs is None else bufs
+    res = {}
+    for name, key, sl in (('left', 'maps_l', slice(0, B)), ('right', 'maps_r', slice(B, 2 * B)),
+                          ('edge_left', 'edge_l', slice(0, B)), ('edge_right', 'edge_r', slice(B, 2 * B))):
+        conv = g[name]
+        ow = w + 4 if key.startswith('maps') else D
+        o = bufs.get(key)
+        if o is None:
+            o = torch.empty((B, 1, h, ow, conv.cout_pad), dtype=torch.float32, device=featp.device)
+        assert o.shape == (B, 1, h, ow, conv.cout_pad) and o.dtype == torch.float32 and o.is_contiguous()
+        res[key] = conv(featp[sl], out=o)
+    if out is None:
+        out = torch.empty((2 * B, D, h, w, 64), dtype=torch.bfloat16, device=featp.device)
+    assert out.is_contiguous() and out.shape == (2 * B, D, h, w, 64) and out.dtype == torch.bfloat16
+    rc = _lib.load().s3d_concat_gonce_assemble(res['maps_l'].data_ptr(), res['maps_r'].data_ptr(), res['edge_l'].data_ptr(),
+                                               res['edge_r'].data_ptr(), pc.bias.data_ptr(), out.data_ptr(), B, D, h, w, w + 4,
+                                               _stream())
+    _lib.check(rc, 's3d_concat_gonce_assemble')
+    _lib.count_launch()
+    return out
+
+
 def cls_soft_argmin(x, w_taps, sign=-1.0, out=None):
     """x bf16 [N,D,h,w,C] (aggregated volume), w_taps bf16 [32,C] (27 classifier taps) -> disp fp32 [N,h,w]: the Cout=1
     3x3x3 classifier and the soft-argmin in one pass (include/s3d.h, s3d_cls_soft_argmin)."""

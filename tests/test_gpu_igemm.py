@@ -291,6 +291,50 @@ def test_conv_concat_volume_ref_once(B, C, D, h, w):
         assert ez <= 2 * TOL['bf16'] * (ref[:, z].abs().max().item() + 1e-6), (z, ez)
 
 
+@pytest.mark.parametrize('B,C,D,h,w', [
+    (1, 32, 32, 64, 64),       # one stereo pair at the benchmark shape
+    (2, 32, 8, 16, 24),
+    (1, 16, 5, 9, 13),         # ragged row blocks, 16 feature channels
+    (2, 32, 2, 8, 8),          # two planes: both border corrections on neighbouring planes
+    (1, 32, 12, 8, 8),         # more disparities than pixels in a row: most target reads fall into the zero margin
+    (3, 32, 16, 33, 40),       # rows longer than one 32-pixel block, odd height
+])
+def test_conv_concat_volume_sheared(B, C, D, h, w):
+    """SHEARED form of the cost volume + first aggregation layer (ops.conv_concat_volume_sheared: 2-D map convolutions on the
+    generic engine + s3d_concat_gonce_assemble): same result as conv3d over the oracle's concat volume on bf16-rounded
+    operands, and as the bit-exact fused kernel, within the bound of the reference-once form (weights summed before the bf16
+    rounding); every border plane and both edge columns checked on their own."""
+    from stereo_3d_reconstruction_b200 import ops
+    from oracle import models as O
+    cout = 64
+    torch.manual_seed(12)
+    conv = _qmod(nn.Conv3d(2 * C, cout, 3, 1, 1, bias=True), 'bf16')
+    pc = PackedConv.from_conv(conv, None, lib.ACT_RELU, _code('bf16'), 'cuda')
+    f = _q(torch.randn(2 * B, C, h, w), 'bf16')
+    feat = to_cl(f).to(torch.bfloat16).cuda()
+    pad, P = max(D, 4), w + 2 * max(D, 4)
+    featp = torch.zeros(2 * B, 1, h, P, C, dtype=torch.bfloat16, device='cuda')
+    featp[:, :, :, pad:pad + w] = feat
+    got = ops.conv_concat_volume_sheared(pc, featp, B, D, pad)
+    exact = ops.conv_concat_volume(pc, featp, B, D, pad)
+    torch.cuda.synchronize()
+    assert got.shape == exact.shape
+    scale = exact.float().abs().max().item() + 1e-6
+    assert (got.float() - exact.float()).abs().max().item() <= 2 * TOL['bf16'] * scale
+    fr = feat.float().cpu()[:, 0].permute(0, 3, 1, 2)
+    ref_vol = torch.cat([O.build_concat_volume(fr[:B], fr[B:], D, -1), O.build_concat_volume(fr[B:], fr[:B], D, +1)], 0)
+    with torch.no_grad():
+        ref = to_cl(F.relu(conv(ref_vol)))
+    g = got.float().cpu()[..., :cout]
+    assert (g - ref).abs().max().item() <= 2 * TOL['bf16'] * (ref.abs().max().item() + 1e-6)
+    for z in sorted({0, 1, D // 2, D - 2, D - 1} & set(range(D))):
+        ez = (g[:, z] - ref[:, z]).abs().max().item()
+        assert ez <= 2 * TOL['bf16'] * (ref[:, z].abs().max().item() + 1e-6), (z, ez)
+    for x in (0, 1, w - 2, w - 1):                      # the edge-column maps (x = w-1 left-referenced, x = 0 right-referenced)
+        ex = (g[:, :, :, x] - ref[:, :, :, x]).abs().max().item()
+        assert ex <= 2 * TOL['bf16'] * (ref[:, :, :, x].abs().max().item() + 1e-6), (x, ex)
+
+
 @pytest.mark.parametrize('nz', [0, 2, 3, 5, 8])
 @pytest.mark.parametrize('prec,N,cin,cout,D,H,W,res', [
     ('bf16', 1, 64, 64, 32, 64, 64, False),      # the aggregation layer at batch 1: 32 columns -> 4 chunks of 8 planes
