@@ -603,6 +603,32 @@ def run_ours(args):
         return r
 
     _ops.conv_concat_volume = hooked_ccv
+    orig_ccs = _ops.conv_concat_volume_sheared       # the same layer in sheared form: 4 map convolutions + the streaming pass
+
+    def hooked_ccs(*a_, **kw):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        r = orig_ccs(*a_, **kw)
+        b.record()
+        agg_events['dres0a'].append((a, b))
+        return r
+
+    _ops.conv_concat_volume_sheared = hooked_ccs
+    # the streaming pass of that form (gonce_assemble_kernel) is the forward's HBM-bound kernel: it reads the fp32 maps once and
+    # writes the bf16 volume.  Timed through the library handle, on the launching stream, inside the steps.
+    L_ = lib.load()
+    orig_asm = L_.s3d_concat_gonce_assemble
+    asm_events = []
+
+    def hooked_asm(ml, mr, el, er, bias, out, B_, D_, h_, w_, mw_, st):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        rc = orig_asm(ml, mr, el, er, bias, out, B_, D_, h_, w_, mw_, st)
+        b.record()
+        asm_events.append((a, b, 2 * B_ * D_ * h_ * w_ * 64 * 2 + 2 * B_ * h_ * (mw_ * 384 + D_ * 256) * 4))
+        return rc
+
+    L_.s3d_concat_gonce_assemble = hooked_asm
     orig_chain = _ops.conv_cls_soft_argmin           # cls_a + classifier + soft-argmin (two launches: the march, the combine)
 
     def hooked_chain(*a_, **kw):
@@ -621,7 +647,10 @@ def run_ours(args):
     n_dom = len(dom_events) // (args.steps + args.warmup)                 # plain aggregation launches per step
     dom_ms = [a.elapsed_time(b) for a, b in dom_events[n_dom * args.warmup:]]
     _ops.conv_concat_volume = orig_ccv
+    _ops.conv_concat_volume_sheared = orig_ccs
+    L_.s3d_concat_gonce_assemble = orig_asm
     _ops.conv_cls_soft_argmin = orig_chain
+    asm_t = [(a.elapsed_time(b), nb) for a, b, nb in asm_events[args.warmup:]]
     # The shipped forward no longer has an HBM-bound classifier kernel (csrc/conv_scatter_cls.cu never writes the volume it would
     # read).  The stand-alone one-pass classifier + soft-argmin (cls_fused_kernel) is still the path of other layer shapes: time
     # it the same way, inside steps of the A/B forward that writes cls_a's output and reads it back.
@@ -706,8 +735,9 @@ def run_ours(args):
                      # power cap allows (ncu: 96.7 % tensor-pipe active) and draws less than cuBLAS, hence frac > 1 above
                      'peak_burst': pk['bf16_tflops'], 'frac_of_burst': achieved / pk['bf16_tflops'],
                      'ms_per_launch': dom, 'flops_per_launch': flops, 'share_of_step': dom * n_dom / (ms / args.steps),
-                     # the other aggregation launches: dres0a = cost volume + first layer in reference-once form (half the MMAs of
-                     # the layer, csrc/conv_scatter_concat.cu), dres1b = the residual layer (residual added as an identity tap on
+                     # the other aggregation launches: dres0a = cost volume + first layer in sheared form (four 2-D map convolutions,
+                     # csrc/map_conv.cu, + the streaming pass csrc/concat_gonce.cu: five launches; knob no_sheared: the reference-once
+                     # tensor-core kernel, csrc/conv_scatter_concat.cu), dres1b = the residual layer (residual added as an identity tap on
                      # the tensor core, +6 % MMAs, csrc/conv_scatter_rm.cu), cls_chain = cls_a + classifier + soft-argmin with the
                      # projections on the tensor core (+4.6 % MMAs, its output volume never written; csrc/conv_scatter_cls.cu,
                      # both of its launches); share of all five layers in the step
@@ -717,7 +747,15 @@ def run_ours(args):
                      # dram__bytes_read.sum + dram__bytes_write.sum = 4.281e9 against 4.295e9 algorithmic bytes (profiles/r1_ncu_summary.md)
                      'traffic': None, 'traffic_source': 'profiles/r1_ncu_summary.md (ncu capture, not live)',
                      'algorithmic_bytes_per_launch': 2 * (2 * B) * D * h * w * pc.cin * 2},
-        'roofline_hbm': None if not cls_t else {
+        # the forward's own HBM-bound kernel: the streaming pass of the sheared first aggregation layer (csrc/concat_gonce.cu),
+        # measured in the steps; algorithmic bytes = the bf16 volume written + the fp32 maps read once
+        'roofline_hbm': None if not asm_t else {
+            'bound': 'hbm', 'kernel': 'gonce_assemble_kernel (cost volume + first aggregation layer, sheared form: adds two maps per '
+                                      'output element, ReLU, writes the bf16 volume)',
+            'achieved': asm_t[0][1] / (sum(t for t, _ in asm_t) / len(asm_t) / 1e3) / 1e9, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
+            'frac': asm_t[0][1] / (sum(t for t, _ in asm_t) / len(asm_t) / 1e3) / 1e9 / pk['hbm_gbs'],
+            'ms_per_launch': sum(t for t, _ in asm_t) / len(asm_t), 'bytes_per_launch': asm_t[0][1]},
+        'roofline_hbm_cls_fused_ab': None if not cls_t else {
             'bound': 'hbm', 'kernel': 'cls_fused_kernel (Cout=1 3x3x3 classifier + soft-argmin, one pass over the aggregated volume)'
                                       + (' -- measured inside steps of the A/B forward (knob no_cls_chain): the shipped forward fuses the '
                                          'classifier into cls_a and has no kernel that reads the volume' if cls_ab else ''),
@@ -752,24 +790,18 @@ def run_ours(args):
         line['fp32_mode'] = guarded(extra_fp32_mode, base_cfg, B, dev, args.steps)
         line['stereo2point_chamfer'] = guarded(extra_stereo2point, base_cfg, dev, pm.get('fp32_fma_per_s'))
         line['costvolume_sweep'] = guarded(extra_costvolume_sweep, dev, pk['hbm_gbs'])
-        # HBM roofline of the path's bandwidth-bound kernels.  The shipped bf16 forward has NO kernel left that reads or writes the
-        # cost volume (the build is fused into the first aggregation layer's TMA loads, the classifier + soft-argmin into the
-        # last one's accumulators), so the headline HBM figure is the stand-alone cost-volume build of configs[4] at the default
-        # point (C = 32, D = 32, batch 64), measured live above with L2 flushed; the soft-argmin kernel at the same point and the
-        # fused classifier of the A/B forward (in-step) are reported beside it.
+        # stand-alone HBM-bound ops of configs[4] at the default point (C = 32, D = 32, batch 64), measured live above with L2 flushed
         sw = line['costvolume_sweep']
         if isinstance(sw, dict) and sw.get('points'):
             p0 = sw['points'][0]
             by = 2 * sw['batch'] * p0['C'] * sw['hw'][0] * sw['hw'][1] * 2 * (1 + 2 * p0['D'])
-            line['roofline_hbm_cls_fused_ab'] = line['roofline_hbm']
-            line['roofline_hbm'] = {
+            line['roofline_hbm_standalone'] = {
                 'bound': 'hbm', 'kernel': 'concat_volume_kernel (cost-volume build, C=%d, D=%d, batch %d, %dx%d; stand-alone op of '
-                                          'configs[4] -- the forward fuses it away)' % (p0['C'], p0['D'], sw['batch'], sw['hw'][0], sw['hw'][1]),
+                                          'configs[4] -- the forward never materialises the volume)' % (p0['C'], p0['D'], sw['batch'], sw['hw'][0], sw['hw'][1]),
                 'achieved': by / p0['concat_ms'] / 1e6, 'peak': pk['hbm_gbs'], 'unit': 'GB/s', 'frac': by / p0['concat_ms'] / 1e6 / pk['hbm_gbs'],
                 'ms_per_launch': p0['concat_ms'], 'bytes_per_launch': by,
                 'soft_argmin_frac_isolated_launch': p0.get('softargmin_frac_hbm'),
-                'soft_argmin_frac_back_to_back': p0.get('softargmin_stream_frac_hbm'),
-                'cls_fused_in_step_frac': (line['roofline_hbm_cls_fused_ab'] or {}).get('frac')}
+                'soft_argmin_frac_back_to_back': p0.get('softargmin_stream_frac_hbm')}
         line['gpu_stock_baseline'] = guarded(extra_gpu_stock_baseline, base_cfg, B, dev)
         if isinstance(line['gpu_stock_baseline'].get('bf16_autocast'), dict) and 'value' in line['gpu_stock_baseline']['bf16_autocast']:
             line['gpu_stock_baseline']['ours_over_stock_bf16'] = value / line['gpu_stock_baseline']['bf16_autocast']['value']

@@ -16,7 +16,7 @@ namespace s3d {
 namespace {
 
 constexpr int kMaps = 6 * 64;      // channels of a map pixel: [Psum | Pm | Pp | G | Hm | Hp]
-constexpr int kEdge = 3 * 64;      //                 edge map: [Ge | Gem | Gep]
+constexpr int kEdge = 4 * 64;      //                 edge map: [Ge | Gem | Gep | unused]
 
 __device__ __forceinline__ void add8(float (&v)[8], const float* __restrict__ p) {
   const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);

@@ -201,7 +201,7 @@ class PackedConv:
         i.e. the layer is a handful of 2-D convolutions (1/14 of its MMAs) plus a streaming pass that writes the volume.
         Returns {'left', 'right': map convs over the zero-margined feature rows of the left / right images
         -> fp32 [B,1,h,w+4,384] = [Psum | -P(dz=-1) | -P(dz=+1) | G | -H(dz=-1) | -H(dz=+1)], map column j <-> u = j - 2;
-        'edge_left', 'edge_right': -> fp32 [B,1,h,D,192] = [Ge | +Ge(dz=-1) | +Ge(dz=+1)], the in-plane taps that reach
+        'edge_left', 'edge_right': -> fp32 [B,1,h,D,256] = [Ge | +Ge(dz=-1) | +Ge(dz=+1) | 0], the in-plane taps that reach
         past the image edge (x' = w for the left-referenced volumes, -1 for the right-referenced ones): the volume is zero
         there but the sheared map reads a real target pixel}.  Weights are summed in fp32 and rounded to bf16 ONCE (like the
         reference-once kernel's sum over kz): same result as the fused layer up to that rounding and the summation order."""
@@ -236,12 +236,13 @@ class PackedConv:
                             if kz == 2:
                                 r[5 * Ap:5 * Ap + A] -= Wr[kz, iy, dx + 1]
             taps = [[(0, dy, e + pad - 2) for dy in (-1, 0, 1) for e in es]]
+            out[name + '_geom'] = (pad - 4, 5, w + 4)             # (input column of output column 0 / tap 0, taps per row, output width)
             out[name] = PackedConv(rows, torch.zeros(6 * Ap), taps, (1, 1, 1), (1, 1, 1), C, 6 * Ap, _lib.ACT_NONE, 0.0,
                                    self.dtype_code, dev, ksize=(1, 3, P - (w + 4) + 1), pad=(0, 1, 0))
             # edge column: left-referenced volumes (targets = RIGHT images, sgn = -1): x = w-1, dx = +1, u = w-1-d;
             #              right-referenced volumes (targets = LEFT images, sgn = +1): x = 0, dx = -1, u = d
             dxe = -1 if name == 'left' else 1
-            rows = torch.zeros(9, 3 * Ap, C)
+            rows = torch.zeros(9, 4 * Ap, C)                      # 4th block zero: s3d_map_conv works in chunks of 128 channels
             for iy in range(3):
                 for kz in range(3):
                     e = dxe + sgn * (kz - 1)                      # left images: e in {-2,-1,0}; right images: e in {0,1,2}
@@ -255,7 +256,8 @@ class PackedConv:
             # output column j <-> u = j (left images) / u = w - D + j (right images); strip tap ie reads u + ie - 2 / u + ie
             off = (pad - 2) if name == 'left' else (pad + w - D)
             taps = [[(0, dy, ie + off) for dy in (-1, 0, 1) for ie in range(3)]]
-            out['edge_' + name] = PackedConv(rows, torch.zeros(3 * Ap), taps, (1, 1, 1), (1, 1, 1), C, 3 * Ap, _lib.ACT_NONE, 0.0,
+            out['edge_' + name + '_geom'] = (off, 3, D)
+            out['edge_' + name] = PackedConv(rows, torch.zeros(4 * Ap), taps, (1, 1, 1), (1, 1, 1), C, 4 * Ap, _lib.ACT_NONE, 0.0,
                                              self.dtype_code, dev, ksize=(1, 3, P - D + 1), pad=(0, 1, 0))
         self._cache[key] = out
         return out

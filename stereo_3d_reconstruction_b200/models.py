@@ -309,14 +309,16 @@ class _StereoBase(nn.Module):
                 # on the target half only (half the tensor-core work of this layer; csrc/conv_scatter_concat.cu)
                 ro = ro_split or (self.precision == 'bf16' and p0.cout_pad == 64 and p0.act == _lib.ACT_RELU and
                                   not _lib.KNOBS['no_ref_once'])
-                if (ro and not self._split and _lib.KNOBS['sheared'] and D >= 2 and pad >= 4 and pad + w - D + 2 <= 127):
-                    # opt-in A/B path (S3D_SHEARED): the layer as 2-D map convolutions + one streaming pass (ops.py,
-                    # conv_concat_volume_sheared).  1/14 of the MMAs, but the generic engine pays a TMA round trip per tap
-                    # and map tile: 1.23 ms against the reference-once kernel's 1.15 ms at batch 64
+                if (ro and not self._split and C == 32 and not _lib.KNOBS['no_sheared'] and D >= 2 and pad >= 4 and
+                        pad + w - D + 2 <= 127):
+                    # SHEARED form: in u = x -/+ d the target half of the volume is the same map on every plane, so the layer is
+                    # four 2-D map convolutions (csrc/map_conv.cu: 1/14 of the layer's MMAs) + one streaming pass that adds two
+                    # maps per output element and writes the volume (csrc/concat_gonce.cu): 0.79 ms against 1.15 ms for the
+                    # reference-once kernel at batch 64 (A/B knob no_sheared)
                     bufs = {'maps_l': self._buf('sh_ml', (B, 1, h, w + 4, 384), torch.float32),
                             'maps_r': self._buf('sh_mr', (B, 1, h, w + 4, 384), torch.float32),
-                            'edge_l': self._buf('sh_el', (B, 1, h, D, 192), torch.float32),
-                            'edge_r': self._buf('sh_er', (B, 1, h, D, 192), torch.float32)}
+                            'edge_l': self._buf('sh_el', (B, 1, h, D, 256), torch.float32),
+                            'edge_r': self._buf('sh_er', (B, 1, h, D, 256), torch.float32)}
                     a = ops.conv_concat_volume_sheared(p0, featp, B, D, pad, out=self._buf('a0', (2 * B, D, h, w, 64), dt), bufs=bufs)
                 else:
                     a = ops.conv_concat_volume(p0, featp, B, D, pad, out=self._buf('a0', (2 * B, D, h, w, cm * p0.cout_pad), dt),

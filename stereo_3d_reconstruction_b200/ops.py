@@ -231,7 +231,7 @@ def conv_concat_volume_sheared(pc, featp, B, D, pad, out=None, bufs=None):
     """Concat cost volume + the 3x3x3 layer `pc` in SHEARED form (bf16, Cout 64, ReLU): four 2-D map convolutions on the
     tensor cores (1/14 of the layer's MMAs) + one streaming pass that writes the volume (include/s3d.h,
     s3d_concat_gonce_assemble; layers.py, PackedConv.gonce_convs).  featp as for conv_concat_volume.  bufs: optional dict of
-    persistent fp32 workspaces {'maps_l', 'maps_r': [B,1,h,w+4,384], 'edge_l', 'edge_r': [B,1,h,D,192]}."""
+    persistent fp32 workspaces {'maps_l', 'maps_r': [B,1,h,w+4,384], 'edge_l', 'edge_r': [B,1,h,D,256]}."""
     _chk(featp, out)
     n2, one, h, pitch, C = featp.shape
     assert n2 == 2 * B and one == 1 and featp.is_contiguous() and featp.dtype == torch.bfloat16
@@ -240,15 +240,24 @@ def conv_concat_volume_sheared(pc, featp, B, D, pad, out=None, bufs=None):
     g = pc.gonce_convs(C, pad, w, D)
     bufs = {} if bufs is None else bufs
     res = {}
+    use_mc = C == 32 and not _lib.KNOBS['no_map_conv']       # the halo-once map engine (csrc/map_conv.cu): 64-byte pixel rows
     for name, key, sl in (('left', 'maps_l', slice(0, B)), ('right', 'maps_r', slice(B, 2 * B)),
                           ('edge_left', 'edge_l', slice(0, B)), ('edge_right', 'edge_r', slice(B, 2 * B))):
         conv = g[name]
-        ow = w + 4 if key.startswith('maps') else D
+        off, ntx, ow = g[name + '_geom']
         o = bufs.get(key)
         if o is None:
             o = torch.empty((B, 1, h, ow, conv.cout_pad), dtype=torch.float32, device=featp.device)
         assert o.shape == (B, 1, h, ow, conv.cout_pad) and o.dtype == torch.float32 and o.is_contiguous()
-        res[key] = conv(featp[sl], out=o)
+        if use_mc:
+            x = featp[sl]
+            rc = _lib.load().s3d_map_conv(x.data_ptr(), conv.weight.data_ptr(), o.data_ptr(), B, h, pitch, ow, off, ntx,
+                                          conv.cout_pad, _stream())
+            _lib.check(rc, 's3d_map_conv')
+            _lib.count_launch()
+            res[key] = o
+        else:
+            res[key] = conv(featp[sl], out=o)
     if out is None:
         out = torch.empty((2 * B, D, h, w, 64), dtype=torch.bfloat16, device=featp.device)
     assert out.is_contiguous() and out.shape == (2 * B, D, h, w, 64) and out.dtype == torch.bfloat16

@@ -83,29 +83,33 @@ def test_default_stereo2voxel_matches_oracle(voxel_case, prec):
     assert torch.equal(iou, O.iou_counts(vox, gt, cfg.TEST.VOXEL_THRESH))      # integer stats exact
 
 
-def test_default_stereo2voxel_sheared_first_layer(voxel_case, knobs):
-    """The opt-in SHEARED form of the cost volume + first aggregation layer (knob `sheared`: 2-D map convolutions + one streaming
-    pass, ops.conv_concat_volume_sheared) inside the default 73 M-parameter network, bf16, held to the bf16 tolerances."""
+def test_default_stereo2voxel_reference_once_first_layer(voxel_case, knobs):
+    """A/B path of the first aggregation layer (knob `no_sheared`: the reference-once tensor-core kernel instead of the sheared
+    form -- 2-D map convolutions + one streaming pass -- that the bf16 forward takes by default) inside the default
+    73 M-parameter network, held to the bf16 tolerances; the launch counts tell the two paths apart."""
     cfg0, sd, left, right, gt, rdl, rdr, rvox = voxel_case
     if left.shape[0] < 3:
         pytest.skip('batch 2 takes the small-batch paths (materialised volume)')
     cfg = cfg0.clone()
     cfg.NETWORK.PRECISION = 'bf16'
-    knobs('sheared', 1)
-    model = M.build_model('Stereo2Voxel', cfg)
-    model.load_state_dict(sd)
-    model.cuda().pack()
     from stereo_3d_reconstruction_b200 import lib as _l
-    n0 = _l.launches()
-    with torch.no_grad():
-        dl, dr, vox, iou = model(left.cuda(), right.cuda(), gt.cuda())
-    assert _l.launches() - n0 == 32 + 4                                        # four map convolutions + the streaming pass replace one kernel
-    td, tv = TOLS['bf16']
-    dmax = max(rdl.abs().max().item(), rdr.abs().max().item())
-    e_d = max((dl.cpu() - rdl).abs().max().item(), (dr.cpu() - rdr).abs().max().item()) / dmax
-    e_v = (vox.cpu() - rvox).abs().max().item()
-    MEASURED['stereo2voxel/bf16+sheared/B%d' % left.shape[0]] = (e_d, e_v, (vox.cpu() - rvox).abs().mean().item())
-    assert e_d <= td and e_v <= tv, (e_d, e_v)
+    counts = {}
+    for no_sheared in (0, 1):
+        knobs('no_sheared', no_sheared)
+        model = M.build_model('Stereo2Voxel', cfg)
+        model.load_state_dict(sd)
+        model.cuda().pack()
+        n0 = _l.launches()
+        with torch.no_grad():
+            dl, dr, vox, iou = model(left.cuda(), right.cuda(), gt.cuda())
+        counts[no_sheared] = _l.launches() - n0
+        td, tv = TOLS['bf16']
+        dmax = max(rdl.abs().max().item(), rdr.abs().max().item())
+        e_d = max((dl.cpu() - rdl).abs().max().item(), (dr.cpu() - rdr).abs().max().item()) / dmax
+        e_v = (vox.cpu() - rvox).abs().max().item()
+        MEASURED['stereo2voxel/bf16%s/B%d' % ('+reference-once' if no_sheared else '', left.shape[0])] = (e_d, e_v, (vox.cpu() - rvox).abs().mean().item())
+        assert e_d <= td and e_v <= tv, (no_sheared, e_d, e_v)
+    assert counts[0] == counts[1] + 4, counts               # four map convolutions + the streaming pass replace one kernel
 
 
 @pytest.mark.parametrize('prec', ['fp32', 'bf16x3', 'bf16'])

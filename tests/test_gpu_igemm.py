@@ -299,13 +299,15 @@ def test_conv_concat_volume_ref_once(B, C, D, h, w):
     (1, 32, 12, 8, 8),         # more disparities than pixels in a row: most target reads fall into the zero margin
     (3, 32, 16, 33, 40),       # rows longer than one 32-pixel block, odd height
 ])
-def test_conv_concat_volume_sheared(B, C, D, h, w):
+@pytest.mark.parametrize('map_engine', ['map_conv', 'generic'])
+def test_conv_concat_volume_sheared(B, C, D, h, w, map_engine, knobs):
     """SHEARED form of the cost volume + first aggregation layer (ops.conv_concat_volume_sheared: 2-D map convolutions on the
     generic engine + s3d_concat_gonce_assemble): same result as conv3d over the oracle's concat volume on bf16-rounded
     operands, and as the bit-exact fused kernel, within the bound of the reference-once form (weights summed before the bf16
     rounding); every border plane and both edge columns checked on their own."""
     from stereo_3d_reconstruction_b200 import ops
     from oracle import models as O
+    knobs('no_map_conv', int(map_engine == 'generic'))      # maps by csrc/map_conv.cu (C = 32) or by the generic engine
     cout = 64
     torch.manual_seed(12)
     conv = _qmod(nn.Conv3d(2 * C, cout, 3, 1, 1, bias=True), 'bf16')

@@ -38,7 +38,7 @@ def test_sheared_form_equals_conv3d_over_the_concat_volume(B, C, h, w, D):
     g = pc.gonce_convs(C, pad, w, D)
     ml, mr = engine(g['left'], featp[:B]), engine(g['right'], featp[B:])
     el, er = engine(g['edge_left'], featp[:B]), engine(g['edge_right'], featp[B:])
-    assert ml.shape == (B, h, w + 4, 384) and el.shape == (B, h, D, 192)
+    assert ml.shape == (B, h, w + 4, 384) and el.shape == (B, h, D, 256)
     out = torch.zeros(2 * B, D, h, w, 64)
     bias = pc.bias.float()
     for n in range(2 * B):
