@@ -283,13 +283,19 @@ class _StereoBase(nn.Module):
         # 'bf16x3' (split operands): the reference-once kernel only (C = 32 feature channels, 64-wide first layer)
         ro_split = (self._split and C == 32 and isinstance(p0, PackedConv) and p0.cout_pad == 64 and p0.act == _lib.ACT_RELU and
                     not _lib.KNOBS['no_ref_once'])
+        # SHEARED form of the cost volume + first aggregation layer (bf16, 32 feature channels, 64-wide ReLU layer): 2-D map
+        # convolutions + one streaming pass; its kernels fill the chip at every batch size
+        sheared = (cfg.NETWORK.COST_VOLUME == 'concat' and self.precision == 'bf16' and C == 32 and p5.cout_pad == C and
+                   isinstance(p0, PackedConv) and p0.weight_ns is not None and p0.cout_pad == 64 and p0.act == _lib.ACT_RELU and
+                   D >= 4 and w + 2 <= 127 and not _lib.KNOBS['no_sheared'] and not _lib.KNOBS['no_concat_fuse'] and
+                   not _lib.KNOBS['no_scatter'])
         fuse_volume = (cfg.NETWORK.COST_VOLUME == 'concat' and (self.precision in ('bf16', 'tf32') or ro_split) and p5.cout_pad == C and
                        isinstance(p0, PackedConv) and p0.weight_ns is not None and
                        (ro_split or C * x.element_size() in (32, 64)) and
                        not _lib.KNOBS['no_concat_fuse'] and not _lib.KNOBS['no_scatter'] and
                        # small batches: fewer columns than SMs -> unfused volume + the z-split plane-scatter kernel (a column of
                        # D planes would be a serial chain on a fraction of the chip; csrc/conv_scatter.cuh, ScArgs::nz)
-                       2 * B * (-(-h // 32)) * (-(-w // 8)) > 74)
+                       (sheared or 2 * B * (-(-h // 32)) * (-(-w // 8)) > 74))
         cm = cmult(self._dtype_code())                           # physical channels per logical channel (2 when split)
         if fuse_volume:
             # features go into rows with D zero pixels on both sides: the fused cost-volume + dres0a kernel reads the shifted
@@ -309,8 +315,7 @@ class _StereoBase(nn.Module):
                 # on the target half only (half the tensor-core work of this layer; csrc/conv_scatter_concat.cu)
                 ro = ro_split or (self.precision == 'bf16' and p0.cout_pad == 64 and p0.act == _lib.ACT_RELU and
                                   not _lib.KNOBS['no_ref_once'])
-                if (ro and not self._split and C == 32 and not _lib.KNOBS['no_sheared'] and D >= 2 and pad >= 4 and
-                        pad + w - D + 2 <= 127):
+                if sheared:
                     # SHEARED form: in u = x -/+ d the target half of the volume is the same map on every plane, so the layer is
                     # four 2-D map convolutions (csrc/map_conv.cu: 1/14 of the layer's MMAs) + one streaming pass that adds two
                     # maps per output element and writes the volume (csrc/concat_gonce.cu): 0.79 ms against 1.15 ms for the
