@@ -6,7 +6,7 @@ nf = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 rows = [r for r in csv.reader(l for l in open(path) if l.startswith('"'))]
 hdr, rows = rows[0], rows[1:]
 ki, vi, ui = hdr.index('Kernel Name'), hdr.index('Metric Value'), hdr.index('Metric Unit')
-ours = re.compile(r'conv_|cls_fused|fuse_views|upsample_disp|depth_to_space|pool_|concat_volume|soft_argmin|corr_|chamfer|pack_image|split_|partials_')
+ours = re.compile(r'conv_|cls_fused|fuse_views|upsample_disp|depth_to_space|pool_|concat_volume|soft_argmin|corr_|chamfer|pack_image|split_|partials_|gonce_')
 L = []
 for r in rows:
     n = r[ki]
@@ -29,7 +29,7 @@ print('%-78s %5s %10s %7s' % ('kernel', 'count', 'total ms', 'share'))
 for n, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     print('%-78s %5d %10.3f %6.1f%%' % (n[:78], c, t, 100 * t / tot))
 print('%-78s %5d %10.3f' % ('TOTAL (%d forwards of %d launches)' % (nf, per), len(win), tot))
-a = [t for n, t in win if re.search(r'conv_scatter_kernel<0, 1, (128|256), 64|conv_scatter_concat|conv_scatter_rm|conv_scatter_cls', n) and t > 1.0]   # (the 2-D encoder layers share the kernel)
+a = [t for n, t in win if re.search(r'conv_scatter_kernel<0, 1, (128|256), 64|conv_scatter_concat|conv_scatter_rm|conv_scatter_cls', n) and t > 1.0 or re.search(r'map_conv|gonce_assemble', n)]   # (the 2-D encoder layers share the kernel)
 if a:
     print('\n# aggregation layers (fused volume + dres0a, dres0b, dres1a, dres1b, cls_a): %d launches, mean %.3f ms, %.1f%% of the window'
           % (len(a), sum(a) / len(a), 100 * sum(a) / tot))

@@ -2,7 +2,7 @@
 
     compute-sanitizer --tool racecheck python scripts/sanitize_small.py scatter_pair
 
-usage: sanitize_small.py <case>      cases: scatter_pair scatter_single scatter_rm scatter_split concat concat_ro cls_fused corr_tc igemm all"""
+usage: sanitize_small.py <case>      cases: scatter_pair scatter_single scatter_rm scatter_split concat concat_ro sheared cls_fused corr_tc chamfer_sym igemm all"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -42,6 +42,22 @@ def run(name):
         featp = torch.zeros(2 * B, 1, h, w + 2 * D, C, dtype=torch.bfloat16, device='cuda')
         featp[:, :, :, D:D + w] = torch.randn(2 * B, 1, h, w, C, device='cuda').to(torch.bfloat16)
         ops.conv_concat_volume(pc, featp, B, D, D, ref_once=name == 'concat_ro')
+    elif name == 'sheared':
+        # map_conv_kernel<5> / <3> (TMA patch ring, resident weight chunk, two TMEM buffers) + gonce_assemble_kernel
+        B, C, D, h, w = 1, 32, 6, 19, 21
+        pc = conv3(2 * C, 64, lib.DTYPE_BF16)
+        featp = torch.zeros(2 * B, 1, h, w + 2 * D, C, dtype=torch.bfloat16, device='cuda')
+        featp[:, :, :, D:D + w] = torch.randn(2 * B, 1, h, w, C, device='cuda').to(torch.bfloat16)
+        ops.conv_concat_volume_sheared(pc, featp, B, D, D)
+    elif name == 'chamfer_sym':
+        # chamfer_sym_kernel<8> / <4> + chamfer_sym_finish_kernel: shared-memory tiles, shuffles, 64-bit atomicMin keys
+        from stereo_3d_reconstruction_b200.utils import synthetic
+        a, b = synthetic.point_clouds(2, 300, 2500, seed=3, duplicates=True, device='cuda')
+        lib.set_knob('chamfer_sym', 1)
+        for r in (8, 4):
+            lib.set_knob('chamfer_sym_r', r)
+            ops.chamfer_forward(a, b)
+        lib.set_knob('chamfer_sym', 0); lib.set_knob('chamfer_sym_r', 0)
     elif name == 'cls_fused':
         x = torch.randn(1, 4, 33, 9, 64, device='cuda').to(torch.bfloat16)
         wt = torch.zeros(32, 64, dtype=torch.bfloat16, device='cuda')
@@ -59,5 +75,5 @@ def run(name):
     print('ran', name)
 
 
-for n in (['scatter_pair', 'scatter_single', 'scatter_rm', 'scatter_split', 'concat', 'concat_ro', 'cls_fused', 'corr_tc', 'igemm'] if case == 'all' else [case]):
+for n in (['scatter_pair', 'scatter_single', 'scatter_rm', 'scatter_split', 'concat', 'concat_ro', 'sheared', 'cls_fused', 'corr_tc', 'chamfer_sym', 'igemm'] if case == 'all' else [case]):
     run(n)
