@@ -117,6 +117,14 @@ int s3d_conv_igemm(const S3dConvParams* p, const void* in, const void* w, const 
 int s3d_conv_direct(const S3dConvParams* p, const void* in, const void* w, const float* bias,
                     const void* residual, void* out, void* stream);
 
+/* Stride-1 3x3 2-D convolution, bf16, 32 / 64 input and output channels, in halo-once form (csrc/conv2d_halo.cu): the feature
+ * encoder's conv1 / conv3 / conv4 / conv5.  in: [nimg,h,w,cin] channels-last; w: the layer's packed weights [9][cout][cin]
+ * (tap order ky*3+kx); bias fp32[cout]; residual: NULL or bf16 addressed like out; out: bf16, element strides osN / osH / osW
+ * of image / row / pixel (channels contiguous; a slice of a wider buffer is allowed); relu: 0 / 1.  Same arithmetic as
+ * s3d_conv_igemm on the same operands (bf16 products, fp32 accumulate, one rounding of the output). */
+int s3d_conv2d_halo(const void* in, const void* w, const float* bias, const void* residual, void* out, int nimg, int h, int wd,
+                    int cin, int cout, int64_t osN, int64_t osH, int64_t osW, int relu, void* stream);
+
 /* --- input staging ------------------------------------------------------------------ */
 /* NCHW fp32 image [B,3,H,W] (+ optional fp32 disparity plane [B,H,W], scaled by disp_scale
  * into channel 3) -> channels-last [B,1,H,W,Cpad], zero padded channels. */

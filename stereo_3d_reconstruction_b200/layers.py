@@ -414,6 +414,8 @@ class PackedConv:
             code = _lib.DTYPE_F32
         else:
             code = _lib.DTYPE_BF16X2 if is_split(self.dtype_code) else _lib.DTYPE_BF16
+        if self._halo2d_ok(x, out, residual, cout_store, out_view, engine):
+            return self._call_halo2d(x, out, residual, out_view)
         if self.vol is not None and engine == 'igemm' and iD == 1 and self.proj is None and \
                 (out_view is None or len(out_view[1]) == 4) and (out.dtype == x.dtype or not is_split(self.dtype_code)) and not _lib.KNOBS['no_vol2d'] and not _lib.KNOBS['no_scatter']:
             return self._call_as_volume(x, out, residual, cout_store, out_view)
@@ -443,6 +445,40 @@ class PackedConv:
         rc = fn(ctypes.byref(p), x.data_ptr(), self.weight.data_ptr(), self.bias.data_ptr(), rptr,
                 out.data_ptr() + off * esz, torch.cuda.current_stream().cuda_stream)
         _lib.check(rc, 's3d_conv_%s' % engine)
+        _lib.count_launch()
+        return out
+
+    def _halo2d_ok(self, x, out, residual, cout_store, out_view, engine):
+        """Stride-1 3x3 2-D layers, bf16, 64 channels in and 32 / 64 out, ReLU or no activation: the halo-once engine
+        (csrc/conv2d_halo.cu; A/B knob no_conv2d_halo falls back to the plane-scatter / generic engines).  Measured per 128
+        images of 64 x 64: conv3 0.078 -> 0.045 ms, conv4 (residual) 0.084 -> 0.070, conv5 0.056 -> 0.041.  32 input channels
+        (conv1, 128 x 128 pixels: 18 small MMAs per tile against the same per-tile chain) are slower there, 0.079 -> 0.090, and
+        keep the plane-scatter path unless the knob conv2d_halo_all is set."""
+        return (engine == 'igemm' and x.shape[1] == 1 and self.dtype_code == _lib.DTYPE_BF16 and out.dtype == torch.bfloat16 and
+                self.ksize == (1, 3, 3) and self.pad == (0, 1, 1) and tuple(self.stride) == (1, 1, 1) and self.n_classes == 1 and
+                (self.cin_pad == 64 or (self.cin_pad == 32 and _lib.KNOBS['conv2d_halo_all'])) and self.cout_pad in (32, 64) and
+                self.act in (_lib.ACT_NONE, _lib.ACT_RELU) and
+                self.proj is None and (cout_store is None or cout_store == self.cout_pad) and
+                (out_view is None or (len(out_view[1]) == 4 and (len(out_view) < 3 or not out_view[2]))) and
+                [tuple(t) for t in self.taps[0]] == [(0, dy, dx) for dy in (-1, 0, 1) for dx in (-1, 0, 1)] and
+                not _lib.KNOBS['no_conv2d_halo'] and not _lib.KNOBS['no_scatter'])
+
+    def _call_halo2d(self, x, out, residual, out_view):
+        N, _, H, W, _ = x.shape
+        if out_view is None:
+            assert out.is_contiguous() and out.dim() == 5 and out.shape[-1] >= self.cout_pad
+            Co = out.shape[-1]
+            off, sN, sH, sW = 0, out.shape[2] * out.shape[3] * Co, out.shape[3] * Co, Co
+        else:
+            off, (sN, _, sH, sW) = out_view[:2]
+        rptr = None
+        if residual is not None:
+            assert residual.dtype == out.dtype and residual.shape == out.shape and residual.is_contiguous()
+            rptr = residual.data_ptr() + off * 2
+        rc = _lib.load().s3d_conv2d_halo(x.data_ptr(), self.weight.data_ptr(), self.bias.data_ptr(), rptr, out.data_ptr() + off * 2,
+                                         N, H, W, self.cin_pad, self.cout_pad, sN, sH, sW, int(self.act == _lib.ACT_RELU),
+                                         torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, 's3d_conv2d_halo')
         _lib.count_launch()
         return out
 

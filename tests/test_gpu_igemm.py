@@ -71,6 +71,48 @@ def test_conv2d(knobs, ts1, prec, cin, cout, H, W, stride):
         _check(pc, x, F.relu(conv(x)), prec, cout)
 
 
+@pytest.mark.parametrize('halo', [1, 0])
+@pytest.mark.parametrize('cin,cout,N,H,W,act,res', [
+    (32, 32, 4, 64, 64, 'relu', False),     # conv1 of the feature encoder
+    (64, 64, 3, 64, 64, 'relu', False),     # conv3
+    (64, 64, 2, 35, 37, 'none', True),      # conv4: residual, no activation, ragged tiles
+    (64, 32, 5, 19, 8, 'none', False),      # conv5
+    (32, 64, 1, 7, 5, 'relu', True),        # smaller than one tile
+    (64, 64, 200, 16, 8, 'relu', False),    # more tiles than SMs x 2: several tiles per CTA, both accumulator buffers reused
+])
+def test_conv2d_halo_engine(knobs, halo, cin, cout, N, H, W, act, res):
+    """Stride-1 3x3 2-D layers with 32 / 64 channels on the halo-once engine (csrc/conv2d_halo.cu) and, with knob
+    no_conv2d_halo, on the engines it replaces: conv2d on bf16-rounded operands at the output's own storage rounding; the two
+    engines agree to one bf16 rounding of the output; a launch into a channel / column slice of a wider buffer (the zero-margined
+    feature rows of the cost-volume kernels) leaves the rest of the buffer untouched."""
+    knobs('no_conv2d_halo', 1 - halo)
+    knobs('conv2d_halo_all', 1)                 # 32 input channels too (the forward keeps them on the plane-scatter path: slower here)
+    torch.manual_seed(3)
+    conv = _qmod(nn.Conv2d(cin, cout, 3, 1, 1), 'bf16')
+    x_nc = _q(torch.randn(N, cin, H, W), 'bf16')
+    r_nc = _q(torch.randn(N, cout, H, W), 'bf16') if res else None
+    code = lib.ACT_RELU if act == 'relu' else lib.ACT_NONE
+    pc = PackedConv.from_conv(conv, None, code, lib.DTYPE_BF16, 'cuda')
+    with torch.no_grad():
+        ref = conv(x_nc) + (r_nc if res else 0)
+        ref = F.relu(ref) if act == 'relu' else ref
+    x = to_cl(x_nc).to(torch.bfloat16).cuda()
+    kw = {'residual': to_cl(r_nc).to(torch.bfloat16).cuda()} if res else {}
+    n0 = lib.launches()
+    got = pc(x, **kw)
+    assert lib.launches() - n0 == 1
+    refc = to_cl(ref)
+    err = (got.float().cpu() - refc).abs().max().item()
+    assert err <= TOL['bf16'] * (refc.abs().max().item() + 1e-6), err
+    if not res:
+        # into a slice of a wider, padded buffer: [N,1,H,W+6,cout] real pixels at columns 3 .. W+2 (as enc5 -> featp)
+        P = W + 6
+        buf = torch.full((N, 1, H, P, cout), 7.0, dtype=torch.bfloat16, device='cuda')
+        pc(x, out=buf, out_view=(3 * cout, (H * P * cout, H * P * cout, P * cout, cout)), cout_store=cout)
+        assert torch.equal(buf[:, :, :, 3:3 + W], got)
+        assert (buf[:, :, :, :3] == 7).all() and (buf[:, :, :, 3 + W:] == 7).all()
+
+
 @pytest.mark.parametrize('prec', ['bf16', 'tf32'])
 @pytest.mark.parametrize('cin,cout,D,H,W', [(64, 64, 8, 16, 16), (32, 32, 5, 9, 11), (9, 16, 8, 8, 8), (64, 1, 4, 8, 8)])
 def test_conv3d(prec, cin, cout, D, H, W):
