@@ -5,7 +5,8 @@
 // plane around ~600 cycles of MMAs; here a 16 x 8 tile is one item of 18-36 MMAs with one patch load and one accumulator hand-off.
 //   epilogue  thread = output pixel (TMEM lane): bias, optional residual, ReLU, bf16; the 16-byte chunks of the 4 / 8 pixels of a
 //             lane group are transposed by shuffles so that a store instruction writes whole pixels contiguously.
-// Warp roles: 0 TMA producer, 1 MMA issuer, 2 TMEM allocator, 4-7 / 8-11 epilogue groups (two accumulator buffers).
+// Warp roles: 0 TMA producer, 1 and 2 MMA issuers (even / odd tiles; warp 2 allocates TMEM first), 4-7 / 8-11 epilogue groups
+// (one accumulator buffer each).
 #include <cuda.h>
 #include <string.h>
 #include "common.cuh"
@@ -81,18 +82,24 @@ conv2d_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
         if (++slot == a.slots) { slot = 0; pphase ^= 1; }
       }
     }
-  } else if (warp == 1) {
-    int slot = 0;  uint32_t pphase = 0, aphase = 0;
-    int buf = 0;
+  } else if (warp == 1 || warp == 2) {
+    // TWO MMA issuers: warp 1 takes the even tiles of this CTA (accumulator buffer 0), warp 2 the odd ones (buffer 1).  A tile is
+    // 18-36 tcgen05.mma from ONE thread (~1000 cycles of issue) + two barrier round trips, more than the MMAs themselves
+    // (1152 cycles at 64 x 64 channels): with one issuer the tensor pipe waited for its instruction stream.
+    const int v = warp - 1;
+    uint32_t aphase = 0;
     const uint64_t hi_a = (static_cast<uint64_t>((kPitch * ROWB) >> 4) << 32) | (1ull << 46) | (kLayout << 61);   // SBO = one patch line
     const uint64_t hi_b = (static_cast<uint64_t>((8 * ROWB) >> 4) << 32) | (1ull << 46) | (kLayout << 61);
     const uint32_t w_u = ptx::smem_u32(smem_w), p_u = ptx::smem_u32(smem_p);
+    const uint32_t d_tmem = tmem_base + v * NC;
     ptx::mbar_wait(&ctrl.w_full, 0);
-    for (int k = 0; k < my_tiles; ++k) {
-      ptx::mbar_wait(&ctrl.acc_empty[buf], aphase ^ 1);
+    for (int k = v; k < my_tiles; k += 2) {
+      const int slot = k % a.slots;
+      const uint32_t pphase = (uint32_t)(k / a.slots) & 1u;
+      ptx::mbar_wait(&ctrl.acc_empty[v], aphase ^ 1);
       ptx::mbar_wait(&ctrl.p_full[slot], pphase);
       ptx::tc_fence_after();
-      const uint32_t pa = p_u + slot * a.patch_bytes, d_tmem = tmem_base + buf * NC;
+      const uint32_t pa = p_u + slot * a.patch_bytes;
       const uint64_t ad0 = hi_a | ((pa >> 4) | (1u << 16)), bd0 = hi_b | ((w_u >> 4) | (1u << 16));
       if (ptx::elect_one()) {
 #pragma unroll
@@ -103,11 +110,10 @@ conv2d_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
           for (int ks = 0; ks < kKSteps; ++ks) ptx::mma_bf16(d_tmem, ad + 2 * ks, bd + 2 * ks, a.idesc, (t | ks) != 0);
         }
         ptx::tc_commit(&ctrl.p_empty[slot]);
-        ptx::tc_commit(&ctrl.acc_full[buf]);
+        ptx::tc_commit(&ctrl.acc_full[v]);
       }
       __syncwarp();
-      if (++slot == a.slots) { slot = 0; pphase ^= 1; }
-      if (++buf == 2) { buf = 0; aphase ^= 1; }
+      aphase ^= 1;
     }
   } else if (warp >= 4) {
     const int q = warp & 3, grp = (warp - 4) >> 2;
@@ -124,6 +130,15 @@ conv2d_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
       const int img = t / a.tiles_per_img, r = t % a.tiles_per_img;
       const int y = (r / a.tiles_x) * kTY + yy, xt = (r % a.tiles_x) * kTX;
       const int64_t row = (int64_t)img * a.osN + (int64_t)y * a.osH;
+      // the residual of this thread's pixel is requested BEFORE the wait for the accumulator: its latency (128-byte-strided
+      // reads, one line per lane) hides behind the tile's MMAs
+      [[maybe_unused]] uint4 rv[NCH];
+      if constexpr (kRes) {
+        const bool ok = y < a.h && xt + xx < a.w;
+        const uint4* rp = reinterpret_cast<const uint4*>(a.residual + row + (int64_t)(xt + xx) * a.osW);
+#pragma unroll
+        for (int j = 0; j < NCH; ++j) rv[j] = ok ? __ldg(rp + j) : make_uint4(0, 0, 0, 0);
+      }
       ptx::mbar_wait(&ctrl.acc_full[grp], aphase);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + grp * NC + (static_cast<uint32_t>(q * 32) << 16);
@@ -141,12 +156,9 @@ conv2d_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
 #pragma unroll
         for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[(8 * j + i) >> 4][(8 * j + i) & 15]) + bias[8 * j + i];
         if constexpr (kRes) {
-          if (y < a.h && xt + xx < a.w) {
-            const uint4 rv = __ldg(reinterpret_cast<const uint4*>(a.residual + row + (int64_t)(xt + xx) * a.osW + 8 * j));
-            const __nv_bfloat162* rp = reinterpret_cast<const __nv_bfloat162*>(&rv);
+          const __nv_bfloat162* rp = reinterpret_cast<const __nv_bfloat162*>(&rv[j]);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { const float2 g2 = __bfloat1622float2(rp[i]);  f[2 * i] += g2.x;  f[2 * i + 1] += g2.y; }
-          }
+          for (int i = 0; i < 4; ++i) { const float2 g2 = __bfloat1622float2(rp[i]);  f[2 * i] += g2.x;  f[2 * i + 1] += g2.y; }
         }
         if (a.relu) {
 #pragma unroll

@@ -451,7 +451,7 @@ class PackedConv:
     def _halo2d_ok(self, x, out, residual, cout_store, out_view, engine):
         """Stride-1 3x3 2-D layers, bf16, 64 channels in and 32 / 64 out, ReLU or no activation: the halo-once engine
         (csrc/conv2d_halo.cu; A/B knob no_conv2d_halo falls back to the plane-scatter / generic engines).  Measured per 128
-        images of 64 x 64: conv3 0.078 -> 0.045 ms, conv4 (residual) 0.084 -> 0.070, conv5 0.056 -> 0.041.  32 input channels
+        images of 64 x 64: conv3 0.078 -> 0.037 ms, conv4 (residual) 0.084 -> 0.056, conv5 0.056 -> 0.035.  32 input channels
         (conv1, 128 x 128 pixels: 18 small MMAs per tile against the same per-tile chain) are slower there, 0.079 -> 0.090, and
         keep the plane-scatter path unless the knob conv2d_halo_all is set."""
         return (engine == 'igemm' and x.shape[1] == 1 and self.dtype_code == _lib.DTYPE_BF16 and out.dtype == torch.bfloat16 and
