@@ -6,7 +6,7 @@ nf = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 rows = [r for r in csv.reader(l for l in open(path) if l.startswith('"'))]
 hdr, rows = rows[0], rows[1:]
 ki, vi, ui = hdr.index('Kernel Name'), hdr.index('Metric Value'), hdr.index('Metric Unit')
-ours = re.compile(r'conv_|cls_fused|fuse_views|upsample_disp|depth_to_space|pool_|concat_volume|soft_argmin|corr_|chamfer|pack_image|split_|partials_|gonce_')
+ours = re.compile(r'conv_|conv2d_|cls_fused|fuse_views|upsample_disp|depth_to_space|pool_|concat_volume|soft_argmin|corr_|chamfer|pack_image|split_|partials_|gonce_')
 L = []
 for r in rows:
     n = r[ki]

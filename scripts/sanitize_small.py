@@ -2,7 +2,7 @@
 
     compute-sanitizer --tool racecheck python scripts/sanitize_small.py scatter_pair
 
-usage: sanitize_small.py <case>      cases: scatter_pair scatter_single scatter_rm scatter_split concat concat_ro sheared cls_fused corr_tc chamfer_sym igemm all"""
+usage: sanitize_small.py <case>      cases: scatter_pair scatter_single scatter_rm scatter_split concat concat_ro sheared halo2d cls_fused corr_tc chamfer_sym igemm all"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -49,6 +49,13 @@ def run(name):
         featp = torch.zeros(2 * B, 1, h, w + 2 * D, C, dtype=torch.bfloat16, device='cuda')
         featp[:, :, :, D:D + w] = torch.randn(2 * B, 1, h, w, C, device='cuda').to(torch.bfloat16)
         ops.conv_concat_volume_sheared(pc, featp, B, D, D)
+    elif name == 'halo2d':
+        # conv2d_halo_kernel (two MMA issuers, TMA patch ring, transposed bf16 epilogue): 64 -> 64 with residual, 64 -> 32 plain
+        x = torch.randn(3, 1, 19, 21, 64, device='cuda').to(torch.bfloat16)
+        pc = PackedConv.from_conv(nn.Conv2d(64, 64, 3, 1, 1), None, lib.ACT_NONE, lib.DTYPE_BF16, 'cuda')
+        pc(x, residual=torch.randn(3, 1, 19, 21, 64, device='cuda').to(torch.bfloat16))
+        pc = PackedConv.from_conv(nn.Conv2d(64, 32, 3, 1, 1), None, lib.ACT_RELU, lib.DTYPE_BF16, 'cuda')
+        pc(x)
     elif name == 'chamfer_sym':
         # chamfer_sym_kernel<8> / <4> + chamfer_sym_finish_kernel: shared-memory tiles, shuffles, 64-bit atomicMin keys
         from stereo_3d_reconstruction_b200.utils import synthetic
@@ -75,5 +82,5 @@ def run(name):
     print('ran', name)
 
 
-for n in (['scatter_pair', 'scatter_single', 'scatter_rm', 'scatter_split', 'concat', 'concat_ro', 'sheared', 'cls_fused', 'corr_tc', 'chamfer_sym', 'igemm'] if case == 'all' else [case]):
+for n in (['scatter_pair', 'scatter_single', 'scatter_rm', 'scatter_split', 'concat', 'concat_ro', 'sheared', 'halo2d', 'cls_fused', 'corr_tc', 'chamfer_sym', 'igemm'] if case == 'all' else [case]):
     run(n)
