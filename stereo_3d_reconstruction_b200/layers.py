@@ -449,14 +449,13 @@ class PackedConv:
         return out
 
     def _halo2d_ok(self, x, out, residual, cout_store, out_view, engine):
-        """Stride-1 3x3 2-D layers, bf16, 64 channels in and 32 / 64 out, ReLU or no activation: the halo-once engine
+        """Stride-1 3x3 2-D layers, bf16, 32 / 64 channels in and out, ReLU or no activation: the halo-once engine
         (csrc/conv2d_halo.cu; A/B knob no_conv2d_halo falls back to the plane-scatter / generic engines).  Measured per 128
-        images of 64 x 64: conv3 0.078 -> 0.037 ms, conv4 (residual) 0.084 -> 0.056, conv5 0.056 -> 0.035.  32 input channels
-        (conv1, 128 x 128 pixels: 18 small MMAs per tile against the same per-tile chain) are slower there, 0.079 -> 0.090, and
-        keep the plane-scatter path unless the knob conv2d_halo_all is set."""
+        images: conv3 0.078 -> 0.037 ms, conv4 (residual) 0.084 -> 0.056, conv5 0.056 -> 0.035 (64 x 64 pixels), conv1
+        (32 -> 32 channels, 128 x 128 pixels: 18 small MMAs per tile) 0.078 -> 0.074."""
         return (engine == 'igemm' and x.shape[1] == 1 and self.dtype_code == _lib.DTYPE_BF16 and out.dtype == torch.bfloat16 and
                 self.ksize == (1, 3, 3) and self.pad == (0, 1, 1) and tuple(self.stride) == (1, 1, 1) and self.n_classes == 1 and
-                (self.cin_pad == 64 or (self.cin_pad == 32 and _lib.KNOBS['conv2d_halo_all'])) and self.cout_pad in (32, 64) and
+                self.cin_pad in (32, 64) and self.cout_pad in (32, 64) and
                 self.act in (_lib.ACT_NONE, _lib.ACT_RELU) and
                 self.proj is None and (cout_store is None or cout_store == self.cout_pad) and
                 (out_view is None or (len(out_view[1]) == 4 and (len(out_view) < 3 or not out_view[2]))) and

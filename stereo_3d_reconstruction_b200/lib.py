@@ -116,7 +116,7 @@ def check(rc, what):
 # Read ONCE (here, at import) from the S3D_* environment variables, never on the forward path.  The host-side ones live
 # in this dict; the launcher-side ones live in the library (include/s3d.h, s3d_set_knob).  set_knob() changes either
 # at run time (tests, A/B scripts) -- a model picks host-side knobs up at its next pack().
-HOST_KNOBS = ('no_vol2d', 'no_concat_fuse', 'no_cls_fused', 'no_conv_first', 'no_d2s', 'no_ref_once', 'no_cls_chain', 'no_sheared', 'no_map_conv', 'no_conv2d_halo', 'conv2d_halo_all')
+HOST_KNOBS = ('no_vol2d', 'no_concat_fuse', 'no_cls_fused', 'no_conv_first', 'no_d2s', 'no_ref_once', 'no_cls_chain', 'no_sheared', 'no_map_conv', 'no_conv2d_halo')
 LIB_KNOBS = ('no_scatter', 'scatter_tps3', 'scatter_no_pair', 'scatter_ring', 'scatter_res_transpose',
              'scatter_no_transpose', 'scatter_generic', 'no_corr_tc', 'scatter_zsplit', 'scatter_no_rm', 'igemm_ts1', 'igemm_one_cta', 'scatter_one_cta', 'no_conv_first_tc', 'chamfer_sym', 'chamfer_sym_r')
 KNOBS = {k: int(os.environ.get('S3D_' + k.upper()) is not None) for k in HOST_KNOBS}

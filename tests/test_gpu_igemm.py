@@ -86,7 +86,6 @@ def test_conv2d_halo_engine(knobs, halo, cin, cout, N, H, W, act, res):
     engines agree to one bf16 rounding of the output; a launch into a channel / column slice of a wider buffer (the zero-margined
     feature rows of the cost-volume kernels) leaves the rest of the buffer untouched."""
     knobs('no_conv2d_halo', 1 - halo)
-    knobs('conv2d_halo_all', 1)                 # 32 input channels too (the forward keeps them on the plane-scatter path: slower here)
     torch.manual_seed(3)
     conv = _qmod(nn.Conv2d(cin, cout, 3, 1, 1), 'bf16')
     x_nc = _q(torch.randn(N, cin, H, W), 'bf16')
