@@ -625,10 +625,10 @@ def run_ours(args):
     orig_asm = L_.s3d_concat_gonce_assemble
     asm_events = []
 
-    def hooked_asm(ml, mr, el, er, bias, out, B_, D_, h_, w_, mw_, st):
+    def hooked_asm(ml, mr, el, er, bias, out, B_, D_, h_, w_, mw_, odt, st):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        rc = orig_asm(ml, mr, el, er, bias, out, B_, D_, h_, w_, mw_, st)
+        rc = orig_asm(ml, mr, el, er, bias, out, B_, D_, h_, w_, mw_, odt, st)
         b.record()
         asm_events.append((a, b, 2 * B_ * D_ * h_ * w_ * 64 * 2 + 2 * B_ * h_ * (mw_ * 384 + D_ * 256) * 4))
         return rc

@@ -169,16 +169,17 @@ int s3d_conv_concat_volume_ro(const S3dConvParams* p, const void* feat, int feat
  * applies the ReLU and writes out bf16 [2B,D,h,w,64] (left-referenced volumes first).  maps_l / maps_r: fp32
  * [B,h,map_w = w+4,384] from the left / right images, channels [Psum | Pm | Pp | G | Hm | Hp], map column j <-> u = j-2;
  * a volume takes its reference maps from its own image and its target maps from the other one.  edge_l / edge_r: fp32
- * [B,h,D,256] = [Ge | Gem | Gep | unused].  Not bit-identical to s3d_conv_concat_volume (weights summed before the bf16 rounding,
+ * [B,h,D,256] = [Ge | Gem | Gep | unused].  out_dtype BF16X2 ('bf16x3'): out is [2B,D,h,w, hi(64) | lo(64)].  Not bit-identical to s3d_conv_concat_volume (weights summed before the bf16 rounding,
  * different summation order). */
 int s3d_concat_gonce_assemble(const float* maps_l, const float* maps_r, const float* edge_l, const float* edge_r,
-                              const float* bias, void* out, int B, int D, int h, int w, int map_w, void* stream);
+                              const float* bias, void* out, int B, int D, int h, int w, int map_w, int out_dtype, void* stream);
 /* The map convolutions of that form on their own engine (csrc/map_conv.cu): in bf16 [nimg,h,in_w,32] (feature rows with their
  * zero margins), w bf16 [3*ntx][cout][32] (taps dy = -1..1 major, ex = 0..ntx-1 minor; ntx = 3 or 5; cout a multiple of 128),
  * out fp32 [nimg,h,ow,cout]:  out[n,y,j,co] = sum_{dy,ex,ci} in[n, y+dy, j+off+ex, ci] * w[(dy+1)*ntx+ex, co, ci]  (zero outside
- * the input).  One TMA box per output tile (patch + halo), every tap a descriptor offset into it. */
+ * the input).  One TMA box per output tile (patch + halo), every tap a descriptor offset into it.  dtype BF16X2: in is
+ * [nimg,h,in_w, hi(32) | lo(32)], w is [3*ntx][cout][hi(32) | lo(32)], three MMAs per product (fp32-grade maps). */
 int s3d_map_conv(const void* in, const void* w, float* out, int nimg, int h, int in_w, int ow, int off, int ntx, int cout,
-                 void* stream);
+                 int dtype, void* stream);
 /* feat: [2B,1,h,w,C] (left maps first, then right).  vol: [2B,D,h,w,2C]; entries [0,B) are
  * left-referenced (target sampled at x-d), [B,2B) right-referenced (target at x+d).
  * dtype BF16X2: feat [.., hi(C) | lo(C)] -> vol [.., hi(2C) | lo(2C)] (C logical channels). */

@@ -22,12 +22,12 @@ L = lib.load()
 st = lambda: torch.cuda.current_stream().cuda_stream
 def mc(name, key):
     off, ntx, ow = g[name + '_geom']
-    lib.check(L.s3d_map_conv(featp[:B].data_ptr(), g[name].weight.data_ptr(), bufs[key].data_ptr(), B, h, w + 2 * D, ow, off, ntx, g[name].cout_pad, st()), 'mc')
+    lib.check(L.s3d_map_conv(featp[:B].data_ptr(), g[name].weight.data_ptr(), bufs[key].data_ptr(), B, h, w + 2 * D, ow, off, ntx, g[name].cout_pad, lib.DTYPE_BF16, st()), 'mc')
 print('  map conv, left images   %.4f ms (generic engine %.4f)' % (bench._events_ms(lambda: mc('left', 'maps_l'), 10, flush=flush),
       bench._events_ms(lambda: g['left'](featp[:B], out=bufs['maps_l']), 10, flush=flush)))
 print('  edge conv, left images  %.4f ms (generic engine %.4f)' % (bench._events_ms(lambda: mc('edge_left', 'edge_l'), 10, flush=flush),
       bench._events_ms(lambda: g['edge_left'](featp[:B], out=bufs['edge_l']), 10, flush=flush)))
 def asm():
     lib.check(L.s3d_concat_gonce_assemble(bufs['maps_l'].data_ptr(), bufs['maps_r'].data_ptr(), bufs['edge_l'].data_ptr(), bufs['edge_r'].data_ptr(),
-                                          pc.bias.data_ptr(), out.data_ptr(), B, D, h, w, w + 4, torch.cuda.current_stream().cuda_stream), 'asm')
+                                          pc.bias.data_ptr(), out.data_ptr(), B, D, h, w, w + 4, lib.DTYPE_BF16, torch.cuda.current_stream().cuda_stream), 'asm')
 print('  streaming pass          %.4f ms' % bench._events_ms(asm, 10, flush=flush))

@@ -23,7 +23,9 @@ __device__ __forceinline__ void add8(float (&v)[8], const float* __restrict__ p)
   v[0] += a.x;  v[1] += a.y;  v[2] += a.z;  v[3] += a.w;  v[4] += b.x;  v[5] += b.y;  v[6] += b.z;  v[7] += b.w;
 }
 
-// grid (ceil(w / 32), h, 2B); 256 threads = 32 pixels of one image row x 8 channel octets; each thread marches over the D planes
+// grid (ceil(w / 32), h, 2B); 256 threads = 32 pixels of one image row x 8 channel octets; each thread marches over the D planes.
+// kSplit ('bf16x3'): the output is the bf16 pair [hi(64) | lo(64)] per pixel, hi = bf16(v), lo = bf16(v - hi).
+template <bool kSplit>
 __global__ void __launch_bounds__(256)
 gonce_assemble_kernel(const float* __restrict__ maps_l, const float* __restrict__ maps_r, const float* __restrict__ edge_l,
                       const float* __restrict__ edge_r, const float* __restrict__ bias, __nv_bfloat16* __restrict__ out,
@@ -43,8 +45,9 @@ gonce_assemble_kernel(const float* __restrict__ maps_l, const float* __restrict_
     base[0] = b0.x;  base[1] = b0.y;  base[2] = b0.z;  base[3] = b0.w;  base[4] = b1.x;  base[5] = b1.y;  base[6] = b1.z;  base[7] = b1.w;
     add8(base, pm);
   }
-  __nv_bfloat16* op = out + ((((int64_t)n * D) * h + y) * w + x) * 64 + co;
-  const int64_t plane = (int64_t)h * w * 64;
+  constexpr int kCo = kSplit ? 128 : 64;                     // bf16 elements of an output pixel
+  __nv_bfloat16* op = out + ((((int64_t)n * D) * h + y) * w + x) * kCo + co;
+  const int64_t plane = (int64_t)h * w * kCo;
 #pragma unroll 4
   for (int d = 0; d < D; ++d) {
     float v[8];
@@ -61,13 +64,21 @@ gonce_assemble_kernel(const float* __restrict__ maps_l, const float* __restrict_
       if (d == 0) add8(v, e + 64);
       if (d == D - 1) add8(v, e + 128);
     }
-    uint4 o;
-    __nv_bfloat162 t;
-    t = __floats2bfloat162_rn(fmax_nan(v[0], 0.f), fmax_nan(v[1], 0.f));  o.x = *reinterpret_cast<uint32_t*>(&t);
-    t = __floats2bfloat162_rn(fmax_nan(v[2], 0.f), fmax_nan(v[3], 0.f));  o.y = *reinterpret_cast<uint32_t*>(&t);
-    t = __floats2bfloat162_rn(fmax_nan(v[4], 0.f), fmax_nan(v[5], 0.f));  o.z = *reinterpret_cast<uint32_t*>(&t);
-    t = __floats2bfloat162_rn(fmax_nan(v[6], 0.f), fmax_nan(v[7], 0.f));  o.w = *reinterpret_cast<uint32_t*>(&t);
+    uint32_t oh[4], ol[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float a0 = fmax_nan(v[2 * i], 0.f), a1 = fmax_nan(v[2 * i + 1], 0.f);
+      __nv_bfloat162 t = __floats2bfloat162_rn(a0, a1);
+      oh[i] = *reinterpret_cast<uint32_t*>(&t);
+      if constexpr (kSplit) {
+        const float2 hf = __bfloat1622float2(t);
+        __nv_bfloat162 l = __floats2bfloat162_rn(a0 - hf.x, a1 - hf.y);
+        ol[i] = *reinterpret_cast<uint32_t*>(&l);
+      }
+    }
+    const uint4 o = make_uint4(oh[0], oh[1], oh[2], oh[3]);
     __stcs(reinterpret_cast<uint4*>(op + d * plane), o);     // streaming store: the volume is read next by another kernel, not by this one
+    if constexpr (kSplit) __stcs(reinterpret_cast<uint4*>(op + d * plane + 64), make_uint4(ol[0], ol[1], ol[2], ol[3]));
   }
 }
 
@@ -75,7 +86,8 @@ gonce_assemble_kernel(const float* __restrict__ maps_l, const float* __restrict_
 }  // namespace s3d
 
 extern "C" int s3d_concat_gonce_assemble(const float* maps_l, const float* maps_r, const float* edge_l, const float* edge_r,
-                                         const float* bias, void* out, int B, int D, int h, int w, int map_w, void* stream) {
+                                         const float* bias, void* out, int B, int D, int h, int w, int map_w, int out_dtype,
+                                         void* stream) {
   using namespace s3d;
   if (!maps_l || !maps_r || !edge_l || !edge_r || !bias || !out) { set_error("concat_gonce_assemble: null argument"); return S3D_ERR_INVALID; }
   S3D_CHECK_ARG(B > 0 && D >= 2 && h > 0 && w > 0 && map_w == w + 4, "concat_gonce_assemble: B=%d D=%d h=%d w=%d map_w=%d (needs D >= 2, map_w = w + 4)", B, D, h, w, map_w);
@@ -83,9 +95,14 @@ extern "C" int s3d_concat_gonce_assemble(const float* maps_l, const float* maps_
                   reinterpret_cast<uintptr_t>(edge_r) | reinterpret_cast<uintptr_t>(bias) | reinterpret_cast<uintptr_t>(out)) & 15) == 0,
                 "concat_gonce_assemble: pointers must be 16-byte aligned");
   S3D_CHECK_ARG(h <= 65535 && 2 * B <= 65535, "concat_gonce_assemble: grid too large");
+  S3D_CHECK_ARG(out_dtype == S3D_DTYPE_BF16 || out_dtype == S3D_DTYPE_BF16X2, "concat_gonce_assemble: out_dtype %d", out_dtype);
   dim3 grid(ceil_div(w, 32), h, 2 * B);
-  gonce_assemble_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(maps_l, maps_r, edge_l, edge_r, bias,
-                                                                             static_cast<__nv_bfloat16*>(out), B, D, h, w, map_w);
+  if (out_dtype == S3D_DTYPE_BF16X2)
+    gonce_assemble_kernel<true><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(maps_l, maps_r, edge_l, edge_r, bias,
+                                                                                     static_cast<__nv_bfloat16*>(out), B, D, h, w, map_w);
+  else
+    gonce_assemble_kernel<false><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(maps_l, maps_r, edge_l, edge_r, bias,
+                                                                                      static_cast<__nv_bfloat16*>(out), B, D, h, w, map_w);
   S3D_LAUNCH_CHECK();
   return S3D_OK;
 }

@@ -23,10 +23,9 @@ namespace {
 
 constexpr int kThreads = 384;
 constexpr int kTY = 16, kTX = 8;           // output tile
-constexpr int kRowB = 64;                  // bytes of a pixel row: 32 bf16 channels
-constexpr int kNC = 128;                   // output channels per chunk (GEMM N)
 constexpr int kMaxSlots = 6;
-constexpr int kTapBytes = kNC * kRowB;     // one tap of a weight chunk
+constexpr int kTapBytes = 8192;            // one tap of a weight chunk: 128 output channels x 64-byte rows (bf16), or, for split
+                                           // (BF16X2, 'bf16x3') operands, 64 output channels x 128-byte rows [hi(32) | lo(32)]
 
 struct McArgs {
   float* out;
@@ -47,9 +46,15 @@ struct McCtrl {
   uint32_t tmem_base;
 };
 
-template <int NTX>
+// kSplit: feature rows and weights are bf16 PAIRS [hi(32) | lo(32)] (128-byte rows, 128B swizzle); every tap issues
+// (x_hi, w_hi), (x_lo, w_hi), (x_hi, w_lo) into the same accumulator (include/s3d.h, S3D_DTYPE_BF16X2); 64 output channels per chunk.
+template <int NTX, bool kSplit>
 __global__ void __launch_bounds__(kThreads, 1)
 map_conv_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const __grid_constant__ McArgs a) {
+  constexpr int kRowB = kSplit ? 128 : 64;                   // bytes of a pixel row
+  constexpr int kNC = kSplit ? 64 : 128;                     // output channels per chunk (GEMM N)
+  constexpr uint64_t kLayout = kSplit ? 2ull : 4ull;         // UMMA layout code of the 128B / 64B swizzle
+  static_assert(kNC * kRowB == kTapBytes, "tap bytes");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_w = smem;                                    // [ntaps][128][64 B], 64B swizzle
@@ -94,8 +99,8 @@ map_conv_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
   } else if (warp == 1) {
     int slot = 0;  uint32_t pphase = 0, wphase = 0, aphase = 0;
     int buf = 0;
-    const uint64_t hi_a = (static_cast<uint64_t>((a.pitch * kRowB) >> 4) << 32) | (1ull << 46) | (4ull << 61);   // SBO = one patch line
-    const uint64_t hi_b = (static_cast<uint64_t>((8 * kRowB) >> 4) << 32) | (1ull << 46) | (4ull << 61);
+    const uint64_t hi_a = (static_cast<uint64_t>((a.pitch * kRowB) >> 4) << 32) | (1ull << 46) | (kLayout << 61);   // SBO = one patch line
+    const uint64_t hi_b = (static_cast<uint64_t>((8 * kRowB) >> 4) << 32) | (1ull << 46) | (kLayout << 61);
     const uint32_t w_u = ptx::smem_u32(smem_w), p_u = ptx::smem_u32(smem_p);
     for (int ch = 0; ch < a.nchunks; ++ch) {
       ptx::mbar_wait(&ctrl.w_full, wphase);
@@ -117,6 +122,10 @@ map_conv_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             const uint64_t bd = bd0 + (uint64_t)((t * kTapBytes) >> 4);
             ptx::mma_bf16(d_tmem, ad, bd, a.idesc, t != 0);
             ptx::mma_bf16(d_tmem, ad + 2, bd + 2, a.idesc, 1u);
+            if constexpr (kSplit) {                          // the lo halves start 64 bytes into the row
+              ptx::mma_bf16(d_tmem, ad + 4, bd, a.idesc, 1u);      ptx::mma_bf16(d_tmem, ad + 6, bd + 2, a.idesc, 1u);   // x_lo * w_hi
+              ptx::mma_bf16(d_tmem, ad, bd + 4, a.idesc, 1u);      ptx::mma_bf16(d_tmem, ad + 2, bd + 6, a.idesc, 1u);   // x_hi * w_lo
+            }
           }
           ptx::tc_commit(&ctrl.p_empty[slot]);
           ptx::tc_commit(&ctrl.acc_full[buf]);
@@ -147,12 +156,12 @@ map_conv_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + grp * kNC + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
+      for (int half = 0; half < kNC / 64; ++half) {
         uint32_t v[4][16];
 #pragma unroll
         for (int g = 0; g < 4; ++g) ptx::tmem_ld16(taddr + half * 64 + g * 16, v[g]);
         ptx::tmem_ld_wait();
-        if (half == 1) {                                     // everything is in registers: hand the buffer back before storing
+        if (half == kNC / 64 - 1) {                          // everything is in registers: hand the buffer back before storing
           ptx::tc_fence_before();
           ptx::mbar_arrive(&ctrl.acc_empty[grp]);
         }
@@ -200,10 +209,13 @@ map_conv_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
 }  // namespace s3d
 
 extern "C" int s3d_map_conv(const void* in, const void* w, float* out, int nimg, int h, int in_w, int ow, int off, int ntx,
-                            int cout, void* stream) {
+                            int cout, int dtype, void* stream) {
   using namespace s3d;
   if (!in || !w || !out) { set_error("map_conv: null argument"); return S3D_ERR_INVALID; }
-  S3D_CHECK_ARG(nimg > 0 && h > 0 && ow > 0 && in_w > 0 && (ntx == 3 || ntx == 5) && cout > 0 && cout % kNC == 0,
+  S3D_CHECK_ARG(dtype == S3D_DTYPE_BF16 || dtype == S3D_DTYPE_BF16X2, "map_conv: dtype %d (bf16 or the bf16 pair)", dtype);
+  const bool split = dtype == S3D_DTYPE_BF16X2;
+  const int kNC = split ? 64 : 128, kRowB = split ? 128 : 64;
+  S3D_CHECK_ARG(nimg > 0 && h > 0 && ow > 0 && in_w > 0 && (ntx == 3 || ntx == 5) && cout > 0 && cout % 128 == 0,
                 "map_conv: nimg=%d h=%d ow=%d in_w=%d ntx=%d cout=%d (ntx 3 or 5, cout a multiple of 128)", nimg, h, ow, in_w, ntx, cout);
   S3D_CHECK_ARG(off >= 0 && off + ow + ntx - 1 <= in_w + 8, "map_conv: output columns reach beyond the input rows");
   S3D_CHECK_ARG(((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(out)) & 15) == 0,
@@ -226,22 +238,26 @@ extern "C" int s3d_map_conv(const void* in, const void* w, float* out, int nimg,
   if (a.slots > kMaxSlots) a.slots = kMaxSlots;
   S3D_CHECK_ARG(a.slots >= 2, "map_conv: shared memory");
   CUtensorMap map_x, map_w;
-  cuuint32_t box[5] = {32, (cuuint32_t)a.pitch, kTY + 2, 1, 1};
+  const CUtensorMapSwizzle sw = split ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  const int cphys = kRowB / 2;                               // bf16 elements of a physical row: 32, or [hi(32) | lo(32)]
+  cuuint32_t box[5] = {(cuuint32_t)cphys, (cuuint32_t)a.pitch, kTY + 2, 1, 1};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  int rc = encode_act_map(&map_x, in, 2, false, 32, in_w, h, 1, nimg, box, estr, CU_TENSOR_MAP_SWIZZLE_64B);
+  int rc = encode_act_map(&map_x, in, 2, false, cphys, in_w, h, 1, nimg, box, estr, sw);
   if (rc != S3D_OK) return rc;
-  rc = encode_weight_map(&map_w, w, 2, false, 32, cout, a.ntaps, 32, kNC, CU_TENSOR_MAP_SWIZZLE_64B, ntx);
+  rc = encode_weight_map(&map_w, w, 2, false, cphys, cout, a.ntaps, cphys, kNC, sw, ntx);
   if (rc != S3D_OK) return rc;
   const int smem_bytes = w_bytes + a.slots * a.patch_bytes + 1024;
   int grid = num_sms();
   if (grid > a.total_tiles) grid = a.total_tiles;
-  if (ntx == 5) {
-    S3D_CUDA(cudaFuncSetAttribute(map_conv_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    map_conv_kernel<5><<<grid, kThreads, smem_bytes, static_cast<cudaStream_t>(stream)>>>(map_x, map_w, a);
-  } else {
-    S3D_CUDA(cudaFuncSetAttribute(map_conv_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    map_conv_kernel<3><<<grid, kThreads, smem_bytes, static_cast<cudaStream_t>(stream)>>>(map_x, map_w, a);
-  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define S3D_MC_LAUNCH(NTX_, SPLIT_)                                                                                              \
+  do {                                                                                                                           \
+    S3D_CUDA(cudaFuncSetAttribute(map_conv_kernel<NTX_, SPLIT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));       \
+    map_conv_kernel<NTX_, SPLIT_><<<grid, kThreads, smem_bytes, st>>>(map_x, map_w, a);                                           \
+  } while (0)
+  if (ntx == 5) { if (split) S3D_MC_LAUNCH(5, true); else S3D_MC_LAUNCH(5, false); }
+  else          { if (split) S3D_MC_LAUNCH(3, true); else S3D_MC_LAUNCH(3, false); }
+#undef S3D_MC_LAUNCH
   S3D_LAUNCH_CHECK();
   return S3D_OK;
 }

@@ -208,7 +208,7 @@ class PackedConv:
         key = ('gonce', C, pad, w, D)
         if key in self._cache:
             return self._cache[key]
-        assert self.ntaps == 27 and self.n_classes == 1 and self.cin == 2 * C and self.dtype_code == _lib.DTYPE_BF16
+        assert self.ntaps == 27 and self.n_classes == 1 and self.cin == 2 * C and self.dtype_code in (_lib.DTYPE_BF16, _lib.DTYPE_BF16X2)
         A = self.cout
         Ap = self.cout_pad
         W = self._ctor[0].view(3, 3, 3, A, 2 * C)                 # [kz, ky, kx, a, c]

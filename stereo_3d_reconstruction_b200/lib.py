@@ -60,8 +60,8 @@ SIGNATURES = {
     's3d_conv_cls_workspace_bytes': ([_i, _i, _i, _i], ctypes.c_int64),
     's3d_conv_cls_soft_argmin': ([ctypes.POINTER(S3dConvParams), _vp, _vp, _vp, _vp, _vp, ctypes.c_float, _vp], _i),
     's3d_conv2d_halo': ([_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i64, _i64, _i64, _i, _vp], _i),
-    's3d_map_conv': ([_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp], _i),
-    's3d_concat_gonce_assemble': ([_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp], _i),
+    's3d_map_conv': ([_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp], _i),
+    's3d_concat_gonce_assemble': ([_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp], _i),
     's3d_cost_volume_concat': ([_vp, _vp, _i, _i, _i, _i, _i, _i, _vp], _i),
     's3d_soft_argmin': ([_vp, _vp, _i, _i, _i, _i, _f, _vp], _i),
     's3d_tap_gather_soft_argmin': ([_vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp], _i),

@@ -283,9 +283,9 @@ class _StereoBase(nn.Module):
         # 'bf16x3' (split operands): the reference-once kernel only (C = 32 feature channels, 64-wide first layer)
         ro_split = (self._split and C == 32 and isinstance(p0, PackedConv) and p0.cout_pad == 64 and p0.act == _lib.ACT_RELU and
                     not _lib.KNOBS['no_ref_once'])
-        # SHEARED form of the cost volume + first aggregation layer (bf16, 32 feature channels, 64-wide ReLU layer): 2-D map
-        # convolutions + one streaming pass; its kernels fill the chip at every batch size
-        sheared = (cfg.NETWORK.COST_VOLUME == 'concat' and self.precision == 'bf16' and C == 32 and p5.cout_pad == C and
+        # SHEARED form of the cost volume + first aggregation layer (bf16 and the bf16 pairs of 'bf16x3', 32 feature channels,
+        # 64-wide ReLU layer): 2-D map convolutions + one streaming pass; its kernels fill the chip at every batch size
+        sheared = (cfg.NETWORK.COST_VOLUME == 'concat' and (self.precision == 'bf16' or ro_split) and C == 32 and p5.cout_pad == C and
                    isinstance(p0, PackedConv) and p0.weight_ns is not None and p0.cout_pad == 64 and p0.act == _lib.ACT_RELU and
                    D >= 4 and w + 2 <= 127 and not _lib.KNOBS['no_sheared'] and not _lib.KNOBS['no_concat_fuse'] and
                    not _lib.KNOBS['no_scatter'])
@@ -324,7 +324,7 @@ class _StereoBase(nn.Module):
                             'maps_r': self._buf('sh_mr', (B, 1, h, w + 4, 384), torch.float32),
                             'edge_l': self._buf('sh_el', (B, 1, h, D, 256), torch.float32),
                             'edge_r': self._buf('sh_er', (B, 1, h, D, 256), torch.float32)}
-                    a = ops.conv_concat_volume_sheared(p0, featp, B, D, pad, out=self._buf('a0', (2 * B, D, h, w, 64), dt), bufs=bufs)
+                    a = ops.conv_concat_volume_sheared(p0, featp, B, D, pad, out=self._buf('a0', (2 * B, D, h, w, cm * 64), dt), bufs=bufs)
                 else:
                     a = ops.conv_concat_volume(p0, featp, B, D, pad, out=self._buf('a0', (2 * B, D, h, w, cm * p0.cout_pad), dt),
                                                ref_once=ro)

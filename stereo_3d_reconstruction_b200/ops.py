@@ -232,15 +232,19 @@ def conv_concat_volume_sheared(pc, featp, B, D, pad, out=None, bufs=None):
     tensor cores (1/14 of the layer's MMAs) + one streaming pass that writes the volume (include/s3d.h,
     s3d_concat_gonce_assemble; layers.py, PackedConv.gonce_convs).  featp as for conv_concat_volume.  bufs: optional dict of
     persistent fp32 workspaces {'maps_l', 'maps_r': [B,1,h,w+4,384], 'edge_l', 'edge_r': [B,1,h,D,256]}."""
+    from .layers import is_split
     _chk(featp, out)
+    split = is_split(pc.dtype_code)              # 'bf16x3': featp rows and the output are bf16 pairs [hi | lo], three MMAs per product
+    cm = 2 if split else 1
     n2, one, h, pitch, C = featp.shape
+    C //= cm
     assert n2 == 2 * B and one == 1 and featp.is_contiguous() and featp.dtype == torch.bfloat16
     assert pc.cin_pad == 2 * C and pc.cout_pad == 64 and pc.act == _lib.ACT_RELU and pad >= D - 1 and D >= 2
     w = pitch - 2 * pad
     g = pc.gonce_convs(C, pad, w, D)
     bufs = {} if bufs is None else bufs
     res = {}
-    use_mc = C == 32 and not _lib.KNOBS['no_map_conv']       # the halo-once map engine (csrc/map_conv.cu): 64-byte pixel rows
+    use_mc = C == 32 and not _lib.KNOBS['no_map_conv']       # the halo-once map engine (csrc/map_conv.cu): 32 feature channels
     for name, key, sl in (('left', 'maps_l', slice(0, B)), ('right', 'maps_r', slice(B, 2 * B)),
                           ('edge_left', 'edge_l', slice(0, B)), ('edge_right', 'edge_r', slice(B, 2 * B))):
         conv = g[name]
@@ -252,18 +256,19 @@ def conv_concat_volume_sheared(pc, featp, B, D, pad, out=None, bufs=None):
         if use_mc:
             x = featp[sl]
             rc = _lib.load().s3d_map_conv(x.data_ptr(), conv.weight.data_ptr(), o.data_ptr(), B, h, pitch, ow, off, ntx,
-                                          conv.cout_pad, _stream())
+                                          conv.cout_pad, pc.dtype_code, _stream())
             _lib.check(rc, 's3d_map_conv')
             _lib.count_launch()
             res[key] = o
         else:
             res[key] = conv(featp[sl], out=o)
+    Co = cm * 64
     if out is None:
-        out = torch.empty((2 * B, D, h, w, 64), dtype=torch.bfloat16, device=featp.device)
-    assert out.is_contiguous() and out.shape == (2 * B, D, h, w, 64) and out.dtype == torch.bfloat16
+        out = torch.empty((2 * B, D, h, w, Co), dtype=torch.bfloat16, device=featp.device)
+    assert out.is_contiguous() and out.shape == (2 * B, D, h, w, Co) and out.dtype == torch.bfloat16
     rc = _lib.load().s3d_concat_gonce_assemble(res['maps_l'].data_ptr(), res['maps_r'].data_ptr(), res['edge_l'].data_ptr(),
                                                res['edge_r'].data_ptr(), pc.bias.data_ptr(), out.data_ptr(), B, D, h, w, w + 4,
-                                               _stream())
+                                               _lib.DTYPE_BF16X2 if split else _lib.DTYPE_BF16, _stream())
     _lib.check(rc, 's3d_concat_gonce_assemble')
     _lib.count_launch()
     return out

@@ -277,3 +277,34 @@ def test_conv_concat_volume_ref_once_split(B, D, h, w):
     for z in range(D):
         ez = (got[:, z] - ref[:, z]).abs().max().item()
         assert ez <= TOL * scale, (z, ez, scale)
+
+
+@pytest.mark.parametrize('B,D,h,w', [(1, 8, 16, 24), (2, 4, 9, 13), (1, 32, 64, 64), (2, 2, 8, 8)])
+def test_conv_concat_volume_sheared_split(B, D, h, w):
+    """SHEARED form of the cost volume + first aggregation layer on split (BF16X2) operands: map convolutions with three MMAs per
+    product (map_conv_kernel<.., kSplit>) + the streaming pass writing bf16 pairs, against Conv3d + ReLU over the oracle's concat
+    volume on UNROUNDED fp32 features, plane by plane and at the edge columns: 1e-4 of the output's max."""
+    C, cout = 32, 64
+    torch.manual_seed(22)
+    conv = nn.Conv3d(2 * C, cout, 3, 1, 1, bias=True)
+    pc = PackedConv.from_conv(conv, None, lib.ACT_RELU, X2, 'cuda')
+    f = torch.randn(2 * B, C, h, w)
+    feat = _split(to_cl(f)).cuda()                                      # [2B,1,h,w, hi(C) | lo(C)]
+    pad = max(D, 4)
+    P = w + 2 * pad
+    featp = torch.zeros(2 * B, 1, h, P, 2 * C, dtype=torch.bfloat16, device='cuda')
+    featp[:, :, :, pad:pad + w] = feat
+    got = ops.conv_concat_volume_sheared(pc, featp, B, D, pad)
+    torch.cuda.synchronize()
+    assert got.shape == (2 * B, D, h, w, 2 * cout)
+    got = _unsplit(got)
+    ref_vol = torch.cat([O.build_concat_volume(f[:B], f[B:], D, -1), O.build_concat_volume(f[B:], f[:B], D, +1)], 0)
+    with torch.no_grad():
+        ref = to_cl(F.relu(conv(ref_vol)))
+    scale = ref.abs().max().item() + 1e-6
+    for z in range(D):
+        ez = (got[:, z] - ref[:, z]).abs().max().item()
+        assert ez <= TOL * scale, (z, ez, scale)
+    for x in (0, w - 1):
+        ex = (got[:, :, :, x] - ref[:, :, :, x]).abs().max().item()
+        assert ex <= TOL * scale, (x, ex, scale)
