@@ -133,18 +133,21 @@ def test_chamfer_bit_exact(B, N, M, dup):
 
 @pytest.mark.parametrize('B,N,M,dup', [(2, 300, 1000, True), (1, 1, 1, False), (3, 17, 5, True), (2, 2048, 4096, True),
                                        (1, 1025, 1023, False), (2, 4100, 2500, True), (1, 257, 33, True), (4, 31, 513, False)])
-def test_chamfer_symmetric_one_pass_bit_exact(B, N, M, dup):
+@pytest.mark.parametrize('R', [4, 8])
+def test_chamfer_symmetric_one_pass_bit_exact(B, N, M, dup, R):
     """The symmetric kernel (every pair evaluated once for both directions; packed fp32 ops, value-only minima, index by
     chunk rescan, 64-bit atomicMin keys) forced at every size: bit-identical to the C oracle, whichever set is the larger,
     with ragged tails, several shared-memory tiles of the streamed set (> 2048 points) and exact ties."""
     a, b = synthetic.point_clouds(B, N, M, seed=7, duplicates=dup)
     rd1, rd2, ri1, ri2 = OC.chamfer_c(a.numpy(), b.numpy())
     lib.set_knob('chamfer_sym', 1)
+    lib.set_knob('chamfer_sym_r', R)                        # resident points per lane: both instantiations
     try:
         assert lib.load().s3d_chamfer_workspace_bytes(B, N, M) == 8 * B * min(N, M)
         d1, d2, i1, i2 = ops.chamfer_forward(a.cuda(), b.cuda())
     finally:
         lib.set_knob('chamfer_sym', 0)
+        lib.set_knob('chamfer_sym_r', 0)
     assert np.array_equal(i1.cpu().numpy(), ri1) and np.array_equal(i2.cpu().numpy(), ri2)
     assert np.array_equal(d1.cpu().numpy(), rd1) and np.array_equal(d2.cpu().numpy(), rd2)
 
