@@ -33,7 +33,7 @@ constexpr int kRows = 2;           // image rows per tile
 constexpr int kM = kWP * kRows;    // 128
 constexpr int kMaxStages = 6;
 constexpr int kTmemCols = kGroups * kM;   // 512
-static_assert(kGroups == 4, "the epilogue maps group g to view g & 1 and pair tiles g >> 1, g >> 1 + 2, ...");
+static_assert(kGroups == 4, "the epilogue maps group g to buffer g, pair tiles g >> 1, g >> 1 + 2, ..., alternating views");
 
 struct CorrArgs {
   float* disp;
@@ -98,13 +98,17 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap map_f, const __grid_constant_
     // 2-4 MMAs, but around them sit ~800 cycles of serial barrier waits, fences and commits (clock64 timeline,
     // profiles/r2_corr_tc_timeline.txt): with one issuer that chain, 28 items long, WAS the kernel.  Both issuers wait on the
     // same `full` barrier of a stage and both commit to its `empty` barrier (count 2).
-    const int view = warp - 1;
+    const int view = warp - 1;                             // buffer parity j of this issuer's items (buffers j, j + 2)
     int stage = 0;  uint32_t phase = 0;
-    int buf = view;  uint32_t acc_phase = 0;               // items alternate views: view v uses accumulator buffers v, v + 2
+    int buf = view;  uint32_t acc_phase = 0;
+    int kt = 0;                                            // running pair-tile index of this CTA
     const int kper = a.row_bytes >> 5;
     const uint64_t hi = ptx::make_smem_desc(0, a.row_bytes) & 0xFFFFFFFF00000000ull;
     const uint32_t smem_u = ptx::smem_u32(smem);
-    for (int pt = blockIdx.x; pt < a.pair_tiles; pt += gridDim.x) {
+    for (int pt = blockIdx.x; pt < a.pair_tiles; pt += gridDim.x, ++kt) {
+      // which view lands in which buffer flips every second pair tile (v = j ^ bit 1 of the pair-tile index), so that an
+      // epilogue group alternates between the two views (see the epilogue)
+      const int v = view ^ ((kt >> 1) & 1);
       ptx::mbar_wait(&ctrl.acc_empty[buf], acc_phase ^ 1);
       const uint32_t d_tmem = tmem_base + buf * kM;
       for (int ch = 0; ch < a.nchunks; ++ch) {
@@ -115,7 +119,7 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap map_f, const __grid_constant_
         const uint64_t rdesc = hi | (((sa + a.op_bytes) >> 4) | (1u << 16));
         if (ptx::elect_one()) {
           for (int k = 0; k < kper; ++k)
-            ptx::mma_bf16(d_tmem, (view ? rdesc : ldesc) + 2 * k, (view ? ldesc : rdesc) + 2 * k, a.idesc, (ch | k) != 0);
+            ptx::mma_bf16(d_tmem, (v ? rdesc : ldesc) + 2 * k, (v ? ldesc : rdesc) + 2 * k, a.idesc, (ch | k) != 0);
           ptx::tc_commit(&ctrl.empty[stage]);              // the stage is free once BOTH views have read it
           if (ch == a.nchunks - 1) ptx::tc_commit(&ctrl.acc_full[buf]);
         }
@@ -132,35 +136,35 @@ corr_tc_kernel(const __grid_constant__ CUtensorMap map_f, const __grid_constant_
     const int xw0 = (q & 1) * 32;              // first x of the warp
     const int D = a.D, w = a.w;
     const float scale2 = a.inv_c * 1.4426950408889634f;     // 1/C * log2(e)
-    // kGroups epilogue groups take the (pair tile, view) items round-robin; item i uses accumulator buffer i % 4 = its group's.
-    // With 4 groups and 2 views a group always serves the SAME view (group g: view g & 1, pair tiles g >> 1, g >> 1 + 2, ...),
-    // so everything that depends on the view -- disparity window, chunk range, closed-form tail -- is computed once per thread.
-    // (The timeline in profiles/r2_corr_tc_timeline.txt showed ~1100 cycles of serial per-item index arithmetic and a chunk
-    // loop bound by one warp's dependent-issue latency; hence: loop-invariant setup, ONE max over all columns first, then
-    // 16-way independent ex2 + four partial sums per chunk instead of an online softmax.)
+    // kGroups epilogue groups take the items round-robin; item i = (pair tile k, buffer parity j) uses accumulator buffer
+    // 2 (k & 1) + j = its group's.  The VIEW of an item is v = j ^ bit 1 of k, so a group ALTERNATES between left- and
+    // right-referenced items: a warp's band covers 2 chunks of 16 target columns for one view and 4 for the other (x < 32 /
+    // x >= 32), and with a fixed view per group the 4-chunk warps paced their group while the 2-chunk warps idled (third timeline
+    // in profiles/r2_corr_tc_timeline.txt).  One max over all columns first, then 16-way independent ex2 + four partial sums per
+    // chunk (no online softmax); tile indices advance incrementally (no division in the loop).
     const int grp = (warp - 4) >> 2;
     const int buf = grp;  uint32_t acc_phase = 0;
-    const bool left_ref = (grp & 1) == 0;
-    // target columns this warp needs: left-ref xt in [xw0-D+1, xw0+31], right-ref xt in [xw0, xw0+31+D-1]
-    const int lo = left_ref ? max(0, xw0 - D + 1) : xw0;
-    const int hi_ = left_ref ? xw0 + 31 : min(kWP - 1, xw0 + 31 + D - 1);
-    const int c_lo = lo >> 4, c_hi = hi_ >> 4;            // 16-column chunks, warp-uniform
-    // out-of-image disparities keep cost 0 (oracle semantics): d in [dz0, D) where
-    //   left-ref : x - d < 0   <=>  d > x            right-ref: x + d >= w  <=>  d >= w - x
-    const int dz0 = left_ref ? min(D, x + 1) : min(D, max(0, w - x));
-    // the target columns inside the window as a 64-bit mask (bit xt): left xt in [x - dz0 + 1, x], right xt in [x, x + dz0 - 1]
-    const uint64_t ones = dz0 >= 64 ? ~0ull : ((1ull << dz0) - 1ull);
-    const uint64_t win = left_ref ? ones << (x - dz0 + 1) : ones << x;
-    const float m0 = dz0 < D ? 0.f : -1e30f;               // the zero-cost tail takes part in the max; else a finite floor
-    const float tail_cnt = (float)(D - dz0), tail_d = 0.5f * (float)(dz0 + D - 1);
-    const float xs = left_ref ? (float)x : -(float)x, sgn = left_ref ? -1.f : 1.f;
     const uint32_t taddr = tmem_base + buf * kM + rowblk * kWP + (static_cast<uint32_t>(q * 32) << 16);
-    // image / row of this group's first pair tile, advanced incrementally (no division in the loop)
     const int step = 2 * (int)gridDim.x;
     const int step_img = step / a.tiles_per_img, step_row = step % a.tiles_per_img;
     int pt = blockIdx.x + (grp >> 1) * gridDim.x;
     int img = pt / a.tiles_per_img, yt = pt % a.tiles_per_img;
-    for (; pt < a.pair_tiles; pt += step) {
+    int mi = 0;                                             // this group's item counter: pair tile k = (grp >> 1) + 2 mi
+    for (; pt < a.pair_tiles; pt += step, ++mi) {
+      const bool left_ref = ((grp ^ mi) & 1) == 0;
+      // target columns this warp needs: left-ref xt in [xw0-D+1, xw0+31], right-ref xt in [xw0, xw0+31+D-1]
+      const int lo = left_ref ? max(0, xw0 - D + 1) : xw0;
+      const int hi_ = left_ref ? xw0 + 31 : min(kWP - 1, xw0 + 31 + D - 1);
+      const int c_lo = lo >> 4, c_hi = hi_ >> 4;            // 16-column chunks, warp-uniform
+      // out-of-image disparities keep cost 0 (oracle semantics): d in [dz0, D) where
+      //   left-ref : x - d < 0   <=>  d > x            right-ref: x + d >= w  <=>  d >= w - x
+      const int dz0 = left_ref ? min(D, x + 1) : min(D, max(0, w - x));
+      // the target columns inside the window as a 64-bit mask (bit xt): left xt in [x - dz0 + 1, x], right xt in [x, x + dz0 - 1]
+      const uint64_t ones = dz0 >= 64 ? ~0ull : ((1ull << dz0) - 1ull);
+      const uint64_t win = left_ref ? ones << (x - dz0 + 1) : ones << x;
+      const float m0 = dz0 < D ? 0.f : -1e30f;               // the zero-cost tail takes part in the max; else a finite floor
+      const float tail_cnt = (float)(D - dz0), tail_d = 0.5f * (float)(dz0 + D - 1);
+      const float xs = left_ref ? (float)x : -(float)x, sgn = left_ref ? -1.f : 1.f;
       const int n = img + (left_ref ? 0 : a.B), y = yt * kRows + rowblk;
       ptx::mbar_wait(&ctrl.acc_full[buf], acc_phase);
       ptx::tc_fence_after();
